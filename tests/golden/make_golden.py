@@ -1,0 +1,305 @@
+"""
+Generate the golden input/output vectors under tests/golden/ by importing the
+UNMODIFIED reference (ddbourgin/numpy-ml at /root/reference) in the build container.
+
+    python tests/golden/make_golden.py
+
+The reference cannot travel to the GPU box, so its outputs are committed here as small
+.npz fixtures.  Every array is float64 exactly as the reference returned it; inputs are
+float32-representable (drawn as float32, upcast) so the CUDA paths can consume them
+without a representation error.  Case hyper-parameters are stored as a JSON string under
+the key "__cases__" of each file.
+"""
+import collections
+import collections.abc
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+warnings.filterwarnings("ignore")
+collections.Hashable = collections.abc.Hashable            # numpy_ml/utils/data_structures.py:3
+sys.modules.setdefault("tensorflow", types.ModuleType("tensorflow"))
+sys.path.insert(0, "/root/reference")
+
+from numpy_ml.neural_nets import utils as U                      # noqa: E402
+from numpy_ml.neural_nets import activations as A                # noqa: E402
+from numpy_ml.neural_nets.layers import Conv2D, Deconv2D, BatchNorm2D, Add   # noqa: E402
+from numpy_ml.neural_nets.modules import SkipConnectionConvModule            # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def f32(rng, shape, scale=1.0):
+    return (scale * rng.standard_normal(shape, dtype=np.float32)).astype(np.float64)
+
+
+ACTS = {
+    "identity": lambda: A.Identity(),
+    "affine": lambda: A.Affine(slope=0.75, intercept=0.125),
+    "relu": lambda: A.ReLU(),
+    "leaky_relu": lambda: A.LeakyReLU(alpha=0.25),
+    "tanh": lambda: A.Tanh(),
+    "sigmoid": lambda: A.Sigmoid(),
+    "elu": lambda: A.ELU(alpha=0.5),
+    "selu": lambda: A.SELU(),
+    "hard_sigmoid": lambda: A.HardSigmoid(),
+    "softplus": lambda: A.SoftPlus(),
+    "gelu": lambda: A.GELU(),
+    "exponential": lambda: A.Exponential(),
+}
+ACT_PARAMS = {"affine": (0.75, 0.125), "leaky_relu": (0.25, 0.0), "elu": (0.5, 0.0)}
+
+
+def save(name, arrays, cases):
+    arrays = {k: np.ascontiguousarray(v) for k, v in arrays.items()}
+    arrays["__cases__"] = np.array(json.dumps(cases))
+    np.savez_compressed(os.path.join(HERE, name), **arrays)
+    print(name, len(cases), "cases,", sum(v.nbytes for v in arrays.values()) // 1024, "KiB")
+
+
+def to_list(p):
+    return list(p) if isinstance(p, tuple) else p
+
+
+def to_pad(p):
+    return tuple(p) if isinstance(p, list) else p
+
+
+# --------------------------------------------------------------------------------------------
+def gen_utils():
+    rng = np.random.default_rng(7)
+    arrays, cases = {}, []
+
+    # calc_pad_dims_2D
+    pads = []
+    for (xs, od, ks, s, d) in [((2, 56, 56, 3), (56, 56), (3, 3), 1, 0), ((1, 28, 28, 2), (28, 28), (3, 3), 2, 2),
+                               ((1, 9, 7, 2), (9, 7), (2, 4), 1, 0), ((1, 8, 8, 1), (8, 8), (4, 4), 1, 0),
+                               ((1, 32, 32, 4), (32, 32), (1, 1), 1, 0), ((3, 11, 13, 2), (6, 7), (3, 5), 2, 1),
+                               ((1, 5, 5, 1), (5, 5), (3, 3), 1, 3)]:
+        pads.append({"X_shape": list(xs), "out_dim": list(od), "kernel_shape": list(ks), "stride": s,
+                     "dilation": d, "out": list(int(v) for v in U.calc_pad_dims_2D(xs, od, ks, s, d))})
+    cases.append({"kind": "calc_pad_dims_2D", "items": pads})
+
+    # pad2D / dilate
+    X = f32(rng, (2, 5, 4, 3))
+    for i, (pad, ks, s, d) in enumerate([(2, None, None, 0), ((1, 2), None, None, 0), ((0, 3, 2, 1), None, None, 0),
+                                         ("same", (3, 3), 1, 0), ("same", (2, 3), 2, 1)]):
+        Xp, p4 = U.pad2D(X, pad, ks, s, d)
+        arrays[f"pad2D{i}/X"], arrays[f"pad2D{i}/out"] = X, Xp
+        cases.append({"kind": "pad2D", "id": f"pad2D{i}", "pad": to_list(pad), "kernel_shape": to_list(ks),
+                      "stride": s, "dilation": d, "p4": [int(v) for v in p4]})
+    for i, d in enumerate([1, 2]):
+        arrays[f"dilate{i}/X"], arrays[f"dilate{i}/out"] = X, U.dilate(X, d)
+        cases.append({"kind": "dilate", "id": f"dilate{i}", "d": d})
+
+    # im2col / col2im / conv2D / conv2D_naive
+    confs = [((2, 6, 5, 3), (3, 3, 3, 4), 1, 1, 0), ((2, 7, 7, 2), (2, 3, 2, 3), 2, (1, 2), 0),
+             ((1, 9, 8, 3), (3, 2, 3, 2), 2, (2, 0, 1, 3), 1), ((3, 8, 8, 2), (3, 3, 2, 5), 1, "same", 0),
+             ((2, 10, 10, 2), (3, 3, 2, 2), 2, "same", 2), ((2, 4, 4, 1), (4, 4, 1, 3), 1, 0, 0),
+             ((2, 5, 6, 4), (1, 1, 4, 3), 1, 0, 0), ((1, 12, 11, 2), (2, 2, 2, 2), 3, 1, 4)]
+    for i, (xs, ws, s, pad, d) in enumerate(confs):
+        X, W = f32(rng, xs), f32(rng, ws)
+        X_col, p4 = U.im2col(X, ws, pad, s, d)
+        Z = U.conv2D(X, W, s, pad, d)
+        Zn = U.conv2D_naive(X, W, s, pad, d)
+        assert np.allclose(Z, Zn)
+        C = f32(rng, X_col.shape)
+        back = U.col2im(C, xs, ws, tuple(int(v) for v in p4), s, d)
+        arrays.update({f"conv{i}/X": X, f"conv{i}/W": W, f"conv{i}/X_col": X_col, f"conv{i}/Z": Z,
+                       f"conv{i}/C": C, f"conv{i}/col2im": back})
+        cases.append({"kind": "conv", "id": f"conv{i}", "stride": s, "pad": to_list(pad), "dilation": d,
+                      "p4": [int(v) for v in p4]})
+
+    # deconv2D_naive (pinned domain: symmetric pads)
+    dconfs = [((2, 4, 4, 3), (4, 4, 3, 2), 2, 1), ((2, 5, 3, 2), (3, 3, 2, 4), 1, 1), ((1, 3, 4, 2), (2, 3, 2, 3), 3, (1, 0)),
+              ((2, 4, 5, 3), (3, 3, 3, 2), 2, 0), ((1, 6, 6, 2), (3, 3, 2, 2), 1, "same"), ((2, 3, 3, 2), (5, 5, 2, 3), 2, 2)]
+    for i, (xs, ws, s, pad) in enumerate(dconfs):
+        X, W = f32(rng, xs), f32(rng, ws)
+        arrays.update({f"deconv{i}/X": X, f"deconv{i}/W": W, f"deconv{i}/Z": U.deconv2D_naive(X, W, s, pad, 0)})
+        cases.append({"kind": "deconv", "id": f"deconv{i}", "stride": s, "pad": to_list(pad)})
+    save("utils.npz", arrays, cases)
+
+
+# --------------------------------------------------------------------------------------------
+def gen_activations():
+    x = np.concatenate([np.linspace(-4, 4, 41), [0.0, -0.0, 2.5, -2.5, 1e-3, -1e-3]]).astype(np.float32).astype(np.float64)
+    arrays, cases = {"x": x}, []
+    for name, mk in ACTS.items():
+        a = mk()
+        arrays[f"{name}/fn"] = np.asarray(a.fn(x), dtype=np.float64)
+        arrays[f"{name}/grad"] = np.asarray(a.grad(x), dtype=np.float64)
+        p0, p1 = ACT_PARAMS.get(name, (0.0, 0.0))
+        cases.append({"act": name, "p0": p0, "p1": p1, "str": str(a)})
+    save("activations.npz", arrays, cases)
+
+
+# --------------------------------------------------------------------------------------------
+def run_conv_layer(rng, cls, xs, out_ch, ks, pad, s, d, act, two_calls=False):
+    kw = dict(out_ch=out_ch, kernel_shape=ks, pad=pad, stride=s, act_fn=ACTS[act]())
+    if cls is Conv2D:
+        kw["dilation"] = d
+    L = cls(**kw)
+    X = f32(rng, xs)
+    L.forward(X, retain_derived=False)           # lazy init only
+    W = f32(rng, L.parameters["W"].shape, 0.4)
+    b = f32(rng, L.parameters["b"].shape, 0.3)
+    L.parameters["W"], L.parameters["b"] = W, b
+    L.flush_gradients()
+    Y = L.forward(X)
+    out = {"X": X, "W": W, "b": b, "Y": Y, "Z": L.derived_variables["Z"][0]}
+    dY = f32(rng, Y.shape)
+    out["dLdy"] = dY
+    if two_calls:
+        X2 = f32(rng, xs)
+        Y2 = L.forward(X2)
+        dY2 = f32(rng, Y2.shape)
+        dXs = L.backward([dY, dY2])
+        out.update({"X2": X2, "Y2": Y2, "dLdy2": dY2, "dX": dXs[0], "dX2": dXs[1]})
+    else:
+        out["dX"] = L.backward(dY)
+    out["dW"], out["db"] = L.gradients["W"], L.gradients["b"]
+    return out
+
+
+def gen_conv2d():
+    rng = np.random.default_rng(11)
+    arrays, cases = {}, []
+    confs = [
+        # xs, out_ch, ks, pad, s, d, act, two_calls
+        ((2, 7, 6, 3), 4, (3, 3), 1, 1, 0, "identity", False),
+        ((2, 8, 8, 2), 3, (3, 3), "same", 1, 0, "relu", False),
+        ((3, 9, 7, 1), 5, (2, 3), (1, 2), 2, 0, "tanh", False),
+        ((2, 10, 9, 3), 2, (3, 2), (2, 0, 1, 3), 2, 1, "sigmoid", False),
+        ((2, 12, 12, 2), 4, (3, 3), 0, 2, 2, "identity", False),       # cfg3 miniature
+        ((2, 12, 12, 2), 3, (3, 3), "same", 2, 2, "affine", False),    # 'same' with stride 2, dilation 2
+        ((2, 5, 5, 4), 6, (1, 1), 0, 1, 0, "leaky_relu", False),
+        ((1, 4, 4, 2), 2, (4, 4), 0, 1, 0, "elu", False),              # kernel == input
+        ((2, 6, 6, 5), 3, (3, 3), 1, 1, 0, "identity", True),          # two forwards, list backward
+        ((2, 11, 10, 3), 17, (3, 3), 1, 3, 0, "softplus", False),      # stride leftovers, odd channels
+        ((2, 6, 7, 2), 2, (2, 2), 1, 1, 4, "selu", False),
+        ((2, 7, 7, 3), 4, (3, 3), 1, 1, 0, "gelu", False),
+        ((2, 7, 7, 3), 4, (3, 3), 1, 1, 0, "hard_sigmoid", False),
+        ((2, 6, 6, 2), 3, (3, 3), 1, 1, 0, "exponential", False),
+        ((4, 28, 28, 1), 32, (3, 3), "same", 1, 0, "identity", False),  # cfg1 at N=4
+    ]
+    for i, (xs, oc, ks, pad, s, d, act, two) in enumerate(confs):
+        out = run_conv_layer(rng, Conv2D, xs, oc, ks, pad, s, d, act, two)
+        arrays.update({f"c{i}/{k}": v for k, v in out.items()})
+        p0, p1 = ACT_PARAMS.get(act, (0.0, 0.0))
+        cases.append({"id": f"c{i}", "out_ch": oc, "kernel_shape": list(ks), "pad": to_list(pad), "stride": s,
+                      "dilation": d, "act": act, "p0": p0, "p1": p1, "two_calls": two})
+    save("conv2d_layer.npz", arrays, cases)
+
+
+def gen_deconv2d():
+    rng = np.random.default_rng(13)
+    arrays, cases = {}, []
+    confs = [
+        ((2, 4, 4, 3), 2, (4, 4), 1, 2, "identity", False),            # cfg5 miniature
+        ((2, 5, 4, 2), 3, (3, 3), 1, 1, "relu", False),
+        ((2, 3, 4, 2), 3, (2, 3), (1, 0), 3, "tanh", False),
+        ((1, 4, 5, 3), 2, (3, 3), 0, 2, "sigmoid", False),
+        ((2, 6, 6, 2), 4, (3, 3), "same", 1, "affine", False),
+        ((2, 3, 3, 2), 5, (5, 5), 2, 2, "leaky_relu", True),
+        ((2, 4, 4, 4), 3, (1, 1), 0, 1, "identity", False),
+        ((2, 4, 3, 2), 3, (2, 2), 0, 2, "identity", False),
+    ]
+    for i, (xs, oc, ks, pad, s, act, two) in enumerate(confs):
+        out = run_conv_layer(rng, Deconv2D, xs, oc, ks, pad, s, 0, act, two)
+        arrays.update({f"d{i}/{k}": v for k, v in out.items()})
+        p0, p1 = ACT_PARAMS.get(act, (0.0, 0.0))
+        cases.append({"id": f"d{i}", "out_ch": oc, "kernel_shape": list(ks), "pad": to_list(pad), "stride": s,
+                      "act": act, "p0": p0, "p1": p1, "two_calls": two})
+    save("deconv2d_layer.npz", arrays, cases)
+
+
+def gen_bn_add():
+    rng = np.random.default_rng(17)
+    arrays, cases = {}, []
+    for i, (xs, mm, eps) in enumerate([((3, 5, 4, 6), 0.9, 1e-5), ((2, 7, 7, 3), 0.5, 1e-3), ((4, 2, 3, 1), 0.99, 1e-5)]):
+        L = BatchNorm2D(momentum=mm, epsilon=eps)
+        X = f32(rng, xs) * 2.0 + 0.5
+        L.forward(X, retain_derived=False)
+        L.parameters["scaler"] = f32(rng, (xs[3],)) * 0.5 + 1.0
+        L.parameters["intercept"] = f32(rng, (xs[3],)) * 0.1
+        g, h = L.parameters["scaler"].copy(), L.parameters["intercept"].copy()
+        y = L.forward(X)
+        dy = f32(rng, xs)
+        dX = L.backward(dy)
+        rm1, rv1 = L.parameters["running_mean"].copy(), L.parameters["running_var"].copy()
+        X2 = f32(rng, xs)
+        y_infer = L.forward(X2, retain_derived=False)       # running-stats path
+        arrays.update({f"bn{i}/X": X, f"bn{i}/scaler": g, f"bn{i}/intercept": h, f"bn{i}/y": y, f"bn{i}/dLdy": dy,
+                       f"bn{i}/dX": dX, f"bn{i}/dScaler": L.gradients["scaler"], f"bn{i}/dIntercept": L.gradients["intercept"],
+                       f"bn{i}/running_mean": rm1, f"bn{i}/running_var": rv1, f"bn{i}/X2": X2, f"bn{i}/y_infer": y_infer})
+        cases.append({"kind": "bn", "id": f"bn{i}", "momentum": mm, "epsilon": eps})
+    for i, (n_in, act) in enumerate([(2, "relu"), (3, "tanh"), (2, "identity")]):
+        L = Add(act_fn=ACTS[act]())
+        Xs = [f32(rng, (2, 4, 3, 5)) for _ in range(n_in)]
+        Y = L.forward(Xs)
+        dY = f32(rng, Y.shape)
+        dXs = L.backward(dY)
+        for j, x in enumerate(Xs):
+            arrays[f"add{i}/X{j}"] = x
+        arrays.update({f"add{i}/Y": Y, f"add{i}/dLdY": dY, f"add{i}/dX": np.asarray(dXs[0], dtype=np.float64)})
+        cases.append({"kind": "add", "id": f"add{i}", "n_in": n_in, "act": act})
+    save("bn_add.npz", arrays, cases)
+
+
+def gen_module():
+    rng = np.random.default_rng(19)
+    arrays, cases = {}, []
+    confs = [
+        ((3, 8, 8, 3), 4, 5, (3, 3), (3, 3), (1, 1), 1, 1, 1, 1, 1, "relu"),          # cfg4 miniature
+        ((2, 9, 7, 2), 3, 4, (3, 2), (2, 3), (2, 2), (1, 2), (2, 1), 1, 1, 1, "identity"),
+        ((2, 10, 10, 2), 3, 3, (3, 3), (3, 3), (3, 3), 1, 1, 2, 1, 2, "tanh"),
+    ]
+    for i, (xs, oc1, oc2, k1, k2, ks, pad1, pad2, s1, s2, ss, act) in enumerate(confs):
+        M = SkipConnectionConvModule(out_ch1=oc1, out_ch2=oc2, kernel_shape1=k1, kernel_shape2=k2, kernel_shape_skip=ks,
+                                     pad1=pad1, pad2=pad2, stride1=s1, stride2=s2, stride_skip=ss,
+                                     act_fn=None if act == "identity" else ACTS[act]())
+        X = f32(rng, xs)
+        M.forward(X, retain_derived=False)          # lazy init of every component
+        P = {}
+        for tag, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
+            conv.parameters["W"] = f32(rng, conv.parameters["W"].shape, 0.4)
+            conv.parameters["b"] = f32(rng, conv.parameters["b"].shape, 0.3)
+            bn.parameters["scaler"] = f32(rng, bn.parameters["scaler"].shape) * 0.5 + 1.0
+            bn.parameters["intercept"] = f32(rng, bn.parameters["intercept"].shape) * 0.1
+            bn.reset_running_stats()
+            P["W" + tag], P["b" + tag] = conv.parameters["W"].copy(), conv.parameters["b"].copy()
+            P["g" + tag], P["h" + tag] = bn.parameters["scaler"].copy(), bn.parameters["intercept"].copy()
+        for c in M.components:                      # per-component flush (module.update() breaks the next forward)
+            c.flush_gradients()
+        Y = M.forward(X)
+        dY = f32(rng, Y.shape)
+        dX = M.backward(dY).copy()
+        out = {"X": X, "dLdY": dY, "Y": Y, "dX": dX, "pad_skip": np.asarray(M.pad_skip)}
+        out.update(P)
+        dv = M.derived_variables
+        for k in ["conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "conv_skip_out", "batchnorm_skip_out",
+                  "dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2", "dLdBnSkip", "dLdConvSkip"]:
+            out[k] = np.asarray(dv[k], dtype=np.float64)
+        for tag, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
+            out["dW" + tag], out["db" + tag] = conv.gradients["W"], conv.gradients["b"]
+            out["dg" + tag], out["dh" + tag] = bn.gradients["scaler"], bn.gradients["intercept"]
+            out["rm" + tag], out["rv" + tag] = bn.parameters["running_mean"], bn.parameters["running_var"]
+        arrays.update({f"m{i}/{k}": v for k, v in out.items()})
+        p0, p1 = ACT_PARAMS.get(act, (0.0, 0.0))
+        cases.append({"id": f"m{i}", "out_ch1": oc1, "out_ch2": oc2, "kernel_shape1": list(k1), "kernel_shape2": list(k2),
+                      "kernel_shape_skip": list(ks), "pad1": to_list(pad1), "pad2": to_list(pad2), "stride1": s1,
+                      "stride2": s2, "stride_skip": ss, "act": act, "p0": p0, "p1": p1})
+    save("skip_conv_module.npz", arrays, cases)
+
+
+if __name__ == "__main__":
+    gen_utils()
+    gen_activations()
+    gen_conv2d()
+    gen_deconv2d()
+    gen_bn_add()
+    gen_module()

@@ -1,0 +1,157 @@
+"""Pins oracle/conv_oracle.py against the golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, to_pad, rel_err
+from oracle import conv_oracle as O
+
+TOL = 1e-12
+
+
+def close(a, b, tol=TOL):
+    assert rel_err(a, b) <= tol, rel_err(a, b)
+
+
+def test_utils_golden():
+    z, cases = load_golden("utils.npz")
+    for c in cases:
+        k = c["kind"]
+        if k == "calc_pad_dims_2D":
+            for it in c["items"]:
+                got = O.calc_pad_dims_2D(tuple(it["X_shape"]), tuple(it["out_dim"]), tuple(it["kernel_shape"]),
+                                         it["stride"], it["dilation"])
+                assert list(got) == it["out"]
+        elif k == "pad2D":
+            ks = tuple(c["kernel_shape"]) if c["kernel_shape"] else None
+            Xp, p4 = O.pad2D(z[c["id"] + "/X"], to_pad(c["pad"]), ks, c["stride"], c["dilation"])
+            assert list(p4) == c["p4"]
+            assert np.array_equal(Xp, z[c["id"] + "/out"])
+        elif k == "dilate":
+            assert np.array_equal(O.dilate(z[c["id"] + "/X"], c["d"]), z[c["id"] + "/out"])
+        elif k == "conv":
+            i = c["id"]
+            X, W = z[i + "/X"], z[i + "/W"]
+            pad = to_pad(c["pad"])
+            X_col, p4 = O.im2col(X, W.shape, pad, c["stride"], c["dilation"])
+            assert list(p4) == c["p4"]
+            assert np.array_equal(X_col, z[i + "/X_col"])
+            close(O.conv2D(X, W, c["stride"], pad, c["dilation"]), z[i + "/Z"])
+            close(O.conv2D_loops(X, W, c["stride"], pad, c["dilation"]), z[i + "/Z"])
+            back = O.col2im(z[i + "/C"], X.shape, W.shape, tuple(c["p4"]), c["stride"], c["dilation"])
+            close(back, z[i + "/col2im"])
+            assert O.calc_conv_out_dims(X.shape, W.shape, c["stride"], tuple(c["p4"]), c["dilation"]) == z[i + "/Z"].shape
+        elif k == "deconv":
+            i = c["id"]
+            close(O.deconv2D_naive(z[i + "/X"], z[i + "/W"], c["stride"], to_pad(c["pad"]), 0), z[i + "/Z"])
+        else:
+            raise AssertionError(k)
+
+
+def test_activations_golden():
+    z, cases = load_golden("activations.npz")
+    x = z["x"]
+    for c in cases:
+        close(O.act_fn(c["act"], x, c["p0"], c["p1"]), z[c["act"] + "/fn"], 1e-15)
+        close(O.act_grad(c["act"], x, c["p0"], c["p1"]), z[c["act"] + "/grad"], 1e-15)
+
+
+def test_conv2d_layer_golden():
+    z, cases = load_golden("conv2d_layer.npz")
+    for c in cases:
+        i, pad = c["id"], to_pad(c["pad"])
+        a = (c["act"], c["p0"], c["p1"])
+        X, W, b = z[i + "/X"], z[i + "/W"], z[i + "/b"]
+        Y, Z = O.conv2d_layer_fwd(X, W, b, c["stride"], pad, c["dilation"], *a)
+        close(Y, z[i + "/Y"])
+        close(Z, z[i + "/Z"])
+        dX, dW, db = O.conv2d_layer_bwd(z[i + "/dLdy"], X, Z, W, c["stride"], pad, c["dilation"], *a)
+        close(dX, z[i + "/dX"])
+        if c["two_calls"]:
+            X2 = z[i + "/X2"]
+            Y2, Z2 = O.conv2d_layer_fwd(X2, W, b, c["stride"], pad, c["dilation"], *a)
+            dX2, dW2, db2 = O.conv2d_layer_bwd(z[i + "/dLdy2"], X2, Z2, W, c["stride"], pad, c["dilation"], *a)
+            close(dX2, z[i + "/dX2"])
+            dW, db = dW + dW2, db + db2
+        close(dW, z[i + "/dW"])
+        close(db, z[i + "/db"])
+
+
+def test_deconv2d_layer_golden():
+    z, cases = load_golden("deconv2d_layer.npz")
+    for c in cases:
+        i, pad = c["id"], to_pad(c["pad"])
+        a = (c["act"], c["p0"], c["p1"])
+        X, W, b = z[i + "/X"], z[i + "/W"], z[i + "/b"]
+        Y, Z = O.deconv2d_layer_fwd(X, W, b, c["stride"], pad, *a)
+        close(Y, z[i + "/Y"])
+        dX, dW, db = O.deconv2d_layer_bwd(z[i + "/dLdy"], X, Z, W, c["stride"], pad, *a)
+        close(dX, z[i + "/dX"])
+        if c["two_calls"]:
+            X2 = z[i + "/X2"]
+            Y2, Z2 = O.deconv2d_layer_fwd(X2, W, b, c["stride"], pad, *a)
+            dX2, dW2, db2 = O.deconv2d_layer_bwd(z[i + "/dLdy2"], X2, Z2, W, c["stride"], pad, *a)
+            close(dX2, z[i + "/dX2"])
+            dW, db = dW + dW2, db + db2
+        close(dW, z[i + "/dW"])
+        close(db, z[i + "/db"])
+
+
+def test_bn_add_golden():
+    z, cases = load_golden("bn_add.npz")
+    for c in cases:
+        i = c["id"]
+        if c["kind"] == "bn":
+            ch = z[i + "/X"].shape[3]
+            y, rm, rv = O.bn2d_fwd(z[i + "/X"], z[i + "/scaler"], z[i + "/intercept"], np.zeros(ch), np.ones(ch),
+                                   c["momentum"], c["epsilon"])
+            close(y, z[i + "/y"])
+            close(rm, z[i + "/running_mean"])
+            close(rv, z[i + "/running_var"])
+            dX, dg, dh = O.bn2d_bwd(z[i + "/dLdy"], z[i + "/X"], z[i + "/scaler"], c["epsilon"])
+            close(dX, z[i + "/dX"], 1e-10)
+            close(dg, z[i + "/dScaler"])
+            close(dh, z[i + "/dIntercept"])
+            y2, _, _ = O.bn2d_fwd(z[i + "/X2"], z[i + "/scaler"], z[i + "/intercept"], rm, rv,
+                                  c["momentum"], c["epsilon"], use_batch_stats=False)
+            close(y2, z[i + "/y_infer"])
+        else:
+            Xs = [z[f"{i}/X{j}"] for j in range(c["n_in"])]
+            Y, total = O.add_fwd(Xs, c["act"])
+            close(Y, z[i + "/Y"])
+            g = O.add_bwd(z[i + "/dLdY"], total, c["n_in"], c["act"])
+            assert len(g) == c["n_in"]
+            close(g[-1], z[i + "/dX"])
+
+
+def test_skip_conv_module_golden():
+    z, cases = load_golden("skip_conv_module.npz")
+    for c in cases:
+        i = c["id"]
+        P = {}
+        for t in "12s":
+            ch = z[f"{i}/g{t}"].shape[0]
+            P.update({"W" + t: z[f"{i}/W{t}"], "b" + t: z[f"{i}/b{t}"], "g" + t: z[f"{i}/g{t}"], "h" + t: z[f"{i}/h{t}"],
+                      "rm" + t: np.zeros(ch), "rv" + t: np.ones(ch)})
+        o = O.skip_conv_module_fwd_bwd(z[i + "/X"], z[i + "/dLdY"], P, tuple(c["kernel_shape1"]), tuple(c["kernel_shape2"]),
+                                       tuple(c["kernel_shape_skip"]), to_pad(c["pad1"]), to_pad(c["pad2"]), c["stride1"],
+                                       c["stride2"], c["stride_skip"], c["act"], c["p0"], c["p1"])
+        assert list(o["pad_skip"]) == list(z[i + "/pad_skip"])
+        for k in ["Y", "dX", "conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "conv_skip_out",
+                  "batchnorm_skip_out", "dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2", "dLdBnSkip", "dLdConvSkip"]:
+            close(o[k], z[f"{i}/{k}"], 1e-9)
+        for t in "12s":
+            for k in ("dW", "db", "dg", "dh", "rm", "rv"):
+                close(np.asarray(o[k + t]).reshape(z[f"{i}/{k}{t}"].shape), z[f"{i}/{k}{t}"], 1e-9)
+
+
+def test_oracle_error_conventions():
+    X = np.zeros((1, 3, 3, 1))
+    with pytest.raises(ValueError):
+        O.im2col(X, (5, 5, 1, 1), 0, 1)                       # kernel > padded input  (utils.py:463-467)
+    with pytest.raises(TypeError):
+        O.col2im(np.zeros((9, 1)), X.shape, (3, 3, 1, 1), 1, 1)     # pad must be a 4-tuple (utils.py:577-578)
+    with pytest.raises(ValueError):
+        O.calc_pad_dims_2D([1, 3, 3, 1], (3, 3), (3, 3), 1)   # X_shape not a tuple   (utils.py:77-87)
+    with pytest.raises(ValueError):
+        O.calc_pad_dims_2D((1, 9, 9, 1), (3, 3), (3, 3), 1)   # negative pad          (utils.py:116-119)
