@@ -1,0 +1,169 @@
+/*
+ * npml_conv.h -- C ABI of libnpmlconv.so, the B200 (sm_100a) implementation of the
+ * numpy-ml convolution hot path.
+ *
+ * The reference (ddbourgin/numpy-ml) is pure Python and has no FFI of its own; the drop-in
+ * surface is the Python layer API (numpy_ml/neural_nets/{utils/utils.py,layers/layers.py}).
+ * Every entry point below therefore names the reference function whose arithmetic it
+ * replaces (file:line relative to numpy_ml/neural_nets/).  The Python host layer under
+ * numpy-ml_b200/ resolves all geometry ('same' pads, output dims, error cases) exactly as
+ * the reference does and passes plain ints here; INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - return 0 on success, non-zero on error; npml_last_error() returns a thread-local message.
+ *   - every pointer is a DEVICE pointer owned by the caller (inputs, outputs, workspace).  The
+ *     library never allocates or frees device memory on these calls and never synchronises:
+ *     all work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - activations are NHWC (n_ex, rows, cols, ch); weights are (fr, fc, in_ch, out_ch) fp32;
+ *     bias / dW / db are fp32.  The element type of activation tensors is selected by
+ *     desc.mode: NPML_MODE_FP32 and NPML_MODE_TF32 -> float, NPML_MODE_BF16 -> bfloat16.
+ *   - "dil" is the tap spacing D = dilation + 1 (numpy-ml's `dilation` counts inserted zeros,
+ *     utils/utils.py:95).
+ */
+#ifndef NPML_CONV_H_
+#define NPML_CONV_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { NPML_MODE_FP32 = 0, NPML_MODE_TF32 = 1, NPML_MODE_BF16 = 2 };
+
+/* activation ids (activations/activations.py); p0/p1 = alpha, or slope/intercept for AFFINE */
+enum {
+  NPML_ACT_IDENTITY = 0, NPML_ACT_AFFINE = 1, NPML_ACT_RELU = 2, NPML_ACT_LEAKY_RELU = 3,
+  NPML_ACT_TANH = 4, NPML_ACT_SIGMOID = 5, NPML_ACT_ELU = 6, NPML_ACT_SELU = 7,
+  NPML_ACT_HARD_SIGMOID = 8, NPML_ACT_SOFTPLUS = 9, NPML_ACT_GELU = 10, NPML_ACT_EXPONENTIAL = 11
+};
+
+/* element types for the dtype-explicit elementwise entry points */
+enum { NPML_F32 = 0, NPML_BF16 = 1, NPML_F64 = 2 };
+
+/* operation ids for npml_workspace_bytes */
+enum {
+  NPML_OP_CONV_FPROP = 0, NPML_OP_CONV_DGRAD = 1, NPML_OP_CONV_WGRAD = 2,
+  NPML_OP_DECONV_FPROP = 3, NPML_OP_DECONV_DGRAD = 4, NPML_OP_DECONV_WGRAD = 5,
+  NPML_OP_DZ_PREP = 6, NPML_OP_BN = 7
+};
+
+/*
+ * Geometry of one Conv2D / Deconv2D layer call.  For both layer kinds (N,H,W,C) is the layer
+ * INPUT volume, K the layer's out_ch and (OH,OW) the layer OUTPUT rows/cols:
+ *   Conv2D  : OH = (H + pr1 + pr2 - (fr*dil - dil + 1)) / stride + 1    (utils/utils.py:653-657)
+ *   Deconv2D: OH = stride*(H-1) + fr - pr1 - pr2, dil must be 1          (utils/utils.py:780-786)
+ */
+typedef struct npml_conv_desc {
+  int32_t N, H, W, C;          /* input volume, NHWC                                   */
+  int32_t K;                   /* out_ch                                               */
+  int32_t fr, fc;              /* kernel rows / cols                                   */
+  int32_t stride;
+  int32_t dil;                 /* tap spacing D = dilation + 1                         */
+  int32_t pr1, pr2, pc1, pc2;  /* (top, bottom, left, right) zero padding              */
+  int32_t OH, OW;              /* output rows / cols                                   */
+  int32_t mode;                /* NPML_MODE_*                                          */
+  int32_t act;                 /* NPML_ACT_* applied in the forward epilogue           */
+  float act_p0, act_p1;
+  int32_t accumulate;          /* wgrad: dW += result (layers/layers.py:3087-3089)      */
+  int32_t reserved;
+} npml_conv_desc;
+
+/* ---- Conv2D (layers/layers.py:2895-3178) --------------------------------------------------
+ * fprop replaces pad2D + im2col + W_col @ X_col + b + act_fn  (utils/utils.py:603-665,
+ * layers/layers.py:3037-3038).  Z (pre-activation) and/or Y (= act(Z)) may be NULL. */
+int npml_conv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b,
+                      void* Z, void* Y, void* ws, size_t ws_bytes, void* stream);
+/* dgrad replaces W_col @ dLdZ_col + col2im / np.add.at  (layers/layers.py:3113-3114,
+ * utils/utils.py:546-595); gather form, no atomics.  dZ already holds dLdy * act'(Z). */
+int npml_conv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX,
+                      void* ws, size_t ws_bytes, void* stream);
+/* wgrad replaces im2col + dLdZ_col @ X_col.T  (layers/layers.py:3106-3110); deterministic
+ * fixed-order split reduction.  dW is (fr, fc, C, K) fp32. */
+int npml_conv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---- Deconv2D (layers/layers.py:3353-3568, utils/utils.py:720-794) ------------------------
+ * fprop: Z[n, iy*s + r - pr1, ix*s + t - pc1, k] += X[n,iy,ix,c] * W[r,t,c,k]  (no zero-stuffing)
+ * dgrad: dX[n,iy,ix,c] = sum dZ[n, iy*s + r - pr1, ix*s + t - pc1, k] * W[r,t,c,k]
+ * wgrad: dW[r,t,c,k]  = sum X[n,iy,ix,c] * dZ[n, iy*s + r - pr1, ix*s + t - pc1, k] */
+int npml_deconv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b,
+                        void* Z, void* Y, void* ws, size_t ws_bytes, void* stream);
+int npml_deconv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX,
+                        void* ws, size_t ws_bytes, void* stream);
+int npml_deconv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW,
+                        void* ws, size_t ws_bytes, void* stream);
+
+size_t npml_workspace_bytes(const npml_conv_desc* d, int op);
+
+/* ---- backward prologue: dZ = dLdy * act'(Z) and db = sum_{n,oh,ow} dZ --------------------
+ * (layers/layers.py:3103, 3109; Add._bwd layers/layers.py:739-742 when db == NULL).
+ * rows = N*OH*OW, ch = K.  Z may be NULL for NPML_ACT_IDENTITY.  dZ may alias dY.
+ * db (fp32, ch entries) may be NULL; accumulate != 0 adds into db. */
+int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, float p1, const void* dY,
+                 int32_t dy_dtype, const void* Z, int32_t z_dtype, void* dZ, int32_t dz_dtype,
+                 float* db, int32_t accumulate, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- elementwise helpers ------------------------------------------------------------------ */
+/* dst = (dst_dtype) src, n elements; used at the NumPy(float64) <-> device boundary. */
+int npml_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
+              void* stream);
+/* Add.forward (layers/layers.py:690-711): sum = x0 + ... + x_{n_in-1}; Y = act(sum).
+ * `sum` may be NULL when act is identity. */
+int npml_add_act_fwd(int32_t n_in, const void* const* xs, int32_t dtype, int64_t n, int32_t act,
+                     float p0, float p1, void* sum, void* Y, void* stream);
+/* activation fn on its own (activations/activations.py `fn`): Y = act(Z) */
+int npml_act_fwd(const void* Z, void* Y, int32_t dtype, int64_t n, int32_t act, float p0, float p1,
+                 void* stream);
+
+/* ---- BatchNorm2D (layers/layers.py:969-1215) ---------------------------------------------
+ * fwd, use_batch_stats != 0: per-channel mean and BIASED variance over rows = N*H*W;
+ *   running = momentum*running + (1-momentum)*batch (layers/layers.py:1146-1150);
+ *   y = scaler*(x-mean)/sqrt(var+eps) + intercept.  save_mean/save_rstd (fp32, ch) receive the
+ *   statistics used.  use_batch_stats == 0 normalises with running_mean/var and leaves them.
+ * bwd (layers/layers.py:1192-1215): d_scaler/d_intercept accumulate (+=) when accumulate != 0.
+ * stats buffers, scaler, intercept, gradients are fp32; x/y/dy/dx are `dtype`. */
+int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, int32_t dtype,
+                  const float* scaler, const float* intercept, float* running_mean,
+                  float* running_var, float momentum, float eps, int32_t use_batch_stats,
+                  float* save_mean, float* save_rstd, void* ws, size_t ws_bytes, void* stream);
+int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const void* x, void* dx, int32_t dtype,
+                  const float* scaler, const float* save_mean, const float* save_rstd,
+                  float* d_scaler, float* d_intercept, int32_t accumulate, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* ---- SGD step on the (all-reduced) gradient (optimizers/optimizers.py:110-148) ----------------
+ * g' = grad * grad_scale (grad_scale carries the clip-norm factor t/||g||, 1 when not clipping);
+ * u = momentum*velocity + lr*g'; velocity = u; param -= u.  All fp32, n elements. */
+int npml_sgd_update(float* param, const float* grad, float* velocity, int64_t n, float lr, float momentum,
+                    float grad_scale, void* stream);
+/* sum of squares of an fp32 buffer into *out (double, device); deterministic two-stage reduction */
+int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- im2col / col2im exports (utils/utils.py:486-595), API parity only; fp32 ---------------
+ * X_col is (fr*fc*C, OH*OW*N) row-major with q = c*fr*fc + r*fc + t, z = (oh*OW + ow)*N + n.
+ * col2im returns NCHW like the reference (utils/utils.py:595). */
+int npml_im2col(const npml_conv_desc* d, const float* X, float* X_col, void* stream);
+int npml_col2im(const npml_conv_desc* d, const float* X_col, float* X_nchw, void* stream);
+
+/* ---- data-parallel gradient exchange (new; the reference is single process) ---------------
+ * One communicator per process (one process per GPU, torch.distributed style).  The 128-byte
+ * ncclUniqueId is created on rank 0 with npml_comm_unique_id and broadcast by the host. */
+int npml_comm_unique_id(void* id128);
+int npml_comm_init_rank(const void* id128, int32_t nranks, int32_t rank);
+int npml_allreduce_sum_f32(float* buf, int64_t n, void* stream);
+int npml_comm_destroy(void);
+
+/* ---- misc --------------------------------------------------------------------------------- */
+const char* npml_last_error(void);
+/* 1 if the tcgen05 tensor-core path will be used for (desc, op), 0 if the CUDA-core path. */
+int npml_uses_tensor_cores(const npml_conv_desc* d, int op);
+/* number of kernels launched by this library on the calling thread since the last reset */
+int64_t npml_launch_count(int32_t reset);
+int npml_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPML_CONV_H_ */

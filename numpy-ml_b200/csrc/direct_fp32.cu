@@ -1,0 +1,286 @@
+// CUDA-core implicit-GEMM convolution kernels with fp32 accumulation: the exactness mode
+// (NPML_MODE_FP32) and the path for shapes the tensor-core kernels do not take (in_ch = 1, odd
+// channel counts).  No im2col is materialised: the gather of utils/utils.py:541 and the
+// scatter-add of utils/utils.py:591 are folded into the tile loads.
+#include "npml_common.cuh"
+
+namespace npml {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256, PADM = 4;
+
+// ---- fprop / dgrad -------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(NT) gather_conv_kernel(GatherConv g, const TIn* __restrict__ in,
+                                                         const float* __restrict__ w,
+                                                         const float* __restrict__ bias, TOut* __restrict__ Z,
+                                                         TOut* __restrict__ Y) {
+  __shared__ __align__(16) float As[BK][BM + PADM];
+  __shared__ __align__(16) float Bs[BK][BN];
+
+  const int tid = threadIdx.x;
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int Ktot = g.fr * g.fc * g.CI;
+
+  // A-load mapping: one k column, four pixel rows per thread
+  const int a_k = tid % BK;
+  const int a_r = tid / BK;  // 0..15
+  int pn[4], py[4], px[4];
+  bool pv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int64_t p = m0 + a_r + 16 * j;
+    pv[j] = p < P;
+    int64_t q = pv[j] ? p : 0;
+    px[j] = (int)(q % g.OW);
+    q /= g.OW;
+    py[j] = (int)(q % g.OH);
+    pn[j] = (int)(q / g.OH);
+  }
+  // B-load mapping: one out channel, four k rows per thread
+  const int b_c = tid % BN;
+  const int b_r = tid / BN;  // 0..3
+
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += BK) {
+    {
+      const int kk = k0 + a_k;
+      const bool kv = kk < Ktot;
+      const int tap = kv ? kk / g.CI : 0;
+      const int ci = kv ? kk - tap * g.CI : 0;
+      const int r = tap / g.fc, t = tap - r * g.fc;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = 0.f;
+        if (kv && pv[j]) {
+          int iy, ix;
+          bool ok = true;
+          if (g.form == 0) {
+            iy = py[j] * g.s + r * g.D - g.pr;
+            ix = px[j] * g.s + t * g.D - g.pc;
+          } else {
+            int ny = py[j] + g.pr - r * g.D, nx = px[j] + g.pc - t * g.D;
+            ok = ny >= 0 && nx >= 0 && (ny % g.s) == 0 && (nx % g.s) == 0;
+            iy = ny / g.s;
+            ix = nx / g.s;
+          }
+          if (ok && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
+            v = ld_f(in, (((int64_t)pn[j] * g.IH + iy) * g.IW + ix) * g.CI + ci);
+        }
+        As[a_k][a_r + 16 * j] = v;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kl = b_r + 4 * j;
+      const int kk = k0 + kl;
+      const int co = n0 + b_c;
+      float v = 0.f;
+      if (kk < Ktot && co < g.CO) {
+        const int tap = kk / g.CI;
+        const int ci = kk - tap * g.CI;
+        v = w[tap * g.w_tap + ci * g.w_ci + co * g.w_co];
+      }
+      Bs[kl][b_c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t p = m0 + ty * 4 + i;
+    if (p >= P) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= g.CO) continue;
+      float z = acc[i][j] + (bias ? bias[co] : 0.f);
+      if (Z) st_f(Z, p * g.CO + co, z);
+      if (Y) st_f(Y, p * g.CO + co, act_fn(g.act, z, g.p0, g.p1));
+    }
+  }
+}
+
+// ---- wgrad: split over pixel chunks, partials to workspace -----------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(NT) wgrad_partial_kernel(GatherWgrad g, const T* __restrict__ in,
+                                                           const T* __restrict__ grad, float* __restrict__ part,
+                                                           int64_t chunk) {
+  __shared__ __align__(16) float As[BK][BM + PADM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int M = g.fr * g.fc * g.CI;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int64_t p_begin = (int64_t)blockIdx.z * chunk;
+  const int64_t p_end = (p_begin + chunk < P) ? p_begin + chunk : P;
+
+  // A mapping: one (tap, ci) column per thread, four pixel rows
+  const int a_m = tid % BM, a_r = tid / BM;  // a_r 0..3
+  const int kk = m0 + a_m;
+  const bool mv = kk < M;
+  const int tap = mv ? kk / g.CI : 0;
+  const int ci = mv ? kk - tap * g.CI : 0;
+  const int r = tap / g.fc, t = tap - r * g.fc;
+  const int b_c = tid % BN, b_r = tid / BN;
+  const int co_l = n0 + b_c;
+
+  const int tx = tid % 16, ty = tid / 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += BK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kl = a_r + 4 * j;
+      const int64_t p = p0 + kl;
+      float va = 0.f, vb = 0.f;
+      if (p < p_end) {
+        int64_t q = p;
+        const int x = (int)(q % g.OW);
+        q /= g.OW;
+        const int y = (int)(q % g.OH);
+        const int n = (int)(q / g.OH);
+        if (mv) {
+          const int iy = y * g.s + r * g.D - g.pr, ix = x * g.s + t * g.D - g.pc;
+          if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
+            va = ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci);
+        }
+        if (co_l < g.CO) vb = ld_f(grad, p * g.CO + co_l);
+      }
+      As[kl][a_m] = va;
+      Bs[kl][b_c] = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = part + (int64_t)blockIdx.z * M * g.CO;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co < g.CO) out[(int64_t)m * g.CO + co] = acc[i][j];
+    }
+  }
+}
+
+}  // namespace
+
+// Fixed-order reduction of split partials [splits][M][CO] -> dW (strided), shared with tc_wgrad.
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int M, int CO, int CI,
+                                    int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
+                                    float* __restrict__ dW) {
+  const int64_t total = (int64_t)M * CO;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + i];
+    const int m = (int)(i / CO), co = (int)(i - (int64_t)m * CO);
+    const int tap = m / CI, ci = m - tap * CI;
+    const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
+    dW[o] = accumulate ? dW[o] + s : s;
+  }
+}
+
+int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
+                        int64_t o_co, int accumulate, float* dW, cudaStream_t st) {
+  const int64_t total = (int64_t)M * CO;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+int direct_gather_conv(const GatherConv& g, const void* in, const float* w, const float* bias, void* Z,
+                       void* Y, int dtype, cudaStream_t st) {
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  if (P == 0 || g.CO == 0) return 0;
+  dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((g.CO + BN - 1) / BN));
+  if (dtype == NPML_F32)
+    gather_conv_kernel<float, float><<<grid, NT, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
+  else
+    gather_conv_kernel<__nv_bfloat16, __nv_bfloat16>
+        <<<grid, NT, 0, st>>>(g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+static int direct_wgrad_splits(const GatherWgrad& g) {
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int M = g.fr * g.fc * g.CI;
+  const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((g.CO + BN - 1) / BN);
+  int64_t splits = (4LL * num_sms() + tiles - 1) / tiles;
+  const int64_t by_len = (P + 4095) / 4096;  // keep every sequential fp32 sum short
+  if (splits < by_len) splits = by_len;
+  const int64_t max_splits = (P + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits > 1024) splits = 1024;
+  if (splits < 1) splits = 1;
+  return (int)splits;
+}
+
+size_t direct_wgrad_ws_bytes(const GatherWgrad& g) {
+  const int M = g.fr * g.fc * g.CI;
+  return (size_t)direct_wgrad_splits(g) * M * g.CO * sizeof(float);
+}
+
+int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* dW, int dtype, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int M = g.fr * g.fc * g.CI;
+  if (M == 0 || g.CO == 0) return 0;
+  const int splits = direct_wgrad_splits(g);
+  NPML_CHECK(ws_bytes >= direct_wgrad_ws_bytes(g), "workspace too small");
+  int64_t chunk = (P + splits - 1) / splits;
+  chunk = (chunk + BK - 1) / BK * BK;
+  dim3 grid((M + BM - 1) / BM, (g.CO + BN - 1) / BN, splits);
+  if (dtype == NPML_F32)
+    wgrad_partial_kernel<float><<<grid, NT, 0, st>>>(g, (const float*)in, (const float*)grad, (float*)ws, chunk);
+  else
+    wgrad_partial_kernel<__nv_bfloat16>
+        <<<grid, NT, 0, st>>>(g, (const __nv_bfloat16*)in, (const __nv_bfloat16*)grad, (float*)ws, chunk);
+  NPML_LAUNCH_OK();
+  return launch_wgrad_reduce((const float*)ws, splits, M, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate,
+                             dW, st);
+}
+
+}  // namespace npml

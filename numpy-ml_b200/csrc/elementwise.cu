@@ -1,0 +1,582 @@
+// HBM-bound passes around the convolution GEMMs: the backward prologue dZ = dLdy * act'(Z) with
+// the db column sum (layers/layers.py:3103, 3109), Add (layers/layers.py:633-742), BatchNorm2D
+// (layers/layers.py:969-1215), dtype casts, and the im2col / col2im exports.
+// All column reductions are two-stage with a fixed order (deterministic, no atomics).
+#include "npml_common.cuh"
+
+namespace npml {
+
+namespace {
+
+// ---- 4-wide typed access -----------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void load_vec(const void* p, int dtype, int64_t i, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    if (dtype == NPML_F32) {
+      const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if (dtype == NPML_BF16) {
+      const uint2 t = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+      v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    } else {
+      const double* d = reinterpret_cast<const double*>(p) + i;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = (float)d[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (dtype == NPML_F32) v[j] = reinterpret_cast<const float*>(p)[i + j];
+      else if (dtype == NPML_BF16) v[j] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i + j]);
+      else v[j] = (float)reinterpret_cast<const double*>(p)[i + j];
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void store_vec(void* p, int dtype, int64_t i, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    if (dtype == NPML_F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (dtype == NPML_BF16) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 t;
+      t.x = *reinterpret_cast<uint32_t*>(&a);
+      t.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = t;
+    } else {
+      double* d = reinterpret_cast<double*>(p) + i;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) d[j] = (double)v[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      if (dtype == NPML_F32) reinterpret_cast<float*>(p)[i + j] = v[j];
+      else if (dtype == NPML_BF16) reinterpret_cast<__nv_bfloat16*>(p)[i + j] = __float2bfloat16_rn(v[j]);
+      else reinterpret_cast<double*>(p)[i + j] = (double)v[j];
+    }
+  }
+}
+
+inline int dtype_size(int dt) { return dt == NPML_F32 ? 4 : (dt == NPML_BF16 ? 2 : 8); }
+inline bool aligned_for_vec4(const void* p, int dt) {
+  return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (size_t)(4 * dtype_size(dt))) == 0;
+}
+
+// ---- column-reduction skeleton ----------------------------------------------------------------------
+// A [rows][ch] tensor is cut into gridDim.x row slabs; block (TX, TY): thread (tx, ty) owns VEC
+// consecutive channels and rows ty, ty+TY, ... of the slab.  The functor both does the elementwise
+// work and returns NV values per element to be column-summed.  part: [gridDim.x][NV][ch].
+struct ColGeom {
+  int64_t rows;
+  int ch;
+  int64_t rows_per_block;
+  int TX, TY;  // threads over channel groups / over rows
+};
+
+template <int VEC, int NV, typename Acc, typename F>
+__global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __restrict__ part) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Acc* red = reinterpret_cast<Acc*>(smem_raw);  // [TY][TX*VEC*NV]
+  const int tx = threadIdx.x % cg.TX, ty = threadIdx.x / cg.TX;
+  const int c0 = (blockIdx.y * cg.TX + tx) * VEC;
+  const bool active = ty < cg.TY && c0 < cg.ch;
+  Acc acc[NV > 0 ? NV : 1][VEC];
+#pragma unroll
+  for (int a = 0; a < NV; ++a)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[a][j] = (Acc)0;
+  const int64_t r0 = (int64_t)blockIdx.x * cg.rows_per_block;
+  const int64_t r1 = (r0 + cg.rows_per_block < cg.rows) ? r0 + cg.rows_per_block : cg.rows;
+  if (active) {
+    for (int64_t r = r0 + ty; r < r1; r += cg.TY) {
+      float out[NV > 0 ? NV : 1][VEC];
+      f.template run<VEC>(r * cg.ch + c0, c0, out);
+#pragma unroll
+      for (int a = 0; a < NV; ++a)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[a][j] += (Acc)out[a][j];
+    }
+  }
+  if (NV == 0 || part == nullptr) return;
+  const int W = cg.TX * VEC * NV;
+  if (ty < cg.TY) {
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red[ty * W + (a * cg.TX + tx) * VEC + j] = active ? acc[a][j] : (Acc)0;
+  }
+  __syncthreads();
+  if (ty == 0 && c0 < cg.ch) {
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        Acc s = (Acc)0;
+        for (int y = 0; y < cg.TY; ++y) s += red[y * W + (a * cg.TX + tx) * VEC + j];
+        if (c0 + j < cg.ch) part[((int64_t)blockIdx.x * NV + a) * cg.ch + c0 + j] = s;
+      }
+  }
+}
+
+// sums[NV*ch] (double) = fixed-order sum over `nblk` partial rows
+template <typename Acc>
+__global__ void col_final_kernel(const Acc* __restrict__ part, int nblk, int width, double* __restrict__ sums) {
+  __shared__ double red[8][33];
+  const int cx = threadIdx.x, sy = threadIdx.y;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0;
+  if (c < width)
+    for (int b = sy; b < nblk; b += 8) s += (double)part[(int64_t)b * width + c];
+  red[sy][cx] = s;
+  __syncthreads();
+  if (sy == 0 && c < width) {
+    double t = 0.0;
+    for (int y = 0; y < 8; ++y) t += red[y][cx];
+    sums[c] = t;
+  }
+}
+
+struct ColPlan {
+  ColGeom cg;
+  dim3 grid;
+  int vec;
+  size_t smem_elems;  // per NV
+};
+
+ColPlan plan_cols(int64_t rows, int ch, bool vec_ok) {
+  ColPlan p;
+  p.vec = (vec_ok && ch % 4 == 0) ? 4 : 1;
+  const int groups = (ch + p.vec - 1) / p.vec;
+  int TX = 1;
+  while (TX < groups && TX < 256) TX <<= 1;
+  if (TX > 256) TX = 256;
+  const int TY = 256 / TX;
+  int64_t nblk = 4LL * num_sms();
+  const int64_t min_rows = 4LL * TY;
+  if (nblk * min_rows > rows) nblk = (rows + min_rows - 1) / min_rows;
+  if (nblk < 1) nblk = 1;
+  p.cg.rows = rows;
+  p.cg.ch = ch;
+  p.cg.rows_per_block = (rows + nblk - 1) / nblk;
+  p.cg.TX = TX;
+  p.cg.TY = TY;
+  nblk = (rows + p.cg.rows_per_block - 1) / p.cg.rows_per_block;
+  if (nblk < 1) nblk = 1;
+  p.grid = dim3((unsigned)nblk, (unsigned)((groups + TX - 1) / TX));
+  p.smem_elems = (size_t)TY * TX * p.vec;
+  return p;
+}
+
+template <int NV, typename Acc, typename F>
+int launch_col_pass(const ColPlan& p, F f, Acc* part, cudaStream_t st) {
+  const size_t smem = NV * p.smem_elems * sizeof(Acc);
+  if (p.vec == 4)
+    col_pass_kernel<4, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
+  else
+    col_pass_kernel<1, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+template <typename Acc>
+int launch_col_final(const Acc* part, int nblk, int width, double* sums, cudaStream_t st) {
+  col_final_kernel<Acc><<<(width + 31) / 32, dim3(32, 8), 0, st>>>(part, nblk, width, sums);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+// ---- functors -----------------------------------------------------------------------------------
+struct DzPrepF {
+  const void* dY; const void* Z; void* dZ;
+  int dy_dt, z_dt, dz_dt, act;
+  float p0, p1;
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, int /*c0*/, float (&out)[1][VEC]) const {
+    float g[VEC], z[VEC];
+    load_vec<VEC>(dY, dy_dt, i, g);
+    if (act != NPML_ACT_IDENTITY) {
+      load_vec<VEC>(Z, z_dt, i, z);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) g[j] *= act_grad(act, z[j], p0, p1);
+    }
+    // the sum is taken over the values the GEMMs will see (after rounding to the dZ dtype)
+    if (dz_dt == NPML_BF16) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) g[j] = __bfloat162float(__float2bfloat16_rn(g[j]));
+    }
+    if (dZ) store_vec<VEC>(dZ, dz_dt, i, g);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[0][j] = g[j];
+  }
+};
+
+struct BnStatsF {
+  const void* x; int dt;
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, int, float (&out)[2][VEC]) const {
+    float v[VEC];
+    load_vec<VEC>(x, dt, i, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { out[0][j] = v[j]; out[1][j] = v[j] * v[j]; }
+  }
+};
+
+struct BnNormF {
+  const void* x; void* y; int dt;
+  const float* mean; const float* rstd; const float* g; const float* h;
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, int c0, float (&)[1][VEC]) const {
+    float v[VEC];
+    load_vec<VEC>(x, dt, i, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) v[j] = g[c0 + j] * ((v[j] - mean[c0 + j]) * rstd[c0 + j]) + h[c0 + j];
+    store_vec<VEC>(y, dt, i, v);
+  }
+};
+
+struct BnBwdStatsF {
+  const void* dy; const void* x; int dt;
+  const float* mean; const float* rstd;
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, int c0, float (&out)[2][VEC]) const {
+    float d[VEC], v[VEC];
+    load_vec<VEC>(dy, dt, i, d);
+    load_vec<VEC>(x, dt, i, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      out[0][j] = d[j];
+      out[1][j] = d[j] * ((v[j] - mean[c0 + j]) * rstd[c0 + j]);
+    }
+  }
+};
+
+struct BnBwdDxF {
+  const void* dy; const void* x; void* dx; int dt;
+  const float* mean; const float* rstd; const float* g;
+  const double* sums;  // [2][ch]: sum dy, sum dy*nhat
+  double inv_m; int ch;
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, int c0, float (&)[1][VEC]) const {
+    float d[VEC], v[VEC];
+    load_vec<VEC>(dy, dt, i, d);
+    load_vec<VEC>(x, dt, i, v);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = c0 + j;
+      const float nh = (v[j] - mean[c]) * rstd[c];
+      const float m1 = (float)(sums[c] * inv_m), m2 = (float)(sums[ch + c] * inv_m);
+      v[j] = g[c] * rstd[c] * (d[j] - m1 - nh * m2);
+    }
+    store_vec<VEC>(dx, dt, i, v);
+  }
+};
+
+__global__ void db_finalize_kernel(const double* sums, int ch, int accumulate, float* db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ch) db[c] = accumulate ? db[c] + (float)sums[c] : (float)sums[c];
+}
+
+__global__ void bn_finalize_kernel(const double* sums, int ch, double inv_m, float momentum, float eps,
+                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  const double mean = sums[c] * inv_m;
+  double var = sums[ch + c] * inv_m - mean * mean;  // biased (layers/layers.py:1147)
+  if (var < 0.0) var = 0.0;
+  running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
+  running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * var);
+  save_mean[c] = (float)mean;
+  save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+__global__ void bn_running_to_saved_kernel(int ch, float eps, const float* running_mean, const float* running_var,
+                                           float* save_mean, float* save_rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  save_mean[c] = running_mean[c];
+  save_rstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* sums, int ch, int accumulate, float* d_scaler,
+                                       float* d_intercept) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  const float di = (float)sums[c], ds = (float)sums[ch + c];
+  d_intercept[c] = accumulate ? d_intercept[c] + di : di;
+  d_scaler[c] = accumulate ? d_scaler[c] + ds : ds;
+}
+
+// ---- flat elementwise ------------------------------------------------------------------------------
+template <int VEC>
+__global__ void cast_kernel(const void* src, int sdt, void* dst, int ddt, int64_t n_vec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[VEC];
+    load_vec<VEC>(src, sdt, i * VEC, v);
+    store_vec<VEC>(dst, ddt, i * VEC, v);
+  }
+}
+
+struct AddArgs {
+  const void* xs[8];
+  int n_in;
+};
+
+template <int VEC>
+__global__ void add_act_kernel(AddArgs a, int dt, int64_t n_vec, int act, float p0, float p1, void* sum, void* Y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float s[VEC];
+    load_vec<VEC>(a.xs[0], dt, i * VEC, s);
+    for (int k = 1; k < a.n_in; ++k) {
+      float v[VEC];
+      load_vec<VEC>(a.xs[k], dt, i * VEC, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[j] += v[j];
+    }
+    // later passes read the stored sum, so activations see the stored (rounded) value
+    if (dt == NPML_BF16) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[j] = __bfloat162float(__float2bfloat16_rn(s[j]));
+    }
+    if (sum) store_vec<VEC>(sum, dt, i * VEC, s);
+    if (Y) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[j] = act_fn(act, s[j], p0, p1);
+      store_vec<VEC>(Y, dt, i * VEC, s);
+    }
+  }
+}
+
+inline int flat_blocks(int64_t n_vec) {
+  int64_t b = (n_vec + 255) / 256;
+  const int64_t cap = 16LL * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, int64_t n, float lr,
+                           float momentum, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float u = momentum * v[i] + lr * (g[i] * gscale);
+    v[i] = u;
+    p[i] -= u;
+  }
+}
+
+struct SumSqF {
+  const float* x;
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, int, float (&out)[1][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[0][j] = x[i + j] * x[i + j];
+  }
+};
+
+// ---- im2col / col2im exports -------------------------------------------------------------------------
+__global__ void im2col_kernel(npml_conv_desc d, const float* __restrict__ X, float* __restrict__ Xc) {
+  const int64_t L = (int64_t)d.OH * d.OW * d.N;
+  const int64_t total = (int64_t)d.fr * d.fc * d.C * L;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = i / L, z = i - q * L;
+    const int c = (int)(q / (d.fr * d.fc));
+    const int rt = (int)(q - (int64_t)c * d.fr * d.fc);
+    const int r = rt / d.fc, t = rt - r * d.fc;
+    const int n = (int)(z % d.N);
+    const int64_t pix = z / d.N;
+    const int oh = (int)(pix / d.OW), ow = (int)(pix - (int64_t)oh * d.OW);
+    const int iy = oh * d.stride + r * d.dil - d.pr1, ix = ow * d.stride + t * d.dil - d.pc1;
+    float v = 0.f;
+    if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) v = X[(((int64_t)n * d.H + iy) * d.W + ix) * d.C + c];
+    Xc[i] = v;
+  }
+}
+
+__global__ void col2im_kernel(npml_conv_desc d, const float* __restrict__ Xc, float* __restrict__ out) {
+  const int64_t L = (int64_t)d.OH * d.OW * d.N;
+  const int64_t total = (int64_t)d.N * d.C * d.H * d.W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t q = i;
+    const int w = (int)(q % d.W); q /= d.W;
+    const int h = (int)(q % d.H); q /= d.H;
+    const int c = (int)(q % d.C);
+    const int n = (int)(q / d.C);
+    float s = 0.f;
+    for (int r = 0; r < d.fr; ++r) {
+      const int ny = h + d.pr1 - r * d.dil;
+      if (ny < 0 || ny % d.stride) continue;
+      const int oh = ny / d.stride;
+      if (oh >= d.OH) continue;
+      for (int t = 0; t < d.fc; ++t) {
+        const int nx = w + d.pc1 - t * d.dil;
+        if (nx < 0 || nx % d.stride) continue;
+        const int ow = nx / d.stride;
+        if (ow >= d.OW) continue;
+        const int64_t row = ((int64_t)c * d.fr + r) * d.fc + t;
+        s += Xc[row * L + ((int64_t)oh * d.OW + ow) * d.N + n];
+      }
+    }
+    out[i] = s;
+  }
+}
+
+}  // namespace
+
+size_t colpass_ws_bytes(int64_t rows, int ch, int nv) {
+  ColPlan p = plan_cols(rows, ch, true);
+  return align_up((size_t)p.grid.x * nv * ch * sizeof(double), 256) + align_up((size_t)nv * ch * sizeof(double), 256);
+}
+
+}  // namespace npml
+
+using namespace npml;
+
+extern "C" int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, float p1, const void* dY,
+                            int32_t dy_dtype, const void* Z, int32_t z_dtype, void* dZ, int32_t dz_dtype, float* db,
+                            int32_t accumulate, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(dY != nullptr, "dY is NULL");
+  NPML_CHECK(act == NPML_ACT_IDENTITY || Z != nullptr, "Z is required for a non-identity activation");
+  const bool vec_ok = aligned_for_vec4(dY, dy_dtype) && aligned_for_vec4(Z, z_dtype) && aligned_for_vec4(dZ, dz_dtype);
+  ColPlan p = plan_cols(rows, ch, vec_ok);
+  DzPrepF f{dY, Z, dZ, dy_dtype, z_dtype, dz_dtype, act, p0, p1};
+  if (!db) return launch_col_pass<1, float>(p, f, (float*)nullptr, st);
+  const size_t part_bytes = align_up((size_t)p.grid.x * ch * sizeof(float), 256);
+  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)ch * sizeof(double), "workspace too small");
+  float* part = (float*)ws;
+  double* sums = (double*)((char*)ws + part_bytes);
+  if (int e = launch_col_pass<1, float>(p, f, part, st)) return e;
+  if (int e = launch_col_final<float>(part, (int)p.grid.x, ch, sums, st)) return e;
+  db_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, accumulate, db);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  if (n % 4 == 0 && aligned_for_vec4(src, src_dtype) && aligned_for_vec4(dst, dst_dtype))
+    cast_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(src, src_dtype, dst, dst_dtype, n / 4);
+  else
+    cast_kernel<1><<<flat_blocks(n), 256, 0, st>>>(src, src_dtype, dst, dst_dtype, n);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_add_act_fwd(int32_t n_in, const void* const* xs, int32_t dtype, int64_t n, int32_t act, float p0,
+                                float p1, void* sum, void* Y, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(n_in >= 1 && n_in <= 8, "between 1 and 8 inputs are supported");
+  if (n <= 0) return 0;
+  AddArgs a;
+  a.n_in = n_in;
+  bool al = aligned_for_vec4(sum, dtype) && aligned_for_vec4(Y, dtype);
+  for (int i = 0; i < n_in; ++i) {
+    a.xs[i] = xs[i];
+    al = al && aligned_for_vec4(xs[i], dtype);
+  }
+  if (n % 4 == 0 && al)
+    add_act_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, sum, Y);
+  else
+    add_act_kernel<1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, sum, Y);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_act_fwd(const void* Z, void* Y, int32_t dtype, int64_t n, int32_t act, float p0, float p1,
+                            void* stream) {
+  const void* xs[1] = {Z};
+  return npml_add_act_fwd(1, xs, dtype, n, act, p0, p1, nullptr, Y, stream);
+}
+
+extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, int32_t dtype, const float* scaler,
+                             const float* intercept, float* running_mean, float* running_var, float momentum,
+                             float eps, int32_t use_batch_stats, float* save_mean, float* save_rstd, void* ws,
+                             size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(save_mean && save_rstd, "save_mean/save_rstd are required");
+  const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(y, dtype);
+  ColPlan p = plan_cols(rows, ch, vec_ok);
+  if (use_batch_stats) {
+    const size_t part_bytes = align_up((size_t)p.grid.x * 2 * ch * sizeof(double), 256);
+    NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)2 * ch * sizeof(double), "workspace too small");
+    double* part = (double*)ws;
+    double* sums = (double*)((char*)ws + part_bytes);
+    BnStatsF fs{x, dtype};
+    if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+    if (int e = launch_col_final<double>(part, (int)p.grid.x, 2 * ch, sums, st)) return e;
+    bn_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, 1.0 / (double)rows, momentum, eps, running_mean,
+                                                         running_var, save_mean, save_rstd);
+    NPML_LAUNCH_OK();
+  } else {
+    bn_running_to_saved_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, eps, running_mean, running_var, save_mean,
+                                                                 save_rstd);
+    NPML_LAUNCH_OK();
+  }
+  BnNormF fn{x, y, dtype, save_mean, save_rstd, scaler, intercept};
+  return launch_col_pass<0, float>(p, fn, (float*)nullptr, st);
+}
+
+extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const void* x, void* dx, int32_t dtype,
+                             const float* scaler, const float* save_mean, const float* save_rstd, float* d_scaler,
+                             float* d_intercept, int32_t accumulate, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(dy, dtype) && aligned_for_vec4(dx, dtype);
+  ColPlan p = plan_cols(rows, ch, vec_ok);
+  const size_t part_bytes = align_up((size_t)p.grid.x * 2 * ch * sizeof(double), 256);
+  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)2 * ch * sizeof(double), "workspace too small");
+  double* part = (double*)ws;
+  double* sums = (double*)((char*)ws + part_bytes);
+  BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
+  if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+  if (int e = launch_col_final<double>(part, (int)p.grid.x, 2 * ch, sums, st)) return e;
+  if (d_scaler && d_intercept) {
+    bn_bwd_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, accumulate, d_scaler, d_intercept);
+    NPML_LAUNCH_OK();
+  }
+  BnBwdDxF fd{dy, x, dx, dtype, save_mean, save_rstd, scaler, sums, 1.0 / (double)rows, ch};
+  return launch_col_pass<0, float>(p, fd, (float*)nullptr, st);
+}
+
+extern "C" int npml_im2col(const npml_conv_desc* d, const float* X, float* X_col, void* stream) {
+  const int64_t total = (int64_t)d->fr * d->fc * d->C * d->OH * d->OW * d->N;
+  if (total <= 0) return 0;
+  im2col_kernel<<<flat_blocks(total), 256, 0, (cudaStream_t)stream>>>(*d, X, X_col);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_col2im(const npml_conv_desc* d, const float* X_col, float* X_nchw, void* stream) {
+  const int64_t total = (int64_t)d->N * d->C * d->H * d->W;
+  if (total <= 0) return 0;
+  col2im_kernel<<<flat_blocks(total), 256, 0, (cudaStream_t)stream>>>(*d, X_col, X_nchw);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_sgd_update(float* param, const float* grad, float* velocity, int64_t n, float lr, float momentum,
+                               float grad_scale, void* stream) {
+  if (n <= 0) return 0;
+  sgd_kernel<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(param, grad, velocity, n, lr, momentum, grad_scale);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(n > 0 && out, "bad arguments");
+  // view the buffer as [n][1]: one column, reduced over rows in a fixed order
+  ColPlan p = plan_cols(n, 1, false);
+  const size_t part_bytes = align_up((size_t)p.grid.x * sizeof(double), 256);
+  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes, "workspace too small");
+  SumSqF f{buf};
+  if (int e = launch_col_pass<1, double>(p, f, (double*)ws, st)) return e;
+  return launch_col_final<double>((const double*)ws, (int)p.grid.x, 1, out, st);
+}

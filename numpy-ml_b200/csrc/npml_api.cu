@@ -1,0 +1,181 @@
+// C-ABI entry points of libnpmlconv.so (declared in include/npml_conv.h): maps the six layer
+// operations onto the internal gather-conv / wgrad forms and picks the tcgen05 or CUDA-core kernel.
+#include "npml_common.cuh"
+
+namespace npml {
+
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches += n; }
+
+static int act_dtype(int mode) { return mode == NPML_MODE_BF16 ? NPML_BF16 : NPML_F32; }
+
+static int check_desc(const npml_conv_desc* d, bool deconv) {
+  NPML_CHECK(d != nullptr, "desc is NULL");
+  NPML_CHECK(d->N >= 0 && d->H > 0 && d->W > 0 && d->C > 0 && d->K > 0, "bad tensor dims");
+  NPML_CHECK(d->fr > 0 && d->fc > 0 && d->stride > 0 && d->dil > 0, "bad kernel/stride/dilation");
+  NPML_CHECK(d->pr1 >= 0 && d->pr2 >= 0 && d->pc1 >= 0 && d->pc2 >= 0, "negative padding");
+  NPML_CHECK(d->OH > 0 && d->OW > 0, "non-positive output dims");
+  NPML_CHECK(d->mode >= NPML_MODE_FP32 && d->mode <= NPML_MODE_BF16, "bad mode");
+  if (deconv) {
+    NPML_CHECK(d->dil == 1, "Deconv2D has no dilation");
+    NPML_CHECK(d->OH == d->stride * (d->H - 1) + d->fr - d->pr1 - d->pr2, "OH inconsistent with deconv geometry");
+    NPML_CHECK(d->OW == d->stride * (d->W - 1) + d->fc - d->pc1 - d->pc2, "OW inconsistent with deconv geometry");
+  } else {
+    const int er = d->fr * d->dil - d->dil + 1, ec = d->fc * d->dil - d->dil + 1;
+    NPML_CHECK(d->OH == (d->H + d->pr1 + d->pr2 - er) / d->stride + 1, "OH inconsistent with conv geometry");
+    NPML_CHECK(d->OW == (d->W + d->pc1 + d->pc2 - ec) / d->stride + 1, "OW inconsistent with conv geometry");
+  }
+  return 0;
+}
+
+// op -> internal forms ---------------------------------------------------------------------------------
+static GatherConv make_gather(const npml_conv_desc* d, int op) {
+  GatherConv g{};
+  g.N = d->N; g.fr = d->fr; g.fc = d->fc; g.s = d->stride; g.D = d->dil; g.pr = d->pr1; g.pc = d->pc1;
+  g.w_tap = (int64_t)d->C * d->K;
+  g.act = NPML_ACT_IDENTITY; g.p0 = 0.f; g.p1 = 0.f;
+  switch (op) {
+    case NPML_OP_CONV_FPROP:    // Z[n,oh,ow,k] = sum X[n, oh*s + r*D - pr1, ow*s + t*D - pc1, c] W[r,t,c,k]
+    case NPML_OP_DECONV_FPROP:  // Z[n,y,x,k]   = sum X[n, (y + pr1 - r)/s, (x + pc1 - t)/s, c] W[r,t,c,k]
+      g.IH = d->H; g.IW = d->W; g.CI = d->C; g.OH = d->OH; g.OW = d->OW; g.CO = d->K;
+      g.w_ci = d->K; g.w_co = 1;
+      g.form = (op == NPML_OP_CONV_FPROP) ? 0 : 1;
+      g.act = d->act; g.p0 = d->act_p0; g.p1 = d->act_p1;
+      break;
+    case NPML_OP_CONV_DGRAD:    // dX[n,h,w,c] = sum dZ[n, (h + pr1 - r*D)/s, (w + pc1 - t*D)/s, k] W[r,t,c,k]
+    case NPML_OP_DECONV_DGRAD:  // dX[n,iy,ix,c] = sum dZ[n, iy*s + r - pr1, ix*s + t - pc1, k] W[r,t,c,k]
+      g.IH = d->OH; g.IW = d->OW; g.CI = d->K; g.OH = d->H; g.OW = d->W; g.CO = d->C;
+      g.w_ci = 1; g.w_co = d->K;
+      g.form = (op == NPML_OP_CONV_DGRAD) ? 1 : 0;
+      break;
+  }
+  return g;
+}
+
+static GatherWgrad make_wgrad(const npml_conv_desc* d, int op) {
+  GatherWgrad g{};
+  g.N = d->N; g.fr = d->fr; g.fc = d->fc; g.s = d->stride; g.D = d->dil; g.pr = d->pr1; g.pc = d->pc1;
+  g.o_tap = (int64_t)d->C * d->K;
+  g.accumulate = d->accumulate;
+  if (op == NPML_OP_CONV_WGRAD) {  // dW[r,t,c,k] = sum X[n, oh*s + r*D - pr1, ...] dZ[n,oh,ow,k]
+    g.IH = d->H; g.IW = d->W; g.CI = d->C; g.OH = d->OH; g.OW = d->OW; g.CO = d->K;
+    g.o_ci = d->K; g.o_co = 1;
+  } else {                         // dW[r,t,c,k] = sum dZ[n, iy*s + r - pr1, ...][k] X[n,iy,ix,c]
+    g.IH = d->OH; g.IW = d->OW; g.CI = d->K; g.OH = d->H; g.OW = d->W; g.CO = d->C;
+    g.o_ci = 1; g.o_co = d->K;
+  }
+  return g;
+}
+
+static int run_gather(const npml_conv_desc* d, int op, const void* in, const float* W, const float* b, void* Z,
+                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (check_desc(d, op == NPML_OP_DECONV_FPROP || op == NPML_OP_DECONV_DGRAD)) return 1;
+  if (d->N == 0) return 0;
+  NPML_CHECK(in && W, "NULL input");
+  NPML_CHECK(Z || Y, "no output buffer");
+  GatherConv g = make_gather(d, op);
+  if (g.act == NPML_ACT_IDENTITY && Z == nullptr) { Z = Y; Y = nullptr; }
+  if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode))
+    return tc_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
+  return direct_gather_conv(g, in, W, b, Z, Y, act_dtype(d->mode), st);
+}
+
+static int run_wgrad(const npml_conv_desc* d, int op, const void* in, const void* grad, float* dW, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  if (check_desc(d, op == NPML_OP_DECONV_WGRAD)) return 1;
+  NPML_CHECK(dW != nullptr, "dW is NULL");
+  GatherWgrad g = make_wgrad(d, op);
+  if (d->N == 0) {
+    if (!d->accumulate) NPML_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * d->fr * d->fc * d->C * d->K, st));
+    return 0;
+  }
+  NPML_CHECK(in && grad, "NULL input");
+  if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode))
+    return tc_wgrad(g, d->mode, in, grad, dW, ws, ws_bytes, st);
+  return direct_wgrad(g, in, grad, dW, act_dtype(d->mode), ws, ws_bytes, st);
+}
+
+size_t colpass_ws_bytes(int64_t rows, int ch, int nv);
+
+}  // namespace npml
+
+using namespace npml;
+
+extern "C" {
+
+int npml_conv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
+                      void* ws, size_t ws_bytes, void* stream) {
+  return run_gather(d, NPML_OP_CONV_FPROP, X, W, b, Z, Y, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_conv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX, void* ws, size_t ws_bytes,
+                      void* stream) {
+  return run_gather(d, NPML_OP_CONV_DGRAD, dZ, W, nullptr, dX, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_conv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW, void* ws, size_t ws_bytes,
+                      void* stream) {
+  return run_wgrad(d, NPML_OP_CONV_WGRAD, X, dZ, dW, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_deconv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
+                        void* ws, size_t ws_bytes, void* stream) {
+  return run_gather(d, NPML_OP_DECONV_FPROP, X, W, b, Z, Y, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_deconv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX, void* ws,
+                        size_t ws_bytes, void* stream) {
+  return run_gather(d, NPML_OP_DECONV_DGRAD, dZ, W, nullptr, dX, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_deconv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW, void* ws,
+                        size_t ws_bytes, void* stream) {
+  // the shifted (gathered) operand is dZ, the per-pixel operand is X
+  return run_wgrad(d, NPML_OP_DECONV_WGRAD, dZ, X, dW, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
+  if (!d) return 0;
+  size_t bytes = 256;
+  switch (op) {
+    case NPML_OP_CONV_FPROP: case NPML_OP_CONV_DGRAD: case NPML_OP_DECONV_FPROP: case NPML_OP_DECONV_DGRAD: {
+      GatherConv g = make_gather(d, op);
+      if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode)) bytes += tc_conv_ws_bytes(g, d->mode);
+      break;
+    }
+    case NPML_OP_CONV_WGRAD: case NPML_OP_DECONV_WGRAD: {
+      GatherWgrad g = make_wgrad(d, op);
+      if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode)) bytes += tc_wgrad_ws_bytes(g, d->mode);
+      else bytes += direct_wgrad_ws_bytes(g);
+      break;
+    }
+    case NPML_OP_DZ_PREP: {
+      const int64_t rows = (int64_t)d->N * d->OH * d->OW;
+      bytes += colpass_ws_bytes(rows, d->K, 1);
+      break;
+    }
+    case NPML_OP_BN: {
+      const int64_t rows = (int64_t)d->N * d->OH * d->OW;
+      bytes += colpass_ws_bytes(rows, d->K, 2);
+      break;
+    }
+  }
+  return bytes;
+}
+
+int npml_uses_tensor_cores(const npml_conv_desc* d, int op) {
+  if (!d || d->mode == NPML_MODE_FP32) return 0;
+  if (op == NPML_OP_CONV_WGRAD || op == NPML_OP_DECONV_WGRAD) return tc_wgrad_supported(make_wgrad(d, op), d->mode);
+  if (op >= NPML_OP_CONV_FPROP && op <= NPML_OP_DECONV_DGRAD) return tc_conv_supported(make_gather(d, op), d->mode);
+  return 0;
+}
+
+const char* npml_last_error(void) { return g_err.c_str(); }
+
+int64_t npml_launch_count(int32_t reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int npml_version(void) { return 100; }
+
+}  // extern "C"

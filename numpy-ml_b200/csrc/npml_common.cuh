@@ -1,0 +1,159 @@
+// Shared device/host helpers for libnpmlconv (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/npml_conv.h"
+
+namespace npml {
+
+// ---- error plumbing --------------------------------------------------------------------------
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define NPML_CHECK(cond, msg)                                            \
+  do {                                                                   \
+    if (!(cond)) {                                                       \
+      npml::set_error(std::string(__func__) + ": " + (msg));             \
+      return 1;                                                          \
+    }                                                                    \
+  } while (0)
+
+#define NPML_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      npml::set_error(std::string(__func__) + ": " #expr " -> " + cudaGetErrorString(_e)); \
+      return 2;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define NPML_LAUNCH_OK()                                                               \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess) {                                                           \
+      npml::set_error(std::string(__func__) + ": launch -> " + cudaGetErrorString(_e)); \
+      return 3;                                                                        \
+    }                                                                                  \
+    npml::count_launch();                                                              \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- element access ---------------------------------------------------------------------------
+__device__ __forceinline__ float ld_f(const float* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ld_f(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ float ld_f(const double* p, int64_t i) { return (float)p[i]; }
+__device__ __forceinline__ void st_f(float* p, int64_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void st_f(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void st_f(double* p, int64_t i, float v) { p[i] = (double)v; }
+
+// ---- activations (activations/activations.py) -------------------------------------------------
+#define NPML_SELU_ALPHA 1.6732632423543772848170429916717f
+#define NPML_SELU_SCALE 1.0507009873554804934193349852946f
+
+__device__ __forceinline__ float act_fn(int act, float z, float p0, float p1) {
+  switch (act) {
+    case NPML_ACT_IDENTITY: return z;
+    case NPML_ACT_AFFINE: return p0 * z + p1;                                  // :362-370
+    case NPML_ACT_RELU: return z > 0.f ? z : 0.f;                              // :104-114
+    case NPML_ACT_LEAKY_RELU: return z < 0.f ? z * p0 : z;                     // :169-181
+    case NPML_ACT_TANH: return tanhf(z);                                       // :313-315
+    case NPML_ACT_SIGMOID: return 1.f / (1.f + expf(-z));                      // :39-47
+    case NPML_ACT_ELU: return z > 0.f ? z : p0 * (expf(z) - 1.f);              // :449-460
+    case NPML_ACT_SELU:                                                        // :568-584
+      return NPML_SELU_SCALE * (z > 0.f ? z : NPML_SELU_ALPHA * (expf(z) - 1.f));
+    case NPML_ACT_HARD_SIGMOID: return fminf(fmaxf(0.2f * z + 0.5f, 0.f), 1.f);  // :631-642
+    case NPML_ACT_SOFTPLUS: return logf(expf(z) + 1.f);                        // :688-696
+    case NPML_ACT_GELU: {                                                      // :239-251
+      float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
+      return 0.5f * z * (1.f + tanhf(u));
+    }
+    case NPML_ACT_EXPONENTIAL: return expf(z);                                 // :500-507
+  }
+  return z;
+}
+
+// derivative conventions at the kinks follow the reference
+__device__ __forceinline__ float act_grad(int act, float x, float p0, float p1) {
+  switch (act) {
+    case NPML_ACT_IDENTITY: return 1.f;
+    case NPML_ACT_AFFINE: return p0;                                           // :372-381
+    case NPML_ACT_RELU: return x > 0.f ? 1.f : 0.f;                            // :116-126
+    case NPML_ACT_LEAKY_RELU: return x < 0.f ? p0 : 1.f;                       // :183-196
+    case NPML_ACT_TANH: { float t = tanhf(x); return 1.f - t * t; }            // :317-326
+    case NPML_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-x)); return s * (1.f - s); }  // :49-58
+    case NPML_ACT_ELU: return x > 0.f ? 1.f : p0 * expf(x);                    // :462-474
+    case NPML_ACT_SELU:                                                        // :586-599
+      return x >= 0.f ? NPML_SELU_SCALE : expf(x) * NPML_SELU_ALPHA * NPML_SELU_SCALE;
+    case NPML_ACT_HARD_SIGMOID: return (x >= -2.5f && x <= 2.5f) ? 0.2f : 0.f;  // :644-655
+    case NPML_ACT_SOFTPLUS: { float e = expf(x); return e / (e + 1.f); }       // :698-708
+    case NPML_ACT_GELU: {                                                      // :254-277 (literal)
+      float s = x * 0.7071067811865475f;
+      float erf_prime = 1.1283791670955126f * expf(-(s * s));
+      float approx = tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x));
+      return 0.5f + 0.5f * approx + (0.5f * x * erf_prime) * 0.7071067811865475f;
+    }
+    case NPML_ACT_EXPONENTIAL: return expf(x);                                 // :509-518
+  }
+  return 1.f;
+}
+
+// ---- internal "gather convolution" description -------------------------------------------------
+// out[n, y, x, co] = sum_{r, t, ci} in[n, iy, ix, ci] * w[(r*fc + t)*w_tap + ci*w_ci + co*w_co]
+//   form 0 (fprop-like):  iy = y*s + r*D - pr,            ix = x*s + t*D - pc
+//   form 1 (dgrad-like):  iy = (y + pr - r*D) / s if s divides it (else the tap is skipped)
+// Conv2D.forward / Deconv2D dX use form 0; Conv2D dX / Deconv2D.forward use form 1.
+struct GatherConv {
+  int N, IH, IW, CI;    // tensor that is gathered from
+  int OH, OW, CO;       // tensor that is produced
+  int fr, fc, s, D, pr, pc;
+  int form;
+  int64_t w_tap, w_ci, w_co;
+  int act;
+  float p0, p1;
+};
+
+// wgrad:  dW[(r*fc+t)*o_tap + ci*o_ci + co*o_co] (+)= sum_{n,y,x} in[n, y*s + r*D - pr, x*s + t*D - pc, ci]
+//                                                                * g[n, y, x, co]
+// where `in` is (N, IH, IW, CI) and `g` is (N, OH, OW, CO).
+struct GatherWgrad {
+  int N, IH, IW, CI;
+  int OH, OW, CO;
+  int fr, fc, s, D, pr, pc;
+  int64_t o_tap, o_ci, o_co;
+  int accumulate;
+};
+
+// direct (CUDA-core, fp32 accumulate) kernels, direct_fp32.cu
+int direct_gather_conv(const GatherConv& g, const void* in, const float* w, const float* bias, void* Z,
+                       void* Y, int dtype, cudaStream_t st);
+size_t direct_wgrad_ws_bytes(const GatherWgrad& g);
+int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* dW, int dtype, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+
+// tensor-core (tcgen05) kernels, tc_conv.cu / tc_wgrad.cu
+bool tc_conv_supported(const GatherConv& g, int mode);
+size_t tc_conv_ws_bytes(const GatherConv& g, int mode);
+int tc_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
+                   void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
+bool tc_wgrad_supported(const GatherWgrad& g, int mode);
+size_t tc_wgrad_ws_bytes(const GatherWgrad& g, int mode);
+int tc_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad, float* dW, void* ws,
+             size_t ws_bytes, cudaStream_t st);
+
+}  // namespace npml

@@ -1,0 +1,121 @@
+"""Batch-sharded data parallelism for the convolution layers: one process per GPU, every rank runs
+forward/backward on its N/g slice of the batch and the summed dW / db (and BatchNorm gradient) buffers
+are exchanged with ONE NCCL all-reduce per step.  Y and dX are per-example, so they need
+no communication.  The reference sums gradients over the batch (layers/layers.py:3087-3089), so the
+reduction is SUM, never an average.
+
+torch.distributed is used only for rendezvous (broadcasting the ncclUniqueId); the all-reduce itself
+is npml_allreduce_sum_f32 in libnpmlconv.so on the caller's stream.  With backend "gloo" (CPU tests)
+the same bucket logic runs through torch.distributed.all_reduce."""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+
+_state = {"ready": False, "world": 1, "rank": 0, "backend": None}
+
+
+def init(backend=None):
+    """Join the job described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun style)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    _state.update(world=world, rank=rank, backend=backend)
+    if world == 1:
+        _state["ready"] = True
+        return _state
+    if torch.cuda.is_available():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", str(rank))))
+    if not dist.is_initialized():
+        # gloo for the control plane (id broadcast, barriers over CPU tensors); data plane = our NCCL comm
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+    if backend == "nccl":
+        lib = L.load()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            L.check(lib.npml_comm_unique_id(buf), "npml_comm_unique_id")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        dist.broadcast(ident, src=0)
+        raw = (C.c_ubyte * 128)(*ident.tolist())
+        L.check(lib.npml_comm_init_rank(raw, world, rank), "npml_comm_init_rank")
+    _state["ready"] = True
+    return _state
+
+
+def world_size():
+    return _state["world"]
+
+
+def rank():
+    return _state["rank"]
+
+
+def shard_batch(n_ex, world=None, r=None):
+    """Contiguous [start, stop) slice of the batch axis owned by rank `r`."""
+    world = _state["world"] if world is None else world
+    r = _state["rank"] if r is None else r
+    per = (n_ex + world - 1) // world
+    return min(r * per, n_ex), min((r + 1) * per, n_ex)
+
+
+class GradBucket(object):
+    """One flat fp32 buffer holding every gradient of a set of layers; the layers' `gradients` entries
+    become views into it, so kernels accumulate straight into the bucket and one all-reduce covers all."""
+
+    def __init__(self, layers):
+        self.layers = list(layers)
+        entries = []
+        for l in self.layers:
+            for k in sorted(l.gradients):
+                entries.append((l, k, l.gradients[k]))
+        total = sum(g.numel() for _, _, g in entries)
+        dev = entries[0][2].device if entries else "cpu"
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for l, k, g in entries:
+            view = self.flat[off:off + g.numel()].view(g.shape)
+            view.copy_(g)
+            l.gradients[k] = view
+            off += g.numel()
+
+    def allreduce(self):
+        """SUM over ranks, in place, on the current stream."""
+        if _state["world"] == 1:
+            return self.flat
+        if _state["backend"] == "nccl":
+            L.check(L.load().npml_allreduce_sum_f32(L.ptr(self.flat), self.flat.numel(), L.stream()),
+                    "npml_allreduce_sum_f32")
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        return self.flat
+
+
+def barrier():
+    if _state["world"] > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+def all_reduce_max(value):
+    """max over ranks of a host float (for max-over-ranks timing)."""
+    if _state["world"] == 1:
+        return value
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def destroy():
+    import torch.distributed as dist
+    if _state["backend"] == "nccl" and _state["world"] > 1:
+        L.load().npml_comm_destroy()
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    _state.update(ready=False, world=1, rank=0)

@@ -1,0 +1,480 @@
+"""Conv2D / Deconv2D / BatchNorm2D / Add with the reference's layer API
+(numpy_ml/neural_nets/layers/layers.py): same constructor arguments, lazy parameter init on the
+first forward, `parameters` / `gradients` / `hyperparameters` / `derived_variables` dicts, list-valued
+`backward`, `+=` gradient accumulation, `flush_gradients` / `update` / `freeze` / `summary`.
+
+Differences a user can see (documented in INTEGRATION.md):
+  * tensors live on the GPU.  NumPy inputs are accepted and answered with float64 NumPy arrays;
+    device tensors are answered with device tensors.  `parameters`, `gradients` and the retained
+    `X` / `Z` are device tensors (fp32 parameters and gradients; activations in the mode's dtype).
+  * one extra constructor keyword, `mode` in {"fp32", "tf32", "bf16"} (default "fp32", the
+    exactness mode), selects the arithmetic of the convolution kernels.
+"""
+import ctypes as C
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import utils as U
+from .activations import ActivationInitializer
+from .optimizers import OptimizerInitializer
+
+
+def _as_param(v):
+    """Parameters may be assigned as NumPy arrays (like the reference); keep fp32 device tensors."""
+    if isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 and v.is_contiguous():
+        return v
+    return L.to_device(v, torch.float32)
+
+
+class LayerBase(ABC):
+    """layers/layers.py:27-136."""
+
+    def __init__(self, optimizer=None):
+        self.X = []
+        self.act_fn = None
+        self.trainable = True
+        self.optimizer = OptimizerInitializer(optimizer)()
+        self.gradients = {}
+        self.parameters = {}
+        self.derived_variables = {}
+        super().__init__()
+
+    @abstractmethod
+    def _init_params(self, **kwargs):
+        raise NotImplementedError
+
+    @abstractmethod
+    def forward(self, z, **kwargs):
+        raise NotImplementedError
+
+    @abstractmethod
+    def backward(self, out, **kwargs):
+        raise NotImplementedError
+
+    def freeze(self):
+        self.trainable = False
+
+    def unfreeze(self):
+        self.trainable = True
+
+    def flush_gradients(self):
+        """Zero the gradients and drop every retained input / derived variable (layers.py:66-74)."""
+        assert self.trainable, "Layer is frozen"
+        self.X = []
+        for k in self.derived_variables:
+            self.derived_variables[k] = []
+        for k, v in self.gradients.items():
+            v.zero_()
+
+    def update(self, cur_loss=None):
+        """Optimizer step on the accrued gradients, then flush (layers.py:76-86)."""
+        assert self.trainable, "Layer is frozen"
+        self.optimizer.step()
+        for k, v in self.gradients.items():
+            if k in self.parameters:
+                self.parameters[k] = self.optimizer(_as_param(self.parameters[k]), v, k, cur_loss)
+        self.flush_gradients()
+
+    def set_params(self, summary_dict):
+        """layers.py:88-128."""
+        layer, sd = self, dict(summary_dict)
+        for k in ["parameters", "hyperparameters"]:
+            if k in sd:
+                entry = sd.pop(k)
+                sd.update(entry)
+        for k, v in sd.items():
+            if k in self.parameters:
+                layer.parameters[k] = _as_param(v)
+            if k in self.hyperparameters:
+                if k == "act_fn":
+                    layer.act_fn = ActivationInitializer(v)()
+                elif k == "optimizer":
+                    layer.optimizer = OptimizerInitializer(sd[k])()
+                elif k not in ["wrappers", "optimizer"]:
+                    setattr(layer, k, v)
+        return layer
+
+    def summary(self):
+        return {"layer": self.hyperparameters["layer"], "parameters": self.parameters,
+                "hyperparameters": self.hyperparameters}
+
+    # ---- helpers shared by the layers ---------------------------------------------------------
+    def _opt_hparams(self):
+        return {"cache": self.optimizer.cache, "hyperparameters": self.optimizer.hyperparameters}
+
+
+class WeightInitializer(object):
+    """initializers/initializers.py:242-308 (consumes np.random exactly like the reference)."""
+
+    def __init__(self, act_fn_str, mode="glorot_uniform"):
+        if mode not in ["he_normal", "he_uniform", "glorot_normal", "glorot_uniform", "std_normal", "trunc_normal"]:
+            raise ValueError("Unrecognize initialization mode: {}".format(mode))
+        self.mode, self.act_fn = mode, act_fn_str
+
+    def __call__(self, weight_shape):
+        if self.mode == "glorot_uniform":
+            return U.glorot_uniform(weight_shape, self._calc_glorot_gain())
+        if self.mode == "glorot_normal":
+            return U.glorot_normal(weight_shape, self._calc_glorot_gain())
+        if self.mode == "he_uniform":
+            return U.he_uniform(weight_shape)
+        if self.mode == "he_normal":
+            return U.he_normal(weight_shape)
+        if self.mode == "std_normal":
+            return np.random.randn(*weight_shape)
+        return U.truncated_normal(0, 1, weight_shape)
+
+    def _calc_glorot_gain(self):
+        import re
+        gain, s = 1.0, self.act_fn.lower()
+        if s == "tanh":
+            gain = 5.0 / 3.0
+        elif s == "relu":
+            gain = np.sqrt(2)
+        elif "leaky relu" in s:
+            alpha = re.match(r"leaky relu\(alpha=(.*)\)", s).groups()[0]
+            gain = np.sqrt(2 / 1 + float(alpha) ** 2)
+        return gain
+
+
+def _dz_prep(dY, Z, act, out_dtype, db=None, accumulate=True):
+    """dZ = dLdy * act'(Z) (+ db += column sums), one fused pass (layers.py:3103, 3109)."""
+    lib = L.load()
+    rows, ch = dY.numel() // dY.shape[-1], dY.shape[-1]
+    identity = act.code == 0
+    if identity and dY.dtype == out_dtype and db is None:
+        return dY
+    dZ = torch.empty(dY.shape, dtype=out_dtype, device=dY.device)
+    ws = None
+    if db is not None:
+        d = U.make_desc(1, 1, 1, 1, ch, 1, 1, 1, 1, (0, 0, 0, 0), 1, 1)
+        d.N, d.OH, d.OW = 1, 1, int(rows)
+        ws = L.workspace(lib.npml_workspace_bytes(d, L.OP_DZ_PREP))
+    L.check(lib.npml_dz_prep(rows, ch, act.code, act.p0, act.p1, L.ptr(dY), L.code_of(dY),
+                             None if identity else L.ptr(Z), 0 if identity else L.code_of(Z), L.ptr(dZ),
+                             L.code_of(dZ), L.ptr(db), 1 if accumulate else 0, L.ptr(ws),
+                             0 if ws is None else ws.numel(), L.stream()), "npml_dz_prep")
+    return dZ
+
+
+class _ConvBase(LayerBase):
+    """State handling shared by Conv2D and Deconv2D (they differ only in geometry and entry points)."""
+    _layer_name = None
+    _ops = None  # (fprop, dgrad, wgrad) op ids
+
+    def _init_params(self):
+        init_weights = WeightInitializer(str(self.act_fn), mode=self.init)
+        fr, fc = self.kernel_shape
+        W = init_weights((fr, fc, self.in_ch, self.out_ch))
+        self.parameters = {"W": L.to_device(W, torch.float32),
+                           "b": torch.zeros((1, 1, 1, self.out_ch), dtype=torch.float32, device=L.device())}
+        self.gradients = {"W": torch.zeros_like(self.parameters["W"]), "b": torch.zeros_like(self.parameters["b"])}
+        self.derived_variables = {"Z": [], "out_rows": [], "out_cols": []}
+        self.is_initialized = True
+
+    def _geometry(self, X_shape):
+        raise NotImplementedError
+
+    def _desc(self, X_shape, accumulate=0):
+        n, h, w, c = X_shape
+        fr, fc = self.kernel_shape
+        p4, oh, ow, dil = self._geometry(X_shape)
+        return U.make_desc(n, h, w, c, self.out_ch, fr, fc, self.stride, dil, p4, oh, ow, self.mode, self.act_fn,
+                           accumulate)
+
+    def _call(self, name, d, op, *args):
+        lib = L.load()
+        ws = L.workspace(lib.npml_workspace_bytes(d, op))
+        prof = L.PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.check(getattr(lib, name)(d, *args, L.ptr(ws), ws.numel(), L.stream()), name)
+        if prof is not None:
+            e1.record()
+            prof.append((name, e0, e1))
+
+    def _uses_tc(self, X_shape=None):
+        """True if the forward of this layer runs on the tcgen05 kernels for the last (or given) input shape."""
+        if X_shape is None:
+            X_shape = tuple(self.X[-1].shape) if self.X else self._last_shape
+        return bool(L.load().npml_uses_tensor_cores(self._desc(tuple(X_shape)), self._ops[0]))
+
+    def forward(self, X, retain_derived=True):
+        """Y = act_fn(conv(X, W) + b); bias and activation are the kernel's epilogue
+        (layers.py:3006-3046 / 3438-3478)."""
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, L.torch_dtype(self.mode))
+        if not self.is_initialized:
+            self.in_ch = Xd.shape[3]
+            self._init_params()
+        W = self.parameters["W"] = _as_param(self.parameters["W"])
+        b = self.parameters["b"] = _as_param(self.parameters["b"])
+        d = self._desc(tuple(Xd.shape))
+        self._last_shape = tuple(Xd.shape)
+        out_shape = (d.N, d.OH, d.OW, d.K)
+        Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
+        Y = Z if self.act_fn.code == 0 else torch.empty_like(Z)
+        pre = "npml_conv2d_" if self._layer_name == "Conv2D" else "npml_deconv2d_"
+        self._call(pre + "fprop", d, self._ops[0], L.ptr(Xd), L.ptr(W), L.ptr(b),
+                   L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
+        if retain_derived:
+            self.X.append(Xd)
+            self.derived_variables["Z"].append(Z)
+            self.derived_variables["out_rows"].append(d.OH)
+            self.derived_variables["out_cols"].append(d.OW)
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdy, retain_grads=True):
+        """dX for every retained forward; dW / db accumulate into `gradients`
+        (layers.py:3048-3116 / 3480-3568)."""
+        assert self.trainable, "Layer is frozen"
+        if not isinstance(dLdy, list):
+            dLdy = [dLdy]
+        dX = []
+        for dy, x, z in zip(dLdy, self.X, self.derived_variables["Z"]):
+            as_np = isinstance(dy, np.ndarray)
+            dx = self._bwd(L.to_device(dy, L.torch_dtype(self.mode)), x, z, retain_grads)
+            dX.append(L.to_numpy(dx) if as_np else dx)
+        return dX[0] if len(self.X) == 1 else dX
+
+    def _bwd(self, dLdy, X, Z, retain_grads=True):
+        W = self.parameters["W"] = _as_param(self.parameters["W"])
+        pre = "npml_conv2d_" if self._layer_name == "Conv2D" else "npml_deconv2d_"
+        dZ = _dz_prep(dLdy, Z, self.act_fn, X.dtype, self.gradients["b"] if retain_grads else None)
+        d = self._desc(tuple(X.shape), accumulate=1)
+        dX = torch.empty_like(X)
+        self._call(pre + "dgrad", d, self._ops[1], L.ptr(dZ), L.ptr(W), L.ptr(dX))
+        if retain_grads:
+            self._call(pre + "wgrad", d, self._ops[2], L.ptr(X), L.ptr(dZ), L.ptr(self.gradients["W"]))
+        return dX
+
+
+class Conv2D(_ConvBase):
+    """layers/layers.py:2895-3178."""
+    _layer_name = "Conv2D"
+    _ops = (L.OP_CONV_FPROP, L.OP_CONV_DGRAD, L.OP_CONV_WGRAD)
+
+    def __init__(self, out_ch, kernel_shape, pad=0, stride=1, dilation=0, act_fn=None, optimizer=None,
+                 init="glorot_uniform", mode="fp32"):
+        super().__init__(optimizer)
+        self.pad = pad
+        self.init = init
+        self.in_ch = None
+        self.out_ch = out_ch
+        self.stride = stride
+        self.dilation = dilation
+        self.kernel_shape = kernel_shape
+        self.act_fn = ActivationInitializer(act_fn)()
+        self.parameters = {"W": None, "b": None}
+        self.is_initialized = False
+        self.mode = mode
+        assert mode in L.MODES
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Conv2D", "pad": self.pad, "init": self.init, "in_ch": self.in_ch, "out_ch": self.out_ch,
+                "stride": self.stride, "dilation": self.dilation, "act_fn": str(self.act_fn),
+                "kernel_shape": self.kernel_shape, "optimizer": self._opt_hparams()}
+
+    def _geometry(self, X_shape):
+        fr, fc = self.kernel_shape
+        p4 = U.resolve_pad_2D(X_shape, self.pad, (fr, fc), self.stride, self.dilation)
+        oh, ow = U.conv_out_hw(X_shape[1], X_shape[2], fr, fc, p4, self.stride, self.dilation)
+        return p4, oh, ow, self.dilation + 1
+
+
+class Deconv2D(_ConvBase):
+    """layers/layers.py:3353-3568 (no dilation argument)."""
+    _layer_name = "Deconv2D"
+    _ops = (L.OP_DECONV_FPROP, L.OP_DECONV_DGRAD, L.OP_DECONV_WGRAD)
+
+    def __init__(self, out_ch, kernel_shape, pad=0, stride=1, act_fn=None, optimizer=None, init="glorot_uniform",
+                 mode="fp32"):
+        super().__init__(optimizer)
+        self.pad = pad
+        self.init = init
+        self.in_ch = None
+        self.stride = stride
+        self.out_ch = out_ch
+        self.kernel_shape = kernel_shape
+        self.act_fn = ActivationInitializer(act_fn)()
+        self.parameters = {"W": None, "b": None}
+        self.is_initialized = False
+        self.mode = mode
+        assert mode in L.MODES
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Deconv2D", "pad": self.pad, "init": self.init, "in_ch": self.in_ch, "out_ch": self.out_ch,
+                "stride": self.stride, "act_fn": str(self.act_fn), "kernel_shape": self.kernel_shape,
+                "optimizer": self._opt_hparams()}
+
+    def _geometry(self, X_shape):
+        fr, fc = self.kernel_shape
+        p4, oh, ow = U.deconv_geometry(X_shape[1], X_shape[2], fr, fc, self.pad, self.stride)
+        return p4, oh, ow, 1
+
+
+class BatchNorm2D(LayerBase):
+    """layers/layers.py:969-1215.  Statistics are per channel over (n_ex, rows, cols); the variance is the
+    biased one for both the normalisation and the running estimate (layers.py:1147)."""
+
+    def __init__(self, momentum=0.9, epsilon=1e-5, optimizer=None):
+        super().__init__(optimizer)
+        self.in_ch = None
+        self.out_ch = None
+        self.epsilon = epsilon
+        self.momentum = momentum
+        self.parameters = {"scaler": None, "intercept": None, "running_var": None, "running_mean": None}
+        self.is_initialized = False
+        self._saved = []      # (mean, rstd) of every retained forward
+
+    def _init_params(self):
+        dev = L.device()
+        scaler = np.random.rand(self.in_ch)
+        self.parameters = {"scaler": L.to_device(scaler, torch.float32),
+                           "intercept": torch.zeros(self.in_ch, dtype=torch.float32, device=dev),
+                           "running_var": torch.ones(self.in_ch, dtype=torch.float32, device=dev),
+                           "running_mean": torch.zeros(self.in_ch, dtype=torch.float32, device=dev)}
+        self.gradients = {"scaler": torch.zeros(self.in_ch, dtype=torch.float32, device=dev),
+                          "intercept": torch.zeros(self.in_ch, dtype=torch.float32, device=dev)}
+        self.is_initialized = True
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "BatchNorm2D", "act_fn": None, "in_ch": self.in_ch, "out_ch": self.out_ch,
+                "epsilon": self.epsilon, "momentum": self.momentum, "optimizer": self._opt_hparams()}
+
+    def reset_running_stats(self):
+        assert self.trainable, "Layer is frozen"
+        self.parameters["running_mean"] = torch.zeros(self.in_ch, dtype=torch.float32, device=L.device())
+        self.parameters["running_var"] = torch.ones(self.in_ch, dtype=torch.float32, device=L.device())
+
+    def flush_gradients(self):
+        super().flush_gradients()
+        self._saved = []
+
+    def _ws(self, rows, ch):
+        d = U.make_desc(1, 1, 1, 1, ch, 1, 1, 1, 1, (0, 0, 0, 0), 1, int(rows))
+        return L.workspace(L.load().npml_workspace_bytes(d, L.OP_BN))
+
+    def forward(self, X, retain_derived=True):
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, torch.float32) if as_np else L.to_device(X, X.dtype if X.dtype != torch.float64
+                                                                   else torch.float32)
+        if not self.is_initialized:
+            self.in_ch = self.out_ch = Xd.shape[3]
+            self._init_params()
+        P = self.parameters
+        for k in P:
+            P[k] = _as_param(P[k])
+        ch = Xd.shape[3]
+        rows = Xd.numel() // ch
+        y = torch.empty_like(Xd)
+        mean = torch.empty(ch, dtype=torch.float32, device=Xd.device)
+        rstd = torch.empty(ch, dtype=torch.float32, device=Xd.device)
+        use_batch = 1 if (self.trainable and retain_derived) else 0
+        ws = self._ws(rows, ch)
+        L.check(L.load().npml_bn2d_fwd(rows, ch, L.ptr(Xd), L.ptr(y), L.code_of(Xd), L.ptr(P["scaler"]),
+                                       L.ptr(P["intercept"]), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
+                                       float(self.momentum), float(self.epsilon), use_batch, L.ptr(mean),
+                                       L.ptr(rstd), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_fwd")
+        if retain_derived:
+            self.X.append(Xd)
+            self._saved.append((mean, rstd) if use_batch else None)
+        return L.to_numpy(y) if as_np else y
+
+    def backward(self, dLdy, retain_grads=True):
+        assert self.trainable, "Layer is frozen"
+        if not isinstance(dLdy, list):
+            dLdy = [dLdy]
+        dX = []
+        for i, (dy, x) in enumerate(zip(dLdy, self.X)):
+            as_np = isinstance(dy, np.ndarray)
+            dx = self._bwd(L.to_device(dy, x.dtype), x, self._saved[i] if i < len(self._saved) else None,
+                           retain_grads)
+            dX.append(L.to_numpy(dx) if as_np else dx)
+        return dX[0] if len(self.X) == 1 else dX
+
+    def _batch_stats(self, X):
+        """(mean, rstd) of X; the reference's _bwd always recomputes them from X (layers.py:1207)."""
+        ch = X.shape[3]
+        rows = X.numel() // ch
+        mean = torch.empty(ch, dtype=torch.float32, device=X.device)
+        rstd = torch.empty(ch, dtype=torch.float32, device=X.device)
+        scratch_rm, scratch_rv = torch.zeros_like(mean), torch.ones_like(mean)
+        ws = self._ws(rows, ch)
+        tmp = torch.empty_like(X)
+        L.check(L.load().npml_bn2d_fwd(rows, ch, L.ptr(X), L.ptr(tmp), L.code_of(X), L.ptr(self.parameters["scaler"]),
+                                       L.ptr(self.parameters["intercept"]), L.ptr(scratch_rm), L.ptr(scratch_rv),
+                                       float(self.momentum), float(self.epsilon), 1, L.ptr(mean), L.ptr(rstd),
+                                       L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_fwd")
+        return mean, rstd
+
+    def _bwd(self, dLdy, X, saved, retain_grads=True):
+        P = self.parameters
+        ch = X.shape[3]
+        rows = X.numel() // ch
+        mean, rstd = saved if saved is not None else self._batch_stats(X)
+        dX = torch.empty_like(X)
+        ws = self._ws(rows, ch)
+        G = self.gradients
+        L.check(L.load().npml_bn2d_bwd(rows, ch, L.ptr(dLdy), L.ptr(X), L.ptr(dX), L.code_of(X),
+                                       L.ptr(_as_param(P["scaler"])), L.ptr(mean), L.ptr(rstd),
+                                       L.ptr(G["scaler"]) if retain_grads else None,
+                                       L.ptr(G["intercept"]) if retain_grads else None, 1, L.ptr(ws), ws.numel(),
+                                       L.stream()), "npml_bn2d_bwd")
+        return dX
+
+
+class Add(LayerBase):
+    """Element-wise sum of several inputs followed by an activation (layers/layers.py:633-742)."""
+
+    def __init__(self, act_fn=None, optimizer=None):
+        super().__init__(optimizer)
+        self.act_fn = ActivationInitializer(act_fn)()
+        self._init_params()
+
+    def _init_params(self):
+        self.gradients = {}
+        self.parameters = {}
+        self.derived_variables = {"sum": []}
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Sum", "act_fn": str(self.act_fn), "optimizer": self._opt_hparams()}
+
+    def forward(self, X, retain_derived=True):
+        as_np = isinstance(X[0], np.ndarray)
+        first = X[0]
+        dt = torch.float32 if (as_np or first.dtype == torch.float64) else first.dtype
+        Xd = [L.to_device(x, dt) for x in X]
+        n = Xd[0].numel()
+        total = torch.empty_like(Xd[0])
+        Y = total if self.act_fn.code == 0 else torch.empty_like(total)
+        arr = (C.c_void_p * len(Xd))(*[x.data_ptr() for x in Xd])
+        a = self.act_fn
+        L.check(L.load().npml_add_act_fwd(len(Xd), arr, L.code_of(total), n, a.code, a.p0, a.p1, L.ptr(total),
+                                          None if Y is total else L.ptr(Y), L.stream()), "npml_add_act_fwd")
+        if retain_derived:
+            self.X.append(Xd)
+            self.derived_variables["sum"].append(total)
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdY, retain_grads=True):
+        if not isinstance(dLdY, list):
+            dLdY = [dLdY]
+        grads = []
+        for dy, x, ss in zip(dLdY, self.X, self.derived_variables["sum"]):
+            as_np = isinstance(dy, np.ndarray)
+            g = self._bwd(L.to_device(dy, ss.dtype), x, ss)
+            grads.append([L.to_numpy(v) for v in g] if as_np else g)
+        return grads[0] if len(self.X) == 1 else grads
+
+    def _bwd(self, dLdY, X, _sum):
+        g = _dz_prep(dLdY, _sum, self.act_fn, _sum.dtype)
+        return [g for _ in X]

@@ -1,0 +1,213 @@
+"""SkipConnectionConvModule, the reference's "ResNet-like convolution shortcut" block
+(numpy_ml/neural_nets/modules/modules.py:615-984): conv1 -> act -> BN1 -> conv2 -> BN2, a
+conv_skip -> BN_skip projection of the input, Add, act.  Note the order Conv -> act -> BN
+(modules.py:646), not Conv -> BN -> act."""
+import ctypes as C
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .activations import ActivationInitializer, Affine
+from .layers import Conv2D, BatchNorm2D, Add
+from .utils import calc_pad_dims_2D
+
+
+def _device_add(a, b):
+    """a + b through npml_add_act_fwd (new tensor)."""
+    out = torch.empty_like(a)
+    arr = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
+    L.check(L.load().npml_add_act_fwd(2, arr, L.code_of(a), a.numel(), 0, 0.0, 0.0, L.ptr(out), None, L.stream()),
+            "npml_add_act_fwd")
+    return out
+
+
+class ModuleBase(ABC):
+    """modules.py:21-116."""
+
+    def __init__(self):
+        self.X = None
+        self.trainable = True
+        super().__init__()
+
+    @abstractmethod
+    def forward(self, z, **kwargs):
+        raise NotImplementedError
+
+    @abstractmethod
+    def backward(self, out, **kwargs):
+        raise NotImplementedError
+
+    @property
+    def components(self):
+        return [getattr(self, c) for c in self.hyperparameters["component_ids"] if hasattr(self, c)]
+
+    def freeze(self):
+        self.trainable = False
+        for c in self.components:
+            c.freeze()
+
+    def unfreeze(self):
+        self.trainable = True
+        for c in self.components:
+            c.unfreeze()
+
+    def update(self, cur_loss=None):
+        assert self.trainable, "Layer is frozen"
+        for c in self.components:
+            c.update(cur_loss)
+        self.flush_gradients()
+
+    def flush_gradients(self):
+        """Unlike modules.py:69-71 (which sets the components' derived variables to None and so breaks
+        the next forward), the components are flushed to empty lists."""
+        assert self.trainable, "Layer is frozen"
+        self.X = []
+        self._dv = {}
+        for c in self.components:
+            c.flush_gradients()
+
+    def set_params(self, summary_dict):
+        cids = self.hyperparameters["component_ids"]
+        for key in ("parameters", "hyperparameters"):
+            for c, cd in summary_dict.get(key, {}).get("components", {}).items():
+                if c in cids and cd is not None and hasattr(self, c):
+                    getattr(self, c).set_params(cd)
+        return self
+
+    def summary(self):
+        return {"parameters": self.parameters, "layer": self.hyperparameters["layer"],
+                "hyperparameters": self.hyperparameters}
+
+
+class SkipConnectionConvModule(ModuleBase):
+    def __init__(self, out_ch1, out_ch2, kernel_shape1, kernel_shape2, kernel_shape_skip, pad1=0, pad2=0, stride1=1,
+                 stride2=1, act_fn=None, epsilon=1e-5, momentum=0.9, stride_skip=1, optimizer=None,
+                 init="glorot_uniform", mode="fp32"):
+        super().__init__()
+        self.init = init
+        self.pad1 = pad1
+        self.pad2 = pad2
+        self.in_ch = None
+        self.out_ch1 = out_ch1
+        self.out_ch2 = out_ch2
+        self.epsilon = epsilon
+        self.stride1 = stride1
+        self.stride2 = stride2
+        self.momentum = momentum
+        self.optimizer = optimizer
+        self.stride_skip = stride_skip
+        self.kernel_shape1 = kernel_shape1
+        self.kernel_shape2 = kernel_shape2
+        self.kernel_shape_skip = kernel_shape_skip
+        self.act_fn = Affine(slope=1, intercept=0) if act_fn is None else ActivationInitializer(act_fn)()
+        self.mode = mode
+        self._init_params()
+
+    def _init_params(self, X=None):
+        self._dv = {}
+        self.conv1 = Conv2D(pad=self.pad1, init=self.init, act_fn=self.act_fn, out_ch=self.out_ch1,
+                            stride=self.stride1, optimizer=self.optimizer, kernel_shape=self.kernel_shape1,
+                            mode=self.mode)
+        self.conv2 = Conv2D(pad=self.pad2, init=self.init, out_ch=self.out_ch2, stride=self.stride2,
+                            optimizer=self.optimizer, kernel_shape=self.kernel_shape2,
+                            act_fn=Affine(slope=1, intercept=0), mode=self.mode)
+        self.batchnorm1 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum)
+        self.batchnorm2 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum)
+        self.batchnorm_skip = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum)
+        self.add3 = Add(self.act_fn)
+
+    def _calc_skip_padding(self, X_shape):
+        """Padding of the skip conv so that it matches conv2's output dims (modules.py:755-788).
+        Like the reference, pad1/pad2 must be ints or 2-tuples (anything else fails here)."""
+        pads = []
+        for p in [self.pad1, self.pad2]:
+            if isinstance(p, int):
+                pads.append((p, p, p, p))
+            elif isinstance(p, tuple) and len(p) == 2:
+                pads.append((p[0], p[0], p[1], p[1]))
+        self.pad1, self.pad2 = pads          # raises ValueError for 'same' / 4-tuples, as upstream
+        _, in_rows, in_cols, _ = X_shape
+        s1, (fr1, fc1) = self.stride1, self.kernel_shape1
+        pr11, pr12, pc11, pc12 = self.pad1
+        out_rows1 = int(np.floor(1 + (in_rows + pr11 + pr12 - fr1) / s1))
+        out_cols1 = int(np.floor(1 + (in_cols + pc11 + pc12 - fc1) / s1))
+        s2, (fr2, fc2) = self.stride2, self.kernel_shape2
+        pr21, pr22, pc21, pc22 = self.pad2
+        out_rows2 = int(np.floor(1 + (out_rows1 + pr21 + pr22 - fr2) / s2))
+        out_cols2 = int(np.floor(1 + (out_cols1 + pc21 + pc22 - fc2) / s2))
+        self.pad_skip = calc_pad_dims_2D(tuple(X_shape), (out_rows2, out_cols2), stride=self.stride_skip,
+                                         kernel_shape=self.kernel_shape_skip)
+
+    def _init_conv_skip(self, X_shape):
+        self._calc_skip_padding(X_shape)
+        self.conv_skip = Conv2D(init=self.init, pad=self.pad_skip, out_ch=self.out_ch2, stride=self.stride_skip,
+                                kernel_shape=self.kernel_shape_skip, act_fn=Affine(slope=1, intercept=0),
+                                optimizer=self.optimizer, mode=self.mode)
+
+    def _by_component(self, attr):
+        names = ["add3", "conv1", "conv2", "conv_skip", "batchnorm1", "batchnorm2", "batchnorm_skip"]
+        return {n: (getattr(getattr(self, n), attr) if hasattr(self, n) else None) for n in names}
+
+    @property
+    def parameters(self):
+        return {"components": self._by_component("parameters")}
+
+    @property
+    def gradients(self):
+        return {"components": self._by_component("gradients")}
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "SkipConnectionConvModule", "init": self.init, "pad1": self.pad1, "pad2": self.pad2,
+                "in_ch": self.in_ch, "out_ch1": self.out_ch1, "out_ch2": self.out_ch2, "epsilon": self.epsilon,
+                "stride1": self.stride1, "stride2": self.stride2, "momentum": self.momentum,
+                "act_fn": str(self.act_fn), "stride_skip": self.stride_skip, "kernel_shape1": self.kernel_shape1,
+                "kernel_shape2": self.kernel_shape2, "kernel_shape_skip": self.kernel_shape_skip,
+                "pad_skip": self.pad_skip if hasattr(self, "pad_skip") else None,
+                "component_ids": ["add3", "conv1", "conv2", "conv_skip", "batchnorm1", "batchnorm2", "batchnorm_skip"],
+                "components": self._by_component("hyperparameters")}
+
+    @property
+    def derived_variables(self):
+        dv = {"conv1_out": None, "conv2_out": None, "conv_skip_out": None, "batchnorm1_out": None,
+              "batchnorm2_out": None, "batchnorm_skip_out": None, "components": self._by_component("derived_variables")}
+        dv.update(self._dv)
+        return dv
+
+    def forward(self, X, retain_derived=True):
+        """modules.py:905-937."""
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, L.torch_dtype(self.mode))
+        if not hasattr(self, "conv_skip"):
+            self._init_conv_skip(tuple(Xd.shape))
+            self.in_ch = Xd.shape[3]
+        conv1_out = self.conv1.forward(Xd, retain_derived)
+        bn1_out = self.batchnorm1.forward(conv1_out, retain_derived)
+        conv2_out = self.conv2.forward(bn1_out, retain_derived)
+        bn2_out = self.batchnorm2.forward(conv2_out, retain_derived)
+        conv_skip_out = self.conv_skip.forward(Xd, retain_derived)
+        bn_skip_out = self.batchnorm_skip.forward(conv_skip_out, retain_derived)
+        Y = self.add3.forward([bn_skip_out, bn2_out], retain_derived)
+        if retain_derived:
+            self._dv.update({"conv1_out": conv1_out, "conv2_out": conv2_out, "conv_skip_out": conv_skip_out,
+                             "batchnorm1_out": bn1_out, "batchnorm2_out": bn2_out,
+                             "batchnorm_skip_out": bn_skip_out})
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdY, retain_grads=True):
+        """modules.py:939-984."""
+        as_np = isinstance(dLdY, np.ndarray)
+        dY = L.to_device(dLdY, L.torch_dtype(self.mode))
+        dBnskip_out, dBn2_out = self.add3.backward(dY)
+        dConvskip_out = self.batchnorm_skip.backward(dBnskip_out)
+        dX = self.conv_skip.backward(dConvskip_out)
+        dConv2_out = self.batchnorm2.backward(dBn2_out)
+        dBn1_out = self.conv2.backward(dConv2_out)
+        dConv1_out = self.batchnorm1.backward(dBn1_out)
+        dX = _device_add(dX, self.conv1.backward(dConv1_out))
+        if retain_grads:
+            self._dv.update({"dLdAdd3_X": dX, "dLdBn2": dBn2_out, "dLdBn1": dBn1_out, "dLdConv2": dConv2_out,
+                             "dLdConv1": dConv1_out, "dLdBnSkip": dBnskip_out, "dLdConvSkip": dConvskip_out})
+        return L.to_numpy(dX) if as_np else dX

@@ -1,3 +1,4 @@
+import importlib
 import json
 import os
 import sys
@@ -10,6 +11,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# tolerances stated by BASELINE.json north_star (normwise relative error vs the float64 reference)
+TOL = {"fp32": 1e-5, "tf32": 5e-3, "bf16": 2e-2}
 
 
 def pytest_configure(config):
@@ -35,6 +39,16 @@ def rel_err(a, ref):
     den = np.linalg.norm(ref.ravel())
     num = np.linalg.norm((a - ref).ravel())
     return num / den if den > 0 else num
+
+
+def npml():
+    """The product package (its directory name is not an identifier)."""
+    return importlib.import_module("numpy-ml_b200")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    return npml()
 
 
 @pytest.fixture(scope="session")

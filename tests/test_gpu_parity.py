@@ -1,0 +1,405 @@
+"""GPU parity tests: the CUDA path (through the layer API -> ctypes -> libnpmlconv.so) against
+ (a) the golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+ (b) the pinned CPU oracle (oracle/conv_oracle.py) on seeded inputs,
+in the three arithmetic modes with the tolerances BASELINE.json states (normwise relative error
+<= 1e-5 fp32, <= 5e-3 TF32, <= 2e-2 BF16), plus size-independent properties at the full
+benchmark shapes.  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from conftest import TOL, load_golden, to_pad, rel_err, npml
+from oracle import conv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp32", "tf32", "bf16"]
+# BatchNorm's dX and everything downstream of it subtracts nearly equal quantities; the reference's own
+# tests use decimal=2..3 for those tensors (tests/test_nn.py:1049, 1918-1965).  fp32-mode bound used here:
+TOL_BN = {"fp32": 5e-5, "tf32": 1e-2, "bf16": 4e-2}
+
+
+def close(a, ref, tol, what=""):
+    e = rel_err(npml().to_numpy(a) if not isinstance(a, np.ndarray) else a, ref)
+    assert e <= tol, "{}: rel err {:.3e} > {:.1e}".format(what, e, tol)
+
+
+def make_act(pkg, name, p0, p1):
+    A = pkg.activations
+    return {"identity": A.Identity, "affine": lambda: A.Affine(p0, p1), "relu": A.ReLU,
+            "leaky_relu": lambda: A.LeakyReLU(p0), "tanh": A.Tanh, "sigmoid": A.Sigmoid, "elu": lambda: A.ELU(p0),
+            "selu": A.SELU, "hard_sigmoid": A.HardSigmoid, "softplus": A.SoftPlus, "gelu": A.GELU,
+            "exponential": A.Exponential}[name]()
+
+
+# ------------------------------------------------------------------------------------------------
+#  golden vectors from the reference
+# ------------------------------------------------------------------------------------------------
+def test_utils_golden(cuda_device):
+    pkg = npml()
+    z, cases = load_golden("utils.npz")
+    for c in cases:
+        i = c.get("id")
+        if c["kind"] == "pad2D":
+            ks = tuple(c["kernel_shape"]) if c["kernel_shape"] else None
+            Xp, p4 = pkg.pad2D(z[i + "/X"], to_pad(c["pad"]), ks, c["stride"], c["dilation"])
+            assert list(p4) == c["p4"] and np.array_equal(Xp, z[i + "/out"])
+        elif c["kind"] == "dilate":
+            assert np.array_equal(pkg.dilate(z[i + "/X"], c["d"]), z[i + "/out"])
+        elif c["kind"] == "conv":
+            X, W, pad = z[i + "/X"], z[i + "/W"], to_pad(c["pad"])
+            X_col, p4 = pkg.im2col(X, W.shape, pad, c["stride"], c["dilation"])
+            assert list(p4) == c["p4"]
+            assert np.array_equal(X_col, z[i + "/X_col"])                      # a pure gather: bit-exact
+            close(pkg.conv2D(X, W, c["stride"], pad, c["dilation"]), z[i + "/Z"], TOL["fp32"], i)
+            close(pkg.conv2D_naive(X, W, c["stride"], pad, c["dilation"]), z[i + "/Z"], TOL["fp32"], i)
+            back = pkg.col2im(z[i + "/C"], X.shape, W.shape, tuple(c["p4"]), c["stride"], c["dilation"])
+            assert back.shape == z[i + "/col2im"].shape                        # NCHW, like the reference
+            close(back, z[i + "/col2im"], TOL["fp32"], i)
+        elif c["kind"] == "deconv":
+            close(pkg.deconv2D_naive(z[i + "/X"], z[i + "/W"], c["stride"], to_pad(c["pad"]), 0), z[i + "/Z"],
+                  TOL["fp32"], i)
+
+
+def test_activations_golden(cuda_device):
+    pkg = npml()
+    z, cases = load_golden("activations.npz")
+    x = z["x"]
+    for c in cases:
+        a = make_act(pkg, c["act"], c["p0"], c["p1"])
+        assert str(a) == c["str"]
+        close(a.fn(x), z[c["act"] + "/fn"], 2e-6, c["act"])
+        close(a.grad(x), z[c["act"] + "/grad"], 2e-6, c["act"] + "'")
+
+
+def _run_layer_case(pkg, cls, z, c, mode):
+    i, pad = c["id"], to_pad(c["pad"])
+    kw = dict(out_ch=c["out_ch"], kernel_shape=tuple(c["kernel_shape"]), pad=pad, stride=c["stride"],
+              act_fn=make_act(pkg, c["act"], c["p0"], c["p1"]), mode=mode)
+    if "dilation" in c:
+        kw["dilation"] = c["dilation"]
+    layer = cls(**kw)
+    X = z[i + "/X"]
+    layer.forward(X, retain_derived=False)
+    layer.parameters["W"], layer.parameters["b"] = z[i + "/W"], z[i + "/b"]    # NumPy assignment, like upstream
+    tol = TOL[mode]
+    Y = layer.forward(X)
+    close(Y, z[i + "/Y"], tol, i + " Y")
+    close(layer.derived_variables["Z"][0], z[i + "/Z"], tol, i + " Z")
+    assert layer.derived_variables["out_rows"][0] == z[i + "/Z"].shape[1]
+    if c["two_calls"]:
+        Y2 = layer.forward(z[i + "/X2"])
+        close(Y2, z[i + "/Y2"], tol, i + " Y2")
+        dXs = layer.backward([z[i + "/dLdy"], z[i + "/dLdy2"]])
+        assert isinstance(dXs, list) and len(dXs) == 2
+        close(dXs[0], z[i + "/dX"], tol, i + " dX")
+        close(dXs[1], z[i + "/dX2"], tol, i + " dX2")
+    else:
+        close(layer.backward(z[i + "/dLdy"]), z[i + "/dX"], tol, i + " dX")
+    close(layer.gradients["W"], z[i + "/dW"], tol, i + " dW")
+    close(layer.gradients["b"], z[i + "/db"], tol, i + " db")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_conv2d_layer_golden(cuda_device, mode):
+    pkg = npml()
+    z, cases = load_golden("conv2d_layer.npz")
+    for c in cases:
+        _run_layer_case(pkg, pkg.Conv2D, z, c, mode)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_deconv2d_layer_golden(cuda_device, mode):
+    pkg = npml()
+    z, cases = load_golden("deconv2d_layer.npz")
+    for c in cases:
+        _run_layer_case(pkg, pkg.Deconv2D, z, c, mode)
+
+
+def test_bn_add_golden(cuda_device):
+    pkg = npml()
+    z, cases = load_golden("bn_add.npz")
+    for c in cases:
+        i = c["id"]
+        if c["kind"] == "bn":
+            L = pkg.BatchNorm2D(momentum=c["momentum"], epsilon=c["epsilon"])
+            L.forward(z[i + "/X"], retain_derived=False)
+            L.parameters["scaler"], L.parameters["intercept"] = z[i + "/scaler"], z[i + "/intercept"]
+            y = L.forward(z[i + "/X"])
+            close(y, z[i + "/y"], 1e-5, i + " y")
+            close(L.parameters["running_mean"], z[i + "/running_mean"], 1e-5, i + " rm")
+            close(L.parameters["running_var"], z[i + "/running_var"], 1e-5, i + " rv")   # biased, layers.py:1147
+            dX = L.backward(z[i + "/dLdy"])
+            close(dX, z[i + "/dX"], TOL_BN["fp32"], i + " dX")
+            close(L.gradients["scaler"], z[i + "/dScaler"], 1e-5, i + " dScaler")
+            close(L.gradients["intercept"], z[i + "/dIntercept"], 1e-5, i + " dIntercept")
+            y2 = L.forward(z[i + "/X2"], retain_derived=False)                           # running-stats path
+            close(y2, z[i + "/y_infer"], 1e-5, i + " y_infer")
+        else:
+            A = pkg.Add(act_fn=make_act(pkg, c["act"], 0, 0))
+            Xs = [z["{}/X{}".format(i, j)] for j in range(c["n_in"])]
+            close(A.forward(Xs), z[i + "/Y"], 1e-6, i + " Y")
+            g = A.backward(z[i + "/dLdY"])
+            assert len(g) == c["n_in"]
+            close(g[-1], z[i + "/dX"], 1e-6, i + " dX")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_skip_conv_module_golden(cuda_device, mode):
+    pkg = npml()
+    z, cases = load_golden("skip_conv_module.npz")
+    tol = TOL_BN[mode]
+    for c in cases:
+        i = c["id"]
+        act = None if c["act"] == "identity" else make_act(pkg, c["act"], c["p0"], c["p1"])
+        M = pkg.SkipConnectionConvModule(out_ch1=c["out_ch1"], out_ch2=c["out_ch2"],
+                                         kernel_shape1=tuple(c["kernel_shape1"]), kernel_shape2=tuple(c["kernel_shape2"]),
+                                         kernel_shape_skip=tuple(c["kernel_shape_skip"]), pad1=to_pad(c["pad1"]),
+                                         pad2=to_pad(c["pad2"]), stride1=c["stride1"], stride2=c["stride2"],
+                                         stride_skip=c["stride_skip"], act_fn=act, mode=mode)
+        X = z[i + "/X"]
+        M.forward(X, retain_derived=False)
+        assert list(M.pad_skip) == list(z[i + "/pad_skip"])
+        for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
+            conv.parameters["W"], conv.parameters["b"] = z["{}/W{}".format(i, t)], z["{}/b{}".format(i, t)]
+            bn.parameters["scaler"], bn.parameters["intercept"] = z["{}/g{}".format(i, t)], z["{}/h{}".format(i, t)]
+            bn.reset_running_stats()
+        M.flush_gradients()
+        Y = M.forward(X)
+        dX = M.backward(z[i + "/dLdY"])
+        close(Y, z[i + "/Y"], tol, i + " Y")
+        close(dX, z[i + "/dX"], tol, i + " dX")
+        dv = M.derived_variables
+        for k in ["conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "conv_skip_out", "batchnorm_skip_out",
+                  "dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2", "dLdBnSkip", "dLdConvSkip"]:
+            close(dv[k], z["{}/{}".format(i, k)], tol, i + " " + k)
+        for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
+            close(conv.gradients["W"], z["{}/dW{}".format(i, t)], tol, i + " dW" + t)
+            # conv biases feed straight into a BatchNorm, so their true gradient is ~0 (pure cancellation):
+            # compare absolutely, scaled by the weight-gradient magnitude
+            db_ref = z["{}/db{}".format(i, t)]
+            db = pkg.to_numpy(conv.gradients["b"])
+            scale = np.linalg.norm(z["{}/dW{}".format(i, t)].ravel())
+            assert np.linalg.norm((db - db_ref).ravel()) <= tol * max(scale, 1.0), i + " db" + t
+            close(bn.gradients["scaler"], z["{}/dg{}".format(i, t)], tol, i + " dg" + t)
+            close(bn.gradients["intercept"], z["{}/dh{}".format(i, t)], tol, i + " dh" + t)
+            close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol, i + " rm" + t)
+            close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol, i + " rv" + t)
+
+
+# ------------------------------------------------------------------------------------------------
+#  seeded inputs vs the pinned oracle, shapes that take the tensor-core kernels
+# ------------------------------------------------------------------------------------------------
+def _f32(rng, shape, scale=1.0):
+    return (scale * rng.standard_normal(shape, dtype=np.float32)).astype(np.float64)
+
+
+CONV_CASES = [
+    # xs, out_ch, kernel, pad, stride, dilation, act
+    ((4, 16, 16, 64), 64, (3, 3), "same", 1, 0, "identity"),        # cfg2 miniature
+    ((3, 28, 28, 128), 256, (3, 3), 0, 2, 2, "identity"),           # cfg3 at N=3
+    ((2, 14, 14, 128), 64, (3, 3), "same", 2, 2, "relu"),           # 'same' with stride 2 / dilation 2
+    ((4, 12, 12, 64), 128, (1, 1), 0, 1, 0, "tanh"),                # 1x1 projection (cfg4 skip)
+    ((2, 9, 11, 72), 40, (3, 2), (1, 2), 1, 0, "sigmoid"),          # channel tails, non-square, ragged tiles
+    ((5, 7, 7, 32), 96, (3, 3), 1, 1, 1, "leaky_relu"),
+    ((2, 10, 10, 16), 24, (2, 2), (1, 0, 2, 1), 3, 0, "identity"),  # stride 3, leftovers, asymmetric pad
+    ((2, 8, 8, 8), 8, (3, 3), 1, 1, 0, "identity"),                 # minimum aligned channels
+    ((3, 6, 6, 5), 17, (3, 3), 1, 1, 0, "identity"),                # odd channels -> CUDA-core path
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", range(len(CONV_CASES)))
+def test_conv2d_vs_oracle(cuda_device, mode, case):
+    pkg = npml()
+    xs, oc, ks, pad, s, d, act = CONV_CASES[case]
+    rng = np.random.default_rng(100 + case)
+    p0 = 0.25 if act == "leaky_relu" else 0.0
+    L = pkg.Conv2D(out_ch=oc, kernel_shape=ks, pad=pad, stride=s, dilation=d, act_fn=make_act(pkg, act, p0, 0.0),
+                   mode=mode)
+    X = _f32(rng, xs)
+    W = _f32(rng, ks + (xs[3], oc), 1.0 / np.sqrt(ks[0] * ks[1] * xs[3]))
+    b = _f32(rng, (1, 1, 1, oc), 0.1)                                # non-zero bias (never exercised upstream)
+    L.forward(X, retain_derived=False)
+    L.parameters["W"], L.parameters["b"] = W, b
+    Y = L.forward(X)
+    Yr, Zr = O.conv2d_layer_fwd(X, W, b, s, pad, d, act, p0, 0.0)
+    tol = TOL[mode]
+    close(Y, Yr, tol, "Y")
+    dY = _f32(rng, Yr.shape)                                         # random dLdy (upstream uses ones)
+    dX = L.backward(dY)
+    dXr, dWr, dbr = O.conv2d_layer_bwd(dY, X, Zr, W, s, pad, d, act, p0, 0.0)
+    close(dX, dXr, tol, "dX")
+    close(L.gradients["W"], dWr, tol, "dW")
+    close(L.gradients["b"], dbr, tol, "db")
+
+
+DECONV_CASES = [
+    ((2, 8, 8, 256), 128, (4, 4), 1, 2, "identity"),                 # cfg5 miniature
+    ((3, 6, 5, 64), 64, (3, 3), 1, 1, "relu"),
+    ((2, 5, 5, 32), 48, (2, 3), (1, 0), 3, "tanh"),
+    ((2, 7, 7, 16), 8, (3, 3), "same", 1, "identity"),
+    ((2, 4, 4, 64), 32, (5, 5), 2, 2, "identity"),
+    ((2, 5, 5, 3), 6, (4, 4), 1, 2, "identity"),                     # odd channels -> CUDA-core path
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", range(len(DECONV_CASES)))
+def test_deconv2d_vs_oracle(cuda_device, mode, case):
+    pkg = npml()
+    xs, oc, ks, pad, s, act = DECONV_CASES[case]
+    rng = np.random.default_rng(200 + case)
+    L = pkg.Deconv2D(out_ch=oc, kernel_shape=ks, pad=pad, stride=s, act_fn=make_act(pkg, act, 0, 0), mode=mode)
+    X = _f32(rng, xs)
+    W = _f32(rng, ks + (xs[3], oc), 1.0 / np.sqrt(ks[0] * ks[1] * xs[3]))
+    b = _f32(rng, (1, 1, 1, oc), 0.1)
+    L.forward(X, retain_derived=False)
+    L.parameters["W"], L.parameters["b"] = W, b
+    Y = L.forward(X)
+    Yr, Zr = O.deconv2d_layer_fwd(X, W, b, s, pad, act)
+    tol = TOL[mode]
+    close(Y, Yr, tol, "Y")
+    dY = _f32(rng, Yr.shape)
+    dX = L.backward(dY)
+    dXr, dWr, dbr = O.deconv2d_layer_bwd(dY, X, Zr, W, s, pad, act)
+    close(dX, dXr, tol, "dX")
+    close(L.gradients["W"], dWr, tol, "dW")
+    close(L.gradients["b"], dbr, tol, "db")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_skip_conv_module_vs_oracle(cuda_device, mode):
+    """cfg4 at N=4, 16x16: 64 -> 128 channels, 3x3 / 3x3 / 1x1, ReLU."""
+    pkg = npml()
+    rng = np.random.default_rng(300)
+    X = _f32(rng, (4, 16, 16, 64))
+    M = pkg.SkipConnectionConvModule(out_ch1=128, out_ch2=128, kernel_shape1=(3, 3), kernel_shape2=(3, 3),
+                                     kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn=pkg.activations.ReLU(), mode=mode)
+    M.forward(X, retain_derived=False)
+    P = {}
+    for t, conv, bn, cin in (("1", M.conv1, M.batchnorm1, 64), ("2", M.conv2, M.batchnorm2, 128),
+                             ("s", M.conv_skip, M.batchnorm_skip, 64)):
+        k = conv.kernel_shape
+        P["W" + t] = _f32(rng, k + (cin, 128), 1.0 / np.sqrt(k[0] * k[1] * cin))
+        P["b" + t] = _f32(rng, (1, 1, 1, 128), 0.1)
+        P["g" + t] = rng.uniform(0.5, 1.5, 128).astype(np.float32).astype(np.float64)
+        P["h" + t] = _f32(rng, (128,), 0.1)
+        P["rm" + t], P["rv" + t] = np.zeros(128), np.ones(128)
+        conv.parameters["W"], conv.parameters["b"] = P["W" + t], P["b" + t]
+        bn.parameters["scaler"], bn.parameters["intercept"] = P["g" + t], P["h" + t]
+        bn.reset_running_stats()
+    M.flush_gradients()
+    Y = M.forward(X)
+    dY = _f32(rng, Y.shape)
+    dX = M.backward(dY)
+    o = O.skip_conv_module_fwd_bwd(X, dY, P, (3, 3), (3, 3), (1, 1), 1, 1, 1, 1, 1, "relu")
+    tol = TOL_BN[mode]
+    close(Y, o["Y"], tol, "Y")
+    close(dX, o["dX"], tol, "dX")
+    for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
+        close(conv.gradients["W"], o["dW" + t], tol, "dW" + t)
+        close(bn.gradients["scaler"], o["dg" + t], tol, "dg" + t)
+        close(bn.gradients["intercept"], o["dh" + t], tol, "dh" + t)
+        close(bn.parameters["running_var"], o["rv" + t], tol, "rv" + t)
+
+
+# ------------------------------------------------------------------------------------------------
+#  layer state semantics (layers.py:3040-3044, 3076-3091, 66-86)
+# ------------------------------------------------------------------------------------------------
+def test_layer_state_semantics(cuda_device):
+    pkg = npml()
+    rng = np.random.default_rng(5)
+    L = pkg.Conv2D(4, (3, 3), pad=1)
+    X = _f32(rng, (2, 6, 6, 3))
+    L.forward(X, retain_derived=False)
+    assert L.X == [] and L.derived_variables["Z"] == []
+    Y = L.forward(X)
+    assert isinstance(Y, np.ndarray) and Y.dtype == np.float64 and len(L.X) == 1
+    dY = _f32(rng, Y.shape)
+    L.backward(dY, retain_grads=False)
+    assert float(pkg.to_numpy(L.gradients["W"]).std()) == 0.0            # untouched
+    L.backward(dY)
+    g1 = pkg.to_numpy(L.gradients["W"]).copy()
+    L.backward(dY)                                                       # accumulates (+=)
+    close(L.gradients["W"], 2 * g1, 1e-6, "accumulate")
+    W0 = pkg.to_numpy(L.parameters["W"]).copy()
+    L.update()                                                           # SGD(lr=0.01) step, then flush
+    close(L.parameters["W"], W0 - 0.01 * 2 * g1, 1e-6, "sgd")
+    assert L.X == [] and float(np.abs(pkg.to_numpy(L.gradients["W"])).max()) == 0.0
+    L.freeze()
+    L.forward(X)
+    with pytest.raises(AssertionError):
+        L.backward(dY)
+    with pytest.raises(AssertionError):
+        L.update()
+    s = L.summary()
+    assert s["layer"] == "Conv2D" and s["hyperparameters"]["kernel_shape"] == (3, 3)
+    with pytest.raises(ValueError):
+        pkg.Conv2D(2, (5, 5)).forward(np.zeros((1, 3, 3, 1)))            # kernel > input (utils.py:463-467)
+
+
+def test_empty_batch_and_device_tensors(cuda_device):
+    import torch
+    pkg = npml()
+    L = pkg.Conv2D(8, (3, 3), pad=1, mode="bf16")
+    X = torch.randn(2, 8, 8, 8, device="cuda")
+    Y = L.forward(X)
+    assert isinstance(Y, torch.Tensor) and Y.dtype == torch.bfloat16 and Y.shape == (2, 8, 8, 8)
+    E = pkg.Conv2D(8, (3, 3), pad=1)
+    E.forward(np.zeros((1, 4, 4, 2)))
+    E.flush_gradients()
+    Ye = E.forward(np.zeros((0, 4, 4, 2)))
+    assert Ye.shape == (0, 4, 4, 8)
+
+
+# ------------------------------------------------------------------------------------------------
+#  full benchmark shapes: size-independent properties
+# ------------------------------------------------------------------------------------------------
+def _dot(a, b):
+    return float((a.double() * b.double()).sum().item())
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg5"])
+def test_full_size_adjoint_identities(cuda_device, mode, cfg):
+    """<conv(X), dY> == <X, dgrad(dY)> == <W, wgrad(X, dY)> + <b, db>-free form, at the BASELINE.json sizes.
+    The three kernels are independent implementations, so agreement to rounding checks all of them;
+    a sampled comparison with the float64 oracle anchors the forward values."""
+    import torch
+    pkg = npml()
+    torch.manual_seed(7)
+    if cfg == "cfg2":
+        L = pkg.Conv2D(64, (3, 3), pad="same", mode=mode)
+        xs = (256, 56, 56, 64)
+    elif cfg == "cfg3":
+        L = pkg.Conv2D(256, (3, 3), pad=0, stride=2, dilation=2, mode=mode)
+        xs = (128, 28, 28, 128)
+    else:
+        L = pkg.Deconv2D(128, (4, 4), pad=1, stride=2, mode=mode)
+        xs = (128, 16, 16, 256)
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32
+    X = torch.randn(xs, device="cuda").to(dt)
+    np.random.seed(11)
+    Y = L.forward(X)
+    dY = torch.randn(Y.shape, device="cuda").to(dt)
+    dX = L.backward(dY)
+    W = L.parameters["W"]
+    lhs = _dot(Y, dY)                      # bias is zero-initialised, so Y = conv(X, W)
+    rhs_x = _dot(X, dX)
+    rhs_w = _dot(W, L.gradients["W"])
+    scale = float(Y.double().norm().item() * dY.double().norm().item())
+    tol = TOL[mode]
+    assert abs(lhs - rhs_x) <= tol * scale, (lhs, rhs_x, scale)
+    assert abs(lhs - rhs_w) <= tol * scale, (lhs, rhs_w, scale)
+    close(L.gradients["b"], pkg.to_numpy(dY.float().sum(dim=(0, 1, 2))).reshape(1, 1, 1, -1), tol, "db")
+    # anchor: first two examples against the float64 oracle
+    Xs = pkg.to_numpy(X[:2])
+    Wn = pkg.to_numpy(W)
+    bz = np.zeros((1, 1, 1, Wn.shape[3]))
+    if cfg == "cfg5":
+        Yr, _ = O.deconv2d_layer_fwd(Xs, Wn, bz, 2, 1)
+    elif cfg == "cfg3":
+        Yr, _ = O.conv2d_layer_fwd(Xs, Wn, bz, 2, 0, 2)
+    else:
+        Yr, _ = O.conv2d_layer_fwd(Xs, Wn, bz, 1, "same", 0)
+    close(Y[:2], Yr, tol, "Y[:2]")

@@ -1,0 +1,142 @@
+"""CPU-only checks of the host side: geometry / error conventions against the reference's golden
+vectors, and that libnpmlconv.so loads and exports every symbol include/npml_conv.h declares.
+No kernels are launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, to_pad, npml
+
+
+def test_library_exports_every_declared_symbol():
+    pkg = npml()
+    pkg.build()
+    lib = pkg._lib.load()
+    hdr = open(os.path.join(ROOT, "include", "npml_conv.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(npml_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(pkg._lib.SIGNATURES), declared ^ set(pkg._lib.SIGNATURES)
+    assert lib.npml_version() >= 100
+
+
+def test_desc_struct_matches_header():
+    pkg = npml()
+    assert ctypes.sizeof(pkg._lib.ConvDesc) == 21 * 4
+    names = [f[0] for f in pkg._lib.ConvDesc._fields_]
+    hdr = open(os.path.join(ROOT, "include", "npml_conv.h")).read()
+    body = hdr[hdr.index("typedef struct npml_conv_desc"):hdr.index("} npml_conv_desc;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body):
+        fields += [v.strip() for v in decl.split(",")]
+    assert fields == names
+
+
+def test_workspace_query_and_tc_predicate_without_gpu():
+    pkg = npml()
+    U, L = pkg.utils, pkg._lib
+    d = U.make_desc(256, 56, 56, 64, 64, 3, 3, 1, 1, (1, 1, 1, 1), 56, 56, "bf16")
+    lib = L.load()
+    for op in range(8):
+        assert lib.npml_workspace_bytes(d, op) >= 256
+    assert lib.npml_uses_tensor_cores(d, L.OP_CONV_FPROP) in (0, 1)
+    d1 = U.make_desc(32, 28, 28, 1, 32, 3, 3, 1, 1, (1, 1, 1, 1), 28, 28, "bf16")
+    assert lib.npml_uses_tensor_cores(d1, L.OP_CONV_FPROP) == 0      # in_ch = 1 -> CUDA-core path
+
+
+def test_geometry_against_reference_golden():
+    U = npml().utils
+    z, cases = load_golden("utils.npz")
+    for c in cases:
+        if c["kind"] == "calc_pad_dims_2D":
+            for it in c["items"]:
+                got = U.calc_pad_dims_2D(tuple(it["X_shape"]), tuple(it["out_dim"]), tuple(it["kernel_shape"]),
+                                         it["stride"], it["dilation"])
+                assert list(got) == it["out"]
+        elif c["kind"] == "pad2D":
+            ks = tuple(c["kernel_shape"]) if c["kernel_shape"] else None
+            p4 = U.resolve_pad_2D(z[c["id"] + "/X"].shape, to_pad(c["pad"]), ks, c["stride"], c["dilation"])
+            assert list(p4) == c["p4"]
+        elif c["kind"] == "conv":
+            X, W = z[c["id"] + "/X"], z[c["id"] + "/W"]
+            p4 = U.resolve_pad_2D(X.shape, to_pad(c["pad"]), W.shape[:2], c["stride"], c["dilation"])
+            assert list(p4) == c["p4"]
+            assert U.calc_conv_out_dims(X.shape, W.shape, c["stride"], p4, c["dilation"]) == z[c["id"] + "/Z"].shape
+            oh, ow = U.conv_out_hw(X.shape[1], X.shape[2], W.shape[0], W.shape[1], p4, c["stride"], c["dilation"])
+            assert (oh, ow) == z[c["id"] + "/Z"].shape[1:3]
+        elif c["kind"] == "deconv":
+            X, W = z[c["id"] + "/X"], z[c["id"] + "/W"]
+            p4, oh, ow = U.deconv_geometry(X.shape[1], X.shape[2], W.shape[0], W.shape[1], to_pad(c["pad"]), c["stride"])
+            assert (oh, ow) == z[c["id"] + "/Z"].shape[1:3]
+            assert oh == c["stride"] * (X.shape[1] - 1) + W.shape[0] - p4[0] - p4[1]
+
+
+def test_benchmark_config_geometry():
+    U = npml().utils
+    assert U.resolve_pad_2D((256, 56, 56, 64), "same", (3, 3), 1, 0) == (1, 1, 1, 1)              # cfg2
+    assert U.resolve_pad_2D((128, 28, 28, 128), "same", (3, 3), 2, 2) == (16, 17, 16, 17)         # cfg3 'same'
+    assert U.conv_out_hw(28, 28, 3, 3, (0, 0, 0, 0), 2, 2) == (11, 11)                            # cfg3
+    assert U.deconv_geometry(16, 16, 4, 4, 1, 2) == ((1, 1, 1, 1), 32, 32)                        # cfg5
+
+
+def test_error_conventions():
+    U = npml().utils
+    with pytest.raises(ValueError):
+        U.calc_pad_dims_2D([1, 3, 3, 1], (3, 3), (3, 3), 1)          # utils.py:77-87
+    with pytest.raises(ValueError):
+        U.calc_pad_dims_2D((1, 9, 9, 1), (3, 3), (3, 3), 1)          # negative pad, utils.py:116-119
+    with pytest.raises(AssertionError):
+        U.calc_pad_dims_2D((1, 8, 8, 1), (3, 3), (3, 3), 1)          # unattainable, utils.py:107-108
+    with pytest.raises(ValueError):
+        U.conv_out_hw(3, 3, 5, 5, (0, 0, 0, 0), 1, 0)                # kernel > padded input, utils.py:463-467
+    with pytest.raises(TypeError):
+        U.col2im(np.zeros((9, 1)), (1, 3, 3, 1), (3, 3, 1, 1), 1, 1)  # pad must be a 4-tuple, utils.py:577-578
+
+
+def test_activation_strings_and_initializer():
+    A = npml().activations
+    assert str(A.ReLU()) == "ReLU" and str(A.LeakyReLU(0.3)) == "Leaky ReLU(alpha=0.3)"
+    assert str(A.Affine(2, 1)) == "Affine(slope=2, intercept=1)"
+    init = A.ActivationInitializer
+    assert isinstance(init(None)(), A.Identity)
+    assert isinstance(init("relu")(), A.ReLU)
+    a = init("Affine(slope=0.5, intercept=2.0)")()
+    assert (a.p0, a.p1) == (0.5, 2.0)
+    assert init("Leaky ReLU(alpha=0.25)")().p0 == 0.25
+    with pytest.raises(ValueError):
+        init("swish")()
+
+
+def test_weight_init_consumes_np_random_like_reference():
+    pkg = npml()
+    from oracle import conv_oracle as O
+    np.random.seed(1002)
+    ours = pkg.layers.WeightInitializer("Identity", "glorot_uniform")((3, 3, 64, 64))
+    np.random.seed(1002)
+    ref = O.glorot_uniform((3, 3, 64, 64))
+    assert np.array_equal(ours, ref)
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    pkg = npml()
+    with pytest.raises(RuntimeError):
+        pkg.conv2D(np.zeros((1, 4, 4, 1)), np.zeros((3, 3, 1, 1)), 1, 0)
+    with pytest.raises(RuntimeError):
+        pkg.Conv2D(2, (3, 3)).forward(np.zeros((1, 4, 4, 1)))
+
+
+def test_shard_batch():
+    D = npml().dist
+    for n, g in [(256, 8), (128, 4), (32, 2), (10, 4)]:
+        spans = [D.shard_batch(n, g, r) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
