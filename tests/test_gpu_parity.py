@@ -16,6 +16,13 @@ MODES = ["fp32", "tf32", "bf16"]
 # BatchNorm's dX and everything downstream of it subtracts nearly equal quantities; the reference's own
 # tests use decimal=2..3 for those tensors (tests/test_nn.py:1049, 1918-1965).  fp32-mode bound used here:
 TOL_BN = {"fp32": 5e-5, "tf32": 1e-2, "bf16": 4e-2}
+# Activations whose derivative jumps at a point.  In the reduced-precision modes a pre-activation that the
+# float64 reference puts within rounding distance of the kink can land on the other side, which switches
+# that element's gradient on or off (the reference's own tests carry the same caveat for ReLU,
+# tests/test_nn.py:1973-1978).  For these activations the reduced-precision backward is therefore checked
+# against the oracle evaluated at the pre-activations the device produced (whose own parity is asserted
+# first), so that the comparison measures the gradient arithmetic and not the mask flips.
+KINKED = {"relu", "leaky_relu", "hard_sigmoid", "elu", "selu"}
 
 
 def close(a, ref, tol, what=""):
@@ -227,6 +234,9 @@ def test_conv2d_vs_oracle(cuda_device, mode, case):
     close(Y, Yr, tol, "Y")
     dY = _f32(rng, Yr.shape)                                         # random dLdy (upstream uses ones)
     dX = L.backward(dY)
+    if mode != "fp32" and act in KINKED:
+        close(L.derived_variables["Z"][0], Zr, tol, "Z")
+        Zr = pkg.to_numpy(L.derived_variables["Z"][0])
     dXr, dWr, dbr = O.conv2d_layer_bwd(dY, X, Zr, W, s, pad, d, act, p0, 0.0)
     close(dX, dXr, tol, "dX")
     close(L.gradients["W"], dWr, tol, "dW")
@@ -261,6 +271,9 @@ def test_deconv2d_vs_oracle(cuda_device, mode, case):
     close(Y, Yr, tol, "Y")
     dY = _f32(rng, Yr.shape)
     dX = L.backward(dY)
+    if mode != "fp32" and act in KINKED:
+        close(L.derived_variables["Z"][0], Zr, tol, "Z")
+        Zr = pkg.to_numpy(L.derived_variables["Z"][0])
     dXr, dWr, dbr = O.deconv2d_layer_bwd(dY, X, Zr, W, s, pad, act)
     close(dX, dXr, tol, "dX")
     close(L.gradients["W"], dWr, tol, "dW")
