@@ -39,7 +39,7 @@ EncodeTiledFn get_encode_tiled() {
 
 // rank-`rank` tensor map over `base`; dims/strides innermost first, strides in bytes (stride[0] implicit).
 int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-              const uint32_t* box) {
+              const uint32_t* box, bool atom32b) {
   EncodeTiledFn enc = get_encode_tiled();
   NPML_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t gd[5], gs[4];
@@ -47,7 +47,8 @@ int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* d
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i + 1];
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base,
-                   gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -59,6 +60,10 @@ int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* d
   }
   return 0;
 }
+
+// also used by tc_wgrad.cu
+int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+              const uint32_t* box, bool atom32b);
 
 namespace {
 
@@ -420,7 +425,7 @@ static int launch_tc(const GatherConv& g, Plan& pl, const void* in, const float*
     const uint64_t dims[3] = {(uint64_t)g.CI, (uint64_t)g.CO, (uint64_t)(g.fr * g.fc)};
     const uint64_t strides[3] = {(uint64_t)es, (uint64_t)g.CI * es, (uint64_t)g.CI * g.CO * es};
     const uint32_t box[3] = {(uint32_t)P.kelems, (uint32_t)P.BN, 1};
-    if (int e = make_tmap(&P.wmap, bf16, wt, 3, dims, strides, box)) return e;
+    if (int e = make_tmap(&P.wmap, bf16, wt, 3, dims, strides, box, false)) return e;
   }
   // activations: one map per input parity plane (form 0) or a single plain map (form 1)
   const int sp = (g.form == 0) ? g.s : 1;
@@ -433,7 +438,7 @@ static int launch_tc(const GatherConv& g, Plan& pl, const void* in, const float*
                                    (uint64_t)g.IH * g.IW * g.CI * es};
       const uint32_t box[4] = {(uint32_t)P.kelems, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
       char* base = (char*)in + ((size_t)py * g.IW + px) * g.CI * es;
-      if (int e = make_tmap(&P.amap[py * sp + px], bf16, base, 4, dims, strides, box)) return e;
+      if (int e = make_tmap(&P.amap[py * sp + px], bf16, base, 4, dims, strides, box, false)) return e;
     }
   auto kern = tc_gather_conv_kernel<T>;
   static bool attr_set[2] = {false, false};

@@ -14,7 +14,7 @@
 namespace npml {
 
 int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-              const uint32_t* box);
+              const uint32_t* box, bool atom32b);
 int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
                         int64_t o_co, int accumulate, float* dW, cudaStream_t st);
 
@@ -125,10 +125,16 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
         ptx::mbar_wait(&full_bar[s], ph);
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-        // MN-major, 128B swizzle: LBO = distance between 128-byte column blocks (one window = 16 KB),
-        // SBO = distance between groups of 8 pixel rows (1 KB)
-        const uint64_t adesc = ptx::smem_desc_sw128(a_addr, kTileBytes, 1024);
-        const uint64_t bdesc = ptx::smem_desc_sw128(a_addr + P.mb * kTileBytes, kTileBytes, 1024);
+        // MN-major: LBO = distance between 128-byte column blocks (one window = 16 KB), SBO = distance between
+        // swizzle-atom groups of pixel rows.  16-bit operands use the plain 128B swizzle (8-row atoms, 1 KB);
+        // MN-major tf32 operands only exist in the 128B swizzle with 32-byte granularity (4-row atoms, 512 B),
+        // which the TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+        uint64_t adesc = ptx::smem_desc_sw128(a_addr, kTileBytes, kTf32 ? 512 : 1024);
+        uint64_t bdesc = ptx::smem_desc_sw128(a_addr + P.mb * kTileBytes, kTileBytes, kTf32 ? 512 : 1024);
+        if (kTf32) {   // layout type 1 = SWIZZLE_128B_BASE32B instead of 2 = SWIZZLE_128B
+          adesc ^= (uint64_t)3 << 61;
+          bdesc ^= (uint64_t)3 << 61;
+        }
         const uint32_t step = (uint32_t)P.kinstr_bytes >> 4;
         for (int j = 0; j < P.mmas_per_tile; ++j)
           ptx::mma_ss<kTf32>(tmem_base, adesc + (uint64_t)(j * step), bdesc + (uint64_t)(j * step), P.idesc,
@@ -281,7 +287,7 @@ int launch_wgrad(const GatherWgrad& g, WPlan& pl, const void* in, const void* gr
     const uint64_t dims[4] = {(uint64_t)g.CO, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
     const uint64_t strides[4] = {(uint64_t)es, (uint64_t)g.CO * es, (uint64_t)g.OW * g.CO * es,
                                  (uint64_t)g.OH * g.OW * g.CO * es};
-    if (int e = make_tmap(&P.gmap, bf16, const_cast<void*>(grad), 4, dims, strides, box)) return e;
+    if (int e = make_tmap(&P.gmap, bf16, const_cast<void*>(grad), 4, dims, strides, box, !bf16)) return e;
   }
   for (int py = 0; py < g.s; ++py)
     for (int px = 0; px < g.s; ++px) {
@@ -291,7 +297,7 @@ int launch_wgrad(const GatherWgrad& g, WPlan& pl, const void* in, const void* gr
       const uint64_t strides[4] = {(uint64_t)es, (uint64_t)g.s * g.CI * es, (uint64_t)g.s * g.IW * g.CI * es,
                                    (uint64_t)g.IH * g.IW * g.CI * es};
       char* base = (char*)in + ((size_t)py * g.IW + px) * g.CI * es;
-      if (int e = make_tmap(&P.amap[py * g.s + px], bf16, base, 4, dims, strides, box)) return e;
+      if (int e = make_tmap(&P.amap[py * g.s + px], bf16, base, 4, dims, strides, box, !bf16)) return e;
     }
   auto kern = tc_wgrad_kernel<T>;
   static bool attr_set[2] = {false, false};

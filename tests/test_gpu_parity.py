@@ -280,14 +280,15 @@ def test_deconv2d_vs_oracle(cuda_device, mode, case):
     close(L.gradients["b"], dbr, tol, "db")
 
 
+@pytest.mark.parametrize("act", ["relu", "tanh"])
 @pytest.mark.parametrize("mode", MODES)
-def test_skip_conv_module_vs_oracle(cuda_device, mode):
-    """cfg4 at N=4, 16x16: 64 -> 128 channels, 3x3 / 3x3 / 1x1, ReLU."""
+def test_skip_conv_module_vs_oracle(cuda_device, mode, act):
+    """cfg4 at N=4, 16x16: 64 -> 128 channels, 3x3 / 3x3 / 1x1 (tensor-core kernels in tf32 / bf16)."""
     pkg = npml()
     rng = np.random.default_rng(300)
     X = _f32(rng, (4, 16, 16, 64))
     M = pkg.SkipConnectionConvModule(out_ch1=128, out_ch2=128, kernel_shape1=(3, 3), kernel_shape2=(3, 3),
-                                     kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn=pkg.activations.ReLU(), mode=mode)
+                                     kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn=make_act(pkg, act, 0, 0), mode=mode)
     M.forward(X, retain_derived=False)
     P = {}
     for t, conv, bn, cin in (("1", M.conv1, M.batchnorm1, 64), ("2", M.conv2, M.batchnorm2, 128),
@@ -305,14 +306,19 @@ def test_skip_conv_module_vs_oracle(cuda_device, mode):
     Y = M.forward(X)
     dY = _f32(rng, Y.shape)
     dX = M.backward(dY)
-    o = O.skip_conv_module_fwd_bwd(X, dY, P, (3, 3), (3, 3), (1, 1), 1, 1, 1, 1, 1, "relu")
+    o = O.skip_conv_module_fwd_bwd(X, dY, P, (3, 3), (3, 3), (1, 1), 1, 1, 1, 1, 1, act)
     tol = TOL_BN[mode]
     close(Y, o["Y"], tol, "Y")
-    close(dX, o["dX"], tol, "dX")
+    for k in ("conv1_out", "batchnorm1_out", "conv2_out", "batchnorm2_out", "conv_skip_out", "batchnorm_skip_out"):
+        close(M.derived_variables[k], o[k], tol, k)
+    # backward: with ReLU in a reduced-precision mode a fraction ~err(Z)/std(Z) of the two ReLU masks flips
+    # (see KINKED above), which bounds the normwise gradient error at roughly sqrt(2 * that fraction)
+    tol_b = tol if (mode == "fp32" or act not in KINKED) else {"tf32": 5e-2, "bf16": 1.5e-1}[mode]
+    close(dX, o["dX"], tol_b, "dX")
     for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
-        close(conv.gradients["W"], o["dW" + t], tol, "dW" + t)
-        close(bn.gradients["scaler"], o["dg" + t], tol, "dg" + t)
-        close(bn.gradients["intercept"], o["dh" + t], tol, "dh" + t)
+        close(conv.gradients["W"], o["dW" + t], tol_b, "dW" + t)
+        close(bn.gradients["scaler"], o["dg" + t], tol_b, "dg" + t)
+        close(bn.gradients["intercept"], o["dh" + t], tol_b, "dh" + t)
         close(bn.parameters["running_var"], o["rv" + t], tol, "rv" + t)
 
 
