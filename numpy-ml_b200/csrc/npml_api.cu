@@ -78,6 +78,8 @@ static int run_gather(const npml_conv_desc* d, int op, const void* in, const flo
   NPML_CHECK(Z || Y, "no output buffer");
   GatherConv g = make_gather(d, op);
   if (g.act == NPML_ACT_IDENTITY && Z == nullptr) { Z = Y; Y = nullptr; }
+  if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode))
+    return slab_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode))
     return tc_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   return direct_gather_conv(g, in, W, b, Z, Y, act_dtype(d->mode), st);
@@ -138,7 +140,8 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
   switch (op) {
     case NPML_OP_CONV_FPROP: case NPML_OP_CONV_DGRAD: case NPML_OP_DECONV_FPROP: case NPML_OP_DECONV_DGRAD: {
       GatherConv g = make_gather(d, op);
-      if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode)) bytes += tc_conv_ws_bytes(g, d->mode);
+      if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode)) bytes += slab_conv_ws_bytes(g, d->mode);
+      else if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode)) bytes += tc_conv_ws_bytes(g, d->mode);
       break;
     }
     case NPML_OP_CONV_WGRAD: case NPML_OP_DECONV_WGRAD: {
@@ -164,7 +167,8 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
 int npml_uses_tensor_cores(const npml_conv_desc* d, int op) {
   if (!d || d->mode == NPML_MODE_FP32) return 0;
   if (op == NPML_OP_CONV_WGRAD || op == NPML_OP_DECONV_WGRAD) return tc_wgrad_supported(make_wgrad(d, op), d->mode);
-  if (op >= NPML_OP_CONV_FPROP && op <= NPML_OP_DECONV_DGRAD) return tc_conv_supported(make_gather(d, op), d->mode);
+  if (op >= NPML_OP_CONV_FPROP && op <= NPML_OP_DECONV_DGRAD)
+    return slab_conv_supported(make_gather(d, op), d->mode) || tc_conv_supported(make_gather(d, op), d->mode);
   return 0;
 }
 

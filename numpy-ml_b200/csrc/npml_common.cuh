@@ -151,6 +151,11 @@ bool tc_conv_supported(const GatherConv& g, int mode);
 size_t tc_conv_ws_bytes(const GatherConv& g, int mode);
 int tc_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
                    void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
+// persistent slab kernel for stride-1 gather convolutions, tc_slab_conv.cu
+bool slab_conv_supported(const GatherConv& g, int mode);
+size_t slab_conv_ws_bytes(const GatherConv& g, int mode);
+int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
+                     void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_wgrad_supported(const GatherWgrad& g, int mode);
 size_t tc_wgrad_ws_bytes(const GatherWgrad& g, int mode);
 int tc_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad, float* dW, void* ws,

@@ -116,34 +116,6 @@ __global__ void repack_weights_kernel(const float* __restrict__ w, T* __restrict
   }
 }
 
-template <typename T>
-__device__ __forceinline__ void store_row_chunk(T* dst, const float (&v)[32], int n_valid);
-
-template <>
-__device__ __forceinline__ void store_row_chunk<float>(float* dst, const float (&v)[32], int n_valid) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (4 * j < n_valid) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-}
-template <>
-__device__ __forceinline__ void store_row_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32], int n_valid) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (8 * j < n_valid) {
-      uint4 u;
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-      __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-      __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-      __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-      u.x = *reinterpret_cast<uint32_t*>(&a);
-      u.y = *reinterpret_cast<uint32_t*>(&b);
-      u.z = *reinterpret_cast<uint32_t*>(&c);
-      u.w = *reinterpret_cast<uint32_t*>(&d);
-      *reinterpret_cast<uint4*>(dst + 8 * j) = u;
-    }
-  }
-}
-
 // ---- the kernel ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_constant__ TcConvParams P,
@@ -406,6 +378,20 @@ size_t tc_conv_ws_bytes(const GatherConv& g, int mode) {
   return pl.wt_bytes + 256;
 }
 
+// w (strided fp32) -> Wt[tap][co][ci] in the operand type (also used by tc_slab_conv.cu)
+int launch_repack_weights(const GatherConv& g, bool bf16, const float* w, void* wt, cudaStream_t st) {
+  const int64_t total = (int64_t)g.fr * g.fc * g.CO * g.CI;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  if (bf16)
+    repack_weights_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(w, (__nv_bfloat16*)wt, g.fr * g.fc, g.CO, g.CI, g.w_tap,
+                                                                 g.w_ci, g.w_co);
+  else
+    repack_weights_kernel<float><<<blocks, 256, 0, st>>>(w, (float*)wt, g.fr * g.fc, g.CO, g.CI, g.w_tap, g.w_ci, g.w_co);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
 template <typename T>
 static int launch_tc(const GatherConv& g, Plan& pl, const void* in, const float* w, const float* bias, void* Z, void* Y,
                      void* ws, cudaStream_t st) {
@@ -413,13 +399,7 @@ static int launch_tc(const GatherConv& g, Plan& pl, const void* in, const float*
   const int es = sizeof(T);
   TcConvParams& P = pl.P;
   T* wt = reinterpret_cast<T*>(ws);
-  {
-    const int64_t total = (int64_t)g.fr * g.fc * g.CO * g.CI;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 2048) blocks = 2048;
-    repack_weights_kernel<T><<<blocks, 256, 0, st>>>(w, wt, g.fr * g.fc, g.CO, g.CI, g.w_tap, g.w_ci, g.w_co);
-    NPML_LAUNCH_OK();
-  }
+  if (int e = launch_repack_weights(g, bf16, w, wt, st)) return e;
   // weights: (ci, co, tap)
   {
     const uint64_t dims[3] = {(uint64_t)g.CI, (uint64_t)g.CO, (uint64_t)(g.fr * g.fc)};

@@ -2,6 +2,7 @@
 // kernels: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 MMA / TMEM.  One function per instruction.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -154,4 +155,34 @@ __host__ __device__ inline uint32_t instr_desc(int fmt, int a_mn_major, int b_mn
 }
 
 }  // namespace ptx
+
+// ---- epilogue helper: 32 consecutive fp32 accumulator columns of one output row -> global --------
+template <typename T>
+__device__ __forceinline__ void store_row_chunk(T* dst, const float (&v)[32], int n_valid);
+
+template <>
+__device__ __forceinline__ void store_row_chunk<float>(float* dst, const float (&v)[32], int n_valid) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (4 * j < n_valid) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+template <>
+__device__ __forceinline__ void store_row_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float (&v)[32], int n_valid) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (8 * j < n_valid) {
+      uint4 u;
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+      __nv_bfloat162 b = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+      __nv_bfloat162 d = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      u.z = *reinterpret_cast<uint32_t*>(&c);
+      u.w = *reinterpret_cast<uint32_t*>(&d);
+      *reinterpret_cast<uint4*>(dst + 8 * j) = u;
+    }
+  }
+}
+
 }  // namespace npml

@@ -1,0 +1,441 @@
+// Persistent "slab" implicit-GEMM convolution for stride-1 gather convolutions on sm_100a
+// (Conv2D.forward and Conv2D dX with stride 1 -- cfg2, and the three convolutions of cfg4).
+//
+// The activation tensor is viewed as ONE flat sequence of zero-padded pixels ("slots", 128 bytes of
+// channels each): slot = (n*Hp + yp)*Wp + xp with Hp = OH + (fr-1)*D, Wp = OW + (fc-1)*D.  In that view
+// the pixel a filter tap (r, t) multiplies with output slot s is simply slot s + r*D*Wp + t*D, so
+//
+//   * an M tile is 128 CONSECUTIVE output slots (the few slots with xp >= OW or yp >= OH are junk and
+//     are masked in the epilogue), and
+//   * the A operand of every tap is the SAME shared-memory slab read at a different start address:
+//     the UMMA descriptor's start address is advanced by (r*D*Wp + t*D)*128 bytes.  The slab (whole padded
+//     rows, one TMA box per row, zero padding = the TMA's out-of-bounds fill, 128B swizzle) is loaded
+//     from L2 once per work unit instead of once per tap.
+//
+// One persistent CTA per SM walks work units of UT consecutive M tiles:
+//   warp 0  slab producer (TMA, 2-stage ring of (unit, channel-block) planes)
+//   warp 1  MMA issuer (tcgen05.mma M=128 N=BN K=32 B, fp32 accumulators in a ring of TMEM tile slots)
+//   warp 2  weight producer (TMA; all taps resident in smem when they fit, else a streamed ring shared by
+//           the UT tiles of the unit) and TMEM allocator
+//   warps 4..7  epilogue (tcgen05.ld -> +bias -> act -> global), overlapped with the next tiles' MMAs
+#include <cstdlib>
+
+#include "npml_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace npml {
+
+int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+              const uint32_t* box, bool atom32b);
+int launch_repack_weights(const GatherConv& g, bool bf16, const float* w, void* wt, cudaStream_t st);
+
+namespace {
+
+constexpr int kMaxTaps = 64;
+constexpr int kRowBytes = 128;
+constexpr int kThreads = 256;
+constexpr int kSlabStages = 2;
+constexpr int kMaxWStages = 8;
+constexpr int kMaxAcc = 16;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct SlabParams {
+  CUtensorMap amap, wmap;
+  uint32_t tap_off16[kMaxTaps];  // (offy*Wp + offx) slots * 128 B >> 4: descriptor start-address advance of the tap
+  int16_t tap_w[kMaxTaps];     // index of the tap in Wt
+  int ntaps, nkb, kelems;
+  int N, OH, OW, CO, Hp, Wp, pady, padx;
+  int UT, SR, BN, n_acc;
+  int plane_bytes, w_block_bytes, w_resident, w_stages;
+  int total_tiles, num_units;
+  uint32_t idesc;
+  int act;
+  float p0, p1;
+};
+
+// Measured on B200: the 128B swizzle of both the TMA write and the UMMA read is a function of the ABSOLUTE
+// shared-memory address bits (chunk ^= (addr >> 7) & 7), so an operand start address that is only 128-byte
+// aligned needs no correction: the descriptor's base_offset field stays 0 (setting it to (addr >> 7) & 7
+// double-counts the phase and gives wrong results).
+// K-major 128B-swizzle operand descriptor split in two words: the high word is constant (SBO = 1024 B,
+// version 1, layout SWIZZLE_128B), the low word is (start address >> 4) | LBO field.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescLoFlag = 1u << 16;
+
+template <bool kTf32>
+__device__ __forceinline__ void mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
+  if (kTf32) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+// the four K slices (32 bytes each) of one 128-byte operand row
+template <bool kTf32>
+__device__ __forceinline__ void mma4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (uint32_t ks = 0; ks < 4; ++ks) mma_lohi<kTf32>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, ks == 0 ? acc0 : 1u);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_constant__ SlabParams P,
+                                                                   const float* __restrict__ bias, T* __restrict__ Z,
+                                                                   T* __restrict__ Y) {
+  constexpr bool kTf32 = sizeof(T) == 4;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_area = smem + (size_t)kSlabStages * P.plane_bytes;
+  const int w_bytes = (P.w_resident ? P.ntaps * P.nkb : P.w_stages) * P.w_block_bytes;
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(w_area + w_bytes);
+  uint64_t* slab_empty = slab_full + kSlabStages;
+  uint64_t* w_full = slab_empty + kSlabStages;
+  uint64_t* w_empty = w_full + kMaxWStages;
+  uint64_t* acc_full = w_empty + kMaxWStages;
+  uint64_t* acc_empty = acc_full + kMaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxAcc);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * P.BN;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kSlabStages; ++i) { ptx::mbar_init(&slab_full[i], 1); ptx::mbar_init(&slab_empty[i], 1); }
+    for (int i = 0; i < kMaxWStages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < kMaxAcc; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== slab producer: whole padded rows [rho0, rho0 + SR) of channel block kb, one TMA box per row =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&P.amap);
+      const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
+      uint32_t p = 0;
+      for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
+        const int rho0 = (unit * P.UT * 128) / P.Wp;
+        for (int kb = 0; kb < P.nkb; ++kb, ++p) {
+          const int st = p & 1;
+          ptx::mbar_wait(&slab_empty[st], ((p >> 1) & 1u) ^ 1u);
+          ptx::mbar_expect_tx(&slab_full[st], (uint32_t)P.SR * row_bytes);
+          uint8_t* dst = smem + (size_t)st * P.plane_bytes;
+          int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
+          for (int i = 0; i < P.SR; ++i) {
+            ptx::tma_load_4d(dst + (size_t)i * row_bytes, &P.amap, &slab_full[st], kb * P.kelems, -P.padx, yp - P.pady, n);
+            if (++yp == P.Hp) { yp = 0; ++n; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&P.wmap);
+      if (P.w_resident) {
+        ptx::mbar_expect_tx(&w_full[0], (uint32_t)w_bytes);
+        for (int t = 0; t < P.ntaps; ++t)
+          for (int kb = 0; kb < P.nkb; ++kb)
+            ptx::tma_load_3d(w_area + (size_t)(t * P.nkb + kb) * P.w_block_bytes, &P.wmap, &w_full[0], kb * P.kelems, co0,
+                             P.tap_w[t]);
+      } else {
+        uint32_t ws = 0, wph = 0;
+        for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x)
+          for (int kb = 0; kb < P.nkb; ++kb)
+            for (int t = 0; t < P.ntaps; ++t) {
+              ptx::mbar_wait(&w_empty[ws], wph ^ 1u);
+              ptx::mbar_expect_tx(&w_full[ws], (uint32_t)P.w_block_bytes);
+              ptx::tma_load_3d(w_area + (size_t)ws * P.w_block_bytes, &P.wmap, &w_full[ws], kb * P.kelems, co0, P.tap_w[t]);
+              if (++ws == (uint32_t)P.w_stages) { ws = 0; wph ^= 1u; }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // The whole warp walks the (warp-uniform) loops and waits; one elected lane issues tcgen05.mma / commit.
+    // Everything the inner loop needs is kept in registers: descriptors are advanced with 32-bit adds on
+    // their low word (start address >> 4), ring positions are counters (no division).
+    const bool leader = ptx::elect_one();
+    const uint32_t BN = (uint32_t)P.BN, n_acc = (uint32_t)P.n_acc, idesc = P.idesc;
+    const int ntaps = P.ntaps, nkb = P.nkb, UT = P.UT, Wp = P.Wp, total_tiles = P.total_tiles, num_units = P.num_units;
+    const bool w_res = P.w_resident != 0;
+    const uint32_t w_stages = (uint32_t)P.w_stages, wbb16 = (uint32_t)P.w_block_bytes >> 4;
+    const uint32_t plane16 = (uint32_t)P.plane_bytes >> 4;
+    const uint32_t slab_lo = (ptx::smem_u32(smem) >> 4) | kDescLoFlag;
+    const uint32_t w_lo = (ptx::smem_u32(w_area) >> 4) | kDescLoFlag;
+    uint32_t p = 0;               // slab ring sequence number
+    uint32_t ws = 0, wph = 0;     // weight ring position / phase
+    uint32_t slot = 0, sph = 0;   // accumulator ring position / phase of the unit's first tile
+    if (w_res) {
+      ptx::mbar_wait(&w_full[0], 0);
+      ptx::tc_fence_after();
+    }
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int s0 = unit * UT * 128;
+      const int ntile = min(UT, total_tiles - unit * UT);
+      const uint32_t a_off16 = (uint32_t)(s0 % Wp) * (kRowBytes >> 4);
+      uint32_t sl[4], ph[4], dt[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sl[j] = slot; ph[j] = sph; dt[j] = tmem_base + slot * BN;
+        if (j < ntile && ++slot == n_acc) { slot = 0; sph ^= 1u; }
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++p) {
+        const uint32_t st = p & 1u;
+        ptx::mbar_wait(&slab_full[st], (p >> 1) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t a_base = slab_lo + st * plane16 + a_off16;
+        for (int t = 0; t < ntaps; ++t) {
+          const uint32_t a_tap = a_base + P.tap_off16[t];
+          uint32_t b_lo;
+          if (w_res) {
+            b_lo = w_lo + (uint32_t)(t * nkb + kb) * wbb16;
+          } else {
+            ptx::mbar_wait(&w_full[ws], wph);
+            ptx::tc_fence_after();
+            b_lo = w_lo + ws * wbb16;
+          }
+          const bool first = (kb == 0 && t == 0), last = (kb == nkb - 1 && t == ntaps - 1);
+          if (!first && !last) {
+            if (leader) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < ntile) mma4<kTf32>(dt[j], a_tap + (uint32_t)j * (128 * kRowBytes >> 4), b_lo, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < ntile) {
+                if (first) {
+                  ptx::mbar_wait(&acc_empty[sl[j]], ph[j] ^ 1u);
+                  ptx::tc_fence_after();
+                }
+                if (leader) {
+                  mma4<kTf32>(dt[j], a_tap + (uint32_t)j * (128 * kRowBytes >> 4), b_lo, idesc, first ? 0u : 1u);
+                  if (last) ptx::tc_commit(&acc_full[sl[j]]);
+                }
+              }
+            }
+          }
+          if (!w_res) {
+            if (leader) ptx::tc_commit(&w_empty[ws]);
+            if (++ws == w_stages) { ws = 0; wph ^= 1u; }
+          }
+        }
+        if (leader) ptx::tc_commit(&slab_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> (+bias, act) -> global =====
+    const int qd = warp & 3;                      // TMEM lane quadrant of this warp
+    const int m = qd * 32 + lane;                 // row of the M tile
+    const int img_slots = P.Hp * P.Wp;
+    uint32_t q = 0;
+    for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
+      const int ntile = min(P.UT, P.total_tiles - unit * P.UT);
+      for (int j = 0; j < ntile; ++j, ++q) {
+        const uint32_t slot = q % (uint32_t)P.n_acc;
+        const int s = (unit * P.UT + j) * 128 + m;
+        const int n = s / img_slots;
+        const int rem = s - n * img_slots;
+        const int yp = rem / P.Wp, xp = rem - yp * P.Wp;
+        const bool row_ok = n < P.N && yp < P.OH && xp < P.OW;
+        const int64_t pix = ((int64_t)n * P.OH + yp) * P.OW + xp;
+        ptx::mbar_wait(&acc_full[slot], (q / (uint32_t)P.n_acc) & 1u);
+        ptx::tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + slot * (uint32_t)P.BN;
+        for (int c = 0; c < P.BN; c += 32) {
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld32(t_addr + (uint32_t)c, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          const int co = co0 + c;
+          const int n_valid = P.CO - co;
+          if (row_ok && n_valid > 0) {
+            if (bias) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += (i < n_valid) ? __ldg(bias + co + i) : 0.f;
+            }
+            if (Z) store_row_chunk<T>(Z + pix * P.CO + co, v, n_valid);
+            if (Y) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = act_fn(P.act, v[i], P.p0, P.p1);
+              store_row_chunk<T>(Y + pix * P.CO + co, v, n_valid);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[slot]);
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline int ceildiv(int a, int b) { return (a + b - 1) / b; }
+
+struct SlabPlan {
+  SlabParams P;
+  dim3 grid;
+  size_t smem = 0, wt_bytes = 0;
+};
+
+bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
+  if (mode != NPML_MODE_BF16 && mode != NPML_MODE_TF32) return false;
+  if (std::getenv("NPML_DISABLE_SLAB")) return false;
+  const bool bf16 = mode == NPML_MODE_BF16;
+  const int es = bf16 ? 2 : 4, vec = 16 / es;
+  if (g.s != 1 || g.N < 1) return false;
+  if (g.CI % vec || g.CO % vec) return false;
+  if (g.fr * g.fc > kMaxTaps) return false;
+  const int Hp = g.OH + (g.fr - 1) * g.D, Wp = g.OW + (g.fc - 1) * g.D;
+  if (Wp > 256) return false;
+  const int64_t slots = (int64_t)g.N * Hp * Wp;
+  if (slots + 128 * 8 >= (1LL << 31) / 2) return false;
+  if ((int64_t)g.N * g.IH * g.IW * g.CI >= (1LL << 31) || (int64_t)g.N * g.OH * g.OW * g.CO >= (1LL << 31)) return false;
+  SlabParams& P = pl.P;
+  memset(&P, 0, sizeof(P));
+  P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.CO = g.CO; P.Hp = Hp; P.Wp = Wp;
+  // both forms reduce to out[y, x] = sum in[y + offy - pady, x + offx - padx] * W[wtap]
+  P.pady = g.form == 0 ? g.pr : (g.fr - 1) * g.D - g.pr;
+  P.padx = g.form == 0 ? g.pc : (g.fc - 1) * g.D - g.pc;
+  int nt = 0;
+  for (int r = 0; r < g.fr; ++r)
+    for (int t = 0; t < g.fc; ++t) {
+      const int offy = g.form == 0 ? r * g.D : (g.fr - 1 - r) * g.D;
+      const int offx = g.form == 0 ? t * g.D : (g.fc - 1 - t) * g.D;
+      P.tap_off16[nt] = (uint32_t)(offy * Wp + offx) * (kRowBytes >> 4);
+      P.tap_w[nt] = (int16_t)(r * g.fc + t);
+      ++nt;
+    }
+  P.ntaps = nt;
+  P.kelems = kRowBytes / es;
+  P.nkb = ceildiv(g.CI, P.kelems);
+  P.act = g.act; P.p0 = g.p0; P.p1 = g.p1;
+  int bn = (g.CO + 15) / 16 * 16;
+  if (bn > 128) bn = 128;
+  if (bn < 32) bn = 32;
+  P.BN = bn;
+  P.n_acc = 512 / bn;
+  if (P.n_acc > kMaxAcc) P.n_acc = kMaxAcc;
+  P.idesc = ptx::instr_desc(bf16 ? 1 : 2, 0, 0, 128, bn);
+  P.w_block_bytes = bn * kRowBytes;
+  const int halo = (g.fr - 1) * g.D * Wp + (g.fc - 1) * g.D;
+  const int total_tiles = (int)((slots + 127) / 128);
+  P.total_tiles = total_tiles;
+  const int fixed = 1024 /*align*/ + 1024 /*barriers*/;
+  const int w_res_bytes = nt * P.nkb * P.w_block_bytes;
+  bool found = false;
+  // weights resident first (no re-streaming), largest unit that fits; then streamed weights
+  for (int resident = 1; resident >= 0 && !found; --resident) {
+    for (int ut = 4; ut >= (resident ? 2 : 1) && !found; --ut) {
+      if (ut * bn > 512) continue;
+      const int sr = (Wp - 1 + 128 * ut + halo - 1) / Wp + 1;
+      const int plane = (int)align_up((size_t)sr * Wp * kRowBytes, 1024);
+      int wst = 4;
+      int wbytes = resident ? w_res_bytes : wst * P.w_block_bytes;
+      if (!resident && fixed + kSlabStages * plane + wbytes > kSmemLimit) { wst = 3; wbytes = wst * P.w_block_bytes; }
+      if (fixed + kSlabStages * plane + wbytes > kSmemLimit) continue;
+      P.UT = ut; P.SR = sr; P.plane_bytes = plane; P.w_resident = resident; P.w_stages = wst;
+      pl.smem = (size_t)fixed + (size_t)kSlabStages * plane + wbytes;
+      found = true;
+    }
+  }
+  if (!found) return false;
+  P.num_units = ceildiv(total_tiles, P.UT);
+  const int nty = ceildiv(g.CO, bn);
+  int ctas = num_sms() / nty;
+  if (ctas < 1) ctas = 1;
+  if (ctas > P.num_units) ctas = P.num_units;
+  pl.grid = dim3((unsigned)ctas, (unsigned)nty, 1);
+  pl.wt_bytes = align_up((size_t)g.fr * g.fc * g.CO * g.CI * es, 256);
+  return true;
+}
+
+template <typename T>
+int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* w, const float* bias, void* Z, void* Y,
+                void* ws, cudaStream_t st) {
+  const bool bf16 = sizeof(T) == 2;
+  const int es = sizeof(T);
+  SlabParams& P = pl.P;
+  if (int e = launch_repack_weights(g, bf16, w, ws, st)) return e;
+  {
+    const uint64_t dims[3] = {(uint64_t)g.CI, (uint64_t)g.CO, (uint64_t)(g.fr * g.fc)};
+    const uint64_t strides[3] = {(uint64_t)es, (uint64_t)g.CI * es, (uint64_t)g.CI * g.CO * es};
+    const uint32_t box[3] = {(uint32_t)P.kelems, (uint32_t)P.BN, 1};
+    if (int e = make_tmap(&P.wmap, bf16, ws, 3, dims, strides, box, false)) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[4] = {(uint64_t)es, (uint64_t)g.CI * es, (uint64_t)g.IW * g.CI * es,
+                                 (uint64_t)g.IH * g.IW * g.CI * es};
+    const uint32_t box[4] = {(uint32_t)P.kelems, (uint32_t)P.Wp, 1, 1};
+    if (int e = make_tmap(&P.amap, bf16, const_cast<void*>(in), 4, dims, strides, box, false)) return e;
+  }
+  auto kern = tc_slab_conv_kernel<T>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[bf16 ? 0 : 1]) {
+    NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set[bf16 ? 0 : 1] = true;
+  }
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, (T*)Z, (T*)Y);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+bool slab_conv_supported(const GatherConv& g, int mode) {
+  SlabPlan pl;
+  return plan_slab(g, mode, pl);
+}
+
+size_t slab_conv_ws_bytes(const GatherConv& g, int mode) {
+  SlabPlan pl;
+  if (!plan_slab(g, mode, pl)) return 0;
+  return pl.wt_bytes + 256;
+}
+
+int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
+  SlabPlan pl;
+  NPML_CHECK(plan_slab(g, mode, pl), "shape not supported by the slab path");
+  NPML_CHECK(ws != nullptr && ws_bytes >= pl.wt_bytes, "workspace too small");
+  NPML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 127) == 0,
+             "activation / workspace pointers must be 16 / 128 byte aligned");
+  if (mode == NPML_MODE_BF16) return launch_slab<__nv_bfloat16>(g, pl, in, w, bias, Z, Y, ws, st);
+  return launch_slab<float>(g, pl, in, w, bias, Z, Y, ws, st);
+}
+
+}  // namespace npml
