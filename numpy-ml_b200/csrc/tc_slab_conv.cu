@@ -19,6 +19,7 @@
 //           the UT tiles of the unit) and TMEM allocator
 //   warps 4..7  epilogue (tcgen05.ld -> +bias -> act -> global), overlapped with the next tiles' MMAs
 #include <cstdlib>
+#include <type_traits>
 
 #include "npml_common.cuh"
 #include "tc_ptx.cuh"
@@ -57,60 +58,30 @@ struct SlabParams {
 // shared-memory address bits (chunk ^= (addr >> 7) & 7), so an operand start address that is only 128-byte
 // aligned needs no correction: the descriptor's base_offset field stays 0 (setting it to (addr >> 7) & 7
 // double-counts the phase and gives wrong results).
-// K-major 128B-swizzle operand descriptor split in two words: the high word is constant (SBO = 1024 B,
-// version 1, layout SWIZZLE_128B), the low word is (start address >> 4) | LBO field.
-constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
-constexpr uint32_t kDescLoFlag = 1u << 16;
+// K-major 128B-swizzle operand descriptor minus its start address: SBO = 1024 B, LBO field = 1, version 1,
+// layout SWIZZLE_128B.  descriptor = kDesc64 + (shared address >> 4).
+constexpr uint64_t kDesc64 = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);
 
-template <bool kTf32>
-__device__ __forceinline__ void mma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {
-  if (kTf32) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t"
-        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.b64 da, {%1, %3};\n\t"
-        "mov.b64 db, {%2, %3};\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
-        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(acc)
-        : "memory");
-  }
-}
-// the four K slices (32 bytes each) of one 128-byte operand row
-template <bool kTf32>
-__device__ __forceinline__ void mma4(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc0) {
-#pragma unroll
-  for (uint32_t ks = 0; ks < 4; ++ks) mma_lohi<kTf32>(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, idesc, ks == 0 ? acc0 : 1u);
-}
-
-template <typename T>
+template <typename T, int NT, int UT>
 __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_constant__ SlabParams P,
                                                                    const float* __restrict__ bias, T* __restrict__ Z,
                                                                    T* __restrict__ Y) {
   constexpr bool kTf32 = sizeof(T) == 4;
+  // [weights (1024-aligned base)] [2 slab planes (128-aligned)] [epilogue staging] [bias] [barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_area = smem + (size_t)kSlabStages * P.plane_bytes;
+  uint8_t* w_area = smem_raw;
   const int w_bytes = (P.w_resident ? P.ntaps * P.nkb : P.w_stages) * P.w_block_bytes;
-  uint64_t* slab_full = reinterpret_cast<uint64_t*>(w_area + w_bytes);
+  uint8_t* smem = w_area + w_bytes;                                     // slab planes
+  uint8_t* staging = smem + (size_t)kSlabStages * P.plane_bytes;         // 4 warps x 32 rows x (32 columns of T)
+  float* bias_s = reinterpret_cast<float*>(staging + 4 * 32 * 32 * sizeof(T));
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(bias_s + 128);
   uint64_t* slab_empty = slab_full + kSlabStages;
   uint64_t* w_full = slab_empty + kSlabStages;
   uint64_t* w_empty = w_full + kMaxWStages;
   uint64_t* acc_full = w_empty + kMaxWStages;
   uint64_t* acc_empty = acc_full + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxAcc);
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) asm volatile("trap;");   // the weight tiles need the 1024-byte base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * P.BN;
@@ -125,6 +96,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
+  if (warp >= 4) {
+    const int i = threadIdx.x - 128;            // BN <= 128
+    bias_s[i] = (bias != nullptr && i < P.BN && co0 + i < P.CO) ? bias[co0 + i] : 0.f;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -137,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
       uint32_t p = 0;
       for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
-        const int rho0 = (unit * P.UT * 128) / P.Wp;
+        const int rho0 = (unit * UT * 128) / P.Wp;
         for (int kb = 0; kb < P.nkb; ++kb, ++p) {
           const int st = p & 1;
           ptx::mbar_wait(&slab_empty[st], ((p >> 1) & 1u) ^ 1u);
@@ -175,17 +150,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    // The whole warp walks the (warp-uniform) loops and waits; one elected lane issues tcgen05.mma / commit.
-    // Everything the inner loop needs is kept in registers: descriptors are advanced with 32-bit adds on
-    // their low word (start address >> 4), ring positions are counters (no division).
+    // The whole warp walks the loops in CONVERGENT control flow (so ptxas keeps every descriptor in uniform
+    // registers and advances it with one UIADD3.64 per MMA); only the tcgen05.mma / commit instructions sit
+    // under the elected-lane branch.  NT (taps) and UT (tiles per unit) are compile-time so the tap loop is
+    // straight-line code with immediate constant-bank offsets.  Ring positions are counters (no division).
     const bool leader = ptx::elect_one();
     const uint32_t BN = (uint32_t)P.BN, n_acc = (uint32_t)P.n_acc, idesc = P.idesc;
-    const int ntaps = P.ntaps, nkb = P.nkb, UT = P.UT, Wp = P.Wp, total_tiles = P.total_tiles, num_units = P.num_units;
+    const int ntaps = NT > 0 ? NT : P.ntaps;
+    const int nkb = P.nkb, Wp = P.Wp, total_tiles = P.total_tiles, num_units = P.num_units;
     const bool w_res = P.w_resident != 0;
     const uint32_t w_stages = (uint32_t)P.w_stages, wbb16 = (uint32_t)P.w_block_bytes >> 4;
     const uint32_t plane16 = (uint32_t)P.plane_bytes >> 4;
-    const uint32_t slab_lo = (ptx::smem_u32(smem) >> 4) | kDescLoFlag;
-    const uint32_t w_lo = (ptx::smem_u32(w_area) >> 4) | kDescLoFlag;
+    const uint64_t slab_d = kDesc64 + (ptx::smem_u32(smem) >> 4);
+    const uint64_t w_d = kDesc64 + (ptx::smem_u32(w_area) >> 4);
     uint32_t p = 0;               // slab ring sequence number
     uint32_t ws = 0, wph = 0;     // weight ring position / phase
     uint32_t slot = 0, sph = 0;   // accumulator ring position / phase of the unit's first tile
@@ -197,101 +174,155 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       const int s0 = unit * UT * 128;
       const int ntile = min(UT, total_tiles - unit * UT);
       const uint32_t a_off16 = (uint32_t)(s0 % Wp) * (kRowBytes >> 4);
-      uint32_t sl[4], ph[4], dt[4];
+      uint32_t sl[UT], ph[UT], dt[UT];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < UT; ++j) {
         sl[j] = slot; ph[j] = sph; dt[j] = tmem_base + slot * BN;
         if (j < ntile && ++slot == n_acc) { slot = 0; sph ^= 1u; }
       }
-      for (int kb = 0; kb < nkb; ++kb, ++p) {
-        const uint32_t st = p & 1u;
-        ptx::mbar_wait(&slab_full[st], (p >> 1) & 1u);
-        ptx::tc_fence_after();
-        const uint32_t a_base = slab_lo + st * plane16 + a_off16;
-        for (int t = 0; t < ntaps; ++t) {
-          const uint32_t a_tap = a_base + P.tap_off16[t];
-          uint32_t b_lo;
-          if (w_res) {
-            b_lo = w_lo + (uint32_t)(t * nkb + kb) * wbb16;
-          } else {
-            ptx::mbar_wait(&w_full[ws], wph);
-            ptx::tc_fence_after();
-            b_lo = w_lo + ws * wbb16;
-          }
-          const bool first = (kb == 0 && t == 0), last = (kb == nkb - 1 && t == ntaps - 1);
-          if (!first && !last) {
+      auto run_unit = [&](auto full_tag, auto res_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;     // every tile of the unit exists
+        constexpr bool kRes = decltype(res_tag)::value;       // weights resident in smem (no ring waits)
+        for (int kb = 0; kb < nkb; ++kb, ++p) {
+          const uint32_t st = p & 1u;
+          ptx::mbar_wait(&slab_full[st], (p >> 1) & 1u);
+          ptx::tc_fence_after();
+          const uint64_t a_base = slab_d + (st * plane16 + a_off16);
+#pragma unroll
+          for (int t = 0; t < ntaps; ++t) {
+            const uint64_t ad = a_base + P.tap_off16[t];
+            uint64_t bd;
+            if (kRes) {
+              bd = w_d + (uint32_t)(t * nkb + kb) * wbb16;
+            } else {
+              ptx::mbar_wait(&w_full[ws], wph);
+              ptx::tc_fence_after();
+              bd = w_d + ws * wbb16;
+            }
+            const bool first = (kb == 0 && t == 0), last = (kb == nkb - 1 && t == ntaps - 1);
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < UT; ++j)
+                if (kFull || j < ntile) ptx::mbar_wait(&acc_empty[sl[j]], ph[j] ^ 1u);
+              ptx::tc_fence_after();
+            }
             if (leader) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < ntile) mma4<kTf32>(dt[j], a_tap + (uint32_t)j * (128 * kRowBytes >> 4), b_lo, idesc, 1u);
-            }
-          } else {
+              for (int j = 0; j < UT; ++j) {
+                if (kFull || j < ntile) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < ntile) {
-                if (first) {
-                  ptx::mbar_wait(&acc_empty[sl[j]], ph[j] ^ 1u);
-                  ptx::tc_fence_after();
-                }
-                if (leader) {
-                  mma4<kTf32>(dt[j], a_tap + (uint32_t)j * (128 * kRowBytes >> 4), b_lo, idesc, first ? 0u : 1u);
+                  for (int ks = 0; ks < 4; ++ks)
+                    ptx::mma_ss<kTf32>(dt[j], ad + (uint64_t)(j * (128 * kRowBytes >> 4) + 2 * ks), bd + (uint64_t)(2 * ks), idesc,
+                                       (first && ks == 0) ? 0u : 1u);
                   if (last) ptx::tc_commit(&acc_full[sl[j]]);
                 }
               }
+              if (!kRes) ptx::tc_commit(&w_empty[ws]);
             }
+            if (!kRes && ++ws == w_stages) { ws = 0; wph ^= 1u; }
           }
-          if (!w_res) {
-            if (leader) ptx::tc_commit(&w_empty[ws]);
-            if (++ws == w_stages) { ws = 0; wph ^= 1u; }
-          }
+          if (leader) ptx::tc_commit(&slab_empty[st]);
         }
-        if (leader) ptx::tc_commit(&slab_empty[st]);
+      };
+      if (w_res) {
+        if (ntile == UT) run_unit(std::true_type{}, std::true_type{});
+        else run_unit(std::false_type{}, std::true_type{});
+      } else {
+        if (ntile == UT) run_unit(std::true_type{}, std::false_type{});
+        else run_unit(std::false_type{}, std::false_type{});
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> (+bias, act) -> global =====
+    // ===== epilogue: TMEM -> registers -> (+bias, act) -> swizzled smem staging -> coalesced global stores =====
+    // A thread owns one accumulator row (TMEM lane = output slot).  Writing rows straight from registers would
+    // touch 32 different 128-byte lines per store instruction, so each 32-column chunk is transposed through a
+    // per-warp staging tile (XOR-swizzled, conflict-free both ways) and written with kCPR lanes per pixel.
+    constexpr int kRB = 32 * (int)sizeof(T);      // bytes of one row of a 32-column chunk (64 bf16 / 128 fp32)
+    constexpr int kCPR = kRB / 16;                // 16-byte pieces per row
+    constexpr int kRPI = 32 / kCPR;               // rows written per store instruction
+    constexpr int kVec = 16 / (int)sizeof(T);     // elements per 16-byte piece
     const int qd = warp & 3;                      // TMEM lane quadrant of this warp
     const int m = qd * 32 + lane;                 // row of the M tile
     const int img_slots = P.Hp * P.Wp;
-    uint32_t q = 0;
+    const int BN = P.BN, CO = P.CO, Wp = P.Wp, n_acc = P.n_acc;
+    uint8_t* stg = staging + (size_t)(warp - 4) * 32 * kRB;
+    const uint32_t stg_u32 = ptx::smem_u32(stg);
+    const int my_swz = kCPR == 4 ? ((lane >> 1) & 3) : (lane & 7);
+    const int rd_row0 = lane / kCPR, rd_cc = lane % kCPR;
+    uint32_t slot = 0, sph = 0;
+
+    auto emit = [&](T* __restrict__ out, const float (&v)[32], int my_pix, int co) {
+      // registers -> staging (row = lane), 16-byte pieces XOR-swizzled
+#pragma unroll
+      for (int cc = 0; cc < kCPR; ++cc) {
+        uint4 u;
+        if constexpr (sizeof(T) == 2) {
+          __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * cc], v[8 * cc + 1]);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(v[8 * cc + 2], v[8 * cc + 3]);
+          __nv_bfloat162 c2 = __floats2bfloat162_rn(v[8 * cc + 4], v[8 * cc + 5]);
+          __nv_bfloat162 d2 = __floats2bfloat162_rn(v[8 * cc + 6], v[8 * cc + 7]);
+          u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b2);
+          u.z = *reinterpret_cast<uint32_t*>(&c2); u.w = *reinterpret_cast<uint32_t*>(&d2);
+        } else {
+          u.x = __float_as_uint(v[4 * cc]); u.y = __float_as_uint(v[4 * cc + 1]);
+          u.z = __float_as_uint(v[4 * cc + 2]); u.w = __float_as_uint(v[4 * cc + 3]);
+        }
+        const uint32_t addr = stg_u32 + (uint32_t)(lane * kRB + ((cc ^ my_swz) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+      }
+      __syncwarp();
+      // staging -> global: kCPR lanes cover one pixel's chunk, kRPI pixels per instruction
+#pragma unroll
+      for (int it = 0; it < kCPR; ++it) {
+        const int r = it * kRPI + rd_row0;
+        const int pr = __shfl_sync(0xffffffffu, my_pix, r);
+        const int swz = kCPR == 4 ? ((r >> 1) & 3) : (r & 7);
+        uint4 u;
+        const uint32_t addr = stg_u32 + (uint32_t)(r * kRB + ((rd_cc ^ swz) << 4));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+        const int c_el = co + rd_cc * kVec;
+        if (pr >= 0 && c_el < CO) *reinterpret_cast<uint4*>(out + (int64_t)pr * CO + c_el) = u;
+      }
+      __syncwarp();
+    };
+
     for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
-      const int ntile = min(P.UT, P.total_tiles - unit * P.UT);
-      for (int j = 0; j < ntile; ++j, ++q) {
-        const uint32_t slot = q % (uint32_t)P.n_acc;
-        const int s = (unit * P.UT + j) * 128 + m;
+      const int ntile = min(UT, P.total_tiles - unit * UT);
+      for (int j = 0; j < ntile; ++j) {
+        const int s = (unit * UT + j) * 128 + m;
         const int n = s / img_slots;
         const int rem = s - n * img_slots;
-        const int yp = rem / P.Wp, xp = rem - yp * P.Wp;
+        const int yp = rem / Wp, xp = rem - yp * Wp;
         const bool row_ok = n < P.N && yp < P.OH && xp < P.OW;
-        const int64_t pix = ((int64_t)n * P.OH + yp) * P.OW + xp;
-        ptx::mbar_wait(&acc_full[slot], (q / (uint32_t)P.n_acc) & 1u);
+        const int my_pix = row_ok ? (n * P.OH + yp) * P.OW + xp : -1;
+        ptx::mbar_wait(&acc_full[slot], sph);
         ptx::tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + slot * (uint32_t)P.BN;
-        for (int c = 0; c < P.BN; c += 32) {
+        const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + slot * (uint32_t)BN;
+        for (int c = 0; c < BN; c += 32) {
           uint32_t r[32];
           float v[32];
           ptx::tmem_ld32(t_addr + (uint32_t)c, r);
           ptx::tmem_ld_wait();
+          if (c + 32 >= BN) {                      // accumulator fully read: hand the TMEM slot back early
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc_empty[slot]);
+          }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + c + i);
+            v[i] = __uint_as_float(r[i]) + bb.x; v[i + 1] = __uint_as_float(r[i + 1]) + bb.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[i + 3]) + bb.w;
+          }
           const int co = co0 + c;
-          const int n_valid = P.CO - co;
-          if (row_ok && n_valid > 0) {
-            if (bias) {
+          if (Z) emit(Z, v, my_pix, co);
+          if (Y) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] += (i < n_valid) ? __ldg(bias + co + i) : 0.f;
-            }
-            if (Z) store_row_chunk<T>(Z + pix * P.CO + co, v, n_valid);
-            if (Y) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = act_fn(P.act, v[i], P.p0, P.p1);
-              store_row_chunk<T>(Y + pix * P.CO + co, v, n_valid);
-            }
+            for (int i = 0; i < 32; ++i) v[i] = act_fn(P.act, v[i], P.p0, P.p1);
+            emit(Y, v, my_pix, co);
           }
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[slot]);
+        if (++slot == (uint32_t)n_acc) { slot = 0; sph ^= 1u; }
       }
     }
   }
@@ -354,7 +385,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   const int halo = (g.fr - 1) * g.D * Wp + (g.fc - 1) * g.D;
   const int total_tiles = (int)((slots + 127) / 128);
   P.total_tiles = total_tiles;
-  const int fixed = 1024 /*align*/ + 1024 /*barriers*/;
+  const int fixed = 4 * 32 * 32 * es /*epilogue staging*/ + 512 /*bias*/ + 512 /*barriers*/;
   const int w_res_bytes = nt * P.nkb * P.w_block_bytes;
   bool found = false;
   // weights resident first (no re-streaming), largest unit that fits; then streamed weights
@@ -362,7 +393,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
     for (int ut = 4; ut >= (resident ? 2 : 1) && !found; --ut) {
       if (ut * bn > 512) continue;
       const int sr = (Wp - 1 + 128 * ut + halo - 1) / Wp + 1;
-      const int plane = (int)align_up((size_t)sr * Wp * kRowBytes, 1024);
+      const int plane = sr * Wp * kRowBytes;   // 128-byte aligned is enough (absolute-address swizzle)
       int wst = 4;
       int wbytes = resident ? w_res_bytes : wst * P.w_block_bytes;
       if (!resident && fixed + kSlabStages * plane + wbytes > kSmemLimit) { wst = 3; wbytes = wst * P.w_block_bytes; }
@@ -403,12 +434,20 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
     const uint32_t box[4] = {(uint32_t)P.kelems, (uint32_t)P.Wp, 1, 1};
     if (int e = make_tmap(&P.amap, bf16, const_cast<void*>(in), 4, dims, strides, box, false)) return e;
   }
-  auto kern = tc_slab_conv_kernel<T>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[bf16 ? 0 : 1]) {
-    NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_set[bf16 ? 0 : 1] = true;
+  typedef void (*Kern)(const SlabParams, const float*, T*, T*);
+  Kern kern = nullptr;
+#define NPML_SLAB_UT(NTV)                                                          \
+  switch (P.UT) {                                                                  \
+    case 1: kern = tc_slab_conv_kernel<T, NTV, 1>; break;                          \
+    case 2: kern = tc_slab_conv_kernel<T, NTV, 2>; break;                          \
+    case 3: kern = tc_slab_conv_kernel<T, NTV, 3>; break;                          \
+    default: kern = tc_slab_conv_kernel<T, NTV, 4>; break;                         \
   }
+  if (P.ntaps == 9) { NPML_SLAB_UT(9) }
+  else if (P.ntaps == 1) { NPML_SLAB_UT(1) }
+  else { NPML_SLAB_UT(0) }
+#undef NPML_SLAB_UT
+  NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, (T*)Z, (T*)Y);
   NPML_LAUNCH_OK();
   return 0;
