@@ -83,6 +83,12 @@ int npml_conv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, v
  * fixed-order split reduction.  dW is (fr, fc, C, K) fp32. */
 int npml_conv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW,
                       void* ws, size_t ws_bytes, void* stream);
+/* wgrad + db in one call: dW as above and db[k] (+)= sum_{n,oh,ow} dZ[n,oh,ow,k] (layers/layers.py:3109);
+ * db (fp32, K entries) may be NULL.  On the slab path db is one more accumulator row of the same
+ * tensor-core pass (no extra read of dZ); desc.accumulate applies to both outputs.  Workspace:
+ * npml_workspace_bytes(d, NPML_OP_CONV_WGRAD). */
+int npml_conv2d_wgrad_db(const npml_conv_desc* d, const void* X, const void* dZ, float* dW, float* db,
+                         void* ws, size_t ws_bytes, void* stream);
 
 /* ---- Deconv2D (layers/layers.py:3353-3568, utils/utils.py:720-794) ------------------------
  * fprop: Z[n, iy*s + r - pr1, ix*s + t - pc1, k] += X[n,iy,ix,c] * W[r,t,c,k]  (no zero-stuffing)

@@ -35,6 +35,7 @@ SIGNATURES = {
     "npml_conv2d_fprop": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_wgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
+    "npml_conv2d_wgrad_db": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_fprop": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_wgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),

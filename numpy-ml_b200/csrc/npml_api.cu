@@ -85,22 +85,33 @@ static int run_gather(const npml_conv_desc* d, int op, const void* in, const flo
   return direct_gather_conv(g, in, W, b, Z, Y, act_dtype(d->mode), st);
 }
 
+size_t colpass_ws_bytes(int64_t rows, int ch, int nv);
+
+// db != nullptr is only passed for Conv2D (grad == dZ); paths without a fused db fall back to one column pass.
 static int run_wgrad(const npml_conv_desc* d, int op, const void* in, const void* grad, float* dW, void* ws,
-                     size_t ws_bytes, cudaStream_t st) {
+                     size_t ws_bytes, cudaStream_t st, float* db = nullptr) {
   if (check_desc(d, op == NPML_OP_DECONV_WGRAD)) return 1;
   NPML_CHECK(dW != nullptr, "dW is NULL");
   GatherWgrad g = make_wgrad(d, op);
   if (d->N == 0) {
     if (!d->accumulate) NPML_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * d->fr * d->fc * d->C * d->K, st));
+    if (db && !d->accumulate) NPML_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * d->K, st));
     return 0;
   }
   NPML_CHECK(in && grad, "NULL input");
+  if (d->mode != NPML_MODE_FP32 && slab_wgrad_supported(g, d->mode))
+    return slab_wgrad(g, d->mode, in, grad, dW, db, ws, ws_bytes, st);
+  int e;
   if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode))
-    return tc_wgrad(g, d->mode, in, grad, dW, ws, ws_bytes, st);
-  return direct_wgrad(g, in, grad, dW, act_dtype(d->mode), ws, ws_bytes, st);
+    e = tc_wgrad(g, d->mode, in, grad, dW, ws, ws_bytes, st);
+  else
+    e = direct_wgrad(g, in, grad, dW, act_dtype(d->mode), ws, ws_bytes, st);
+  if (e || !db) return e;
+  // the workspace is free again once the reduction above has been enqueued (stream order)
+  const int dt = act_dtype(d->mode);
+  return npml_dz_prep((int64_t)d->N * d->OH * d->OW, d->K, NPML_ACT_IDENTITY, 0.f, 0.f, grad, dt, nullptr, dt, nullptr, dt,
+                      db, d->accumulate, ws, ws_bytes, (void*)st);
 }
-
-size_t colpass_ws_bytes(int64_t rows, int ch, int nv);
 
 }  // namespace npml
 
@@ -119,6 +130,10 @@ int npml_conv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, v
 int npml_conv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW, void* ws, size_t ws_bytes,
                       void* stream) {
   return run_wgrad(d, NPML_OP_CONV_WGRAD, X, dZ, dW, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_conv2d_wgrad_db(const npml_conv_desc* d, const void* X, const void* dZ, float* dW, float* db, void* ws,
+                         size_t ws_bytes, void* stream) {
+  return run_wgrad(d, NPML_OP_CONV_WGRAD, X, dZ, dW, ws, ws_bytes, (cudaStream_t)stream, db);
 }
 int npml_deconv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
                         void* ws, size_t ws_bytes, void* stream) {
@@ -146,8 +161,12 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
     }
     case NPML_OP_CONV_WGRAD: case NPML_OP_DECONV_WGRAD: {
       GatherWgrad g = make_wgrad(d, op);
-      if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode)) bytes += tc_wgrad_ws_bytes(g, d->mode);
-      else bytes += direct_wgrad_ws_bytes(g);
+      size_t w;
+      if (d->mode != NPML_MODE_FP32 && slab_wgrad_supported(g, d->mode)) w = slab_wgrad_ws_bytes(g, d->mode);
+      else if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode)) w = tc_wgrad_ws_bytes(g, d->mode);
+      else w = direct_wgrad_ws_bytes(g);
+      const size_t c = colpass_ws_bytes((int64_t)d->N * d->OH * d->OW, d->K, 1);   // db fallback of npml_conv2d_wgrad_db
+      bytes += w > c ? w : c;
       break;
     }
     case NPML_OP_DZ_PREP: {
@@ -166,7 +185,8 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
 
 int npml_uses_tensor_cores(const npml_conv_desc* d, int op) {
   if (!d || d->mode == NPML_MODE_FP32) return 0;
-  if (op == NPML_OP_CONV_WGRAD || op == NPML_OP_DECONV_WGRAD) return tc_wgrad_supported(make_wgrad(d, op), d->mode);
+  if (op == NPML_OP_CONV_WGRAD || op == NPML_OP_DECONV_WGRAD)
+    return slab_wgrad_supported(make_wgrad(d, op), d->mode) || tc_wgrad_supported(make_wgrad(d, op), d->mode);
   if (op >= NPML_OP_CONV_FPROP && op <= NPML_OP_DECONV_DGRAD)
     return slab_conv_supported(make_gather(d, op), d->mode) || tc_conv_supported(make_gather(d, op), d->mode);
   return 0;

@@ -1,0 +1,376 @@
+// Persistent "slab" weight-gradient kernel for stride-1 convolutions on sm_100a (bf16 operands):
+//
+//   dW[tap, ci, co] = sum_slots  X[slot + off(tap), ci] * dZ[slot, co]        (layers/layers.py:3106-3110)
+//   db[co]          = sum_slots  1                      * dZ[slot, co]        (layers/layers.py:3109)
+//
+// Same flat padded-pixel ("slot") view as tc_slab_conv.cu: slot = (n*Hp + yp)*Wp + xp, off(tap) = r*D*Wp + t*D.
+// The reduction runs over slots, so both operands are MN-major: a slot is one 128-byte row of 64 channels,
+// exactly the K index of a 128B-swizzled MN-major tile.  One CTA keeps R padded rows of dZ and the R + halo
+// rows of X in shared memory (TMA, zero padding = out-of-bounds fill, so junk slots of dZ are zero and add
+// nothing) and feeds EVERY filter tap from that one X slab: the A descriptor of a tap is the slab's start
+// address advanced by off(tap)*128 bytes.  An M = 128 tile stacks two (tap, channel-block) windows; the
+// descriptor's leading-dimension offset is simply the byte distance between the two windows.  db rides along
+// as one more window made of ones.  Accumulators for all taps stay in TMEM for the CTA's whole slot range;
+// each CTA writes one fp32 partial and a second kernel adds the partials in a fixed order (deterministic).
+#include <cstdlib>
+#include <vector>
+
+#include "npml_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace npml {
+
+int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+              const uint32_t* box, bool atom32b);
+int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
+                        int64_t o_co, int accumulate, float* dW, cudaStream_t st);
+
+namespace {
+
+constexpr int kMaxMT = 40;           // M tiles (pairs of windows) over all groups
+constexpr int kRowBytes = 128;
+constexpr int kKI = 16;              // slots (K) per tcgen05.mma for 16-bit operands
+constexpr int kThreads = 256;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+
+struct SlabWgradParams {
+  CUtensorMap xmap, gmap;
+  uint32_t a16[kMaxMT];          // start of window 0 inside an X stage, >> 4 (kind 2: unused)
+  uint32_t lbo16[kMaxMT];        // kind 0: byte distance window 0 -> window 1, >> 4
+  int16_t tap[kMaxMT][2];        // filter tap of each window (-1 = the ones window, i.e. db)
+  int16_t cb[kMaxMT][2];         // channel block of each window
+  uint8_t kind[kMaxMT];          // 0 = (X, X), 1 = (X, ones), 2 = (ones, ones)
+  int nmt_total, mt_per_group, n_mgroups;
+  int ncb, nb, BN;
+  int N, Hp, Wp, pady, padx, CI, CO, Mrows;
+  int R, SRX, KS, num_units;
+  int xplane_bytes, xstage_bytes, gplane_bytes, gstage_bytes;
+  uint32_t idesc;
+};
+
+__global__ void db_reduce_kernel(const float* __restrict__ part, int splits, int CO, int accumulate,
+                                 float* __restrict__ db) {
+  const int co = blockIdx.x * blockDim.x + threadIdx.x;
+  if (co >= CO) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * CO + co];
+  db[co] = accumulate ? db[co] + s : s;
+}
+
+// The MMA issue loop for a group of NT accumulator tiles.  The whole warp walks the loops in convergent control
+// flow so the descriptors live in uniform registers; one elected lane issues.  Tiles 0 .. NT-2 of any group are
+// plain (X, X) pairs whose descriptor advances by a compile-time constant per K step; only the last tile of the
+// last group can involve the ones window (kinds 1, 2) and carries run-time deltas.
+template <int NT>
+__device__ __forceinline__ void issue_units(const SlabWgradParams& P, int mt0, bool leader, uint32_t tmem_base,
+                                            uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar,
+                                            const uint8_t* xs, const uint8_t* gs, const uint8_t* ones) {
+  const uint32_t idesc = P.idesc, BN = (uint32_t)P.BN;
+  const int KS = P.KS, num_units = P.num_units;
+  const uint32_t xs16 = ptx::smem_u32(xs) >> 4, gs16 = ptx::smem_u32(gs) >> 4, ones16 = ptx::smem_u32(ones) >> 4;
+  const uint32_t xstage16 = (uint32_t)P.xstage_bytes >> 4, gstage16 = (uint32_t)P.gstage_bytes >> 4;
+  constexpr uint64_t kStep = (kKI * kRowBytes) >> 4;                 // descriptor advance of one K step
+  constexpr uint64_t kHi64 = (uint64_t)kHi << 32;
+  uint64_t d0[NT];                                                    // descriptor at (stage 0, k = 0)
+#pragma unroll
+  for (int i = 0; i < NT - 1; ++i) d0[i] = kHi64 | (uint64_t)((xs16 + P.a16[mt0 + i]) | (P.lbo16[mt0 + i] << 16));
+  int64_t dk_last, ds_last;                                           // last tile: change per K step / per stage
+  {
+    const int gi = mt0 + NT - 1;
+    const uint32_t kind = P.kind[gi];
+    const uint32_t s = xs16 + P.a16[gi];
+    if (kind == 0) {
+      d0[NT - 1] = kHi64 | (uint64_t)(s | (P.lbo16[gi] << 16));
+      dk_last = (int64_t)kStep; ds_last = (int64_t)xstage16;
+    } else if (kind == 1) {       // window 1 = ones: its distance from window 0 shrinks as window 0 advances
+      d0[NT - 1] = kHi64 | (uint64_t)(s | ((ones16 - s) << 16));
+      dk_last = (int64_t)kStep - ((int64_t)kStep << 16); ds_last = (int64_t)xstage16 - ((int64_t)xstage16 << 16);
+    } else {
+      d0[NT - 1] = kHi64 | (uint64_t)ones16;
+      dk_last = 0; ds_last = 0;
+    }
+  }
+  const uint64_t g0 = kHi64 | (uint64_t)(gs16 | (((uint32_t)P.gplane_bytes >> 4) << 16));
+  uint32_t uc = 0;
+  for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
+    const uint32_t st = uc & 1u;
+    ptx::mbar_wait(&full_bar[st], (uc >> 1) & 1u);
+    ptx::tc_fence_after();
+    uint64_t ad[NT];
+#pragma unroll
+    for (int i = 0; i < NT - 1; ++i) ad[i] = d0[i] + (uint64_t)(st * xstage16);
+    ad[NT - 1] = d0[NT - 1] + (uint64_t)((int64_t)st * ds_last);
+    uint64_t bd = g0 + (uint64_t)(st * gstage16);
+#pragma unroll 2
+    for (int k = 0; k < KS; ++k) {
+      if (leader) {
+        const uint32_t acc = (uc | (uint32_t)k) ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) ptx::mma_ss<false>(tmem_base + (uint32_t)i * BN, ad[i], bd, idesc, acc);
+      }
+#pragma unroll
+      for (int i = 0; i < NT - 1; ++i) ad[i] += kStep;
+      ad[NT - 1] += (uint64_t)dk_last;
+      bd += kStep;
+    }
+    if (leader) ptx::tc_commit(&empty_bar[st]);
+  }
+  if (leader) ptx::tc_commit(acc_bar);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid_constant__ SlabWgradParams P,
+                                                                    float* __restrict__ part,
+                                                                    float* __restrict__ part_db) {
+  // [X stage 0][X stage 1][dZ stage 0][dZ stage 1][ones][barriers]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* xs = smem_raw;
+  uint8_t* gs = xs + 2 * (size_t)P.xstage_bytes;
+  uint8_t* ones = gs + 2 * (size_t)P.gstage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + kKI * kRowBytes);
+  uint64_t* empty_bar = full_bar + 2;
+  uint64_t* acc_bar = empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) asm volatile("trap;");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mgroup = blockIdx.y % P.n_mgroups, cotile = blockIdx.y / P.n_mgroups;
+  const int co0 = cotile * P.BN;
+  const int mt0 = mgroup * P.mt_per_group;
+  const int nmt = min(P.mt_per_group, P.nmt_total - mt0);
+  const int rows_g = P.R * P.Wp;                 // dZ slots the TMA writes per plane
+
+  // constant regions: the ones window and the zero slack behind every dZ plane (K steps may overrun the unit)
+  for (int i = threadIdx.x; i < kKI * kRowBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  for (int pl = 0; pl < 2 * P.nb; ++pl) {
+    uint32_t* z = reinterpret_cast<uint32_t*>(gs + (size_t)pl * P.gplane_bytes + (size_t)rows_g * kRowBytes);
+    for (int i = threadIdx.x; i < kKI * kRowBytes / 4; i += kThreads) z[i] = 0u;
+  }
+  ptx::fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    ptx::mbar_init(acc_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: X rows [u*R, u*R + SRX) of every channel block, dZ rows [u*R, u*R + R) of the CO tile =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&P.xmap);
+      ptx::prefetch_tmap(&P.gmap);
+      const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
+      const uint32_t tx = (uint32_t)(P.ncb * P.SRX + P.nb * P.R) * row_bytes;
+      uint32_t uc = 0;
+      for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x, ++uc) {
+        const uint32_t st = uc & 1u;
+        ptx::mbar_wait(&empty_bar[st], ((uc >> 1) & 1u) ^ 1u);
+        ptx::mbar_expect_tx(&full_bar[st], tx);
+        const int rho0 = unit * P.R;
+        int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
+        uint8_t* xd = xs + (size_t)st * P.xstage_bytes;
+        uint8_t* gd = gs + (size_t)st * P.gstage_bytes;
+        for (int i = 0; i < P.SRX; ++i) {
+          for (int c = 0; c < P.ncb; ++c)
+            ptx::tma_load_4d(xd + (size_t)c * P.xplane_bytes + (size_t)i * row_bytes, &P.xmap, &full_bar[st], c * 64, -P.padx,
+                             yp - P.pady, n);
+          if (i < P.R)
+            for (int b = 0; b < P.nb; ++b)
+              ptx::tma_load_4d(gd + (size_t)b * P.gplane_bytes + (size_t)i * row_bytes, &P.gmap, &full_bar[st], co0 + b * 64, 0,
+                               yp, n);
+          if (++yp == P.Hp) { yp = 0; ++n; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (issue_units<NT>, NT = tiles of this CTA's group, compile-time) =====
+    const bool leader = ptx::elect_one();
+    switch (nmt) {
+      case 1: issue_units<1>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 2: issue_units<2>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 3: issue_units<3>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 4: issue_units<4>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 5: issue_units<5>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 6: issue_units<6>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 7: issue_units<7>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      default: issue_units<8>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (once): TMEM -> this CTA's fp32 partial =====
+    const int qd = warp & 3;
+    const int l = qd * 32 + lane;                 // accumulator row
+    const int w = l >> 6, cl = l & 63;            // window of the pair, channel inside the window
+    ptx::mbar_wait(acc_bar, 0);
+    ptx::tc_fence_after();
+    for (int i = 0; i < nmt; ++i) {
+      const int gi = mt0 + i;
+      const int tap = P.tap[gi][w];
+      const int ci = P.cb[gi][w] * 64 + cl;
+      float* out = nullptr;
+      if (tap >= 0) {
+        if (ci < P.CI) out = part + ((int64_t)blockIdx.x * P.Mrows + (int64_t)tap * P.CI + ci) * P.CO;
+      } else if (tap == -1 && cl == 0 && (w == 0 || P.kind[gi] == 1)) {
+        out = part_db + (int64_t)blockIdx.x * P.CO;
+      }
+      for (int c = 0; c < P.BN; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(i * P.BN + c), r);
+        ptx::tmem_ld_wait();
+        const int co = co0 + c;
+        if (out != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (co + 4 * j < P.CO)
+              *reinterpret_cast<uint4*>(out + co + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline int ceildiv(int a, int b) { return (a + b - 1) / b; }
+
+struct SlabWgradPlan {
+  SlabWgradParams P;
+  dim3 grid;
+  size_t smem = 0, part_bytes = 0, partdb_bytes = 0;
+  int splits = 0;
+};
+
+bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
+  if (mode != NPML_MODE_BF16) return false;       // MN-major tf32 needs the 32B-atom layout: tc_wgrad.cu
+  if (std::getenv("NPML_DISABLE_SLAB")) return false;
+  if (g.s != 1 || g.N < 1) return false;
+  if (g.CI % 8 || g.CO % 8) return false;
+  const int Hp = g.OH + (g.fr - 1) * g.D, Wp = g.OW + (g.fc - 1) * g.D;
+  if (Wp > 256) return false;
+  if ((int64_t)g.N * Hp * Wp >= (1LL << 30)) return false;
+  if ((int64_t)g.N * g.IH * g.IW * g.CI >= (1LL << 31) || (int64_t)g.N * g.OH * g.OW * g.CO >= (1LL << 31)) return false;
+  SlabWgradParams& P = pl.P;
+  memset(&P, 0, sizeof(P));
+  P.N = g.N; P.Hp = Hp; P.Wp = Wp; P.pady = g.pr; P.padx = g.pc; P.CI = g.CI; P.CO = g.CO;
+  P.Mrows = g.fr * g.fc * g.CI;
+  P.ncb = ceildiv(g.CI, 64);
+  int bn = ceildiv(g.CO, 64) * 64;
+  if (bn > 128) bn = 128;
+  P.BN = bn;
+  P.nb = bn / 64;
+  const int ncot = ceildiv(g.CO, bn);
+  P.idesc = ptx::instr_desc(1, 1, 1, 128, bn);
+  const int halo = (g.fr - 1) * g.D * Wp + (g.fc - 1) * g.D;
+  // largest unit (R padded rows) whose two stages fit
+  int R = 0;
+  for (int r = 32; r >= 1; --r) {
+    const int ks = ceildiv(r * Wp, kKI);
+    const int srx = ceildiv(ks * kKI + halo, Wp);
+    const size_t xplane = (size_t)srx * Wp * kRowBytes;
+    const size_t gplane = (size_t)(r * Wp + kKI) * kRowBytes;
+    const size_t need = 2 * (P.ncb * xplane + P.nb * gplane) + kKI * kRowBytes + 256;
+    if (need <= (size_t)kSmemLimit) {
+      R = r; P.KS = ks; P.SRX = srx; P.xplane_bytes = (int)xplane; P.gplane_bytes = (int)gplane;
+      P.xstage_bytes = (int)(P.ncb * xplane); P.gstage_bytes = (int)(P.nb * gplane);
+      pl.smem = need;
+      break;
+    }
+  }
+  if (R == 0) return false;
+  P.R = R;
+  P.num_units = ceildiv(g.N * Hp, R);
+  // windows: every (channel block, tap) in ascending smem address order, then the ones window (db)
+  struct Win { int tap, cb; uint32_t a16; };
+  std::vector<Win> wins;
+  for (int c = 0; c < P.ncb; ++c)
+    for (int r = 0; r < g.fr; ++r)
+      for (int t = 0; t < g.fc; ++t)
+        wins.push_back({r * g.fc + t, c, (uint32_t)(((size_t)c * P.xplane_bytes + (size_t)(r * g.D * Wp + t * g.D) * kRowBytes) >> 4)});
+  wins.push_back({-1, 0, 0});
+  if (wins.size() & 1) wins.push_back({-1, 0, 0});
+  const int nmt = (int)wins.size() / 2;
+  if (nmt > kMaxMT) return false;
+  for (int i = 0; i < nmt; ++i) {
+    const Win &a = wins[2 * i], &b = wins[2 * i + 1];
+    P.tap[i][0] = (int16_t)a.tap; P.tap[i][1] = (int16_t)b.tap;
+    P.cb[i][0] = (int16_t)a.cb; P.cb[i][1] = (int16_t)b.cb;
+    P.a16[i] = a.a16;
+    if (a.tap >= 0 && b.tap >= 0) { P.kind[i] = 0; P.lbo16[i] = b.a16 - a.a16; if (P.lbo16[i] >= (1u << 14)) return false; }
+    else if (a.tap >= 0) P.kind[i] = 1;
+    else P.kind[i] = 2;
+  }
+  P.nmt_total = nmt;
+  const int cap = 512 / bn;                       // accumulator tiles that fit in TMEM
+  P.n_mgroups = ceildiv(nmt, cap);
+  P.mt_per_group = ceildiv(nmt, P.n_mgroups);
+  const int ngroups = P.n_mgroups * ncot;
+  int ctas = num_sms() / ngroups;
+  if (ctas < 1) ctas = 1;
+  if (ctas > P.num_units) ctas = P.num_units;
+  pl.splits = ctas;
+  pl.grid = dim3((unsigned)ctas, (unsigned)ngroups, 1);
+  pl.part_bytes = align_up((size_t)ctas * P.Mrows * g.CO * sizeof(float), 256);
+  pl.partdb_bytes = align_up((size_t)ctas * g.CO * sizeof(float), 256);
+  return true;
+}
+
+}  // namespace
+
+bool slab_wgrad_supported(const GatherWgrad& g, int mode) {
+  SlabWgradPlan pl;
+  return plan_slab_wgrad(g, mode, pl);
+}
+
+size_t slab_wgrad_ws_bytes(const GatherWgrad& g, int mode) {
+  SlabWgradPlan pl;
+  if (!plan_slab_wgrad(g, mode, pl)) return 0;
+  return pl.part_bytes + pl.partdb_bytes + 256;
+}
+
+// dW (+)= X (*) dZ and, when db != nullptr, db (+)= column sums of dZ, both from one pass over X and dZ.
+int slab_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad, float* dW, float* db, void* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  SlabWgradPlan pl;
+  NPML_CHECK(plan_slab_wgrad(g, mode, pl), "shape not supported by the slab wgrad path");
+  NPML_CHECK(ws != nullptr && ws_bytes >= pl.part_bytes + pl.partdb_bytes, "workspace too small");
+  NPML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0,
+             "activation pointers must be 16-byte aligned");
+  SlabWgradParams& P = pl.P;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[4] = {2, (uint64_t)g.CI * 2, (uint64_t)g.IW * g.CI * 2, (uint64_t)g.IH * g.IW * g.CI * 2};
+    const uint32_t box[4] = {64, (uint32_t)P.Wp, 1, 1};
+    if (int e = make_tmap(&P.xmap, true, const_cast<void*>(in), 4, dims, strides, box, false)) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)g.CO, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
+    const uint64_t strides[4] = {2, (uint64_t)g.CO * 2, (uint64_t)g.OW * g.CO * 2, (uint64_t)g.OH * g.OW * g.CO * 2};
+    const uint32_t box[4] = {64, (uint32_t)P.Wp, 1, 1};
+    if (int e = make_tmap(&P.gmap, true, const_cast<void*>(grad), 4, dims, strides, box, false)) return e;
+  }
+  float* part = reinterpret_cast<float*>(ws);
+  float* part_db = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
+  auto kern = tc_slab_wgrad_kernel;
+  NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, part, part_db);
+  NPML_LAUNCH_OK();
+  if (int e = launch_wgrad_reduce(part, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st))
+    return e;
+  if (db != nullptr) {
+    db_reduce_kernel<<<ceildiv(g.CO, 128), 128, 0, st>>>(part_db, pl.splits, g.CO, g.accumulate, db);
+    NPML_LAUNCH_OK();
+  }
+  return 0;
+}
+
+}  // namespace npml

@@ -244,11 +244,16 @@ class _ConvBase(LayerBase):
     def _bwd(self, dLdy, X, Z, retain_grads=True):
         W = self.parameters["W"] = _as_param(self.parameters["W"])
         pre = "npml_conv2d_" if self._layer_name == "Conv2D" else "npml_deconv2d_"
-        dZ = _dz_prep(dLdy, Z, self.act_fn, X.dtype, self.gradients["b"] if retain_grads else None)
+        conv = self._layer_name == "Conv2D"
+        # Conv2D: db is one more accumulator row of the wgrad pass; Deconv2D: db comes with the dZ prologue
+        dZ = _dz_prep(dLdy, Z, self.act_fn, X.dtype, self.gradients["b"] if (retain_grads and not conv) else None)
         d = self._desc(tuple(X.shape), accumulate=1)
         dX = torch.empty_like(X)
         self._call(pre + "dgrad", d, self._ops[1], L.ptr(dZ), L.ptr(W), L.ptr(dX))
-        if retain_grads:
+        if retain_grads and conv:
+            self._call("npml_conv2d_wgrad_db", d, self._ops[2], L.ptr(X), L.ptr(dZ), L.ptr(self.gradients["W"]),
+                       L.ptr(self.gradients["b"]))
+        elif retain_grads:
             self._call(pre + "wgrad", d, self._ops[2], L.ptr(X), L.ptr(dZ), L.ptr(self.gradients["W"]))
         return dX
 
