@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_c
   uint64_t* tmem_full_bar = empty_bar + P.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast from lane 0: tells ptxas it is warp-uniform, so the role branches are uniform branches and
+  // everything the MMA issuer computes stays on the uniform datapath (no R2UR per descriptor)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const ClassInfo& C = P.cls[blockIdx.z];
 
   // tile -> (image block, patch row, patch col) of this class
@@ -168,38 +170,41 @@ __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_c
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&P.wmap);
       const uint32_t tx_bytes = (uint32_t)(P.TW * P.TH * P.TN * kRowBytes + b_tile_bytes);
-      int k = 0;
+      uint32_t s = 0, ph = 0;     // ring position / phase (counters: no division in the loop)
       for (int t = 0; t < C.ntaps; ++t) {
         const Tap tap = P.taps[C.tap_begin + t];
-        for (int kb = 0; kb < P.nkb; ++kb, ++k) {
-          const int s = k % P.stages;
-          const uint32_t ph = (uint32_t)(k / P.stages) & 1u;
+        for (int kb = 0; kb < P.nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* a_dst = smem + (size_t)s * stage_bytes;
           ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
           ptx::tma_load_4d(a_dst, &P.amap[tap.amap], &full_bar[s], kb * P.kelems, ox0 + tap.dx, oy0 + tap.dy, n0);
           ptx::tma_load_3d(a_dst + kATileBytes, &P.wmap, &full_bar[s], kb * P.kelems, co0, tap.wtap);
+          if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (ptx::elect_one()) {
-      for (int k = 0; k < nk; ++k) {
-        const int s = k % P.stages;
-        const uint32_t ph = (uint32_t)(k / P.stages) & 1u;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t adesc = ptx::smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t bdesc = ptx::smem_desc_sw128(a_addr + kATileBytes, 16, 1024);
+    // ===== MMA issuer: the warp walks the loop in convergent control flow (descriptors stay in uniform
+    // registers), one elected lane issues =====
+    const bool leader = ptx::elect_one();
+    constexpr uint64_t kDesc64 = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);
+    const uint32_t base16 = ((ptx::smem_u32(smem_raw) + 1023u) & ~1023u) >> 4;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, stages = (uint32_t)P.stages, idesc = P.idesc;
+    uint32_t s = 0, ph = 0;
+    for (int k = 0; k < nk; ++k) {
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after();
+      const uint64_t adesc = kDesc64 + (base16 + s * stage16);
+      const uint64_t bdesc = adesc + (uint64_t)(kATileBytes >> 4);
+      if (leader) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)   // 4 x 32-byte K slices inside the 128-byte swizzle atom
-          ptx::mma_ss<kTf32>(tmem_base, adesc + 2 * j, bdesc + 2 * j, P.idesc, (k | j) ? 1u : 0u);
+          ptx::mma_ss<kTf32>(tmem_base, adesc + 2 * j, bdesc + 2 * j, idesc, (k | j) ? 1u : 0u);
         ptx::tc_commit(&empty_bar[s]);   // frees the smem slot once these MMAs have read it
       }
-      ptx::tc_commit(tmem_full_bar);     // accumulator complete
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
+    if (leader) ptx::tc_commit(tmem_full_bar);     // accumulator complete
   } else {
     // ===== epilogue: TMEM -> registers -> (+bias, act) -> global =====
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read

@@ -83,7 +83,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kMaxAcc);
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) asm volatile("trap;");   // the weight tiles need the 1024-byte base
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast from lane 0: tells ptxas it is warp-uniform, so the role branches are uniform branches and
+  // everything the MMA issuer computes stays on the uniform datapath (no R2UR per descriptor)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * P.BN;
 
   if (warp == 0 && lane == 0) {

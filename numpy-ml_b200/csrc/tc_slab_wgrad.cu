@@ -65,10 +65,10 @@ __global__ void db_reduce_kernel(const float* __restrict__ part, int splits, int
 template <int NT>
 __device__ __forceinline__ void issue_units(const SlabWgradParams& P, int mt0, bool leader, uint32_t tmem_base,
                                             uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar,
-                                            const uint8_t* xs, const uint8_t* gs, const uint8_t* ones) {
+                                            uint32_t xs_u32, uint32_t gs_u32, uint32_t ones_u32) {
   const uint32_t idesc = P.idesc, BN = (uint32_t)P.BN;
   const int KS = P.KS, num_units = P.num_units;
-  const uint32_t xs16 = ptx::smem_u32(xs) >> 4, gs16 = ptx::smem_u32(gs) >> 4, ones16 = ptx::smem_u32(ones) >> 4;
+  const uint32_t xs16 = xs_u32 >> 4, gs16 = gs_u32 >> 4, ones16 = ones_u32 >> 4;
   const uint32_t xstage16 = (uint32_t)P.xstage_bytes >> 4, gstage16 = (uint32_t)P.gstage_bytes >> 4;
   constexpr uint64_t kStep = (kKI * kRowBytes) >> 4;                 // descriptor advance of one K step
   constexpr uint64_t kHi64 = (uint64_t)kHi << 32;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void issue_units(const SlabWgradParams& P, int mt0, b
     uint64_t ad[NT];
 #pragma unroll
     for (int i = 0; i < NT - 1; ++i) ad[i] = d0[i] + (uint64_t)(st * xstage16);
-    ad[NT - 1] = d0[NT - 1] + (uint64_t)((int64_t)st * ds_last);
+    ad[NT - 1] = d0[NT - 1] + (uint64_t)(st ? ds_last : (int64_t)0);
     uint64_t bd = g0 + (uint64_t)(st * gstage16);
 #pragma unroll 2
     for (int k = 0; k < KS; ++k) {
@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
   if ((ptx::smem_u32(smem_raw) & 1023u) != 0) asm volatile("trap;");
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mgroup = blockIdx.y % P.n_mgroups, cotile = blockIdx.y / P.n_mgroups;
+  // warp index broadcast from lane 0: tells ptxas it is warp-uniform, so the role branches are uniform branches and
+  // everything the MMA issuer computes stays on the uniform datapath (no R2UR per descriptor)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int mgroup = blockIdx.y, cotile = blockIdx.z;   // (no division: keeps the tile indices warp-uniform)
   const int co0 = cotile * P.BN;
   const int mt0 = mgroup * P.mt_per_group;
   const int nmt = min(P.mt_per_group, P.nmt_total - mt0);
@@ -191,16 +193,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===== MMA issuer (issue_units<NT>, NT = tiles of this CTA's group, compile-time) =====
+    // shared-window addresses as plain integers off the (link-time constant) base of the dynamic smem array,
+    // so that ptxas sees them as warp-uniform (a cvta of a computed generic pointer is not)
     const bool leader = ptx::elect_one();
+    const uint32_t xs_u32 = ptx::smem_u32(smem_raw);
+    const uint32_t gs_u32 = xs_u32 + 2u * (uint32_t)P.xstage_bytes;
+    const uint32_t ones_u32 = gs_u32 + 2u * (uint32_t)P.gstage_bytes;
     switch (nmt) {
-      case 1: issue_units<1>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      case 2: issue_units<2>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      case 3: issue_units<3>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      case 4: issue_units<4>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      case 5: issue_units<5>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      case 6: issue_units<6>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      case 7: issue_units<7>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
-      default: issue_units<8>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs, gs, ones); break;
+      case 1: issue_units<1>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 2: issue_units<2>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 3: issue_units<3>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 4: issue_units<4>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 5: issue_units<5>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 6: issue_units<6>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 7: issue_units<7>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      default: issue_units<8>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
     }
   } else if (warp >= 4) {
     // ===== epilogue (once): TMEM -> this CTA's fp32 partial =====
@@ -318,7 +325,7 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   if (ctas < 1) ctas = 1;
   if (ctas > P.num_units) ctas = P.num_units;
   pl.splits = ctas;
-  pl.grid = dim3((unsigned)ctas, (unsigned)ngroups, 1);
+  pl.grid = dim3((unsigned)ctas, (unsigned)P.n_mgroups, (unsigned)ncot);
   pl.part_bytes = align_up((size_t)ctas * P.Mrows * g.CO * sizeof(float), 256);
   pl.partdb_bytes = align_up((size_t)ctas * g.CO * sizeof(float), 256);
   return true;

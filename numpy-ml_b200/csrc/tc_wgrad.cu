@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + P.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast from lane 0: tells ptxas it is warp-uniform, so the role branches are uniform branches and
+  // everything the MMA issuer computes stays on the uniform datapath (no R2UR per descriptor)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int blk0 = blockIdx.x * P.mb;                       // first A window of this M tile
   const int nblk = min(P.mb, P.nblocks - blk0);             // windows that exist
   const int co0 = blockIdx.y * P.nb * P.kelems;
@@ -98,14 +100,13 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
       ptx::prefetch_tmap(&P.gmap);
       const uint32_t tx_bytes = (uint32_t)((nblk + nbn) * P.rows_used * kRowBytes);
       const int per_img = P.tiles_x * P.tiles_y;
+      uint32_t s = 0, ph = 0;     // ring position / phase
       for (int k = 0; k < nk; ++k) {
         int tile = t_begin + k;
         const int tn = tile / per_img;
         tile -= tn * per_img;
         const int ty = tile / P.tiles_x, tx = tile - ty * P.tiles_x;
         const int n0 = tn * P.TN, oy0 = ty * P.TH, ox0 = tx * P.TW;
-        const int s = k % P.stages;
-        const uint32_t ph = (uint32_t)(k / P.stages) & 1u;
         ptx::mbar_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* dst = smem + (size_t)s * stage_bytes;
         ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
@@ -115,34 +116,37 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
         }
         for (int b = 0; b < nbn; ++b)
           ptx::tma_load_4d(dst + (P.mb + b) * kTileBytes, &P.gmap, &full_bar[s], co0 + b * P.kelems, ox0, oy0, n0);
+        if (++s == (uint32_t)P.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (ptx::elect_one()) {
-      for (int k = 0; k < nk; ++k) {
-        const int s = k % P.stages;
-        const uint32_t ph = (uint32_t)(k / P.stages) & 1u;
-        ptx::mbar_wait(&full_bar[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-        // MN-major: LBO = distance between 128-byte column blocks (one window = 16 KB), SBO = distance between
-        // swizzle-atom groups of pixel rows.  16-bit operands use the plain 128B swizzle (8-row atoms, 1 KB);
-        // MN-major tf32 operands only exist in the 128B swizzle with 32-byte granularity (4-row atoms, 512 B),
-        // which the TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
-        uint64_t adesc = ptx::smem_desc_sw128(a_addr, kTileBytes, kTf32 ? 512 : 1024);
-        uint64_t bdesc = ptx::smem_desc_sw128(a_addr + P.mb * kTileBytes, kTileBytes, kTf32 ? 512 : 1024);
-        if (kTf32) {   // layout type 1 = SWIZZLE_128B_BASE32B instead of 2 = SWIZZLE_128B
-          adesc ^= (uint64_t)3 << 61;
-          bdesc ^= (uint64_t)3 << 61;
-        }
-        const uint32_t step = (uint32_t)P.kinstr_bytes >> 4;
-        for (int j = 0; j < P.mmas_per_tile; ++j)
-          ptx::mma_ss<kTf32>(tmem_base, adesc + (uint64_t)(j * step), bdesc + (uint64_t)(j * step), P.idesc,
-                             (k | j) ? 1u : 0u);
-        ptx::tc_commit(&empty_bar[s]);
+    // MMA issuer: convergent loop (uniform-register descriptors), one elected lane issues.
+    // MN-major: LBO = distance between 128-byte column blocks (one window = 16 KB), SBO = distance between
+    // swizzle-atom groups of pixel rows.  16-bit operands use the plain 128B swizzle (8-row atoms, 1 KB);
+    // MN-major tf32 operands only exist in the 128B swizzle with 32-byte granularity (4-row atoms, 512 B),
+    // which the TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (layout type 1 = SWIZZLE_128B_BASE32B).
+    const bool leader = ptx::elect_one();
+    constexpr uint64_t kDescMN = ((uint64_t)(((kTf32 ? 512u : 1024u) >> 4) | (1u << 14) | ((kTf32 ? 1u : 2u) << 29)) << 32) |
+                                 ((uint64_t)(kTileBytes >> 4) << 16);
+    const uint32_t base16 = ((ptx::smem_u32(smem_raw) + 1023u) & ~1023u) >> 4;
+    const uint32_t stage16 = (uint32_t)stage_bytes >> 4, stages = (uint32_t)P.stages, idesc = P.idesc;
+    const uint32_t step = (uint32_t)P.kinstr_bytes >> 4, b_off16 = (uint32_t)(P.mb * kTileBytes) >> 4;
+    const int mmas = P.mmas_per_tile;
+    uint32_t s = 0, ph = 0;
+    for (int k = 0; k < nk; ++k) {
+      ptx::mbar_wait(&full_bar[s], ph);
+      ptx::tc_fence_after();
+      uint64_t adesc = kDescMN + (base16 + s * stage16);
+      uint64_t bdesc = adesc + b_off16;
+      for (int j = 0; j < mmas; ++j) {
+        if (leader) ptx::mma_ss<kTf32>(tmem_base, adesc, bdesc, idesc, (k | j) ? 1u : 0u);
+        adesc += step;
+        bdesc += step;
       }
-      ptx::tc_commit(tmem_full_bar);
+      if (leader) ptx::tc_commit(&empty_bar[s]);
+      if (++s == stages) { s = 0; ph ^= 1u; }
     }
+    if (leader) ptx::tc_commit(tmem_full_bar);
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
