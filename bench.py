@@ -39,6 +39,8 @@ CONFIGS = {
                  name="Conv2D 3x3 s1 same, N=256, 56x56x64->64"),
     "cfg3": dict(kind="conv", N=128, H=28, W=28, C=128, K=256, k=(3, 3), pad=0, stride=2, dilation=2,
                  name="Conv2D 3x3 s2 dilation2, N=128, 28x28x128->256"),
+    "cfg4": dict(kind="skip", N=256, H=32, W=32, C=64, K=128, k=(3, 3), pad=1, stride=1, dilation=0,
+                 name="SkipConnectionConvModule 3x3/3x3/1x1 + 3 BatchNorm2D + ReLU, N=256, 32x32x64->128"),
     "cfg5": dict(kind="deconv", N=128, H=16, W=16, C=256, K=128, k=(4, 4), pad=1, stride=2, dilation=0,
                  name="Deconv2D 4x4 s2 pad1, N=128, 16x16x256->128"),
 }
@@ -58,6 +60,8 @@ def peaks():
 
 def out_hw(cfg):
     pkg_u = importlib.import_module("numpy-ml_b200").utils
+    if cfg["kind"] == "skip":
+        return cfg["H"], cfg["W"]
     if cfg["kind"] == "conv":
         p4 = pkg_u.resolve_pad_2D((cfg["N"], cfg["H"], cfg["W"], cfg["C"]), cfg["pad"], cfg["k"], cfg["stride"],
                                   cfg["dilation"])
@@ -70,6 +74,8 @@ def flops_per_pass(cfg, n):
     """Nominal MACs*2 of ONE pass (fwd, dgrad or wgrad), padded taps counted."""
     oh, ow = out_hw(cfg)
     taps = cfg["k"][0] * cfg["k"][1]
+    if cfg["kind"] == "skip":      # conv1 (C->K, 3x3) + conv2 (K->K, 3x3) + skip (C->K, 1x1); BN / Add are not counted
+        return 2.0 * n * oh * ow * cfg["K"] * (cfg["C"] * taps + cfg["K"] * taps + cfg["C"])
     if cfg["kind"] == "conv":
         return 2.0 * n * oh * ow * cfg["K"] * cfg["C"] * taps
     return 2.0 * n * cfg["H"] * cfg["W"] * taps * cfg["C"] * cfg["K"]
@@ -92,15 +98,36 @@ def make_inputs(cfg, n, seed):
     X = rng.standard_normal((n, cfg["H"], cfg["W"], cfg["C"]), dtype=np.float32)
     dY = rng.standard_normal((n, oh, ow, cfg["K"]), dtype=np.float32)
     from oracle import conv_oracle as O
+    if cfg["kind"] == "skip":
+        return X, dY, skip_params(cfg, seed), None
     np.random.seed(seed)
     W = O.glorot_uniform(cfg["k"] + (cfg["C"], cfg["K"])).astype(np.float32)
     b = (0.1 * rng.standard_normal((1, 1, 1, cfg["K"]))).astype(np.float32)
     return X, dY, W, b
 
 
+def skip_params(cfg, seed):
+    """Parameters of the cfg4 module (same on every rank): glorot conv weights, small biases, BN affine."""
+    from oracle import conv_oracle as O
+    rng = np.random.default_rng(seed)
+    np.random.seed(seed)
+    C, K = cfg["C"], cfg["K"]
+    P = {}
+    for t, shape in (("1", (3, 3, C, K)), ("2", (3, 3, K, K)), ("s", (1, 1, C, K))):
+        P["W" + t] = O.glorot_uniform(shape).astype(np.float32).astype(np.float64)
+        P["b" + t] = (0.1 * rng.standard_normal((1, 1, 1, K))).astype(np.float32).astype(np.float64)
+        P["g" + t] = rng.uniform(0.5, 1.5, K).astype(np.float32).astype(np.float64)
+        P["h" + t] = (0.1 * rng.standard_normal(K)).astype(np.float32).astype(np.float64)
+        P["rm" + t], P["rv" + t] = np.zeros(K), np.ones(K)
+    return P
+
+
 def cpu_step(cfg, X, dY, W, b):
     """forward + backward of the reference algorithm in float64 (oracle port)."""
     from oracle import conv_oracle as O
+    if cfg["kind"] == "skip":
+        return O.skip_conv_module_fwd_bwd(X.astype(np.float64), dY.astype(np.float64), W, (3, 3), (3, 3), (1, 1), 1, 1,
+                                          1, 1, 1, "relu")
     X, dY, W, b = (a.astype(np.float64) for a in (X, dY, W, b))
     if cfg["kind"] == "conv":
         Y, Z = O.conv2d_layer_fwd(X, W, b, cfg["stride"], cfg["pad"], cfg["dilation"])
@@ -130,7 +157,7 @@ def time_cpu(cfg, n_sample, reps, warmup, seed):
 
 def cpu_sample_size(cfg, budget_s, steps):
     # survey-time throughput of the reference on 8 vCPU, images/s
-    rate = {"cfg1": 1250.0, "cfg2": 6.9, "cfg3": 110.0, "cfg5": 2.75}[cfg["_id"]]
+    rate = {"cfg1": 1250.0, "cfg2": 6.9, "cfg3": 110.0, "cfg4": 4.8, "cfg5": 2.75}[cfg["_id"]]
     n = int(max(2, min(cfg["N"], budget_s * rate / max(steps, 1))))
     return n
 
@@ -209,6 +236,18 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------------
 #  GPU arm
 # ---------------------------------------------------------------------------------------------------
+ELEMENTWISE = ("npml_bn2d_fwd", "npml_bn2d_bwd", "npml_add_act_fwd", "npml_dz_prep")
+
+
+def measured_traffic(cfg_id, mode, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get("{}/{}/{}".format(cfg_id, mode, kernel))
+    except Exception:
+        return None
+
+
 def run_gpu(args, cfg):
     import torch
     pkg = importlib.import_module("numpy-ml_b200")
@@ -220,28 +259,44 @@ def run_gpu(args, cfg):
     dev = torch.device("cuda", torch.cuda.current_device())
     mode = args.mode
     n = cfg["N"]
+    kind = cfg["kind"]
     seed = 1000 + int(cfg["_id"][3:])
     X, dY, W, b = make_inputs(cfg, n, seed + 17 * rank)
     _, _, W, b = make_inputs(cfg, 2, seed)          # identical parameters on every rank
     act_dt = L.torch_dtype(mode)
     esize = 2 if mode == "bf16" else 4
 
-    if cfg["kind"] == "conv":
-        layer = pkg.Conv2D(cfg["K"], cfg["k"], pad=cfg["pad"], stride=cfg["stride"], dilation=cfg["dilation"], mode=mode)
+    if kind == "conv":
+        model = pkg.Conv2D(cfg["K"], cfg["k"], pad=cfg["pad"], stride=cfg["stride"], dilation=cfg["dilation"], mode=mode)
+    elif kind == "deconv":
+        model = pkg.Deconv2D(cfg["K"], cfg["k"], pad=cfg["pad"], stride=cfg["stride"], mode=mode)
     else:
-        layer = pkg.Deconv2D(cfg["K"], cfg["k"], pad=cfg["pad"], stride=cfg["stride"], mode=mode)
+        model = pkg.SkipConnectionConvModule(out_ch1=cfg["K"], out_ch2=cfg["K"], kernel_shape1=(3, 3), kernel_shape2=(3, 3),
+                                             kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn="relu", mode=mode)
     Xh = torch.from_numpy(X).pin_memory()
     dYh = torch.from_numpy(dY).pin_memory()
     Xd = L.to_device(Xh.to(dev), act_dt)
     dYd = L.to_device(dYh.to(dev), act_dt)
-    layer.forward(Xd, retain_derived=False)
-    layer.parameters["W"], layer.parameters["b"] = L.to_device(W, torch.float32), L.to_device(b, torch.float32)
-    bucket = D.GradBucket([layer])
+    model.forward(Xd, retain_derived=False)
+    if kind == "skip":
+        layers = [model.conv1, model.conv2, model.conv_skip, model.batchnorm1, model.batchnorm2, model.batchnorm_skip]
+        for t, conv, bn in (("1", model.conv1, model.batchnorm1), ("2", model.conv2, model.batchnorm2),
+                            ("s", model.conv_skip, model.batchnorm_skip)):
+            conv.parameters["W"], conv.parameters["b"] = (L.to_device(W["W" + t], torch.float32),
+                                                          L.to_device(W["b" + t], torch.float32))
+            bn.parameters["scaler"], bn.parameters["intercept"] = (L.to_device(W["g" + t], torch.float32),
+                                                                   L.to_device(W["h" + t], torch.float32))
+        conv_layers = layers[:3]
+    else:
+        layers = conv_layers = [model]
+        model.parameters["W"], model.parameters["b"] = L.to_device(W, torch.float32), L.to_device(b, torch.float32)
+    # dW / db of a layer are all-reduced on a side stream while its dX is still being computed
+    bucket = D.GradBucket(layers, overlap=True)
 
     def step():
-        layer.flush_gradients()
-        Y = layer.forward(Xd)
-        dX = layer.backward(dYd)
+        model.flush_gradients()
+        Y = model.forward(Xd)
+        dX = model.backward(dYd)
         if world > 1:
             bucket.allreduce()
         return Y, dX
@@ -250,7 +305,7 @@ def run_gpu(args, cfg):
         step()
     torch.cuda.synchronize()
 
-    # ---- timed region: K steps, CUDA events on the launching stream, per-kernel events inside -------
+    # ---- timed region: K steps, CUDA events on the launching stream, per-call events inside ----------
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
     L.PROFILE = []
@@ -271,49 +326,98 @@ def run_gpu(args, cfg):
     ms_step = ms_total / args.steps
     value = world * n * args.steps / (ms_total * 1e-3)
 
-    # ---- per-kernel shares and the roofline of the dominant kernel -----------------------------------
-    per = {}
+    # ---- per-call shares and the roofline of the dominant call ----------------------------------------
+    per, count = {}, {}
     for name, a, z in prof:
-        per.setdefault(name, []).append(a.elapsed_time(z))
-    kern = {k: float(np.mean(v)) for k, v in per.items()}
+        per[name] = per.get(name, 0.0) + a.elapsed_time(z)
+        count[name] = count.get(name, 0) + 1
+    step_ms = {k: v / args.steps for k, v in per.items()}          # time per step spent in each entry point
+    call_ms = {k: per[k] / count[k] for k in per}                   # mean duration of one call
     fl = flops_per_pass(cfg, n)
     pk = peaks()
-    dominant = max(kern, key=kern.get)
-    tc = bool(layer._uses_tc())
-    if tc:
+    dominant = max(step_ms, key=step_ms.get)
+    tc = all(bool(l._uses_tc()) for l in conv_layers)
+    calls_per_step = count[dominant] / args.steps
+    if dominant in ELEMENTWISE:
+        oh, ow = out_hw(cfg)
+        elems = n * oh * ow * cfg["K"]
+        passes = {"npml_bn2d_fwd": 2, "npml_bn2d_bwd": 3, "npml_add_act_fwd": 3, "npml_dz_prep": 3}[dominant]
+        byt = float(elems * esize * passes)
+        achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
+    elif tc:
         peak = pk["bf16_tflops_sustained"] if mode == "bf16" else pk["bf16_tflops_sustained"] / 2.0
-        achieved = fl / (kern[dominant] * 1e-3) / 1e12
+        achieved = fl / calls_per_step / (call_ms[dominant] * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak,
                 "peak_source": pk["source"] + (" bf16 sustained" if mode == "bf16" else " bf16 sustained / 2 (tf32)")}
     else:
         byt = min_bytes_per_pass(cfg, n, esize)
-        achieved = byt / (kern[dominant] * 1e-3) / 1e9
+        achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"]}
-    roof["kernel_ms"] = {k: round(v, 4) for k, v in kern.items()}
-    roof["share_of_step"] = round(kern[dominant] / ms_step, 3)
-    tflops_step = 3.0 * fl / (ms_step * 1e-3) / 1e12
+                "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
+    roof["traffic"] = measured_traffic(cfg["_id"], mode, dominant)
+    roof["kernel_ms"] = {k: round(v, 4) for k, v in call_ms.items()}
+    roof["step_ms_by_call"] = {k: round(v, 4) for k, v in step_ms.items()}
+    roof["share_of_step"] = round(step_ms[dominant] / ms_step, 3)
+    tflops_step = 3.0 * fl * world / (ms_step * 1e-3) / 1e12
 
-    # ---- end to end through the public API with host buffers -----------------------------------------
+    # ---- end to end through the public API with HOST buffers ----------------------------------------------
+    # X and dLdy start in pinned host memory (fp32); Y, dX, dW, db end in pinned host memory.  Host->device and
+    # device->host copies run on their own streams so the two PCIe directions overlap; Conv2D / Deconv2D batches
+    # are pipelined in chunks (forward / backward of chunk i while chunk i+1 is in flight).  The module of cfg4
+    # needs whole-batch BatchNorm statistics, so it is not chunked.
     e2e_steps = max(1, min(args.steps, 5))
-    Yh = torch.empty((n,) + tuple(out_hw(cfg)) + (cfg["K"],), dtype=act_dt).pin_memory()
+    oh, ow = out_hw(cfg)
+    Yh = torch.empty((n, oh, ow, cfg["K"]), dtype=act_dt).pin_memory()
     dXh = torch.empty(X.shape, dtype=act_dt).pin_memory()
-    dWh = torch.empty(W.shape, dtype=torch.float32).pin_memory()
-    dbh = torch.empty(b.shape, dtype=torch.float32).pin_memory()
+    gradh = torch.empty(bucket.flat.numel(), dtype=torch.float32).pin_memory()
+    chunks = 1 if kind == "skip" else 4
+    bounds = [(i * n // chunks, (i + 1) * n // chunks) for i in range(chunks)]
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    xs32 = [torch.empty((hi - lo,) + X.shape[1:], dtype=torch.float32, device=dev) for lo, hi in bounds]
+    dys32 = [torch.empty((hi - lo, oh, ow, cfg["K"]), dtype=torch.float32, device=dev) for lo, hi in bounds]
 
     def e2e_step():
-        xd = L.cast(Xh.to(dev, non_blocking=True), act_dt)
-        dyd = L.cast(dYh.to(dev, non_blocking=True), act_dt)
-        layer.flush_gradients()
-        Y = layer.forward(xd)
-        dX = layer.backward(dyd)
+        cur = torch.cuda.current_stream()
+        s_in.wait_stream(cur)
+        s_out.wait_stream(cur)
+        ev_x, ev_dy = [], []
+        with torch.cuda.stream(s_in):
+            for i, (lo, hi) in enumerate(bounds):
+                xs32[i].copy_(Xh[lo:hi], non_blocking=True)
+                ev_x.append(torch.cuda.Event()); ev_x[-1].record()
+            for i, (lo, hi) in enumerate(bounds):
+                dys32[i].copy_(dYh[lo:hi], non_blocking=True)
+                ev_dy.append(torch.cuda.Event()); ev_dy[-1].record()
+        model.flush_gradients()
+        outs = []
+        for i, (lo, hi) in enumerate(bounds):
+            cur.wait_event(ev_x[i])
+            Y = model.forward(L.cast(xs32[i], act_dt))
+            outs.append(Y)
+            ev = torch.cuda.Event(); ev.record()
+            s_out.wait_event(ev)
+            with torch.cuda.stream(s_out):
+                Yh[lo:hi].copy_(Y, non_blocking=True)
+        for i, (lo, hi) in enumerate(bounds):
+            cur.wait_event(ev_dy[i])
+            dyd = L.cast(dys32[i], act_dt)
+            dX = model.backward(dyd) if chunks == 1 else model.backward(dyd, index=i)
+            outs.append(dX)
+            ev = torch.cuda.Event(); ev.record()
+            s_out.wait_event(ev)
+            with torch.cuda.stream(s_out):
+                dXh[lo:hi].copy_(dX, non_blocking=True)
         if world > 1:
             bucket.allreduce()
-        Yh.copy_(Y, non_blocking=True)
-        dXh.copy_(dX, non_blocking=True)
-        dWh.copy_(layer.gradients["W"], non_blocking=True)
-        dbh.copy_(layer.gradients["b"], non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        s_out.wait_event(ev)
+        with torch.cuda.stream(s_out):
+            gradh.copy_(bucket.flat, non_blocking=True)
+        cur.wait_stream(s_out)
+        return outs
 
     e2e_step()
     torch.cuda.synchronize()
@@ -328,8 +432,9 @@ def run_gpu(args, cfg):
     e2e_ms = D.all_reduce_max(f0.elapsed_time(f1))
     e2e = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
            "h2d_bytes_per_step": int(Xh.numel() * 4 + dYh.numel() * 4),
-           "d2h_bytes_per_step": int(Yh.numel() * esize + dXh.numel() * esize + dWh.numel() * 4 + dbh.numel() * 4),
-           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps}
+           "d2h_bytes_per_step": int(Yh.numel() * esize + dXh.numel() * esize + gradh.numel() * 4),
+           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "chunks": chunks,
+           "host_dtype_in": "f32", "host_dtype_out": "bf16" if mode == "bf16" else "f32"}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------------
     cpu = None
@@ -348,7 +453,7 @@ def run_gpu(args, cfg):
                            "parallelism": "dp{}".format(world), "tensor_cores": tc,
                            "l2": "inputs X + dLdy are {:.0f} MB per step (L2 is 126 MB); no explicit flush".format(
                                (Xd.numel() + dYd.numel()) * esize / 1e6)},
-                "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / pk["bf16_tflops_sustained"],
+                "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / (world * pk["bf16_tflops_sustained"]),
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     D.destroy()

@@ -61,8 +61,27 @@ SIGNATURES = {
 }
 
 _lib = None
-# when a list, the layers append (entry point, start event, end event) around every conv C-ABI call
+# when a list, the layers append (entry point, start event, end event) around every C-ABI call
 PROFILE = None
+
+
+class profiled(object):
+    """Context manager: CUDA events on the launching stream around one C-ABI call when PROFILE is a list."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            PROFILE.append((self.name, self.e0, self.e1))
+        return False
 
 
 def load():

@@ -50,6 +50,8 @@ class Affine(ActivationBase):                       # activations.py:342-381
     def __init__(self, slope=1, intercept=0):
         self.slope, self.intercept = slope, intercept
         self.p0, self.p1 = float(slope), float(intercept)
+        if self.p0 == 1.0 and self.p1 == 0.0:
+            self.code = 0     # Affine(1, 0) is the identity: the kernels skip the epilogue / write Y once
 
     def __str__(self):
         return "Affine(slope={}, intercept={})".format(self.slope, self.intercept)

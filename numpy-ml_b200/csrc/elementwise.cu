@@ -11,7 +11,25 @@ namespace {
 // ---- 4-wide typed access -----------------------------------------------------------------------
 template <int VEC>
 __device__ __forceinline__ void load_vec(const void* p, int dtype, int64_t i, float (&v)[VEC]) {
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 8) {        // 16-byte (bf16) / 2 x 16-byte (fp32) accesses
+    if (dtype == NPML_F32) {
+      const float4 t0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+      const float4 t1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i + 4);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    } else if (dtype == NPML_BF16) {
+      const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        v[2 * j] = __low2float(a); v[2 * j + 1] = __high2float(a);
+      }
+    } else {
+      const double* d = reinterpret_cast<const double*>(p) + i;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = (float)d[j];
+    }
+  } else if constexpr (VEC == 4) {
     if (dtype == NPML_F32) {
       const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
       v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -37,7 +55,24 @@ __device__ __forceinline__ void load_vec(const void* p, int dtype, int64_t i, fl
 
 template <int VEC>
 __device__ __forceinline__ void store_vec(void* p, int dtype, int64_t i, const float (&v)[VEC]) {
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 8) {
+    if (dtype == NPML_F32) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if (dtype == NPML_BF16) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&a);
+      }
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      double* d = reinterpret_cast<double*>(p) + i;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) d[j] = (double)v[j];
+    }
+  } else if constexpr (VEC == 4) {
     if (dtype == NPML_F32) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
     } else if (dtype == NPML_BF16) {
@@ -66,6 +101,9 @@ inline int dtype_size(int dt) { return dt == NPML_F32 ? 4 : (dt == NPML_BF16 ? 2
 inline bool aligned_for_vec4(const void* p, int dt) {
   return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (size_t)(4 * dtype_size(dt))) == 0;
 }
+inline bool aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// widest per-thread vector (elements): 8 when every tensor is 16-byte aligned and n % 8 == 0, else 4, else 1
+inline int pick_vec(int64_t n, bool ok4, bool ok16) { return (ok16 && n % 8 == 0) ? 8 : ((ok4 && n % 4 == 0) ? 4 : 1); }
 
 // ---- column-reduction skeleton ----------------------------------------------------------------------
 // A [rows][ch] tensor is cut into gridDim.x row slabs; block (TX, TY): thread (tx, ty) owns VEC
@@ -93,9 +131,13 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
   const int64_t r0 = (int64_t)blockIdx.x * cg.rows_per_block;
   const int64_t r1 = (r0 + cg.rows_per_block < cg.rows) ? r0 + cg.rows_per_block : cg.rows;
   if (active) {
+    // a thread keeps the same VEC channels for all of its rows: per-channel constants are loaded once
+    float kc[F::kConsts > 0 ? F::kConsts : 1][VEC];
+    f.template init<VEC>(c0, cg.ch, kc);
+#pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += cg.TY) {
       float out[NV > 0 ? NV : 1][VEC];
-      f.template run<VEC>(r * cg.ch + c0, c0, out);
+      f.template run<VEC>(r * cg.ch + c0, kc, out);
 #pragma unroll
       for (int a = 0; a < NV; ++a)
 #pragma unroll
@@ -148,15 +190,17 @@ struct ColPlan {
   size_t smem_elems;  // per NV
 };
 
-ColPlan plan_cols(int64_t rows, int ch, bool vec_ok) {
+ColPlan plan_cols(int64_t rows, int ch, int vec, bool reduce = true) {
   ColPlan p;
-  p.vec = (vec_ok && ch % 4 == 0) ? 4 : 1;
+  p.vec = vec;
   const int groups = (ch + p.vec - 1) / p.vec;
   int TX = 1;
   while (TX < groups && TX < 256) TX <<= 1;
   if (TX > 256) TX = 256;
   const int TY = 256 / TX;
-  int64_t nblk = 4LL * num_sms();
+  // passes that end in a block reduction keep the grid small (the reduction is a fixed cost per block) and get
+  // their memory-level parallelism from the unrolled row loop; pure elementwise passes use a larger grid
+  int64_t nblk = (reduce ? 4LL : 16LL) * num_sms();
   const int64_t min_rows = 4LL * TY;
   if (nblk * min_rows > rows) nblk = (rows + min_rows - 1) / min_rows;
   if (nblk < 1) nblk = 1;
@@ -175,7 +219,9 @@ ColPlan plan_cols(int64_t rows, int ch, bool vec_ok) {
 template <int NV, typename Acc, typename F>
 int launch_col_pass(const ColPlan& p, F f, Acc* part, cudaStream_t st) {
   const size_t smem = NV * p.smem_elems * sizeof(Acc);
-  if (p.vec == 4)
+  if (p.vec == 8)
+    col_pass_kernel<8, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
+  else if (p.vec == 4)
     col_pass_kernel<4, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
   else
     col_pass_kernel<1, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
@@ -191,12 +237,17 @@ int launch_col_final(const Acc* part, int nblk, int width, double* sums, cudaStr
 }
 
 // ---- functors -----------------------------------------------------------------------------------
+// Functor protocol: kConsts per-channel constants are fetched once per thread by init(c0, ch, kc); run(i, kc, out)
+// handles the VEC elements at flat index i and returns the NV values to be column-summed.
 struct DzPrepF {
+  static constexpr int kConsts = 0;
   const void* dY; const void* Z; void* dZ;
   int dy_dt, z_dt, dz_dt, act;
   float p0, p1;
   template <int VEC>
-  __device__ __forceinline__ void run(int64_t i, int /*c0*/, float (&out)[1][VEC]) const {
+  __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[1][VEC]) const {
     float g[VEC], z[VEC];
     load_vec<VEC>(dY, dy_dt, i, g);
     if (act != NPML_ACT_IDENTITY) {
@@ -216,9 +267,12 @@ struct DzPrepF {
 };
 
 struct BnStatsF {
+  static constexpr int kConsts = 0;
   const void* x; int dt;
   template <int VEC>
-  __device__ __forceinline__ void run(int64_t i, int, float (&out)[2][VEC]) const {
+  __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[2][VEC]) const {
     float v[VEC];
     load_vec<VEC>(x, dt, i, v);
 #pragma unroll
@@ -226,51 +280,74 @@ struct BnStatsF {
   }
 };
 
+// y = a*(x - mean) + h with a = scaler*rstd (coef: [3][ch] = mean, a, h, written by the finalize kernels)
 struct BnNormF {
+  static constexpr int kConsts = 3;
   const void* x; void* y; int dt;
-  const float* mean; const float* rstd; const float* g; const float* h;
+  const float* coef;
   template <int VEC>
-  __device__ __forceinline__ void run(int64_t i, int c0, float (&)[1][VEC]) const {
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[3][VEC]) const {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
+  }
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, const float (&kc)[3][VEC], float (&)[1][VEC]) const {
     float v[VEC];
     load_vec<VEC>(x, dt, i, v);
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) v[j] = g[c0 + j] * ((v[j] - mean[c0 + j]) * rstd[c0 + j]) + h[c0 + j];
+    for (int j = 0; j < VEC; ++j) v[j] = fmaf(kc[1][j], v[j] - kc[0][j], kc[2][j]);
     store_vec<VEC>(y, dt, i, v);
   }
 };
 
 struct BnBwdStatsF {
+  static constexpr int kConsts = 2;
   const void* dy; const void* x; int dt;
   const float* mean; const float* rstd;
   template <int VEC>
-  __device__ __forceinline__ void run(int64_t i, int c0, float (&out)[2][VEC]) const {
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[2][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = c0 + j < ch ? c0 + j : ch - 1;
+      kc[0][j] = mean[c]; kc[1][j] = rstd[c];
+    }
+  }
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, const float (&kc)[2][VEC], float (&out)[2][VEC]) const {
     float d[VEC], v[VEC];
     load_vec<VEC>(dy, dt, i, d);
     load_vec<VEC>(x, dt, i, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       out[0][j] = d[j];
-      out[1][j] = d[j] * ((v[j] - mean[c0 + j]) * rstd[c0 + j]);
+      out[1][j] = d[j] * ((v[j] - kc[0][j]) * kc[1][j]);
     }
   }
 };
 
+// dx = g*rstd*(dy - m1 - nhat*m2), nhat = (x - mean)*rstd; coef: [5][ch] = mean, rstd, g*rstd, m1, m2
 struct BnBwdDxF {
+  static constexpr int kConsts = 5;
   const void* dy; const void* x; void* dx; int dt;
-  const float* mean; const float* rstd; const float* g;
-  const double* sums;  // [2][ch]: sum dy, sum dy*nhat
-  double inv_m; int ch;
+  const float* coef;
   template <int VEC>
-  __device__ __forceinline__ void run(int64_t i, int c0, float (&)[1][VEC]) const {
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[5][VEC]) const {
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
+  }
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, const float (&kc)[5][VEC], float (&)[1][VEC]) const {
     float d[VEC], v[VEC];
     load_vec<VEC>(dy, dt, i, d);
     load_vec<VEC>(x, dt, i, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const int c = c0 + j;
-      const float nh = (v[j] - mean[c]) * rstd[c];
-      const float m1 = (float)(sums[c] * inv_m), m2 = (float)(sums[ch + c] * inv_m);
-      v[j] = g[c] * rstd[c] * (d[j] - m1 - nh * m2);
+      const float nh = (v[j] - kc[0][j]) * kc[1][j];
+      v[j] = kc[2][j] * (d[j] - kc[3][j] - nh * kc[4][j]);
     }
     store_vec<VEC>(dx, dt, i, v);
   }
@@ -282,7 +359,8 @@ __global__ void db_finalize_kernel(const double* sums, int ch, int accumulate, f
 }
 
 __global__ void bn_finalize_kernel(const double* sums, int ch, double inv_m, float momentum, float eps,
-                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd) {
+                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd,
+                                   const float* scaler, const float* intercept, float* coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ch) return;
   const double mean = sums[c] * inv_m;
@@ -290,25 +368,40 @@ __global__ void bn_finalize_kernel(const double* sums, int ch, double inv_m, flo
   if (var < 0.0) var = 0.0;
   running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
   running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * var);
+  const float rs = (float)(1.0 / sqrt(var + (double)eps));
   save_mean[c] = (float)mean;
-  save_rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  save_rstd[c] = rs;
+  coef[c] = (float)mean;
+  coef[ch + c] = scaler[c] * rs;
+  coef[2 * ch + c] = intercept[c];
 }
 
 __global__ void bn_running_to_saved_kernel(int ch, float eps, const float* running_mean, const float* running_var,
-                                           float* save_mean, float* save_rstd) {
+                                           float* save_mean, float* save_rstd, const float* scaler,
+                                           const float* intercept, float* coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ch) return;
+  const float rs = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
   save_mean[c] = running_mean[c];
-  save_rstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  save_rstd[c] = rs;
+  coef[c] = running_mean[c];
+  coef[ch + c] = scaler[c] * rs;
+  coef[2 * ch + c] = intercept[c];
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* sums, int ch, int accumulate, float* d_scaler,
-                                       float* d_intercept) {
+                                       float* d_intercept, double inv_m, const float* mean, const float* rstd,
+                                       const float* scaler, float* coef) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ch) return;
   const float di = (float)sums[c], ds = (float)sums[ch + c];
-  d_intercept[c] = accumulate ? d_intercept[c] + di : di;
-  d_scaler[c] = accumulate ? d_scaler[c] + ds : ds;
+  if (d_intercept) d_intercept[c] = accumulate ? d_intercept[c] + di : di;
+  if (d_scaler) d_scaler[c] = accumulate ? d_scaler[c] + ds : ds;
+  coef[c] = mean[c];
+  coef[ch + c] = rstd[c];
+  coef[2 * ch + c] = scaler[c] * rstd[c];
+  coef[3 * ch + c] = (float)(sums[c] * inv_m);
+  coef[4 * ch + c] = (float)(sums[ch + c] * inv_m);
 }
 
 // ---- flat elementwise ------------------------------------------------------------------------------
@@ -369,9 +462,12 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 }
 
 struct SumSqF {
+  static constexpr int kConsts = 0;
   const float* x;
   template <int VEC>
-  __device__ __forceinline__ void run(int64_t i, int, float (&out)[1][VEC]) const {
+  __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
+  template <int VEC>
+  __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[1][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) out[0][j] = x[i + j] * x[i + j];
   }
@@ -427,8 +523,9 @@ __global__ void col2im_kernel(npml_conv_desc d, const float* __restrict__ Xc, fl
 }  // namespace
 
 size_t colpass_ws_bytes(int64_t rows, int ch, int nv) {
-  ColPlan p = plan_cols(rows, ch, true);
-  return align_up((size_t)p.grid.x * nv * ch * sizeof(double), 256) + align_up((size_t)nv * ch * sizeof(double), 256);
+  ColPlan p = plan_cols(rows, ch, 1);     // vec = 1 gives the largest grid.x any plan for this shape can have
+  return align_up((size_t)p.grid.x * nv * ch * sizeof(double), 256) + align_up((size_t)nv * ch * sizeof(double), 256) +
+         align_up((size_t)5 * ch * sizeof(float), 256);   // partials, sums, per-channel coefficient table
 }
 
 }  // namespace npml
@@ -443,7 +540,7 @@ extern "C" int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, flo
   NPML_CHECK(dY != nullptr, "dY is NULL");
   NPML_CHECK(act == NPML_ACT_IDENTITY || Z != nullptr, "Z is required for a non-identity activation");
   const bool vec_ok = aligned_for_vec4(dY, dy_dtype) && aligned_for_vec4(Z, z_dtype) && aligned_for_vec4(dZ, dz_dtype);
-  ColPlan p = plan_cols(rows, ch, vec_ok);
+  ColPlan p = plan_cols(rows, ch, pick_vec(ch, vec_ok, aligned16(dY) && aligned16(Z) && aligned16(dZ)), db != nullptr);
   DzPrepF f{dY, Z, dZ, dy_dtype, z_dtype, dz_dtype, act, p0, p1};
   if (!db) return launch_col_pass<1, float>(p, f, (float*)nullptr, st);
   const size_t part_bytes = align_up((size_t)p.grid.x * ch * sizeof(float), 256);
@@ -460,7 +557,11 @@ extern "C" int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, flo
 extern "C" int npml_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) return 0;
-  if (n % 4 == 0 && aligned_for_vec4(src, src_dtype) && aligned_for_vec4(dst, dst_dtype))
+  const int vec = pick_vec(n, aligned_for_vec4(src, src_dtype) && aligned_for_vec4(dst, dst_dtype),
+                           aligned16(src) && aligned16(dst));
+  if (vec == 8)
+    cast_kernel<8><<<flat_blocks(n / 8), 256, 0, st>>>(src, src_dtype, dst, dst_dtype, n / 8);
+  else if (vec == 4)
     cast_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(src, src_dtype, dst, dst_dtype, n / 4);
   else
     cast_kernel<1><<<flat_blocks(n), 256, 0, st>>>(src, src_dtype, dst, dst_dtype, n);
@@ -480,7 +581,12 @@ extern "C" int npml_add_act_fwd(int32_t n_in, const void* const* xs, int32_t dty
     a.xs[i] = xs[i];
     al = al && aligned_for_vec4(xs[i], dtype);
   }
-  if (n % 4 == 0 && al)
+  bool al16 = aligned16(sum) && aligned16(Y);
+  for (int i = 0; i < n_in; ++i) al16 = al16 && aligned16(xs[i]);
+  const int vec = pick_vec(n, al, al16);
+  if (vec == 8)
+    add_act_kernel<8><<<flat_blocks(n / 8), 256, 0, st>>>(a, dtype, n / 8, act, p0, p1, sum, Y);
+  else if (vec == 4)
     add_act_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, sum, Y);
   else
     add_act_kernel<1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, sum, Y);
@@ -502,25 +608,28 @@ extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, i
   if (rows <= 0 || ch <= 0) return 0;
   NPML_CHECK(save_mean && save_rstd, "save_mean/save_rstd are required");
   const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(y, dtype);
-  ColPlan p = plan_cols(rows, ch, vec_ok);
+  const int vec = pick_vec(ch, vec_ok, aligned16(x) && aligned16(y));
+  ColPlan p = plan_cols(rows, ch, vec, true);
+  const size_t part_bytes = align_up((size_t)p.grid.x * 2 * ch * sizeof(double), 256);
+  const size_t sums_bytes = align_up((size_t)2 * ch * sizeof(double), 256);
+  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + sums_bytes + (size_t)3 * ch * sizeof(float), "workspace too small");
+  double* part = (double*)ws;
+  double* sums = (double*)((char*)ws + part_bytes);
+  float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   if (use_batch_stats) {
-    const size_t part_bytes = align_up((size_t)p.grid.x * 2 * ch * sizeof(double), 256);
-    NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)2 * ch * sizeof(double), "workspace too small");
-    double* part = (double*)ws;
-    double* sums = (double*)((char*)ws + part_bytes);
     BnStatsF fs{x, dtype};
     if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
     if (int e = launch_col_final<double>(part, (int)p.grid.x, 2 * ch, sums, st)) return e;
     bn_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, 1.0 / (double)rows, momentum, eps, running_mean,
-                                                         running_var, save_mean, save_rstd);
+                                                         running_var, save_mean, save_rstd, scaler, intercept, coef);
     NPML_LAUNCH_OK();
   } else {
     bn_running_to_saved_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, eps, running_mean, running_var, save_mean,
-                                                                 save_rstd);
+                                                                 save_rstd, scaler, intercept, coef);
     NPML_LAUNCH_OK();
   }
-  BnNormF fn{x, y, dtype, save_mean, save_rstd, scaler, intercept};
-  return launch_col_pass<0, float>(p, fn, (float*)nullptr, st);
+  BnNormF fn{x, y, dtype, coef};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fn, (float*)nullptr, st);
 }
 
 extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const void* x, void* dx, int32_t dtype,
@@ -529,20 +638,22 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   cudaStream_t st = (cudaStream_t)stream;
   if (rows <= 0 || ch <= 0) return 0;
   const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(dy, dtype) && aligned_for_vec4(dx, dtype);
-  ColPlan p = plan_cols(rows, ch, vec_ok);
+  const int vec = pick_vec(ch, vec_ok, aligned16(x) && aligned16(dy) && aligned16(dx));
+  ColPlan p = plan_cols(rows, ch, vec, true);
   const size_t part_bytes = align_up((size_t)p.grid.x * 2 * ch * sizeof(double), 256);
-  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)2 * ch * sizeof(double), "workspace too small");
+  const size_t sums_bytes = align_up((size_t)2 * ch * sizeof(double), 256);
+  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + sums_bytes + (size_t)5 * ch * sizeof(float), "workspace too small");
   double* part = (double*)ws;
   double* sums = (double*)((char*)ws + part_bytes);
+  float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
   if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
   if (int e = launch_col_final<double>(part, (int)p.grid.x, 2 * ch, sums, st)) return e;
-  if (d_scaler && d_intercept) {
-    bn_bwd_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, accumulate, d_scaler, d_intercept);
-    NPML_LAUNCH_OK();
-  }
-  BnBwdDxF fd{dy, x, dx, dtype, save_mean, save_rstd, scaler, sums, 1.0 / (double)rows, ch};
-  return launch_col_pass<0, float>(p, fd, (float*)nullptr, st);
+  bn_bwd_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, accumulate, d_scaler, d_intercept, 1.0 / (double)rows,
+                                                           save_mean, save_rstd, scaler, coef);
+  NPML_LAUNCH_OK();
+  BnBwdDxF fd{dy, x, dx, dtype, coef};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st);
 }
 
 extern "C" int npml_im2col(const npml_conv_desc* d, const float* X, float* X_col, void* stream) {
@@ -573,7 +684,7 @@ extern "C" int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws
   cudaStream_t st = (cudaStream_t)stream;
   NPML_CHECK(n > 0 && out, "bad arguments");
   // view the buffer as [n][1]: one column, reduced over rows in a fixed order
-  ColPlan p = plan_cols(n, 1, false);
+  ColPlan p = plan_cols(n, 1, 1);
   const size_t part_bytes = align_up((size_t)p.grid.x * sizeof(double), 256);
   NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes, "workspace too small");
   SumSqF f{buf};

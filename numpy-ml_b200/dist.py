@@ -65,9 +65,16 @@ def shard_batch(n_ex, world=None, r=None):
 
 class GradBucket(object):
     """One flat fp32 buffer holding every gradient of a set of layers; the layers' `gradients` entries
-    become views into it, so kernels accumulate straight into the bucket and one all-reduce covers all."""
+    become views into it, so kernels accumulate straight into the bucket.
 
-    def __init__(self, layers):
+    overlap=False: `allreduce()` sums the whole bucket over ranks with ONE call on the current stream.
+    overlap=True : every Conv2D / Deconv2D layer of the bucket announces its dW / db as soon as its wgrad
+        kernel is enqueued (layers._ConvBase._bwd computes parameter gradients before dX); that layer's slice is
+        all-reduced on a side stream while dX is still being computed, and `allreduce()` only reduces what is
+        left (BatchNorm gradients) and joins the side stream.  Valid when there is ONE backward per step
+        (gradients that keep accumulating over several backward calls must use overlap=False)."""
+
+    def __init__(self, layers, overlap=False):
         self.layers = list(layers)
         entries = []
         for l in self.layers:
@@ -76,23 +83,53 @@ class GradBucket(object):
         total = sum(g.numel() for _, _, g in entries)
         dev = entries[0][2].device if entries else "cpu"
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slices = {}           # id(layer) -> (offset, numel) of its contiguous run in the bucket
         off = 0
         for l, k, g in entries:
             view = self.flat[off:off + g.numel()].view(g.shape)
             view.copy_(g)
             l.gradients[k] = view
+            o0, n0 = self.slices.get(id(l), (off, 0))
+            self.slices[id(l)] = (o0, n0 + g.numel())
             off += g.numel()
+        self.overlap = bool(overlap) and _state["world"] > 1 and self.flat.is_cuda
+        self._done = set()
+        self._side = torch.cuda.Stream() if self.overlap else None
+        if self.overlap:
+            for l in self.layers:
+                if hasattr(l, "_bwd") and hasattr(l, "kernel_shape"):
+                    l._grads_ready_hook = self._on_ready
 
-    def allreduce(self):
-        """SUM over ranks, in place, on the current stream."""
-        if _state["world"] == 1:
-            return self.flat
+    def _reduce(self, off, n):
+        buf = self.flat[off:off + n]
         if _state["backend"] == "nccl":
-            L.check(L.load().npml_allreduce_sum_f32(L.ptr(self.flat), self.flat.numel(), L.stream()),
-                    "npml_allreduce_sum_f32")
+            L.check(L.load().npml_allreduce_sum_f32(L.ptr(buf), n, L.stream()), "npml_allreduce_sum_f32")
         else:
             import torch.distributed as dist
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+
+    def _on_ready(self, layer):
+        """dW / db of `layer` are enqueued on the current stream: reduce that slice on the side stream."""
+        off, n = self.slices[id(layer)]
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            self._reduce(off, n)
+        self._done.add(id(layer))
+
+    def allreduce(self):
+        """SUM over ranks, in place; on return the current stream is ordered after every reduction."""
+        if _state["world"] == 1:
+            return self.flat
+        if not self.overlap:
+            self._reduce(0, self.flat.numel())
+            return self.flat
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            for l in self.layers:
+                if id(l) not in self._done:
+                    self._reduce(*self.slices[id(l)])
+        torch.cuda.current_stream().wait_stream(self._side)
+        self._done = set()
         return self.flat
 
 

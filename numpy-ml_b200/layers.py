@@ -153,10 +153,11 @@ def _dz_prep(dY, Z, act, out_dtype, db=None, accumulate=True):
         d = U.make_desc(1, 1, 1, 1, ch, 1, 1, 1, 1, (0, 0, 0, 0), 1, 1)
         d.N, d.OH, d.OW = 1, 1, int(rows)
         ws = L.workspace(lib.npml_workspace_bytes(d, L.OP_DZ_PREP))
-    L.check(lib.npml_dz_prep(rows, ch, act.code, act.p0, act.p1, L.ptr(dY), L.code_of(dY),
-                             None if identity else L.ptr(Z), 0 if identity else L.code_of(Z), L.ptr(dZ),
-                             L.code_of(dZ), L.ptr(db), 1 if accumulate else 0, L.ptr(ws),
-                             0 if ws is None else ws.numel(), L.stream()), "npml_dz_prep")
+    with L.profiled("npml_dz_prep"):
+        L.check(lib.npml_dz_prep(rows, ch, act.code, act.p0, act.p1, L.ptr(dY), L.code_of(dY),
+                                 None if identity else L.ptr(Z), 0 if identity else L.code_of(Z), L.ptr(dZ),
+                                 L.code_of(dZ), L.ptr(db), 1 if accumulate else 0, L.ptr(ws),
+                                 0 if ws is None else ws.numel(), L.stream()), "npml_dz_prep")
     return dZ
 
 
@@ -188,14 +189,8 @@ class _ConvBase(LayerBase):
     def _call(self, name, d, op, *args):
         lib = L.load()
         ws = L.workspace(lib.npml_workspace_bytes(d, op))
-        prof = L.PROFILE
-        if prof is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        L.check(getattr(lib, name)(d, *args, L.ptr(ws), ws.numel(), L.stream()), name)
-        if prof is not None:
-            e1.record()
-            prof.append((name, e0, e1))
+        with L.profiled(name):
+            L.check(getattr(lib, name)(d, *args, L.ptr(ws), ws.numel(), L.stream()), name)
 
     def _uses_tc(self, X_shape=None):
         """True if the forward of this layer runs on the tcgen05 kernels for the last (or given) input shape."""
@@ -228,10 +223,16 @@ class _ConvBase(LayerBase):
             self.derived_variables["out_cols"].append(d.OW)
         return L.to_numpy(Y) if as_np else Y
 
-    def backward(self, dLdy, retain_grads=True):
+    def backward(self, dLdy, retain_grads=True, index=None):
         """dX for every retained forward; dW / db accumulate into `gradients`
-        (layers.py:3048-3116 / 3480-3568)."""
+        (layers.py:3048-3116 / 3480-3568).  `index` (an extension) runs the backward of ONE retained forward,
+        so that a pipelined caller can interleave the chunks of a batch with their host copies."""
         assert self.trainable, "Layer is frozen"
+        if index is not None:
+            as_np = isinstance(dLdy, np.ndarray)
+            dx = self._bwd(L.to_device(dLdy, L.torch_dtype(self.mode)), self.X[index],
+                           self.derived_variables["Z"][index], retain_grads)
+            return L.to_numpy(dx) if as_np else dx
         if not isinstance(dLdy, list):
             dLdy = [dLdy]
         dX = []
@@ -248,13 +249,18 @@ class _ConvBase(LayerBase):
         # Conv2D: db is one more accumulator row of the wgrad pass; Deconv2D: db comes with the dZ prologue
         dZ = _dz_prep(dLdy, Z, self.act_fn, X.dtype, self.gradients["b"] if (retain_grads and not conv) else None)
         d = self._desc(tuple(X.shape), accumulate=1)
-        dX = torch.empty_like(X)
-        self._call(pre + "dgrad", d, self._ops[1], L.ptr(dZ), L.ptr(W), L.ptr(dX))
+        # parameter gradients first (the reference's order, layers.py:3106-3114): a data-parallel bucket can then
+        # all-reduce dW / db on its own stream while dX is still being computed (dist.GradBucket, overlap=True)
         if retain_grads and conv:
             self._call("npml_conv2d_wgrad_db", d, self._ops[2], L.ptr(X), L.ptr(dZ), L.ptr(self.gradients["W"]),
                        L.ptr(self.gradients["b"]))
         elif retain_grads:
             self._call(pre + "wgrad", d, self._ops[2], L.ptr(X), L.ptr(dZ), L.ptr(self.gradients["W"]))
+        hook = getattr(self, "_grads_ready_hook", None)
+        if retain_grads and hook is not None:
+            hook(self)
+        dX = torch.empty_like(X)
+        self._call(pre + "dgrad", d, self._ops[1], L.ptr(dZ), L.ptr(W), L.ptr(dX))
         return dX
 
 
@@ -384,10 +390,11 @@ class BatchNorm2D(LayerBase):
         rstd = torch.empty(ch, dtype=torch.float32, device=Xd.device)
         use_batch = 1 if (self.trainable and retain_derived) else 0
         ws = self._ws(rows, ch)
-        L.check(L.load().npml_bn2d_fwd(rows, ch, L.ptr(Xd), L.ptr(y), L.code_of(Xd), L.ptr(P["scaler"]),
-                                       L.ptr(P["intercept"]), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
-                                       float(self.momentum), float(self.epsilon), use_batch, L.ptr(mean),
-                                       L.ptr(rstd), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_fwd")
+        with L.profiled("npml_bn2d_fwd"):
+            L.check(L.load().npml_bn2d_fwd(rows, ch, L.ptr(Xd), L.ptr(y), L.code_of(Xd), L.ptr(P["scaler"]),
+                                           L.ptr(P["intercept"]), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
+                                           float(self.momentum), float(self.epsilon), use_batch, L.ptr(mean),
+                                           L.ptr(rstd), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_fwd")
         if retain_derived:
             self.X.append(Xd)
             self._saved.append((mean, rstd) if use_batch else None)
@@ -428,11 +435,12 @@ class BatchNorm2D(LayerBase):
         dX = torch.empty_like(X)
         ws = self._ws(rows, ch)
         G = self.gradients
-        L.check(L.load().npml_bn2d_bwd(rows, ch, L.ptr(dLdy), L.ptr(X), L.ptr(dX), L.code_of(X),
-                                       L.ptr(_as_param(P["scaler"])), L.ptr(mean), L.ptr(rstd),
-                                       L.ptr(G["scaler"]) if retain_grads else None,
-                                       L.ptr(G["intercept"]) if retain_grads else None, 1, L.ptr(ws), ws.numel(),
-                                       L.stream()), "npml_bn2d_bwd")
+        with L.profiled("npml_bn2d_bwd"):
+            L.check(L.load().npml_bn2d_bwd(rows, ch, L.ptr(dLdy), L.ptr(X), L.ptr(dX), L.code_of(X),
+                                           L.ptr(_as_param(P["scaler"])), L.ptr(mean), L.ptr(rstd),
+                                           L.ptr(G["scaler"]) if retain_grads else None,
+                                           L.ptr(G["intercept"]) if retain_grads else None, 1, L.ptr(ws), ws.numel(),
+                                           L.stream()), "npml_bn2d_bwd")
         return dX
 
 
@@ -463,8 +471,9 @@ class Add(LayerBase):
         Y = total if self.act_fn.code == 0 else torch.empty_like(total)
         arr = (C.c_void_p * len(Xd))(*[x.data_ptr() for x in Xd])
         a = self.act_fn
-        L.check(L.load().npml_add_act_fwd(len(Xd), arr, L.code_of(total), n, a.code, a.p0, a.p1, L.ptr(total),
-                                          None if Y is total else L.ptr(Y), L.stream()), "npml_add_act_fwd")
+        with L.profiled("npml_add_act_fwd"):
+            L.check(L.load().npml_add_act_fwd(len(Xd), arr, L.code_of(total), n, a.code, a.p0, a.p1, L.ptr(total),
+                                              None if Y is total else L.ptr(Y), L.stream()), "npml_add_act_fwd")
         if retain_derived:
             self.X.append(Xd)
             self.derived_variables["sum"].append(total)

@@ -18,8 +18,9 @@ def _device_add(a, b):
     """a + b through npml_add_act_fwd (new tensor)."""
     out = torch.empty_like(a)
     arr = (C.c_void_p * 2)(a.data_ptr(), b.data_ptr())
-    L.check(L.load().npml_add_act_fwd(2, arr, L.code_of(a), a.numel(), 0, 0.0, 0.0, L.ptr(out), None, L.stream()),
-            "npml_add_act_fwd")
+    with L.profiled("npml_add_act_fwd"):
+        L.check(L.load().npml_add_act_fwd(2, arr, L.code_of(a), a.numel(), 0, 0.0, 0.0, L.ptr(out), None, L.stream()),
+                "npml_add_act_fwd")
     return out
 
 
