@@ -204,28 +204,37 @@ __global__ void __launch_bounds__(NT) wgrad_partial_kernel(GatherWgrad g, const 
 
 }  // namespace
 
-// Fixed-order reduction of split partials [splits][M][CO] -> dW (strided), shared with tc_wgrad.
+// Fixed-order reduction of split partials [splits][M][CO] -> dW (strided), shared with the tensor-core wgrad
+// kernels.  When part_db != nullptr the same launch also reduces [splits][CO] -> db.
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int M, int CO, int CI,
                                     int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
-                                    float* __restrict__ dW) {
+                                    float* __restrict__ dW, const float* __restrict__ part_db, float* __restrict__ db) {
   const int64_t total = (int64_t)M * CO;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+  const int64_t total_all = total + (part_db != nullptr ? CO : 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_all;
        i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + i];
-    const int m = (int)(i / CO), co = (int)(i - (int64_t)m * CO);
-    const int tap = m / CI, ci = m - tap * CI;
-    const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
-    dW[o] = accumulate ? dW[o] + s : s;
+    if (i < total) {
+      for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + i];
+      const int m = (int)(i / CO), co = (int)(i - (int64_t)m * CO);
+      const int tap = m / CI, ci = m - tap * CI;
+      const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
+      dW[o] = accumulate ? dW[o] + s : s;
+    } else {
+      const int co = (int)(i - total);
+      for (int z = 0; z < splits; ++z) s += part_db[(int64_t)z * CO + co];
+      db[co] = accumulate ? db[co] + s : s;
+    }
   }
 }
 
 int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
-                        int64_t o_co, int accumulate, float* dW, cudaStream_t st) {
-  const int64_t total = (int64_t)M * CO;
+                        int64_t o_co, int accumulate, float* dW, cudaStream_t st, const float* part_db = nullptr,
+                        float* db = nullptr) {
+  const int64_t total = (int64_t)M * CO + (part_db != nullptr ? CO : 0);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW, part_db, db);
   NPML_LAUNCH_OK();
   return 0;
 }

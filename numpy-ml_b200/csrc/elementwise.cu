@@ -123,11 +123,13 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
   const int tx = threadIdx.x % cg.TX, ty = threadIdx.x / cg.TX;
   const int c0 = (blockIdx.y * cg.TX + tx) * VEC;
   const bool active = ty < cg.TY && c0 < cg.ch;
-  Acc acc[NV > 0 ? NV : 1][VEC];
+  // per-thread partial sums stay in fp32 (a thread adds at most rows_per_block / TY ~ tens of terms); the block
+  // and grid levels of the reduction run in Acc
+  float acc[NV > 0 ? NV : 1][VEC];
 #pragma unroll
   for (int a = 0; a < NV; ++a)
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[a][j] = (Acc)0;
+    for (int j = 0; j < VEC; ++j) acc[a][j] = 0.f;
   const int64_t r0 = (int64_t)blockIdx.x * cg.rows_per_block;
   const int64_t r1 = (r0 + cg.rows_per_block < cg.rows) ? r0 + cg.rows_per_block : cg.rows;
   if (active) {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
 #pragma unroll
       for (int a = 0; a < NV; ++a)
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[a][j] += (Acc)out[a][j];
+        for (int j = 0; j < VEC; ++j) acc[a][j] += out[a][j];
     }
   }
   if (NV == 0 || part == nullptr) return;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
 #pragma unroll
     for (int a = 0; a < NV; ++a)
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) red[ty * W + (a * cg.TX + tx) * VEC + j] = active ? acc[a][j] : (Acc)0;
+      for (int j = 0; j < VEC; ++j) red[ty * W + (a * cg.TX + tx) * VEC + j] = active ? (Acc)acc[a][j] : (Acc)0;
   }
   __syncthreads();
   if (ty == 0 && c0 < cg.ch) {
@@ -163,6 +165,23 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
         if (c0 + j < cg.ch) part[((int64_t)blockIdx.x * NV + a) * cg.ch + c0 + j] = s;
       }
   }
+}
+
+// Fixed-order sum of column `c` over the `nblk` partial rows, for a (32, 32) thread block: thread (cx, sy) adds
+// rows sy, sy + 32, ...; the 32 row-lanes are then added in order by every thread of the column (deterministic).
+template <typename Acc>
+__device__ __forceinline__ double block_col_sum(const Acc* __restrict__ part, int nblk, int width, int c, bool ok,
+                                                double (*red)[33]) {
+  const int cx = threadIdx.x, sy = threadIdx.y;
+  double s = 0.0;
+  if (ok)
+    for (int b = sy; b < nblk; b += 32) s += (double)part[(int64_t)b * width + c];
+  __syncthreads();
+  red[sy][cx] = s;
+  __syncthreads();
+  double t = 0.0;
+  for (int y = 0; y < 32; ++y) t += red[y][cx];
+  return t;
 }
 
 // sums[NV*ch] (double) = fixed-order sum over `nblk` partial rows
@@ -200,7 +219,7 @@ ColPlan plan_cols(int64_t rows, int ch, int vec, bool reduce = true) {
   const int TY = 256 / TX;
   // passes that end in a block reduction keep the grid small (the reduction is a fixed cost per block) and get
   // their memory-level parallelism from the unrolled row loop; pure elementwise passes use a larger grid
-  int64_t nblk = (reduce ? 4LL : 16LL) * num_sms();
+  int64_t nblk = (reduce ? 4LL : 8LL) * num_sms();
   const int64_t min_rows = 4LL * TY;
   if (nblk * min_rows > rows) nblk = (rows + min_rows - 1) / min_rows;
   if (nblk < 1) nblk = 1;
@@ -353,18 +372,24 @@ struct BnBwdDxF {
   }
 };
 
-__global__ void db_finalize_kernel(const double* sums, int ch, int accumulate, float* db) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < ch) db[c] = accumulate ? db[c] + (float)sums[c] : (float)sums[c];
+// grid = ceil(ch / 32), block = (32, 32): column reduction of the partials + the per-channel finalize in one launch
+__global__ void db_finalize_kernel(const float* __restrict__ part, int nblk, int ch, int accumulate, float* db) {
+  __shared__ double red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const double s = block_col_sum<float>(part, nblk, ch, c, c < ch, red);
+  if (threadIdx.y == 0 && c < ch) db[c] = accumulate ? db[c] + (float)s : (float)s;
 }
 
-__global__ void bn_finalize_kernel(const double* sums, int ch, double inv_m, float momentum, float eps,
-                                   float* running_mean, float* running_var, float* save_mean, float* save_rstd,
-                                   const float* scaler, const float* intercept, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ch) return;
-  const double mean = sums[c] * inv_m;
-  double var = sums[ch + c] * inv_m - mean * mean;  // biased (layers/layers.py:1147)
+__global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, int ch, double inv_m, float momentum,
+                                   float eps, float* running_mean, float* running_var, float* save_mean,
+                                   float* save_rstd, const float* scaler, const float* intercept, float* coef) {
+  __shared__ double red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const double s1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
+  const double s2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+  if (threadIdx.y != 0 || c >= ch) return;
+  const double mean = s1 * inv_m;
+  double var = s2 * inv_m - mean * mean;  // biased (layers/layers.py:1147)
   if (var < 0.0) var = 0.0;
   running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
   running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * var);
@@ -389,19 +414,22 @@ __global__ void bn_running_to_saved_kernel(int ch, float eps, const float* runni
   coef[2 * ch + c] = intercept[c];
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* sums, int ch, int accumulate, float* d_scaler,
-                                       float* d_intercept, double inv_m, const float* mean, const float* rstd,
-                                       const float* scaler, float* coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ch) return;
-  const float di = (float)sums[c], ds = (float)sums[ch + c];
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, int ch, int accumulate,
+                                       float* d_scaler, float* d_intercept, double inv_m, const float* mean,
+                                       const float* rstd, const float* scaler, float* coef) {
+  __shared__ double red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const double s1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
+  const double s2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+  if (threadIdx.y != 0 || c >= ch) return;
+  const float di = (float)s1, ds = (float)s2;
   if (d_intercept) d_intercept[c] = accumulate ? d_intercept[c] + di : di;
   if (d_scaler) d_scaler[c] = accumulate ? d_scaler[c] + ds : ds;
   coef[c] = mean[c];
   coef[ch + c] = rstd[c];
   coef[2 * ch + c] = scaler[c] * rstd[c];
-  coef[3 * ch + c] = (float)(sums[c] * inv_m);
-  coef[4 * ch + c] = (float)(sums[ch + c] * inv_m);
+  coef[3 * ch + c] = (float)(s1 * inv_m);
+  coef[4 * ch + c] = (float)(s2 * inv_m);
 }
 
 // ---- flat elementwise ------------------------------------------------------------------------------
@@ -546,10 +574,8 @@ extern "C" int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, flo
   const size_t part_bytes = align_up((size_t)p.grid.x * ch * sizeof(float), 256);
   NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)ch * sizeof(double), "workspace too small");
   float* part = (float*)ws;
-  double* sums = (double*)((char*)ws + part_bytes);
   if (int e = launch_col_pass<1, float>(p, f, part, st)) return e;
-  if (int e = launch_col_final<float>(part, (int)p.grid.x, ch, sums, st)) return e;
-  db_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, accumulate, db);
+  db_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, db);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -619,9 +645,9 @@ extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, i
   if (use_batch_stats) {
     BnStatsF fs{x, dtype};
     if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
-    if (int e = launch_col_final<double>(part, (int)p.grid.x, 2 * ch, sums, st)) return e;
-    bn_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, 1.0 / (double)rows, momentum, eps, running_mean,
-                                                         running_var, save_mean, save_rstd, scaler, intercept, coef);
+    bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, 1.0 / (double)rows, momentum, eps,
+                                                                running_mean, running_var, save_mean, save_rstd, scaler,
+                                                                intercept, coef);
     NPML_LAUNCH_OK();
   } else {
     bn_running_to_saved_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, eps, running_mean, running_var, save_mean,
@@ -648,9 +674,8 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
   if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
-  if (int e = launch_col_final<double>(part, (int)p.grid.x, 2 * ch, sums, st)) return e;
-  bn_bwd_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(sums, ch, accumulate, d_scaler, d_intercept, 1.0 / (double)rows,
-                                                           save_mean, save_rstd, scaler, coef);
+  bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
+                                                                  1.0 / (double)rows, save_mean, save_rstd, scaler, coef);
   NPML_LAUNCH_OK();
   BnBwdDxF fd{dy, x, dx, dtype, coef};
   return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st);

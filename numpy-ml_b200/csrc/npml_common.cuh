@@ -88,6 +88,27 @@ __device__ __forceinline__ float act_fn(int act, float z, float p0, float p1) {
   return z;
 }
 
+// Epilogue form: act over 32 accumulator columns held in registers.  Identity and ReLU are inlined; every other
+// activation goes through ONE out-of-line copy of the switch (8 values per call) so that the tensor-core kernels
+// stay small enough for the instruction cache (4 values per call; 32 inlined copies of the full switch made the conv1 + ReLU
+// epilogue of cfg4 instruction-fetch bound).
+static __device__ __noinline__ float4 act_fn4(int act, float p0, float p1, float4 x) {
+  return make_float4(act_fn(act, x.x, p0, p1), act_fn(act, x.y, p0, p1), act_fn(act, x.z, p0, p1), act_fn(act, x.w, p0, p1));
+}
+__device__ __forceinline__ void act_apply32(int act, float p0, float p1, float (&v)[32]) {
+  if (act == NPML_ACT_IDENTITY) return;
+  if (act == NPML_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {     // values travel in registers (by value), so v[] never needs a stack slot
+    const float4 r = act_fn4(act, p0, p1, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    v[i] = r.x; v[i + 1] = r.y; v[i + 2] = r.z; v[i + 3] = r.w;
+  }
+}
+
 // derivative conventions at the kinks follow the reference
 __device__ __forceinline__ float act_grad(int act, float x, float p0, float p1) {
   switch (act) {

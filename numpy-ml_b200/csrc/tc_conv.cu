@@ -240,8 +240,7 @@ __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_c
         }
         if (Z) store_row_chunk<T>(Z + pix * P.CO + co, v, n_valid);
         if (Y) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = act_fn(P.act, v[j], P.p0, P.p1);
+          act_apply32(P.act, P.p0, P.p1, v);
           store_row_chunk<T>(Y + pix * P.CO + co, v, n_valid);
         }
       }

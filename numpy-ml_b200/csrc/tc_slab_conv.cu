@@ -319,8 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
           const int co = co0 + c;
           if (Z) emit(Z, v, my_pix, co);
           if (Y) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = act_fn(P.act, v[i], P.p0, P.p1);
+            act_apply32(P.act, P.p0, P.p1, v);
             emit(Y, v, my_pix, co);
           }
         }

@@ -23,7 +23,8 @@ namespace npml {
 int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
               const uint32_t* box, bool atom32b);
 int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
-                        int64_t o_co, int accumulate, float* dW, cudaStream_t st);
+                        int64_t o_co, int accumulate, float* dW, cudaStream_t st, const float* part_db = nullptr,
+                        float* db = nullptr);
 
 namespace {
 
@@ -48,15 +49,6 @@ struct SlabWgradParams {
   int xplane_bytes, xstage_bytes, gplane_bytes, gstage_bytes;
   uint32_t idesc;
 };
-
-__global__ void db_reduce_kernel(const float* __restrict__ part, int splits, int CO, int accumulate,
-                                 float* __restrict__ db) {
-  const int co = blockIdx.x * blockDim.x + threadIdx.x;
-  if (co >= CO) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[(int64_t)z * CO + co];
-  db[co] = accumulate ? db[co] + s : s;
-}
 
 // The MMA issue loop for a group of NT accumulator tiles.  The whole warp walks the loops in convergent control
 // flow so the descriptors live in uniform registers; one elected lane issues.  Tiles 0 .. NT-2 of any group are
@@ -371,13 +363,8 @@ int slab_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad,
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
   kern<<<pl.grid, kThreads, pl.smem, st>>>(P, part, part_db);
   NPML_LAUNCH_OK();
-  if (int e = launch_wgrad_reduce(part, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st))
-    return e;
-  if (db != nullptr) {
-    db_reduce_kernel<<<ceildiv(g.CO, 128), 128, 0, st>>>(part_db, pl.splits, g.CO, g.accumulate, db);
-    NPML_LAUNCH_OK();
-  }
-  return 0;
+  return launch_wgrad_reduce(part, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st,
+                             db != nullptr ? part_db : nullptr, db);
 }
 
 }  // namespace npml

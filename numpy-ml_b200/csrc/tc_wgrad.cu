@@ -16,7 +16,8 @@ namespace npml {
 int make_tmap(CUtensorMap* m, bool bf16, void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
               const uint32_t* box, bool atom32b);
 int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
-                        int64_t o_co, int accumulate, float* dW, cudaStream_t st);
+                        int64_t o_co, int accumulate, float* dW, cudaStream_t st, const float* part_db = nullptr,
+                        float* db = nullptr);
 
 namespace {
 

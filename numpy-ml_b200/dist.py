@@ -92,6 +92,8 @@ class GradBucket(object):
             o0, n0 = self.slices.get(id(l), (off, 0))
             self.slices[id(l)] = (o0, n0 + g.numel())
             off += g.numel()
+        for l in self.layers:
+            l._bucket = self
         self.overlap = bool(overlap) and _state["world"] > 1 and self.flat.is_cuda
         self._done = set()
         self._side = torch.cuda.Stream() if self.overlap else None
@@ -99,6 +101,18 @@ class GradBucket(object):
             for l in self.layers:
                 if hasattr(l, "_bwd") and hasattr(l, "kernel_shape"):
                     l._grads_ready_hook = self._on_ready
+
+    def zero_layer(self, layer):
+        """Zero the contiguous slice that holds every gradient of `layer`."""
+        off, n = self.slices.get(id(layer), (0, 0))
+        if n:
+            self.flat[off:off + n].zero_()
+
+    def owns_only(self, layers):
+        """True if the bucket holds the gradients of exactly the layers of `layers` that have any."""
+        mine = {id(l) for l in self.layers}
+        theirs = {id(l) for l in layers if l.gradients}
+        return mine == theirs
 
     def _reduce(self, off, n):
         buf = self.flat[off:off + n]

@@ -60,14 +60,22 @@ class LayerBase(ABC):
     def unfreeze(self):
         self.trainable = True
 
-    def flush_gradients(self):
-        """Zero the gradients and drop every retained input / derived variable (layers.py:66-74)."""
+    def flush_gradients(self, zero=True):
+        """Zero the gradients and drop every retained input / derived variable (layers.py:66-74).
+        Gradients that live in a dist.GradBucket are one contiguous slice: one memset instead of one per tensor
+        (`zero=False`: the caller has already zeroed the whole bucket)."""
         assert self.trainable, "Layer is frozen"
         self.X = []
         for k in self.derived_variables:
             self.derived_variables[k] = []
-        for k, v in self.gradients.items():
-            v.zero_()
+        if not zero:
+            return
+        bucket = getattr(self, "_bucket", None)
+        if bucket is not None:
+            bucket.zero_layer(self)
+        else:
+            for k, v in self.gradients.items():
+                v.zero_()
 
     def update(self, cur_loss=None):
         """Optimizer step on the accrued gradients, then flush (layers.py:76-86)."""
@@ -365,8 +373,8 @@ class BatchNorm2D(LayerBase):
         self.parameters["running_mean"] = torch.zeros(self.in_ch, dtype=torch.float32, device=L.device())
         self.parameters["running_var"] = torch.ones(self.in_ch, dtype=torch.float32, device=L.device())
 
-    def flush_gradients(self):
-        super().flush_gradients()
+    def flush_gradients(self, zero=True):
+        super().flush_gradients(zero)
         self._saved = []
 
     def _ws(self, rows, ch):

@@ -66,8 +66,16 @@ class ModuleBase(ABC):
         assert self.trainable, "Layer is frozen"
         self.X = []
         self._dv = {}
-        for c in self.components:
-            c.flush_gradients()
+        comps = self.components
+        buckets = {id(getattr(c, "_bucket", None)) for c in comps if c.gradients}
+        shared = getattr(comps[0], "_bucket", None) if len(buckets) == 1 else None
+        if shared is not None and shared.owns_only(comps):
+            shared.flat.zero_()                      # every component gradient in one memset
+            for c in comps:
+                c.flush_gradients(zero=False)
+        else:
+            for c in comps:
+                c.flush_gradients()
 
     def set_params(self, summary_dict):
         cids = self.hyperparameters["component_ids"]
