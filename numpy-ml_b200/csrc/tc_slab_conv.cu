@@ -50,6 +50,9 @@ struct SlabParams {
   int plane_bytes, w_block_bytes, w_resident, w_stages;
   int total_tiles, num_units;
   uint32_t idesc;
+  int epi_direct;               // 1 (NPML_SLAB_EPI=direct, experiment): rows go straight from registers to global
+                                // memory with 256-bit stores; measured equal to the staged path (the kernel is
+                                // bound by the MMA operand fetch, not by the epilogue)
   int act;
   float p0, p1;
 };
@@ -288,6 +291,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       __syncwarp();
     };
 
+    // alternative without the staging round trip: every thread writes its own row with 32-byte stores
+    auto emit_direct = [&](T* __restrict__ out, const float (&v)[32], int my_pix, int co) {
+      if (my_pix < 0) return;
+      T* dst = out + (int64_t)my_pix * CO + co;
+      constexpr int kPer = 32 / (int)sizeof(T);          // elements per 32-byte store
+#pragma unroll
+      for (int h = 0; h < 32 / kPer; ++h) {
+        uint32_t w[8];
+        if constexpr (sizeof(T) == 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[h * 16 + 2 * i], v[h * 16 + 2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&a);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(v[h * 8 + i]);
+        }
+        if (co + h * kPer < CO)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + h * kPer), "r"(w[0]), "r"(w[1]),
+                       "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                       : "memory");
+      }
+    };
+    const bool direct = P.epi_direct != 0;
+
     for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
       const int ntile = min(UT, P.total_tiles - unit * UT);
       for (int j = 0; j < ntile; ++j) {
@@ -317,10 +346,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
             v[i + 2] = __uint_as_float(r[i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[i + 3]) + bb.w;
           }
           const int co = co0 + c;
-          if (Z) emit(Z, v, my_pix, co);
-          if (Y) {
-            act_apply32(P.act, P.p0, P.p1, v);
-            emit(Y, v, my_pix, co);
+          if (direct) {
+            if (Z) emit_direct(Z, v, my_pix, co);
+            if (Y) {
+              act_apply32(P.act, P.p0, P.p1, v);
+              emit_direct(Y, v, my_pix, co);
+            }
+          } else {
+            if (Z) emit(Z, v, my_pix, co);
+            if (Y) {
+              act_apply32(P.act, P.p0, P.p1, v);
+              emit(Y, v, my_pix, co);
+            }
           }
         }
         if (++slot == (uint32_t)n_acc) { slot = 0; sph ^= 1u; }
@@ -406,6 +443,10 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   }
   if (!found) return false;
   P.num_units = ceildiv(total_tiles, P.UT);
+  {
+    const char* e = std::getenv("NPML_SLAB_EPI");
+    P.epi_direct = (e && e[0] == 'd' && (g.CO * es) % 32 == 0) ? 1 : 0;
+  }
   const int nty = ceildiv(g.CO, bn);
   int ctas = num_sms() / nty;
   if (ctas < 1) ctas = 1;

@@ -32,10 +32,10 @@ def short(name):
 
 
 def launches(src, dst):
-    rows = [r for r in csv.reader(open(src)) if len(r) > 14 and r[0].isdigit()]
+    rows = [r for r in csv.reader(open(src)) if len(r) > 14 and r[0].isdigit() and r[12] == "gpu__time_duration.sum"]
     per = OrderedDict()
     for r in rows:
-        per.setdefault(short(r[4]), []).append(float(r[14]) / 1e3)
+        per.setdefault(short(r[4]), []).append(float(r[14]) / (1e3 if r[13] in ("ns", "nsecond") else 1.0))
     total = sum(sum(v) for v in per.values())
     with open(dst, "w") as f:
         f.write("# ncu launch list summary ({} launches, source {})\n\n".format(len(rows), src))
