@@ -272,7 +272,8 @@ def run_gpu(args, cfg):
         model = pkg.Deconv2D(cfg["K"], cfg["k"], pad=cfg["pad"], stride=cfg["stride"], mode=mode)
     else:
         model = pkg.SkipConnectionConvModule(out_ch1=cfg["K"], out_ch2=cfg["K"], kernel_shape1=(3, 3), kernel_shape2=(3, 3),
-                                             kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn="relu", mode=mode)
+                                             kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn="relu", mode=mode,
+                                             sync_bn=(world > 1))
     Xh = torch.from_numpy(X).pin_memory()
     dYh = torch.from_numpy(dY).pin_memory()
     Xd = L.to_device(Xh.to(dev), act_dt)
@@ -450,7 +451,8 @@ def run_gpu(args, cfg):
                 "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[mode],
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "mode": mode, "per_gpu_batch": n, "global_batch": n * world,
-                           "parallelism": "dp{}".format(world), "tensor_cores": tc,
+                           "parallelism": "dp{}".format(world) + ("+syncbn" if (kind == "skip" and world > 1) else ""),
+                           "tensor_cores": tc,
                            "l2": "inputs X + dLdy are {:.0f} MB per step (L2 is 126 MB); no explicit flush".format(
                                (Xd.numel() + dYd.numel()) * esize / 1e6)},
                 "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / (world * pk["bf16_tflops_sustained"]),

@@ -139,6 +139,25 @@ int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const void* x, void*
                   float* d_scaler, float* d_intercept, int32_t accumulate, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* sync-BN under batch sharding (new): the two passes above split at the point where the per-channel
+ * sums cross ranks.  stats: sums[0..ch) = sum x, sums[ch..2ch) = sum x^2 over this rank's rows (double, device).
+ * The host all-reduces `sums` (npml_allreduce_sum_f64) and calls apply with rows_total = rows over all ranks.
+ * bwd_stats: sums = [sum dy, sum dy*nhat]; bwd_apply accumulates THIS rank's sums into d_intercept / d_scaler
+ * (the gradient bucket is all-reduced later) and uses the all-rank sums for dX. */
+int npml_bn2d_stats(int64_t rows, int32_t ch, const void* x, int32_t dtype, double* sums, void* ws,
+                    size_t ws_bytes, void* stream);
+int npml_bn2d_apply(int64_t rows, int64_t rows_total, int32_t ch, const void* x, void* y, int32_t dtype,
+                    const float* scaler, const float* intercept, float* running_mean, float* running_var,
+                    float momentum, float eps, const double* sums, float* save_mean, float* save_rstd,
+                    void* ws, size_t ws_bytes, void* stream);
+int npml_bn2d_bwd_stats(int64_t rows, int32_t ch, const void* dy, const void* x, int32_t dtype,
+                        const float* save_mean, const float* save_rstd, double* sums, void* ws,
+                        size_t ws_bytes, void* stream);
+int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch, const void* dy, const void* x, void* dx,
+                        int32_t dtype, const float* scaler, const float* save_mean, const float* save_rstd,
+                        const double* sums_local, const double* sums_global, float* d_scaler,
+                        float* d_intercept, int32_t accumulate, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- SGD step on the (all-reduced) gradient (optimizers/optimizers.py:110-148) ----------------
  * g' = grad * grad_scale (grad_scale carries the clip-norm factor t/||g||, 1 when not clipping);
  * u = momentum*velocity + lr*g'; velocity = u; param -= u.  All fp32, n elements. */
@@ -159,6 +178,7 @@ int npml_col2im(const npml_conv_desc* d, const float* X_col, float* X_nchw, void
 int npml_comm_unique_id(void* id128);
 int npml_comm_init_rank(const void* id128, int32_t nranks, int32_t rank);
 int npml_allreduce_sum_f32(float* buf, int64_t n, void* stream);
+int npml_allreduce_sum_f64(double* buf, int64_t n, void* stream);   /* sync-BN statistics */
 int npml_comm_destroy(void);
 
 /* ---- misc --------------------------------------------------------------------------------- */

@@ -46,6 +46,10 @@ SIGNATURES = {
     "npml_act_fwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _F, _F, _P]),
     "npml_bn2d_fwd": (C.c_int, [_I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _F, _F, _I32, _P, _P, _P, _SZ, _P]),
     "npml_bn2d_bwd": (C.c_int, [_I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "npml_bn2d_stats": (C.c_int, [_I64, _I32, _P, _I32, _P, _P, _SZ, _P]),
+    "npml_bn2d_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _SZ, _P]),
+    "npml_bn2d_bwd_stats": (C.c_int, [_I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
+    "npml_bn2d_bwd_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
     "npml_sgd_update": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P]),
     "npml_sumsq_f32": (C.c_int, [_P, _I64, _P, _P, _SZ, _P]),
     "npml_im2col": (C.c_int, [_DESC, _P, _P, _P]),
@@ -53,6 +57,7 @@ SIGNATURES = {
     "npml_comm_unique_id": (C.c_int, [_P]),
     "npml_comm_init_rank": (C.c_int, [_P, _I32, _I32]),
     "npml_allreduce_sum_f32": (C.c_int, [_P, _I64, _P]),
+    "npml_allreduce_sum_f64": (C.c_int, [_P, _I64, _P]),
     "npml_comm_destroy": (C.c_int, []),
     "npml_last_error": (C.c_char_p, []),
     "npml_uses_tensor_cores": (C.c_int, [_DESC, C.c_int]),

@@ -14,7 +14,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat32 = 7, ncclSum = 0 };
+enum { ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0 };
 
 struct Nccl {
   void* h = nullptr;
@@ -80,6 +80,14 @@ extern "C" int npml_allreduce_sum_f32(float* buf, int64_t n, void* stream) {
   NPML_CHECK(g_nccl.comm != nullptr, "communicator not initialised");
   if (n <= 0) return 0;
   NPML_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, g_nccl.comm, (cudaStream_t)stream));
+  npml::count_launch();
+  return 0;
+}
+
+extern "C" int npml_allreduce_sum_f64(double* buf, int64_t n, void* stream) {
+  NPML_CHECK(g_nccl.comm != nullptr, "communicator not initialised");
+  if (n <= 0) return 0;
+  NPML_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, g_nccl.comm, (cudaStream_t)stream));
   npml::count_launch();
   return 0;
 }

@@ -372,6 +372,14 @@ struct BnBwdDxF {
   }
 };
 
+// part [nblk][width] -> sums[width] (double), fixed order
+__global__ void col_sums_kernel(const double* __restrict__ part, int nblk, int width, double* __restrict__ sums) {
+  __shared__ double red[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const double s = block_col_sum<double>(part, nblk, width, c, c < width, red);
+  if (threadIdx.y == 0 && c < width) sums[c] = s;
+}
+
 // grid = ceil(ch / 32), block = (32, 32): column reduction of the partials + the per-channel finalize in one launch
 __global__ void db_finalize_kernel(const float* __restrict__ part, int nblk, int ch, int accumulate, float* db) {
   __shared__ double red[32][33];
@@ -380,13 +388,21 @@ __global__ void db_finalize_kernel(const float* __restrict__ part, int nblk, int
   if (threadIdx.y == 0 && c < ch) db[c] = accumulate ? db[c] + (float)s : (float)s;
 }
 
+// sums_in != nullptr: the column sums are already reduced (possibly over several ranks, sync-BN) and `part` is unused
 __global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, int ch, double inv_m, float momentum,
                                    float eps, float* running_mean, float* running_var, float* save_mean,
-                                   float* save_rstd, const float* scaler, const float* intercept, float* coef) {
+                                   float* save_rstd, const float* scaler, const float* intercept, float* coef,
+                                   const double* __restrict__ sums_in) {
   __shared__ double red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  const double s1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
-  const double s2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+  double s1, s2;
+  if (sums_in != nullptr) {
+    s1 = c < ch ? sums_in[c] : 0.0;
+    s2 = c < ch ? sums_in[ch + c] : 0.0;
+  } else {
+    s1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
+    s2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+  }
   if (threadIdx.y != 0 || c >= ch) return;
   const double mean = s1 * inv_m;
   double var = s2 * inv_m - mean * mean;  // biased (layers/layers.py:1147)
@@ -414,15 +430,26 @@ __global__ void bn_running_to_saved_kernel(int ch, float eps, const float* runni
   coef[2 * ch + c] = intercept[c];
 }
 
+// sums_local / sums_global != nullptr (sync-BN): the parameter gradients accumulate this rank's sums (the gradient
+// bucket is all-reduced later), the dX coefficients use the sums over all ranks
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, int ch, int accumulate,
                                        float* d_scaler, float* d_intercept, double inv_m, const float* mean,
-                                       const float* rstd, const float* scaler, float* coef) {
+                                       const float* rstd, const float* scaler, float* coef,
+                                       const double* __restrict__ sums_local, const double* __restrict__ sums_global) {
   __shared__ double red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  const double s1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
-  const double s2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+  double s1, s2, l1, l2;
+  if (sums_global != nullptr) {
+    s1 = c < ch ? sums_global[c] : 0.0;
+    s2 = c < ch ? sums_global[ch + c] : 0.0;
+    l1 = c < ch ? sums_local[c] : 0.0;
+    l2 = c < ch ? sums_local[ch + c] : 0.0;
+  } else {
+    s1 = l1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
+    s2 = l2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+  }
   if (threadIdx.y != 0 || c >= ch) return;
-  const float di = (float)s1, ds = (float)s2;
+  const float di = (float)l1, ds = (float)l2;
   if (d_intercept) d_intercept[c] = accumulate ? d_intercept[c] + di : di;
   if (d_scaler) d_scaler[c] = accumulate ? d_scaler[c] + ds : ds;
   coef[c] = mean[c];
@@ -647,7 +674,7 @@ extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, i
     if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
     bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, 1.0 / (double)rows, momentum, eps,
                                                                 running_mean, running_var, save_mean, save_rstd, scaler,
-                                                                intercept, coef);
+                                                                intercept, coef, nullptr);
     NPML_LAUNCH_OK();
   } else {
     bn_running_to_saved_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, eps, running_mean, running_var, save_mean,
@@ -675,8 +702,79 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
   if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
   bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
-                                                                  1.0 / (double)rows, save_mean, save_rstd, scaler, coef);
+                                                                  1.0 / (double)rows, save_mean, save_rstd, scaler, coef,
+                                                                  nullptr, nullptr);
   NPML_LAUNCH_OK();
+  BnBwdDxF fd{dy, x, dx, dtype, coef};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st);
+}
+
+// ---- sync-BN: the same passes split at the point where the per-channel sums cross ranks ---------------------
+extern "C" int npml_bn2d_stats(int64_t rows, int32_t ch, const void* x, int32_t dtype, double* sums, void* ws,
+                               size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(sums != nullptr, "sums is NULL");
+  if (rows <= 0 || ch <= 0) return 0;
+  ColPlan p = plan_cols(rows, ch, pick_vec(ch, aligned_for_vec4(x, dtype), aligned16(x)), true);
+  NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 2 * ch * sizeof(double), "workspace too small");
+  double* part = (double*)ws;
+  BnStatsF fs{x, dtype};
+  if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+  col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_bn2d_apply(int64_t rows, int64_t rows_total, int32_t ch, const void* x, void* y, int32_t dtype,
+                               const float* scaler, const float* intercept, float* running_mean, float* running_var,
+                               float momentum, float eps, const double* sums, float* save_mean, float* save_rstd,
+                               void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(sums && save_mean && save_rstd && rows_total >= rows, "bad arguments");
+  NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)3 * ch * sizeof(float), "workspace too small");
+  float* coef = (float*)ws;
+  bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(nullptr, 0, ch, 1.0 / (double)rows_total, momentum, eps,
+                                                              running_mean, running_var, save_mean, save_rstd, scaler,
+                                                              intercept, coef, sums);
+  NPML_LAUNCH_OK();
+  const int vec = pick_vec(ch, aligned_for_vec4(x, dtype) && aligned_for_vec4(y, dtype), aligned16(x) && aligned16(y));
+  BnNormF fn{x, y, dtype, coef};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fn, (float*)nullptr, st);
+}
+
+extern "C" int npml_bn2d_bwd_stats(int64_t rows, int32_t ch, const void* dy, const void* x, int32_t dtype,
+                                   const float* save_mean, const float* save_rstd, double* sums, void* ws,
+                                   size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(sums != nullptr, "sums is NULL");
+  if (rows <= 0 || ch <= 0) return 0;
+  const int vec = pick_vec(ch, aligned_for_vec4(x, dtype) && aligned_for_vec4(dy, dtype), aligned16(x) && aligned16(dy));
+  ColPlan p = plan_cols(rows, ch, vec, true);
+  NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 2 * ch * sizeof(double), "workspace too small");
+  double* part = (double*)ws;
+  BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
+  if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+  col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch, const void* dy, const void* x, void* dx,
+                                   int32_t dtype, const float* scaler, const float* save_mean, const float* save_rstd,
+                                   const double* sums_local, const double* sums_global, float* d_scaler,
+                                   float* d_intercept, int32_t accumulate, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(sums_local && sums_global && rows_total >= rows, "bad arguments");
+  NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)5 * ch * sizeof(float), "workspace too small");
+  float* coef = (float*)ws;
+  bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(nullptr, 0, ch, accumulate, d_scaler, d_intercept,
+                                                                  1.0 / (double)rows_total, save_mean, save_rstd, scaler,
+                                                                  coef, sums_local, sums_global);
+  NPML_LAUNCH_OK();
+  const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(dy, dtype) && aligned_for_vec4(dx, dtype);
+  const int vec = pick_vec(ch, vec_ok, aligned16(x) && aligned16(dy) && aligned16(dx));
   BnBwdDxF fd{dy, x, dx, dtype, coef};
   return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st);
 }

@@ -147,6 +147,18 @@ class GradBucket(object):
         return self.flat
 
 
+def allreduce_sum_f64(t):
+    """In-place SUM over ranks of a small float64 device tensor (sync-BN statistics) on the current stream."""
+    if _state["world"] == 1:
+        return t
+    if _state["backend"] == "nccl":
+        L.check(L.load().npml_allreduce_sum_f64(L.ptr(t), t.numel(), L.stream()), "npml_allreduce_sum_f64")
+    else:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
 def barrier():
     if _state["world"] > 1:
         import torch.distributed as dist

@@ -342,12 +342,15 @@ class BatchNorm2D(LayerBase):
     """layers/layers.py:969-1215.  Statistics are per channel over (n_ex, rows, cols); the variance is the
     biased one for both the normalisation and the running estimate (layers.py:1147)."""
 
-    def __init__(self, momentum=0.9, epsilon=1e-5, optimizer=None):
+    def __init__(self, momentum=0.9, epsilon=1e-5, optimizer=None, sync=False):
         super().__init__(optimizer)
         self.in_ch = None
         self.out_ch = None
         self.epsilon = epsilon
         self.momentum = momentum
+        # sync (extension, SURVEY.md 8e): under batch sharding the per-channel sums are all-reduced over ranks, so
+        # every rank normalises with the statistics of the WHOLE batch exactly like the single-process reference
+        self.sync = bool(sync)
         self.parameters = {"scaler": None, "intercept": None, "running_var": None, "running_mean": None}
         self.is_initialized = False
         self._saved = []      # (mean, rstd) of every retained forward
@@ -398,6 +401,23 @@ class BatchNorm2D(LayerBase):
         rstd = torch.empty(ch, dtype=torch.float32, device=Xd.device)
         use_batch = 1 if (self.trainable and retain_derived) else 0
         ws = self._ws(rows, ch)
+        if use_batch and self.sync:
+            from . import dist as D
+            lib = L.load()
+            sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
+            with L.profiled("npml_bn2d_fwd"):
+                L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(),
+                                            L.stream()), "npml_bn2d_stats")
+                D.allreduce_sum_f64(sums)
+                total = rows * D.world_size()
+                L.check(lib.npml_bn2d_apply(rows, total, ch, L.ptr(Xd), L.ptr(y), L.code_of(Xd), L.ptr(P["scaler"]),
+                                            L.ptr(P["intercept"]), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
+                                            float(self.momentum), float(self.epsilon), L.ptr(sums), L.ptr(mean),
+                                            L.ptr(rstd), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_apply")
+            if retain_derived:
+                self.X.append(Xd)
+                self._saved.append((mean, rstd))
+            return L.to_numpy(y) if as_np else y
         with L.profiled("npml_bn2d_fwd"):
             L.check(L.load().npml_bn2d_fwd(rows, ch, L.ptr(Xd), L.ptr(y), L.code_of(Xd), L.ptr(P["scaler"]),
                                            L.ptr(P["intercept"]), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
@@ -443,6 +463,21 @@ class BatchNorm2D(LayerBase):
         dX = torch.empty_like(X)
         ws = self._ws(rows, ch)
         G = self.gradients
+        if self.sync and saved is not None:
+            from . import dist as D
+            lib = L.load()
+            local = torch.empty(2 * ch, dtype=torch.float64, device=X.device)
+            with L.profiled("npml_bn2d_bwd"):
+                L.check(lib.npml_bn2d_bwd_stats(rows, ch, L.ptr(dLdy), L.ptr(X), L.code_of(X), L.ptr(mean), L.ptr(rstd),
+                                                L.ptr(local), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_bwd_stats")
+                glob = D.allreduce_sum_f64(local.clone()) if D.world_size() > 1 else local
+                L.check(lib.npml_bn2d_bwd_apply(rows, rows * D.world_size(), ch, L.ptr(dLdy), L.ptr(X), L.ptr(dX),
+                                                L.code_of(X), L.ptr(_as_param(P["scaler"])), L.ptr(mean), L.ptr(rstd),
+                                                L.ptr(local), L.ptr(glob),
+                                                L.ptr(G["scaler"]) if retain_grads else None,
+                                                L.ptr(G["intercept"]) if retain_grads else None, 1, L.ptr(ws),
+                                                ws.numel(), L.stream()), "npml_bn2d_bwd_apply")
+            return dX
         with L.profiled("npml_bn2d_bwd"):
             L.check(L.load().npml_bn2d_bwd(rows, ch, L.ptr(dLdy), L.ptr(X), L.ptr(dX), L.code_of(X),
                                            L.ptr(_as_param(P["scaler"])), L.ptr(mean), L.ptr(rstd),

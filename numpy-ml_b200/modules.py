@@ -93,7 +93,7 @@ class ModuleBase(ABC):
 class SkipConnectionConvModule(ModuleBase):
     def __init__(self, out_ch1, out_ch2, kernel_shape1, kernel_shape2, kernel_shape_skip, pad1=0, pad2=0, stride1=1,
                  stride2=1, act_fn=None, epsilon=1e-5, momentum=0.9, stride_skip=1, optimizer=None,
-                 init="glorot_uniform", mode="fp32"):
+                 init="glorot_uniform", mode="fp32", sync_bn=False):
         super().__init__()
         self.init = init
         self.pad1 = pad1
@@ -112,6 +112,7 @@ class SkipConnectionConvModule(ModuleBase):
         self.kernel_shape_skip = kernel_shape_skip
         self.act_fn = Affine(slope=1, intercept=0) if act_fn is None else ActivationInitializer(act_fn)()
         self.mode = mode
+        self.sync_bn = sync_bn      # extension: all-reduce the BatchNorm statistics over the data-parallel ranks
         self._init_params()
 
     def _init_params(self, X=None):
@@ -122,9 +123,9 @@ class SkipConnectionConvModule(ModuleBase):
         self.conv2 = Conv2D(pad=self.pad2, init=self.init, out_ch=self.out_ch2, stride=self.stride2,
                             optimizer=self.optimizer, kernel_shape=self.kernel_shape2,
                             act_fn=Affine(slope=1, intercept=0), mode=self.mode)
-        self.batchnorm1 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum)
-        self.batchnorm2 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum)
-        self.batchnorm_skip = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum)
+        self.batchnorm1 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
+        self.batchnorm2 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
+        self.batchnorm_skip = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
         self.add3 = Add(self.act_fn)
 
     def _calc_skip_padding(self, X_shape):

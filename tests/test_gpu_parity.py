@@ -322,6 +322,79 @@ def test_skip_conv_module_vs_oracle(cuda_device, mode, act):
         close(bn.parameters["running_var"], o["rv" + t], tol, "rv" + t)
 
 
+@pytest.mark.gpu
+def test_sync_batchnorm_split_equals_whole_batch(cuda_device):
+    """sync-BN: per-shard statistics summed over two emulated ranks, then applied per shard, reproduce
+    the whole-batch BatchNorm2D forward and backward of the oracle (layers.py:1146-1156, 1192-1215)."""
+    import ctypes as C
+    import torch
+    pkg = npml()
+    L = pkg._lib
+    lib = L.load()
+    rng = np.random.default_rng(77)
+    N, H, W, ch = 8, 9, 7, 24
+    X = _f32(rng, (N, H, W, ch)) * 2.0 + 0.5
+    dY = _f32(rng, (N, H, W, ch))
+    g = rng.uniform(0.5, 1.5, ch).astype(np.float32).astype(np.float64)
+    h = _f32(rng, (ch,), 0.1)
+    Yr, rm_r, rv_r = O.bn2d_fwd(X, g, h, np.zeros(ch), np.ones(ch), 0.9, 1e-5)
+    dXr, dgr, dhr = O.bn2d_bwd(dY, X, g, 1e-5)
+    halves = [(0, N // 2), (N // 2, N)]
+    dev = torch.device("cuda:0")
+    f32 = lambda a: torch.tensor(np.ascontiguousarray(a), dtype=torch.float32, device=dev)
+    gd, hd = f32(g), f32(h)
+    xs = [f32(X[a:b]) for a, b in halves]
+    dys = [f32(dY[a:b]) for a, b in halves]
+    rows = [x.numel() // ch for x in xs]
+    ws = L.workspace(1 << 22)
+    sums = [torch.empty(2 * ch, dtype=torch.float64, device=dev) for _ in halves]
+    for x, r, s_ in zip(xs, rows, sums):
+        L.check(lib.npml_bn2d_stats(r, ch, L.ptr(x), L.F32, L.ptr(s_), L.ptr(ws), ws.numel(), L.stream()), "stats")
+    tot = sums[0] + sums[1]                       # what the all-reduce produces on every rank
+    ys, means, rstds, rms = [], [], [], []
+    for x, r in zip(xs, rows):
+        y = torch.empty_like(x)
+        mean, rstd = torch.empty(ch, device=dev), torch.empty(ch, device=dev)
+        rm, rv = torch.zeros(ch, device=dev), torch.ones(ch, device=dev)
+        L.check(lib.npml_bn2d_apply(r, sum(rows), ch, L.ptr(x), L.ptr(y), L.F32, L.ptr(gd), L.ptr(hd), L.ptr(rm), L.ptr(rv),
+                                    0.9, 1e-5, L.ptr(tot), L.ptr(mean), L.ptr(rstd), L.ptr(ws), ws.numel(), L.stream()),
+                "apply")
+        ys.append(y); means.append(mean); rstds.append(rstd); rms.append((rm, rv))
+    Y = np.concatenate([pkg.to_numpy(y) for y in ys], axis=0)
+    close(Y, Yr, 1e-5, "sync-BN Y")
+    close(pkg.to_numpy(rms[0][0]), rm_r, 1e-5, "running_mean")
+    close(pkg.to_numpy(rms[1][1]), rv_r, 1e-5, "running_var")
+    bs = [torch.empty(2 * ch, dtype=torch.float64, device=dev) for _ in halves]
+    for x, dy, r, s_, m, rs in zip(xs, dys, rows, bs, means, rstds):
+        L.check(lib.npml_bn2d_bwd_stats(r, ch, L.ptr(dy), L.ptr(x), L.F32, L.ptr(m), L.ptr(rs), L.ptr(s_), L.ptr(ws),
+                                        ws.numel(), L.stream()), "bwd_stats")
+    btot = bs[0] + bs[1]
+    dxs = []
+    dg, dh = torch.zeros(ch, device=dev), torch.zeros(ch, device=dev)    # "bucket": both ranks accumulate, i.e. SUM
+    for x, dy, r, s_, m, rs in zip(xs, dys, rows, bs, means, rstds):
+        dx = torch.empty_like(x)
+        L.check(lib.npml_bn2d_bwd_apply(r, sum(rows), ch, L.ptr(dy), L.ptr(x), L.ptr(dx), L.F32, L.ptr(gd), L.ptr(m),
+                                        L.ptr(rs), L.ptr(s_), L.ptr(btot), L.ptr(dg), L.ptr(dh), 1, L.ptr(ws), ws.numel(),
+                                        L.stream()), "bwd_apply")
+        dxs.append(dx)
+    close(np.concatenate([pkg.to_numpy(d) for d in dxs], axis=0), dXr, 2e-5, "sync-BN dX")
+    close(pkg.to_numpy(dg), dgr, 2e-5, "dScaler")
+    close(pkg.to_numpy(dh), dhr, 2e-5, "dIntercept")
+    # the layer-level switch (one rank: the split path must equal the fused path)
+    A, B = pkg.BatchNorm2D(sync=True), pkg.BatchNorm2D(sync=False)
+    outs = []
+    for layer in (A, B):
+        layer.forward(X, retain_derived=False)
+        layer.parameters["scaler"], layer.parameters["intercept"] = g, h
+        layer.reset_running_stats()
+        y = layer.forward(X)
+        dx = layer.backward(dY)
+        outs.append((y, dx, pkg.to_numpy(layer.gradients["scaler"])))
+    for a, b in zip(*outs):
+        close(a, b, 1e-6, "sync vs fused")
+    close(outs[0][0], Yr, 1e-5, "layer sync Y")
+
+
 # ------------------------------------------------------------------------------------------------
 #  layer state semantics (layers.py:3040-3044, 3076-3091, 66-86)
 # ------------------------------------------------------------------------------------------------
