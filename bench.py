@@ -306,22 +306,61 @@ def run_gpu(args, cfg):
         step()
     torch.cuda.synchronize()
 
+    # ---- CUDA graph of one step (launch-bound configs: the host needs ~0.18 ms to enqueue a step) -------------
+    # forward + backward (+ all-reduce) are captured ONCE through the public layer API; the timed region replays the
+    # graph.  The per-call CUDA events are captured as external event-record nodes, so the per-call durations are
+    # still measured inside the timed region (those of the last replay).
+    graph = None
+    if not args.no_graph:
+        try:
+            torch.cuda.synchronize()
+            L.PROFILE, L.PROFILE_EXTERNAL = [], True
+            L.launch_count(reset=True)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            graph, graph_prof, graph_launches = g, L.PROFILE, L.launch_count()
+        except Exception as e:      # capture not possible (e.g. torch without external events): eager timed region
+            if rank == 0:
+                print("bench: CUDA graph capture failed ({}); timing eagerly".format(str(e).splitlines()[0]), file=sys.stderr)
+            graph = None
+            try:
+                torch.cuda.synchronize()
+            except Exception:
+                pass
+        L.PROFILE, L.PROFILE_EXTERNAL = None, False
+        if graph is not None:
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+
     # ---- timed region: K steps, CUDA events on the launching stream, per-call events inside ----------
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
-    L.PROFILE = []
+    if graph is None:
+        L.PROFILE = []
     L.launch_count(reset=True)
     D.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+    host_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # time the host needs to ENQUEUE one step
     e1.record()
     torch.cuda.synchronize()
     D.barrier()
-    launches = L.launch_count()
-    prof, L.PROFILE = L.PROFILE, None
+    if graph is not None:
+        launches = graph_launches * args.steps
+        prof, prof_steps = graph_prof, 1
+    else:
+        launches = L.launch_count()
+        prof, L.PROFILE = L.PROFILE, None
+        prof_steps = args.steps
     clocks = sampler.stop()
     ms_total = D.all_reduce_max(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
@@ -332,13 +371,13 @@ def run_gpu(args, cfg):
     for name, a, z in prof:
         per[name] = per.get(name, 0.0) + a.elapsed_time(z)
         count[name] = count.get(name, 0) + 1
-    step_ms = {k: v / args.steps for k, v in per.items()}          # time per step spent in each entry point
+    step_ms = {k: v / prof_steps for k, v in per.items()}          # time per step spent in each entry point
     call_ms = {k: per[k] / count[k] for k in per}                   # mean duration of one call
     fl = flops_per_pass(cfg, n)
     pk = peaks()
     dominant = max(step_ms, key=step_ms.get)
     tc = all(bool(l._uses_tc()) for l in conv_layers)
-    calls_per_step = count[dominant] / args.steps
+    calls_per_step = count[dominant] / prof_steps
     if dominant in ELEMENTWISE:
         oh, ow = out_hw(cfg)
         elems = n * oh * ow * cfg["K"]
@@ -455,7 +494,7 @@ def run_gpu(args, cfg):
                            "tensor_cores": tc,
                            "l2": "inputs X + dLdy are {:.0f} MB per step (L2 is 126 MB); no explicit flush".format(
                                (Xd.numel() + dYd.numel()) * esize / 1e6)},
-                "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / (world * pk["bf16_tflops_sustained"]),
+                "host_enqueue_ms_per_step": host_ms, "cuda_graph": graph is not None, "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / (world * pk["bf16_tflops_sustained"]),
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     D.destroy()
@@ -470,6 +509,7 @@ def main():
     ap.add_argument("--mode", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     cfg["_id"] = args.config

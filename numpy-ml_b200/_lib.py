@@ -68,6 +68,9 @@ SIGNATURES = {
 _lib = None
 # when a list, the layers append (entry point, start event, end event) around every C-ABI call
 PROFILE = None
+# True while a step is being captured into a CUDA graph: the events must be "external" so that they become
+# event-record nodes of the graph (and can be timed after a replay)
+PROFILE_EXTERNAL = False
 
 
 class profiled(object):
@@ -78,7 +81,8 @@ class profiled(object):
 
     def __enter__(self):
         if PROFILE is not None:
-            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kw = {"external": True} if PROFILE_EXTERNAL else {}
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True, **kw), torch.cuda.Event(enable_timing=True, **kw)
             self.e0.record()
         return self
 

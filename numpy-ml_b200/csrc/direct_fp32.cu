@@ -228,9 +228,46 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
   }
 }
 
+// Same reduction when the output's fastest dimension is ci (Deconv2D: dW[r,t,c,k] with the roles of c and k
+// swapped): a 32x32 (ci, co) tile is summed with reads coalesced along co, transposed through shared memory and
+// written coalesced along ci.
+__global__ void wgrad_reduce_t_kernel(const float* __restrict__ part, int splits, int taps, int CO, int CI,
+                                      int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
+                                      float* __restrict__ dW) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int ci0 = blockIdx.y * 32, co0 = blockIdx.x * 32;
+  const int64_t total = (int64_t)taps * CI * CO;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    float s = 0.f;
+    if (ci < CI && co < CO) {
+      const int64_t i = ((int64_t)tap * CI + ci) * CO + co;
+      for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + i];
+    }
+    tile[r][threadIdx.x] = s;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    if (ci < CI && co < CO) {
+      const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
+      const float s = tile[threadIdx.x][r];
+      dW[o] = accumulate ? dW[o] + s : s;
+    }
+  }
+}
+
 int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, int64_t o_tap, int64_t o_ci,
                         int64_t o_co, int accumulate, float* dW, cudaStream_t st, const float* part_db = nullptr,
                         float* db = nullptr) {
+  if (o_ci == 1 && o_co != 1 && part_db == nullptr) {
+    const int taps = M / CI;
+    dim3 grid((unsigned)((CO + 31) / 32), (unsigned)((CI + 31) / 32), (unsigned)taps);
+    wgrad_reduce_t_kernel<<<grid, dim3(32, 8), 0, st>>>(part, splits, taps, CO, CI, o_tap, o_ci, o_co, accumulate, dW);
+    NPML_LAUNCH_OK();
+    return 0;
+  }
   const int64_t total = (int64_t)M * CO + (part_db != nullptr ? CO : 0);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
