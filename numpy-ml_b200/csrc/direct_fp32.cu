@@ -202,6 +202,121 @@ __global__ void __launch_bounds__(NT) wgrad_partial_kernel(GatherWgrad g, const 
   }
 }
 
+// ---- thin shapes (cfg1: in_ch = 1): the 64x64 tiles above would be almost empty ---------------------------
+// gather conv with CO <= 4 (Conv2D dX when in_ch is tiny): one THREAD per output pixel (the index arithmetic is paid
+// once per pixel, not once per lane), the taps' channel vectors are read with 16-byte loads, the weights sit in
+// shared memory (every thread reads the same address: broadcast).
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(128) thin_co_conv_kernel(GatherConv g, const TIn* __restrict__ in,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           TOut* __restrict__ Z, TOut* __restrict__ Y, int w_in_smem) {
+  extern __shared__ float ws_[];            // [tap][ci][co] when it fits
+  const int taps = g.fr * g.fc;
+  if (w_in_smem) {
+    for (int i = threadIdx.x; i < taps * g.CI * g.CO; i += blockDim.x) {
+      const int co = i % g.CO, ci = (i / g.CO) % g.CI, tp = i / (g.CO * g.CI);
+      ws_[i] = w[(int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co];
+    }
+    __syncthreads();
+  }
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const int pi = (int)p;
+  const int x = pi % g.OW, y = (pi / g.OW) % g.OH, n = pi / (g.OW * g.OH);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int V = 16 / (int)sizeof(TIn);                 // elements per 16-byte load
+  const bool vec = (g.CI % V) == 0;
+  for (int r = 0; r < g.fr; ++r) {
+    int iy;
+    if (g.form == 0) iy = y * g.s + r * g.D - g.pr;
+    else { const int ny = y + g.pr - r * g.D; if (ny < 0 || ny % g.s) continue; iy = ny / g.s; }
+    if (iy < 0 || iy >= g.IH) continue;
+    for (int t = 0; t < g.fc; ++t) {
+      int ix;
+      if (g.form == 0) ix = x * g.s + t * g.D - g.pc;
+      else { const int nx = x + g.pc - t * g.D; if (nx < 0 || nx % g.s) continue; ix = nx / g.s; }
+      if (ix < 0 || ix >= g.IW) continue;
+      const int64_t base = (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI;
+      const int tp = r * g.fc + t;
+      if (vec) {
+        for (int c0 = 0; c0 < g.CI; c0 += V) {
+          float v[V];
+          const uint4 u = *reinterpret_cast<const uint4*>(in + base + c0);
+          if constexpr (sizeof(TIn) == 4) {
+            v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+          } else {
+            const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&q[j]);
+              v[2 * j] = __low2float(h); v[2 * j + 1] = __high2float(h);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) {
+            const int ci = c0 + j;
+#pragma unroll
+            for (int co = 0; co < 4; ++co)
+              if (co < g.CO) {
+                const float wv = w_in_smem ? ws_[(tp * g.CI + ci) * g.CO + co]
+                                           : __ldg(w + (int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co);
+                acc[co] = fmaf(v[j], wv, acc[co]);
+              }
+          }
+        }
+      } else {
+        for (int ci = 0; ci < g.CI; ++ci) {
+          const float v = ld_f(in, base + ci);
+#pragma unroll
+          for (int co = 0; co < 4; ++co)
+            if (co < g.CO) {
+              const float wv = w_in_smem ? ws_[(tp * g.CI + ci) * g.CO + co]
+                                         : __ldg(w + (int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co);
+              acc[co] = fmaf(v, wv, acc[co]);
+            }
+        }
+      }
+    }
+  }
+  for (int co = 0; co < g.CO; ++co) {
+    const float z = acc[co] + (bias ? bias[co] : 0.f);
+    if (Z) st_f(Z, p * g.CO + co, z);
+    if (Y) st_f(Y, p * g.CO + co, act_fn(g.act, z, g.p0, g.p1));
+  }
+}
+
+// wgrad with (taps*CI + 1) * CO <= 1024: one thread per (row m, out channel), a block per pixel chunk; the extra row
+// m = M has the constant input 1 and yields db.  Partials [chunk][M][CO] (+ [chunk][CO]) go to the fixed-order reduce.
+template <typename T>
+__global__ void __launch_bounds__(1024) thin_m_wgrad_kernel(GatherWgrad g, const T* __restrict__ in,
+                                                            const T* __restrict__ grad, float* __restrict__ part,
+                                                            float* __restrict__ part_db, int64_t chunk) {
+  const int M = g.fr * g.fc * g.CI;
+  const int m = threadIdx.x / g.CO, co = threadIdx.x - m * g.CO;
+  if (m > M) return;
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int64_t p_begin = (int64_t)blockIdx.x * chunk;
+  const int64_t p_end = (p_begin + chunk < P) ? p_begin + chunk : P;
+  const int tap = m < M ? m / g.CI : 0, ci = m < M ? m - tap * g.CI : 0;
+  const int r = tap / g.fc, t = tap - r * g.fc;
+  float acc = 0.f;
+  const int q0 = (int)p_begin;
+  int x = q0 % g.OW, y = (q0 / g.OW) % g.OH, n = q0 / (g.OW * g.OH);
+#pragma unroll 4
+  for (int64_t p = p_begin; p < p_end; ++p) {
+    float a = 1.f;
+    if (m < M) {
+      const int iy = y * g.s + r * g.D - g.pr, ix = x * g.s + t * g.D - g.pc;
+      a = (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+    }
+    acc = fmaf(a, ld_f(grad, p * g.CO + co), acc);
+    if (++x == g.OW) { x = 0; if (++y == g.OH) { y = 0; ++n; } }
+  }
+  if (m < M) part[((int64_t)blockIdx.x * M + m) * g.CO + co] = acc;
+  else part_db[(int64_t)blockIdx.x * g.CO + co] = acc;
+}
+
 }  // namespace
 
 // Fixed-order reduction of split partials [splits][M][CO] -> dW (strided), shared with the tensor-core wgrad
@@ -225,6 +340,33 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
       for (int z = 0; z < splits; ++z) s += part_db[(int64_t)z * CO + co];
       db[co] = accumulate ? db[co] + s : s;
     }
+  }
+}
+
+// Few outputs, many splits (thin shapes): one warp per output element, lanes stride over the splits, fixed-order
+// shuffle tree (deterministic).
+__global__ void wgrad_reduce_warp_kernel(const float* __restrict__ part, int splits, int M, int CO, int CI,
+                                         int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
+                                         float* __restrict__ dW, const float* __restrict__ part_db, float* __restrict__ db) {
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)M * CO;
+  const int64_t total_all = total + (part_db != nullptr ? CO : 0);
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= total_all) return;
+  float s = 0.f;
+  if (i < total) for (int z = lane; z < splits; z += 32) s += part[(int64_t)z * total + i];
+  else for (int z = lane; z < splits; z += 32) s += part_db[(int64_t)z * CO + (i - total)];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
+  if (i < total) {
+    const int m = (int)(i / CO), co = (int)(i - (int64_t)m * CO);
+    const int tap = m / CI, ci = m - tap * CI;
+    const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
+    dW[o] = accumulate ? dW[o] + s : s;
+  } else {
+    const int co = (int)(i - total);
+    db[co] = accumulate ? db[co] + s : s;
   }
 }
 
@@ -269,6 +411,12 @@ int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, in
     return 0;
   }
   const int64_t total = (int64_t)M * CO + (part_db != nullptr ? CO : 0);
+  if (total <= 8192 && splits >= 64) {
+    wgrad_reduce_warp_kernel<<<(unsigned)((total + 7) / 8), 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co,
+                                                                         accumulate, dW, part_db, db);
+    NPML_LAUNCH_OK();
+    return 0;
+  }
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW, part_db, db);
@@ -280,6 +428,19 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
                        void* Y, int dtype, cudaStream_t st) {
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
   if (P == 0 || g.CO == 0) return 0;
+  if (g.CO <= 4 && P < (1LL << 31) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    const unsigned blocks = (unsigned)((P + 127) / 128);
+    const size_t wn = (size_t)g.fr * g.fc * g.CI * g.CO * sizeof(float);
+    const int w_smem = wn <= 40 * 1024;
+    if (dtype == NPML_F32)
+      thin_co_conv_kernel<float, float><<<blocks, 128, w_smem ? wn : 0, st>>>(g, (const float*)in, w, bias, (float*)Z,
+                                                                             (float*)Y, w_smem);
+    else
+      thin_co_conv_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 128, w_smem ? wn : 0, st>>>(
+          g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y, w_smem);
+    NPML_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((g.CO + BN - 1) / BN));
   if (dtype == NPML_F32)
     gather_conv_kernel<float, float><<<grid, NT, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
@@ -290,9 +451,18 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
   return 0;
 }
 
+static bool thin_wgrad(const GatherWgrad& g) {
+  return (int64_t)(g.fr * g.fc * g.CI + 1) * g.CO <= 1024;
+}
+
 static int direct_wgrad_splits(const GatherWgrad& g) {
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
   const int M = g.fr * g.fc * g.CI;
+  if (thin_wgrad(g)) {               // one block per pixel chunk; the kernel is latency-bound, so many short chunks
+    int64_t splits = 8LL * num_sms();
+    if (splits * 16 > P) splits = (P + 15) / 16;
+    return (int)(splits < 1 ? 1 : splits);
+  }
   const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((g.CO + BN - 1) / BN);
   int64_t splits = (4LL * num_sms() + tiles - 1) / tiles;
   const int64_t by_len = (P + 4095) / 4096;  // keep every sequential fp32 sum short
@@ -306,16 +476,34 @@ static int direct_wgrad_splits(const GatherWgrad& g) {
 
 size_t direct_wgrad_ws_bytes(const GatherWgrad& g) {
   const int M = g.fr * g.fc * g.CI;
-  return (size_t)direct_wgrad_splits(g) * M * g.CO * sizeof(float);
+  return (size_t)direct_wgrad_splits(g) * (M + 1) * g.CO * sizeof(float);   // + one db row per split (thin shapes)
 }
 
+// *db_done (when not null) tells the caller whether db was produced here (thin shapes) or still has to be computed
 int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* dW, int dtype, void* ws,
-                 size_t ws_bytes, cudaStream_t st) {
+                 size_t ws_bytes, cudaStream_t st, float* db, bool* db_done) {
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
   const int M = g.fr * g.fc * g.CI;
+  if (db_done) *db_done = false;
   if (M == 0 || g.CO == 0) return 0;
   const int splits = direct_wgrad_splits(g);
   NPML_CHECK(ws_bytes >= direct_wgrad_ws_bytes(g), "workspace too small");
+  if (thin_wgrad(g)) {
+    const int64_t chunk = (P + splits - 1) / splits;
+    const int nsplit = (int)((P + chunk - 1) / chunk);
+    float* part = (float*)ws;
+    float* part_db = part + (size_t)nsplit * M * g.CO;
+    const int threads = (M + 1) * g.CO;
+    if (dtype == NPML_F32)
+      thin_m_wgrad_kernel<float><<<nsplit, threads, 0, st>>>(g, (const float*)in, (const float*)grad, part, part_db, chunk);
+    else
+      thin_m_wgrad_kernel<__nv_bfloat16>
+          <<<nsplit, threads, 0, st>>>(g, (const __nv_bfloat16*)in, (const __nv_bfloat16*)grad, part, part_db, chunk);
+    NPML_LAUNCH_OK();
+    if (db_done) *db_done = db != nullptr;
+    return launch_wgrad_reduce(part, nsplit, M, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st,
+                               db != nullptr ? part_db : nullptr, db);
+  }
   int64_t chunk = (P + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
   dim3 grid((M + BM - 1) / BM, (g.CO + BN - 1) / BN, splits);

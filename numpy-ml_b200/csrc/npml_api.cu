@@ -102,11 +102,12 @@ static int run_wgrad(const npml_conv_desc* d, int op, const void* in, const void
   if (d->mode != NPML_MODE_FP32 && slab_wgrad_supported(g, d->mode))
     return slab_wgrad(g, d->mode, in, grad, dW, db, ws, ws_bytes, st);
   int e;
+  bool db_done = false;
   if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode))
     e = tc_wgrad(g, d->mode, in, grad, dW, ws, ws_bytes, st);
   else
-    e = direct_wgrad(g, in, grad, dW, act_dtype(d->mode), ws, ws_bytes, st);
-  if (e || !db) return e;
+    e = direct_wgrad(g, in, grad, dW, act_dtype(d->mode), ws, ws_bytes, st, db, &db_done);
+  if (e || !db || db_done) return e;
   // the workspace is free again once the reduction above has been enqueued (stream order)
   const int dt = act_dtype(d->mode);
   return npml_dz_prep((int64_t)d->N * d->OH * d->OW, d->K, NPML_ACT_IDENTITY, 0.f, 0.f, grad, dt, nullptr, dt, nullptr, dt,

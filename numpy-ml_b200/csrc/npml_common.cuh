@@ -165,7 +165,7 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
                        void* Y, int dtype, cudaStream_t st);
 size_t direct_wgrad_ws_bytes(const GatherWgrad& g);
 int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* dW, int dtype, void* ws,
-                 size_t ws_bytes, cudaStream_t st);
+                 size_t ws_bytes, cudaStream_t st, float* db = nullptr, bool* db_done = nullptr);
 
 // tensor-core (tcgen05) kernels, tc_conv.cu / tc_wgrad.cu
 bool tc_conv_supported(const GatherConv& g, int mode);
