@@ -497,7 +497,20 @@ def run_gpu(args, cfg):
                 "host_enqueue_ms_per_step": host_ms, "cuda_graph": graph is not None, "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / (world * pk["bf16_tflops_sustained"]),
                 "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
+    # teardown must never hang the job: a captured graph that contains NCCL kernels has to be destroyed before the
+    # communicator, and a watchdog forces the exit if the clean shutdown still blocks
+    watchdog = threading.Timer(30.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+    sys.stdout.flush()
+    if graph is not None:
+        graph_prof = None
+        graph.reset()
+        graph = None
+    torch.cuda.synchronize()
+    D.barrier()
     D.destroy()
+    watchdog.cancel()
 
 
 def main():
