@@ -116,7 +116,10 @@ struct ColGeom {
   int TX, TY;  // threads over channel groups / over rows
 };
 
-template <int VEC, int NV, typename Acc, typename F>
+// DT >= 0: every tensor of the pass has element type DT, known at compile time -- the dtype switch of load_vec /
+// store_vec then folds away, which is what lets the unrolled row loop keep several 16-byte loads in flight (with a
+// run-time dtype there is a branch in front of every load).  DT = -1: run-time element types.
+template <int VEC, int NV, typename Acc, typename F, int DT>
 __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __restrict__ part) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Acc* red = reinterpret_cast<Acc*>(smem_raw);  // [TY][TX*VEC*NV]
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
 #pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += cg.TY) {
       float out[NV > 0 ? NV : 1][VEC];
-      f.template run<VEC>(r * cg.ch + c0, kc, out);
+      f.template run<VEC, DT>(r * cg.ch + c0, kc, out);
 #pragma unroll
       for (int a = 0; a < NV; ++a)
 #pragma unroll
@@ -155,15 +158,13 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
       for (int j = 0; j < VEC; ++j) red[ty * W + (a * cg.TX + tx) * VEC + j] = active ? (Acc)acc[a][j] : (Acc)0;
   }
   __syncthreads();
-  if (ty == 0 && c0 < cg.ch) {
-#pragma unroll
-    for (int a = 0; a < NV; ++a)
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        Acc s = (Acc)0;
-        for (int y = 0; y < cg.TY; ++y) s += red[y * W + (a * cg.TX + tx) * VEC + j];
-        if (c0 + j < cg.ch) part[((int64_t)blockIdx.x * NV + a) * cg.ch + c0 + j] = s;
-      }
+  // every thread adds one column of the TY x W staging matrix (fixed order over the rows)
+  for (int col = threadIdx.x; col < W; col += blockDim.x) {
+    Acc s = (Acc)0;
+    for (int y = 0; y < cg.TY; ++y) s += red[y * W + col];
+    const int a = col / (cg.TX * VEC), rem = col - a * cg.TX * VEC;
+    const int c = (blockIdx.y * cg.TX + rem / VEC) * VEC + rem % VEC;
+    if (c < cg.ch) part[((int64_t)blockIdx.x * NV + a) * cg.ch + c] = s;
   }
 }
 
@@ -235,17 +236,25 @@ ColPlan plan_cols(int64_t rows, int ch, int vec, bool reduce = true) {
   return p;
 }
 
-template <int NV, typename Acc, typename F>
-int launch_col_pass(const ColPlan& p, F f, Acc* part, cudaStream_t st) {
+template <int NV, typename Acc, typename F, int DT>
+int launch_col_pass_dt(const ColPlan& p, F f, Acc* part, cudaStream_t st) {
   const size_t smem = NV * p.smem_elems * sizeof(Acc);
   if (p.vec == 8)
-    col_pass_kernel<8, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
+    col_pass_kernel<8, NV, Acc, F, DT><<<p.grid, 256, smem, st>>>(f, p.cg, part);
   else if (p.vec == 4)
-    col_pass_kernel<4, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
+    col_pass_kernel<4, NV, Acc, F, DT><<<p.grid, 256, smem, st>>>(f, p.cg, part);
   else
-    col_pass_kernel<1, NV, Acc, F><<<p.grid, 256, smem, st>>>(f, p.cg, part);
+    col_pass_kernel<1, NV, Acc, F, DT><<<p.grid, 256, smem, st>>>(f, p.cg, part);
   NPML_LAUNCH_OK();
   return 0;
+}
+
+// dt: the element type shared by every tensor of the pass (NPML_F32 / NPML_BF16), or -1 when they differ
+template <int NV, typename Acc, typename F>
+int launch_col_pass(const ColPlan& p, F f, Acc* part, cudaStream_t st, int dt = -1) {
+  if (dt == NPML_F32) return launch_col_pass_dt<NV, Acc, F, NPML_F32>(p, f, part, st);
+  if (dt == NPML_BF16) return launch_col_pass_dt<NV, Acc, F, NPML_BF16>(p, f, part, st);
+  return launch_col_pass_dt<NV, Acc, F, -1>(p, f, part, st);
 }
 
 template <typename Acc>
@@ -256,6 +265,9 @@ int launch_col_final(const Acc* part, int nblk, int width, double* sums, cudaStr
 }
 
 // ---- functors -----------------------------------------------------------------------------------
+template <int DT>
+__device__ __forceinline__ int sel(int runtime_dt) { return DT >= 0 ? DT : runtime_dt; }
+
 // Functor protocol: kConsts per-channel constants are fetched once per thread by init(c0, ch, kc); run(i, kc, out)
 // handles the VEC elements at flat index i and returns the NV values to be column-summed.
 struct DzPrepF {
@@ -265,21 +277,21 @@ struct DzPrepF {
   float p0, p1;
   template <int VEC>
   __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
-  template <int VEC>
+  template <int VEC, int DT>
   __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[1][VEC]) const {
     float g[VEC], z[VEC];
-    load_vec<VEC>(dY, dy_dt, i, g);
+    load_vec<VEC>(dY, sel<DT>(dy_dt), i, g);
     if (act != NPML_ACT_IDENTITY) {
-      load_vec<VEC>(Z, z_dt, i, z);
+      load_vec<VEC>(Z, sel<DT>(z_dt), i, z);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) g[j] *= act_grad(act, z[j], p0, p1);
     }
     // the sum is taken over the values the GEMMs will see (after rounding to the dZ dtype)
-    if (dz_dt == NPML_BF16) {
+    if (sel<DT>(dz_dt) == NPML_BF16) {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) g[j] = __bfloat162float(__float2bfloat16_rn(g[j]));
     }
-    if (dZ) store_vec<VEC>(dZ, dz_dt, i, g);
+    if (dZ) store_vec<VEC>(dZ, sel<DT>(dz_dt), i, g);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) out[0][j] = g[j];
   }
@@ -290,10 +302,10 @@ struct BnStatsF {
   const void* x; int dt;
   template <int VEC>
   __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
-  template <int VEC>
+  template <int VEC, int DT>
   __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[2][VEC]) const {
     float v[VEC];
-    load_vec<VEC>(x, dt, i, v);
+    load_vec<VEC>(x, sel<DT>(dt), i, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) { out[0][j] = v[j]; out[1][j] = v[j] * v[j]; }
   }
@@ -311,13 +323,13 @@ struct BnNormF {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
-  template <int VEC>
+  template <int VEC, int DT>
   __device__ __forceinline__ void run(int64_t i, const float (&kc)[3][VEC], float (&)[1][VEC]) const {
     float v[VEC];
-    load_vec<VEC>(x, dt, i, v);
+    load_vec<VEC>(x, sel<DT>(dt), i, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) v[j] = fmaf(kc[1][j], v[j] - kc[0][j], kc[2][j]);
-    store_vec<VEC>(y, dt, i, v);
+    store_vec<VEC>(y, sel<DT>(dt), i, v);
   }
 };
 
@@ -333,11 +345,11 @@ struct BnBwdStatsF {
       kc[0][j] = mean[c]; kc[1][j] = rstd[c];
     }
   }
-  template <int VEC>
+  template <int VEC, int DT>
   __device__ __forceinline__ void run(int64_t i, const float (&kc)[2][VEC], float (&out)[2][VEC]) const {
     float d[VEC], v[VEC];
-    load_vec<VEC>(dy, dt, i, d);
-    load_vec<VEC>(x, dt, i, v);
+    load_vec<VEC>(dy, sel<DT>(dt), i, d);
+    load_vec<VEC>(x, sel<DT>(dt), i, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       out[0][j] = d[j];
@@ -358,17 +370,17 @@ struct BnBwdDxF {
 #pragma unroll
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
-  template <int VEC>
+  template <int VEC, int DT>
   __device__ __forceinline__ void run(int64_t i, const float (&kc)[5][VEC], float (&)[1][VEC]) const {
     float d[VEC], v[VEC];
-    load_vec<VEC>(dy, dt, i, d);
-    load_vec<VEC>(x, dt, i, v);
+    load_vec<VEC>(dy, sel<DT>(dt), i, d);
+    load_vec<VEC>(x, sel<DT>(dt), i, v);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float nh = (v[j] - kc[0][j]) * kc[1][j];
       v[j] = kc[2][j] * (d[j] - kc[3][j] - nh * kc[4][j]);
     }
-    store_vec<VEC>(dx, dt, i, v);
+    store_vec<VEC>(dx, sel<DT>(dt), i, v);
   }
 };
 
@@ -474,8 +486,10 @@ struct AddArgs {
   int n_in;
 };
 
-template <int VEC>
-__global__ void add_act_kernel(AddArgs a, int dt, int64_t n_vec, int act, float p0, float p1, void* sum, void* Y) {
+template <int VEC, int DT>
+__global__ void add_act_kernel(AddArgs a, int dt_rt, int64_t n_vec, int act, float p0, float p1, void* sum, void* Y) {
+  const int dt = sel<DT>(dt_rt);
+#pragma unroll 2
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
     float s[VEC];
     load_vec<VEC>(a.xs[0], dt, i * VEC, s);
@@ -521,7 +535,7 @@ struct SumSqF {
   const float* x;
   template <int VEC>
   __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
-  template <int VEC>
+  template <int VEC, int DT>
   __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[1][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) out[0][j] = x[i + j] * x[i + j];
@@ -597,11 +611,12 @@ extern "C" int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, flo
   const bool vec_ok = aligned_for_vec4(dY, dy_dtype) && aligned_for_vec4(Z, z_dtype) && aligned_for_vec4(dZ, dz_dtype);
   ColPlan p = plan_cols(rows, ch, pick_vec(ch, vec_ok, aligned16(dY) && aligned16(Z) && aligned16(dZ)), db != nullptr);
   DzPrepF f{dY, Z, dZ, dy_dtype, z_dtype, dz_dtype, act, p0, p1};
-  if (!db) return launch_col_pass<1, float>(p, f, (float*)nullptr, st);
+  const int same_dt = (dy_dtype == dz_dtype && (act == NPML_ACT_IDENTITY || z_dtype == dy_dtype)) ? dy_dtype : -1;
+  if (!db) return launch_col_pass<1, float>(p, f, (float*)nullptr, st, same_dt);
   const size_t part_bytes = align_up((size_t)p.grid.x * ch * sizeof(float), 256);
   NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)ch * sizeof(double), "workspace too small");
   float* part = (float*)ws;
-  if (int e = launch_col_pass<1, float>(p, f, part, st)) return e;
+  if (int e = launch_col_pass<1, float>(p, f, part, st, same_dt)) return e;
   db_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, db);
   NPML_LAUNCH_OK();
   return 0;
@@ -637,12 +652,16 @@ extern "C" int npml_add_act_fwd(int32_t n_in, const void* const* xs, int32_t dty
   bool al16 = aligned16(sum) && aligned16(Y);
   for (int i = 0; i < n_in; ++i) al16 = al16 && aligned16(xs[i]);
   const int vec = pick_vec(n, al, al16);
-  if (vec == 8)
-    add_act_kernel<8><<<flat_blocks(n / 8), 256, 0, st>>>(a, dtype, n / 8, act, p0, p1, sum, Y);
+  if (vec == 8 && dtype == NPML_BF16)
+    add_act_kernel<8, NPML_BF16><<<flat_blocks(n / 8), 256, 0, st>>>(a, dtype, n / 8, act, p0, p1, sum, Y);
+  else if (vec == 8 && dtype == NPML_F32)
+    add_act_kernel<8, NPML_F32><<<flat_blocks(n / 8), 256, 0, st>>>(a, dtype, n / 8, act, p0, p1, sum, Y);
+  else if (vec == 8)
+    add_act_kernel<8, -1><<<flat_blocks(n / 8), 256, 0, st>>>(a, dtype, n / 8, act, p0, p1, sum, Y);
   else if (vec == 4)
-    add_act_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, sum, Y);
+    add_act_kernel<4, -1><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, sum, Y);
   else
-    add_act_kernel<1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, sum, Y);
+    add_act_kernel<1, -1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, sum, Y);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -671,7 +690,7 @@ extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, i
   float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   if (use_batch_stats) {
     BnStatsF fs{x, dtype};
-    if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+    if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
     bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, 1.0 / (double)rows, momentum, eps,
                                                                 running_mean, running_var, save_mean, save_rstd, scaler,
                                                                 intercept, coef, nullptr);
@@ -682,7 +701,7 @@ extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, i
     NPML_LAUNCH_OK();
   }
   BnNormF fn{x, y, dtype, coef};
-  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fn, (float*)nullptr, st);
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fn, (float*)nullptr, st, dtype);
 }
 
 extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const void* x, void* dx, int32_t dtype,
@@ -700,13 +719,13 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   double* sums = (double*)((char*)ws + part_bytes);
   float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
-  if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+  if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
                                                                   1.0 / (double)rows, save_mean, save_rstd, scaler, coef,
                                                                   nullptr, nullptr);
   NPML_LAUNCH_OK();
   BnBwdDxF fd{dy, x, dx, dtype, coef};
-  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st);
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st, dtype);
 }
 
 // ---- sync-BN: the same passes split at the point where the per-channel sums cross ranks ---------------------
@@ -719,7 +738,7 @@ extern "C" int npml_bn2d_stats(int64_t rows, int32_t ch, const void* x, int32_t 
   NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 2 * ch * sizeof(double), "workspace too small");
   double* part = (double*)ws;
   BnStatsF fs{x, dtype};
-  if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+  if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
   NPML_LAUNCH_OK();
   return 0;
@@ -740,7 +759,7 @@ extern "C" int npml_bn2d_apply(int64_t rows, int64_t rows_total, int32_t ch, con
   NPML_LAUNCH_OK();
   const int vec = pick_vec(ch, aligned_for_vec4(x, dtype) && aligned_for_vec4(y, dtype), aligned16(x) && aligned16(y));
   BnNormF fn{x, y, dtype, coef};
-  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fn, (float*)nullptr, st);
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fn, (float*)nullptr, st, dtype);
 }
 
 extern "C" int npml_bn2d_bwd_stats(int64_t rows, int32_t ch, const void* dy, const void* x, int32_t dtype,
@@ -754,7 +773,7 @@ extern "C" int npml_bn2d_bwd_stats(int64_t rows, int32_t ch, const void* dy, con
   NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 2 * ch * sizeof(double), "workspace too small");
   double* part = (double*)ws;
   BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
-  if (int e = launch_col_pass<2, double>(p, fs, part, st)) return e;
+  if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
   NPML_LAUNCH_OK();
   return 0;
@@ -776,7 +795,7 @@ extern "C" int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch,
   const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(dy, dtype) && aligned_for_vec4(dx, dtype);
   const int vec = pick_vec(ch, vec_ok, aligned16(x) && aligned16(dy) && aligned16(dx));
   BnBwdDxF fd{dy, x, dx, dtype, coef};
-  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st);
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st, dtype);
 }
 
 extern "C" int npml_im2col(const npml_conv_desc* d, const float* X, float* X_col, void* stream) {
