@@ -211,6 +211,18 @@ CONV_CASES = [
     ((2, 10, 10, 16), 24, (2, 2), (1, 0, 2, 1), 3, 0, "identity"),  # stride 3, leftovers, asymmetric pad
     ((2, 8, 8, 8), 8, (3, 3), 1, 1, 0, "identity"),                 # minimum aligned channels
     ((3, 6, 6, 5), 17, (3, 3), 1, 1, 0, "identity"),                # odd channels -> CUDA-core path
+    # slab kernels (stride 1): weight streaming, two channel blocks, several N tiles, generic tap count, units that
+    # span images, and the shapes that must fall back to the per-tile kernels
+    ((3, 12, 12, 128), 128, (3, 3), 1, 1, 0, "identity"),           # cfg4 conv2 miniature: nkb = 2, streamed weights
+    ((5, 10, 10, 64), 128, (3, 3), 1, 1, 0, "relu"),                # cfg4 conv1 miniature: Z and Y both written
+    ((2, 6, 6, 64), 192, (3, 3), "same", 1, 0, "identity"),         # out_ch > 128: two N tiles per unit
+    ((2, 9, 9, 32), 32, (5, 5), 2, 1, 0, "tanh"),                   # 25 taps: run-time tap loop
+    ((1, 3, 3, 16), 16, (3, 3), 0, 1, 0, "identity"),               # one output pixel per image
+    ((1, 2, 260, 8), 8, (3, 3), "same", 1, 0, "identity"),          # padded row wider than a TMA box: per-tile path
+    ((9, 5, 5, 64), 64, (3, 3), "same", 1, 3, "identity"),          # dilation 3 at stride 1, units span images
+    # thin shapes (cfg1): in_ch = 1 and out_ch <= 4 take the CUDA-core thin kernels in every mode
+    ((4, 12, 12, 1), 32, (3, 3), "same", 1, 0, "identity"),         # cfg1 miniature
+    ((3, 7, 9, 24), 2, (3, 3), 1, 1, 0, "sigmoid"),                 # out_ch = 2 forward
 ]
 
 
