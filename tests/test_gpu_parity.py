@@ -464,7 +464,7 @@ def _dot(a, b):
 
 
 @pytest.mark.parametrize("mode", ["tf32", "bf16"])
-@pytest.mark.parametrize("cfg", ["cfg2", "cfg3", "cfg5"])
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2", "cfg3", "cfg4-conv1", "cfg4-conv2", "cfg4-skip", "cfg5"])
 def test_full_size_adjoint_identities(cuda_device, mode, cfg):
     """<conv(X), dY> == <X, dgrad(dY)> == <W, wgrad(X, dY)> + <b, db>-free form, at the BASELINE.json sizes.
     The three kernels are independent implementations, so agreement to rounding checks all of them;
@@ -475,6 +475,14 @@ def test_full_size_adjoint_identities(cuda_device, mode, cfg):
     if cfg == "cfg2":
         L = pkg.Conv2D(64, (3, 3), pad="same", mode=mode)
         xs = (256, 56, 56, 64)
+    elif cfg == "cfg1":
+        L = pkg.Conv2D(32, (3, 3), pad="same", mode=mode)
+        xs = (32, 28, 28, 1)
+    elif cfg.startswith("cfg4"):         # the three convolutions of the SkipConnectionConvModule config
+        oc, ks, pad, cin = {"cfg4-conv1": (128, (3, 3), 1, 64), "cfg4-conv2": (128, (3, 3), 1, 128),
+                            "cfg4-skip": (128, (1, 1), 0, 64)}[cfg]
+        L = pkg.Conv2D(oc, ks, pad=pad, mode=mode)
+        xs = (256, 32, 32, cin)
     elif cfg == "cfg3":
         L = pkg.Conv2D(256, (3, 3), pad=0, stride=2, dilation=2, mode=mode)
         xs = (128, 28, 28, 128)
@@ -504,6 +512,8 @@ def test_full_size_adjoint_identities(cuda_device, mode, cfg):
         Yr, _ = O.deconv2d_layer_fwd(Xs, Wn, bz, 2, 1)
     elif cfg == "cfg3":
         Yr, _ = O.conv2d_layer_fwd(Xs, Wn, bz, 2, 0, 2)
+    elif cfg.startswith("cfg4"):
+        Yr, _ = O.conv2d_layer_fwd(Xs, Wn, bz, 1, L.pad, 0)
     else:
         Yr, _ = O.conv2d_layer_fwd(Xs, Wn, bz, 1, "same", 0)
     close(Y[:2], Yr, tol, "Y[:2]")
