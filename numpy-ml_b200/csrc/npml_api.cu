@@ -103,9 +103,10 @@ static int run_wgrad(const npml_conv_desc* d, int op, const void* in, const void
     return slab_wgrad(g, d->mode, in, grad, dW, db, ws, ws_bytes, st);
   int e;
   bool db_done = false;
-  if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode))
-    e = tc_wgrad(g, d->mode, in, grad, dW, ws, ws_bytes, st);
-  else
+  if (d->mode != NPML_MODE_FP32 && tc_wgrad_supported(g, d->mode)) {
+    e = tc_wgrad(g, d->mode, in, grad, dW, ws, ws_bytes, st, db);
+    db_done = db != nullptr;
+  } else
     e = direct_wgrad(g, in, grad, dW, act_dtype(d->mode), ws, ws_bytes, st, db, &db_done);
   if (e || !db || db_done) return e;
   // the workspace is free again once the reduction above has been enqueued (stream order)

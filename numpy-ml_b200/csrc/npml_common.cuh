@@ -185,6 +185,6 @@ int slab_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad,
 bool tc_wgrad_supported(const GatherWgrad& g, int mode);
 size_t tc_wgrad_ws_bytes(const GatherWgrad& g, int mode);
 int tc_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad, float* dW, void* ws,
-             size_t ws_bytes, cudaStream_t st);
+             size_t ws_bytes, cudaStream_t st, float* db = nullptr);
 
 }  // namespace npml

@@ -51,7 +51,7 @@ struct TcWgradParams {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constant__ TcWgradParams P,
-                                                            float* __restrict__ part) {
+                                                            float* __restrict__ part, float* __restrict__ part_db) {
   constexpr bool kTf32 = sizeof(T) == 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -79,6 +79,19 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
     for (int i = threadIdx.x; i < n16; i += kThreads) p[i] = make_uint4(0, 0, 0, 0);
     ptx::fence_proxy_async();
   }
+  // the db window (tap < 0) is never loaded: it is a constant block of ones in every stage, so the rows of the
+  // accumulator it owns receive sum_pixels 1 * dZ[pixel, co] = db (pixel rows the TMA leaves zero add nothing)
+  int n_tma = 0;
+  for (int b = 0; b < nblk; ++b) {
+    if (P.blocks[blk0 + b].tap >= 0) { ++n_tma; continue; }
+    __syncthreads();
+    const uint32_t one = kTf32 ? 0x3F800000u : 0x3F803F80u;
+    for (int st = 0; st < P.stages; ++st) {
+      uint32_t* q = reinterpret_cast<uint32_t*>(smem + (size_t)st * stage_bytes + (size_t)b * kTileBytes);
+      for (int i = threadIdx.x; i < kTileBytes / 4; i += kThreads) q[i] = one;
+    }
+    ptx::fence_proxy_async();
+  }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < P.stages; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
   if (warp == 0) {
     if (ptx::elect_one()) {
       ptx::prefetch_tmap(&P.gmap);
-      const uint32_t tx_bytes = (uint32_t)((nblk + nbn) * P.rows_used * kRowBytes);
+      const uint32_t tx_bytes = (uint32_t)((n_tma + nbn) * P.rows_used * kRowBytes);
       const int per_img = P.tiles_x * P.tiles_y;
       uint32_t s = 0, ph = 0;     // ring position / phase
       for (int k = 0; k < nk; ++k) {
@@ -113,6 +126,7 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
         ptx::mbar_expect_tx(&full_bar[s], tx_bytes);
         for (int b = 0; b < nblk; ++b) {
           const ABlock ab = P.blocks[blk0 + b];
+          if (ab.tap < 0) continue;
           ptx::tma_load_4d(dst + b * kTileBytes, &P.amap[ab.amap], &full_bar[s], ab.c0, ox0 + ab.dx, oy0 + ab.dy, n0);
         }
         for (int b = 0; b < nbn; ++b)
@@ -154,13 +168,15 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
     const int b = m / P.kelems, cl = m - b * P.kelems;
     bool row_ok = b < nblk;
     int64_t row = 0;
+    bool is_db = false;
     if (row_ok) {
       const ABlock ab = P.blocks[blk0 + b];
       const int ci = ab.c0 + cl;
-      row_ok = ci < P.CI;
+      is_db = ab.tap < 0;
+      row_ok = is_db ? (cl == 0) : (ci < P.CI);
       row = (int64_t)ab.tap * P.CI + ci;
     }
-    float* out = part + ((int64_t)blockIdx.z * P.Mrows + row) * P.CO;
+    float* out = is_db ? part_db + (int64_t)blockIdx.z * P.CO : part + ((int64_t)blockIdx.z * P.Mrows + row) * P.CO;
     if (nk > 0) {
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
@@ -213,11 +229,11 @@ void choose_patch_w(int ow, int oh, int n, int& TW, int& TH, int& TN) {
 struct WPlan {
   TcWgradParams P;
   dim3 grid;
-  size_t smem = 0, part_bytes = 0;
+  size_t smem = 0, part_bytes = 0, partdb_bytes = 0;
   int splits = 1;
 };
 
-bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl) {
+bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl, bool want_db = false) {
   const bool bf16 = mode == NPML_MODE_BF16;
   if (mode != NPML_MODE_BF16 && mode != NPML_MODE_TF32) return false;
   const int es = bf16 ? 2 : 4, vec = 16 / es;
@@ -228,7 +244,7 @@ bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl) {
   memset(&P, 0, sizeof(P));
   P.kelems = kRowBytes / es;
   const int cblocks = ceildiv(g.CI, P.kelems);
-  if (g.fr * g.fc * cblocks > kMaxBlocks) return false;
+  if (g.fr * g.fc * cblocks + 1 > kMaxBlocks) return false;
   P.CI = g.CI; P.CO = g.CO; P.Mrows = g.fr * g.fc * g.CI;
   P.N = g.N; P.OH = g.OH; P.OW = g.OW;
   P.mb = 128 / P.kelems;                                   // 2 (bf16) or 4 (tf32) windows per M tile
@@ -258,6 +274,10 @@ bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl) {
         b.c0 = cb * P.kelems;
       }
     }
+  if (want_db) {                                           // the constant ones window that yields db
+    ABlock& b = P.blocks[nb++];
+    b.dy = 0; b.dx = 0; b.amap = 0; b.tap = -1; b.c0 = 0;
+  }
   P.nblocks = nb;
   choose_patch_w(g.OW, g.OH, g.N, P.TW, P.TH, P.TN);
   P.rows_used = P.TW * P.TH * P.TN;
@@ -278,11 +298,12 @@ bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl) {
   pl.splits = splits;
   pl.grid = dim3((unsigned)mt, (unsigned)nt, (unsigned)splits);
   pl.part_bytes = align_up((size_t)splits * P.Mrows * g.CO * sizeof(float), 256);
+  pl.partdb_bytes = align_up((size_t)splits * g.CO * sizeof(float), 256);
   return true;
 }
 
 template <typename T>
-int launch_wgrad(const GatherWgrad& g, WPlan& pl, const void* in, const void* grad, float* dW, void* ws,
+int launch_wgrad(const GatherWgrad& g, WPlan& pl, const void* in, const void* grad, float* dW, float* db, void* ws,
                  cudaStream_t st) {
   const bool bf16 = sizeof(T) == 2;
   const int es = sizeof(T);
@@ -310,10 +331,11 @@ int launch_wgrad(const GatherWgrad& g, WPlan& pl, const void* in, const void* gr
     NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[bf16 ? 0 : 1] = true;
   }
-  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, (float*)ws);
+  float* part_db = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, (float*)ws, part_db);
   NPML_LAUNCH_OK();
   return launch_wgrad_reduce((const float*)ws, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate,
-                             dW, st);
+                             dW, st, db != nullptr ? part_db : nullptr, db);
 }
 
 }  // namespace
@@ -325,19 +347,21 @@ bool tc_wgrad_supported(const GatherWgrad& g, int mode) {
 
 size_t tc_wgrad_ws_bytes(const GatherWgrad& g, int mode) {
   WPlan pl;
-  if (!plan_wgrad(g, mode, pl)) return 0;
-  return pl.part_bytes + 256;
+  if (!plan_wgrad(g, mode, pl, true)) return 0;
+  return pl.part_bytes + pl.partdb_bytes + 256;
 }
 
+// db != nullptr: db (+)= column sums of `grad` from the same pass (one extra window of ones); only meaningful when
+// `grad` is dZ (Conv2D).  The fixed-order reduction of the partials writes dW and db.
 int tc_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad, float* dW, void* ws, size_t ws_bytes,
-             cudaStream_t st) {
+             cudaStream_t st, float* db) {
   WPlan pl;
-  NPML_CHECK(plan_wgrad(g, mode, pl), "shape not supported by the tensor-core path");
-  NPML_CHECK(ws != nullptr && ws_bytes >= pl.part_bytes, "workspace too small");
+  NPML_CHECK(plan_wgrad(g, mode, pl, db != nullptr), "shape not supported by the tensor-core path");
+  NPML_CHECK(ws != nullptr && ws_bytes >= pl.part_bytes + pl.partdb_bytes, "workspace too small");
   NPML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0,
              "activation pointers must be 16-byte aligned");
-  if (mode == NPML_MODE_BF16) return launch_wgrad<__nv_bfloat16>(g, pl, in, grad, dW, ws, st);
-  return launch_wgrad<float>(g, pl, in, grad, dW, ws, st);
+  if (mode == NPML_MODE_BF16) return launch_wgrad<__nv_bfloat16>(g, pl, in, grad, dW, db, ws, st);
+  return launch_wgrad<float>(g, pl, in, grad, dW, db, ws, st);
 }
 
 }  // namespace npml
