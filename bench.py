@@ -337,6 +337,25 @@ def run_gpu(args, cfg):
     # ---- timed region: K steps, CUDA events on the launching stream, per-call events inside ----------
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
+    # pre-roll: keep the GPU under the same load for ~0.4 s so that nvidia-smi (50 ms period) samples the clocks of
+    # a loaded device; these steps are extra warm-up, not part of the timed region.  The number of steps is derived
+    # from a max-over-ranks estimate so that every rank issues the same number of collectives.
+    def one():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(5):
+        one()
+    p1.record()
+    torch.cuda.synchronize()
+    est_ms = max(D.all_reduce_max(p0.elapsed_time(p1)) / 5.0, 1e-3)
+    for _ in range(int(min(5000, max(10, 400.0 / est_ms)))):
+        one()
+    torch.cuda.synchronize()
     if graph is None:
         L.PROFILE = []
     L.launch_count(reset=True)
