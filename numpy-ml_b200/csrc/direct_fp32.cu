@@ -320,10 +320,48 @@ __global__ void __launch_bounds__(1024) thin_m_wgrad_kernel(GatherWgrad g, const
 }  // namespace
 
 // Fixed-order reduction of split partials [splits][M][CO] -> dW (strided), shared with the tensor-core wgrad
-// kernels.  When part_db != nullptr the same launch also reduces [splits][CO] -> db.
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int M, int CO, int CI,
-                                    int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
-                                    float* __restrict__ dW, const float* __restrict__ part_db, float* __restrict__ db) {
+// kernels.  When part_db != nullptr the same launch also reduces [splits][CO] -> db.  Block = (64 outputs, 8 split
+// groups): thread (x, y) adds the splits z = y, y + 8, ... of output x (reads coalesced along x), the 8 group sums
+// are then added in a fixed order -- deterministic, and 8x the memory-level parallelism of one thread per output.
+__global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restrict__ part, int splits, int M, int CO,
+                                                           int CI, int64_t o_tap, int64_t o_ci, int64_t o_co,
+                                                           int accumulate, float* __restrict__ dW,
+                                                           const float* __restrict__ part_db, float* __restrict__ db) {
+  __shared__ float red[8][64];
+  const int64_t total = (int64_t)M * CO;
+  const int64_t total_all = total + (part_db != nullptr ? CO : 0);
+  for (int64_t i0 = (int64_t)blockIdx.x * 64; i0 < total_all; i0 += (int64_t)gridDim.x * 64) {
+    const int64_t i = i0 + threadIdx.x;
+    float s = 0.f;
+    if (i < total) {
+      for (int z = threadIdx.y; z < splits; z += 8) s += part[(int64_t)z * total + i];
+    } else if (i < total_all) {
+      for (int z = threadIdx.y; z < splits; z += 8) s += part_db[(int64_t)z * CO + (i - total)];
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < total_all) {
+      float t = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x];
+      if (i < total) {
+        const int m = (int)(i / CO), co = (int)(i - (int64_t)m * CO);
+        const int tap = m / CI, ci = m - tap * CI;
+        const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
+        dW[o] = accumulate ? dW[o] + t : t;
+      } else {
+        const int co = (int)(i - total);
+        db[co] = accumulate ? db[co] + t : t;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// few splits: one thread per output element is enough
+__global__ void wgrad_reduce_simple_kernel(const float* __restrict__ part, int splits, int M, int CO, int CI,
+                                           int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
+                                           float* __restrict__ dW, const float* __restrict__ part_db, float* __restrict__ db) {
   const int64_t total = (int64_t)M * CO;
   const int64_t total_all = total + (part_db != nullptr ? CO : 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_all;
@@ -417,9 +455,17 @@ int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, in
     NPML_LAUNCH_OK();
     return 0;
   }
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW, part_db, db);
+  if (splits < 32) {
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    wgrad_reduce_simple_kernel<<<blocks, 256, 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW, part_db,
+                                                       db);
+    NPML_LAUNCH_OK();
+    return 0;
+  }
+  int blocks = (int)((total + 63) / 64);
+  if (blocks > 8192) blocks = 8192;
+  wgrad_reduce_kernel<<<blocks, dim3(64, 8), 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW, part_db, db);
   NPML_LAUNCH_OK();
   return 0;
 }

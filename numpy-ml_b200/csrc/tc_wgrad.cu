@@ -347,8 +347,11 @@ bool tc_wgrad_supported(const GatherWgrad& g, int mode) {
 
 size_t tc_wgrad_ws_bytes(const GatherWgrad& g, int mode) {
   WPlan pl;
-  if (!plan_wgrad(g, mode, pl, true)) return 0;
-  return pl.part_bytes + pl.partdb_bytes + 256;
+  // the split count depends on the number of M tiles, which the optional db window can change: cover both plans
+  WPlan pl2;
+  if (!plan_wgrad(g, mode, pl, true) || !plan_wgrad(g, mode, pl2, false)) return 0;
+  const size_t a = pl.part_bytes + pl.partdb_bytes, b = pl2.part_bytes + pl2.partdb_bytes;
+  return (a > b ? a : b) + 256;
 }
 
 // db != nullptr: db (+)= column sums of `grad` from the same pass (one extra window of ones); only meaningful when
