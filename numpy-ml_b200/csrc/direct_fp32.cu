@@ -203,30 +203,33 @@ __global__ void __launch_bounds__(NT) wgrad_partial_kernel(GatherWgrad g, const 
 }
 
 // ---- thin shapes (cfg1: in_ch = 1): the 64x64 tiles above would be almost empty ---------------------------
-// gather conv with CO <= 4 (Conv2D dX when in_ch is tiny): one THREAD per output pixel (the index arithmetic is paid
-// once per pixel, not once per lane), the taps' channel vectors are read with 16-byte loads, the weights sit in
-// shared memory (every thread reads the same address: broadcast).
-template <typename TIn, typename TOut>
+// gather conv with CO <= 4 (Conv2D dX when in_ch is tiny).  Four lanes share one output pixel and split the input
+// channels of every tap (16-byte loads); the index arithmetic is paid once per pixel, the weights sit in shared
+// memory as [tap][ci][co] (broadcast reads), CO is a template parameter so the inner loop is pure FMA.
+template <typename TIn, typename TOut, int CO_T>
 __global__ void __launch_bounds__(128) thin_co_conv_kernel(GatherConv g, const TIn* __restrict__ in,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
-                                                           TOut* __restrict__ Z, TOut* __restrict__ Y, int w_in_smem) {
-  extern __shared__ float ws_[];            // [tap][ci][co] when it fits
+                                                           TOut* __restrict__ Z, TOut* __restrict__ Y) {
+  extern __shared__ __align__(16) float ws_[];          // [tap][ci][co]
   const int taps = g.fr * g.fc;
-  if (w_in_smem) {
-    for (int i = threadIdx.x; i < taps * g.CI * g.CO; i += blockDim.x) {
-      const int co = i % g.CO, ci = (i / g.CO) % g.CI, tp = i / (g.CO * g.CI);
-      ws_[i] = w[(int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co];
-    }
-    __syncthreads();
+  for (int i = threadIdx.x; i < taps * g.CI * CO_T; i += blockDim.x) {
+    const int co = i % CO_T, ci = (i / CO_T) % g.CI, tp = i / (CO_T * g.CI);
+    ws_[i] = w[(int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co];
   }
-  const int64_t P = (int64_t)g.N * g.OH * g.OW;
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const int pi = (int)p;
-  const int x = pi % g.OW, y = (pi / g.OW) % g.OH, n = pi / (g.OW * g.OH);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
   constexpr int V = 16 / (int)sizeof(TIn);                 // elements per 16-byte load
-  const bool vec = (g.CI % V) == 0;
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int sub = threadIdx.x & 3;                         // channel quarter of this lane
+  const int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 2) + (threadIdx.x >> 2);
+  const bool live = p < P;
+  const int pi = live ? (int)p : 0;
+  const int x = pi % g.OW, y = (pi / g.OW) % g.OH, n = pi / (g.OW * g.OH);
+  // channels [c_lo, c_hi) of every tap belong to this lane (multiples of V)
+  const int per = ((g.CI / V + 3) / 4) * V;
+  const int c_lo = sub * per, c_hi = min(g.CI, c_lo + per);
+  float acc[CO_T];
+#pragma unroll
+  for (int co = 0; co < CO_T; ++co) acc[co] = 0.f;
   for (int r = 0; r < g.fr; ++r) {
     int iy;
     if (g.form == 0) iy = y * g.s + r * g.D - g.pr;
@@ -237,81 +240,82 @@ __global__ void __launch_bounds__(128) thin_co_conv_kernel(GatherConv g, const T
       if (g.form == 0) ix = x * g.s + t * g.D - g.pc;
       else { const int nx = x + g.pc - t * g.D; if (nx < 0 || nx % g.s) continue; ix = nx / g.s; }
       if (ix < 0 || ix >= g.IW) continue;
-      const int64_t base = (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI;
-      const int tp = r * g.fc + t;
-      if (vec) {
-        for (int c0 = 0; c0 < g.CI; c0 += V) {
-          float v[V];
-          const uint4 u = *reinterpret_cast<const uint4*>(in + base + c0);
-          if constexpr (sizeof(TIn) == 4) {
-            v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
-          } else {
-            const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+      const TIn* src = in + (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI;
+      const float* wt = ws_ + (size_t)(r * g.fc + t) * g.CI * CO_T;
+      for (int c0 = c_lo; c0 < c_hi; c0 += V) {
+        float v[V];
+        const uint4 u = *reinterpret_cast<const uint4*>(src + c0);
+        if constexpr (sizeof(TIn) == 4) {
+          v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+        } else {
+          const uint32_t q[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&q[j]);
-              v[2 * j] = __low2float(h); v[2 * j + 1] = __high2float(h);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < V; ++j) {
-            const int ci = c0 + j;
-#pragma unroll
-            for (int co = 0; co < 4; ++co)
-              if (co < g.CO) {
-                const float wv = w_in_smem ? ws_[(tp * g.CI + ci) * g.CO + co]
-                                           : __ldg(w + (int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co);
-                acc[co] = fmaf(v[j], wv, acc[co]);
-              }
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&q[j]);
+            v[2 * j] = __low2float(h); v[2 * j + 1] = __high2float(h);
           }
         }
-      } else {
-        for (int ci = 0; ci < g.CI; ++ci) {
-          const float v = ld_f(in, base + ci);
 #pragma unroll
-          for (int co = 0; co < 4; ++co)
-            if (co < g.CO) {
-              const float wv = w_in_smem ? ws_[(tp * g.CI + ci) * g.CO + co]
-                                         : __ldg(w + (int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co);
-              acc[co] = fmaf(v, wv, acc[co]);
-            }
-        }
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+          for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(v[j], wt[(c0 + j) * CO_T + co], acc[co]);
       }
     }
   }
-  for (int co = 0; co < g.CO; ++co) {
-    const float z = acc[co] + (bias ? bias[co] : 0.f);
-    if (Z) st_f(Z, p * g.CO + co, z);
-    if (Y) st_f(Y, p * g.CO + co, act_fn(g.act, z, g.p0, g.p1));
+#pragma unroll
+  for (int co = 0; co < CO_T; ++co) {
+    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 1);
+    acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], 2);
+  }
+  if (live && sub == 0) {
+#pragma unroll
+    for (int co = 0; co < CO_T; ++co) {
+      const float z = acc[co] + (bias ? bias[co] : 0.f);
+      if (Z) st_f(Z, p * CO_T + co, z);
+      if (Y) st_f(Y, p * CO_T + co, act_fn(g.act, z, g.p0, g.p1));
+    }
   }
 }
 
-// wgrad with (taps*CI + 1) * CO <= 1024: one thread per (row m, out channel), a block per pixel chunk; the extra row
-// m = M has the constant input 1 and yields db.  Partials [chunk][M][CO] (+ [chunk][CO]) go to the fixed-order reduce.
+// wgrad with (taps*CI + 1) * CO <= 1024: a block owns a chunk of pixels.  The chunk's gathered inputs (an im2col tile
+// of kThinPix pixels x M rows, plus a row of ones that yields db) and its dZ rows are staged in shared memory once,
+// then thread (m, co) does 2 shared loads + 1 FMA per pixel.  Partials [chunk][M][CO] (+ [chunk][CO]) go to the
+// fixed-order reduce.
+constexpr int kThinPix = 64;
 template <typename T>
 __global__ void __launch_bounds__(1024) thin_m_wgrad_kernel(GatherWgrad g, const T* __restrict__ in,
                                                             const T* __restrict__ grad, float* __restrict__ part,
                                                             float* __restrict__ part_db, int64_t chunk) {
-  const int M = g.fr * g.fc * g.CI;
+  extern __shared__ float sm_[];
+  const int M = g.fr * g.fc * g.CI, M1 = M + 1;
+  float* As = sm_;                       // [kThinPix][M1]
+  float* Gs = sm_ + kThinPix * M1;       // [kThinPix][CO]
+  const int nthr = M1 * g.CO;
   const int m = threadIdx.x / g.CO, co = threadIdx.x - m * g.CO;
-  if (m > M) return;
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
   const int64_t p_begin = (int64_t)blockIdx.x * chunk;
   const int64_t p_end = (p_begin + chunk < P) ? p_begin + chunk : P;
-  const int tap = m < M ? m / g.CI : 0, ci = m < M ? m - tap * g.CI : 0;
-  const int r = tap / g.fc, t = tap - r * g.fc;
   float acc = 0.f;
-  const int q0 = (int)p_begin;
-  int x = q0 % g.OW, y = (q0 / g.OW) % g.OH, n = q0 / (g.OW * g.OH);
-#pragma unroll 4
-  for (int64_t p = p_begin; p < p_end; ++p) {
-    float a = 1.f;
-    if (m < M) {
-      const int iy = y * g.s + r * g.D - g.pr, ix = x * g.s + t * g.D - g.pc;
-      a = (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += kThinPix) {
+    const int np = (int)((p_end - p0 < kThinPix) ? p_end - p0 : kThinPix);
+    __syncthreads();
+    for (int i = threadIdx.x; i < np * M1; i += nthr) {
+      const int pp = i / M1, mm = i - pp * M1;
+      float a = 1.f;
+      if (mm < M) {
+        const int q = (int)(p0 + pp);
+        const int x = q % g.OW, y = (q / g.OW) % g.OH, n = q / (g.OW * g.OH);
+        const int tap = mm / g.CI, ci = mm - tap * g.CI;
+        const int r = tap / g.fc, t = tap - r * g.fc;
+        const int iy = y * g.s + r * g.D - g.pr, ix = x * g.s + t * g.D - g.pc;
+        a = (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+      }
+      As[i] = a;
     }
-    acc = fmaf(a, ld_f(grad, p * g.CO + co), acc);
-    if (++x == g.OW) { x = 0; if (++y == g.OH) { y = 0; ++n; } }
+    for (int i = threadIdx.x; i < np * g.CO; i += nthr) Gs[i] = ld_f(grad, p0 * g.CO + i);
+    __syncthreads();
+#pragma unroll 4
+    for (int pp = 0; pp < np; ++pp) acc = fmaf(As[pp * M1 + m], Gs[pp * g.CO + co], acc);
   }
   if (m < M) part[((int64_t)blockIdx.x * M + m) * g.CO + co] = acc;
   else part_db[(int64_t)blockIdx.x * g.CO + co] = acc;
@@ -474,16 +478,23 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
                        void* Y, int dtype, cudaStream_t st) {
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
   if (P == 0 || g.CO == 0) return 0;
-  if (g.CO <= 4 && P < (1LL << 31) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
-    const unsigned blocks = (unsigned)((P + 127) / 128);
-    const size_t wn = (size_t)g.fr * g.fc * g.CI * g.CO * sizeof(float);
-    const int w_smem = wn <= 40 * 1024;
-    if (dtype == NPML_F32)
-      thin_co_conv_kernel<float, float><<<blocks, 128, w_smem ? wn : 0, st>>>(g, (const float*)in, w, bias, (float*)Z,
-                                                                             (float*)Y, w_smem);
-    else
-      thin_co_conv_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 128, w_smem ? wn : 0, st>>>(
-          g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y, w_smem);
+  const int vin = dtype == NPML_F32 ? 4 : 8;                  // elements per 16-byte load
+  const size_t wn = (size_t)g.fr * g.fc * g.CI * g.CO * sizeof(float);
+  if (g.CO <= 4 && P < (1LL << 31) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && g.CI % vin == 0 && wn <= 40 * 1024) {
+    const unsigned blocks = (unsigned)((P + 31) / 32);         // 32 pixels x 4 channel quarters per block
+#define NPML_THIN_CO(COV)                                                                                        \
+    if (dtype == NPML_F32)                                                                                         \
+      thin_co_conv_kernel<float, float, COV><<<blocks, 128, wn, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y); \
+    else                                                                                                           \
+      thin_co_conv_kernel<__nv_bfloat16, __nv_bfloat16, COV><<<blocks, 128, wn, st>>>(                             \
+          g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y);
+    switch (g.CO) {
+      case 1: NPML_THIN_CO(1) break;
+      case 2: NPML_THIN_CO(2) break;
+      case 3: NPML_THIN_CO(3) break;
+      default: NPML_THIN_CO(4) break;
+    }
+#undef NPML_THIN_CO
     NPML_LAUNCH_OK();
     return 0;
   }
@@ -498,15 +509,16 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
 }
 
 static bool thin_wgrad(const GatherWgrad& g) {
-  return (int64_t)(g.fr * g.fc * g.CI + 1) * g.CO <= 1024;
+  const int64_t m1 = (int64_t)g.fr * g.fc * g.CI + 1;
+  return m1 * g.CO <= 1024 && (m1 + g.CO) * kThinPix * (int64_t)sizeof(float) <= 40 * 1024;
 }
 
 static int direct_wgrad_splits(const GatherWgrad& g) {
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
   const int M = g.fr * g.fc * g.CI;
-  if (thin_wgrad(g)) {               // one block per pixel chunk; the kernel is latency-bound, so many short chunks
-    int64_t splits = 8LL * num_sms();
-    if (splits * 16 > P) splits = (P + 15) / 16;
+  if (thin_wgrad(g)) {               // one block per pixel chunk, about two blocks per SM
+    int64_t splits = 2LL * num_sms();
+    if (splits * kThinPix > P) splits = (P + kThinPix - 1) / kThinPix;
     return (int)(splits < 1 ? 1 : splits);
   }
   const int64_t tiles = (int64_t)((M + BM - 1) / BM) * ((g.CO + BN - 1) / BN);
@@ -540,11 +552,12 @@ int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* 
     float* part = (float*)ws;
     float* part_db = part + (size_t)nsplit * M * g.CO;
     const int threads = (M + 1) * g.CO;
+    const size_t smem = (size_t)kThinPix * (M + 1 + g.CO) * sizeof(float);
     if (dtype == NPML_F32)
-      thin_m_wgrad_kernel<float><<<nsplit, threads, 0, st>>>(g, (const float*)in, (const float*)grad, part, part_db, chunk);
+      thin_m_wgrad_kernel<float><<<nsplit, threads, smem, st>>>(g, (const float*)in, (const float*)grad, part, part_db, chunk);
     else
       thin_m_wgrad_kernel<__nv_bfloat16>
-          <<<nsplit, threads, 0, st>>>(g, (const __nv_bfloat16*)in, (const __nv_bfloat16*)grad, part, part_db, chunk);
+          <<<nsplit, threads, smem, st>>>(g, (const __nv_bfloat16*)in, (const __nv_bfloat16*)grad, part, part_db, chunk);
     NPML_LAUNCH_OK();
     if (db_done) *db_done = db != nullptr;
     return launch_wgrad_reduce(part, nsplit, M, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st,
