@@ -277,6 +277,58 @@ __global__ void __launch_bounds__(128) thin_co_conv_kernel(GatherConv g, const T
   }
 }
 
+// gather conv with a tiny reduction (taps * CI <= 64, e.g. Conv2D.forward with in_ch = 1): thread = (pixel, 4 output
+// channels); the K gathered inputs are read once per thread (neighbouring threads share them through L1), the weights
+// sit in shared memory as [k][co] and are read 16 bytes at a time; bias + activation in the same pass.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) thin_ci_conv_kernel(GatherConv g, const TIn* __restrict__ in,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           TOut* __restrict__ Z, TOut* __restrict__ Y) {
+  extern __shared__ __align__(16) float ws_[];          // [tap*CI + ci][co]
+  const int K = g.fr * g.fc * g.CI;
+  for (int i = threadIdx.x; i < K * g.CO; i += blockDim.x) {
+    const int co = i % g.CO, k = i / g.CO;
+    const int tp = k / g.CI, ci = k - tp * g.CI;
+    ws_[i] = w[(int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co];
+  }
+  __syncthreads();
+  const int cog = g.CO >> 2;                              // groups of 4 output channels
+  const int64_t total = (int64_t)g.N * g.OH * g.OW * cog;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % cog) * 4;
+  const int pi = (int)(idx / cog);
+  const int x = pi % g.OW, y = (pi / g.OW) % g.OH, n = pi / (g.OW * g.OH);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < g.fr; ++r) {
+    int iy;
+    if (g.form == 0) iy = y * g.s + r * g.D - g.pr;
+    else { const int ny = y + g.pr - r * g.D; if (ny < 0 || ny % g.s) continue; iy = ny / g.s; }
+    if (iy < 0 || iy >= g.IH) continue;
+    for (int t = 0; t < g.fc; ++t) {
+      int ix;
+      if (g.form == 0) ix = x * g.s + t * g.D - g.pc;
+      else { const int nx = x + g.pc - t * g.D; if (nx < 0 || nx % g.s) continue; ix = nx / g.s; }
+      if (ix < 0 || ix >= g.IW) continue;
+      const int64_t base = (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI;
+      const float* wt = ws_ + (size_t)(r * g.fc + t) * g.CI * g.CO + c4;
+      for (int ci = 0; ci < g.CI; ++ci) {
+        const float a = ld_f(in, base + ci);
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (size_t)ci * g.CO);
+        acc[0] = fmaf(a, wv.x, acc[0]); acc[1] = fmaf(a, wv.y, acc[1]);
+        acc[2] = fmaf(a, wv.z, acc[2]); acc[3] = fmaf(a, wv.w, acc[3]);
+      }
+    }
+  }
+  const int64_t o = (int64_t)pi * g.CO + c4;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float z = acc[j] + (bias ? bias[c4 + j] : 0.f);
+    if (Z) st_f(Z, o + j, z);
+    if (Y) st_f(Y, o + j, act_fn(g.act, z, g.p0, g.p1));
+  }
+}
+
 // wgrad with (taps*CI + 1) * CO <= 1024: a block owns a chunk of pixels.  The chunk's gathered inputs (an im2col tile
 // of kThinPix pixels x M rows, plus a row of ones that yields db) and its dZ rows are staged in shared memory once,
 // then thread (m, co) does 2 shared loads + 1 FMA per pixel.  Partials [chunk][M][CO] (+ [chunk][CO]) go to the
@@ -495,6 +547,17 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
       default: NPML_THIN_CO(4) break;
     }
 #undef NPML_THIN_CO
+    NPML_LAUNCH_OK();
+    return 0;
+  }
+  if (g.fr * g.fc * g.CI <= 64 && g.CO % 4 == 0 && wn <= 40 * 1024 && P * (g.CO / 4) < (1LL << 31)) {
+    const int64_t total = P * (g.CO / 4);
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (dtype == NPML_F32)
+      thin_ci_conv_kernel<float, float><<<blocks, 256, wn, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
+    else
+      thin_ci_conv_kernel<__nv_bfloat16, __nv_bfloat16>
+          <<<blocks, 256, wn, st>>>(g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y);
     NPML_LAUNCH_OK();
     return 0;
   }
