@@ -163,6 +163,18 @@ int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch, const void
  * u = momentum*velocity + lr*g'; velocity = u; param -= u.  All fp32, n elements. */
 int npml_sgd_update(float* param, const float* grad, float* velocity, int64_t n, float lr, float momentum,
                     float grad_scale, void* stream);
+/* All four reference optimizers as one elementwise step on the (all-reduced) gradient
+ * (optimizers/optimizers.py:133-148 SGD, 243-259 AdaGrad, 345-361 RMSProp, 450-482 Adam); g' = grad*grad_scale.
+ *   SGD     : state0 = velocity, a = momentum                      u = a*state0 + lr*g'; state0 = u; p -= u
+ *   AdaGrad : state0 = cache                                       state0 += g'^2; p -= lr*g'/(sqrt(state0)+eps)
+ *   RMSProp : state0 = cache, a = decay                            state0 = a*state0+(1-a)*g'^2; p -= lr*g'/(sqrt(state0)+eps)
+ *   Adam    : state0 = mean, state1 = var, a/b = decay1/decay2, c1 = 1-decay1^t, c2 = 1-decay2^t (host computes them)
+ *             p -= lr*(mean/c1)/(sqrt(var/c2)+eps)
+ * All buffers fp32, n elements; the scalars are doubles so that 1 - decay is formed in double. */
+enum { NPML_OPT_SGD = 0, NPML_OPT_ADAGRAD = 1, NPML_OPT_RMSPROP = 2, NPML_OPT_ADAM = 3 };
+int npml_optimizer_update(int32_t kind, float* param, const float* grad, float* state0, float* state1, int64_t n,
+                          double lr, double a, double b, double eps, double c1, double c2, double grad_scale,
+                          void* stream);
 /* sum of squares of an fp32 buffer into *out (double, device); deterministic two-stage reduction */
 int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream);
 

@@ -7,6 +7,7 @@ The directory name is not a Python identifier; import it with
 from . import _lib
 from . import utils
 from . import activations
+from . import schedulers
 from . import optimizers
 from . import layers
 from . import modules

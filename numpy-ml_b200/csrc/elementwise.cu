@@ -530,6 +530,32 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
   }
 }
 
+// AdaGrad / RMSProp / Adam steps on the (all-reduced) fp32 gradient (optimizers/optimizers.py:243-259, 345-361,
+// 450-482).  g' = grad * gscale carries the clip-norm factor.  KIND: 1 AdaGrad, 2 RMSProp, 3 Adam.
+template <int KIND>
+__global__ void adaptive_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
+                                    float* __restrict__ s1, int64_t n, float lr, float a, float oma, float b, float omb,
+                                    float eps, float c1, float c2, float gscale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    if (KIND == 1) {                       // cache += g^2 ; p -= lr * g / (sqrt(cache) + eps)
+      const float c = s0[i] + gi * gi;
+      s0[i] = c;
+      p[i] -= lr * gi / (sqrtf(c) + eps);
+    } else if (KIND == 2) {                // cache = decay*cache + (1-decay)*g^2
+      const float c = a * s0[i] + oma * gi * gi;
+      s0[i] = c;
+      p[i] -= lr * gi / (sqrtf(c) + eps);
+    } else {                               // Adam: s0 = mean, s1 = var; c1 = 1 - d1^t, c2 = 1 - d2^t
+      const float m = a * s0[i] + oma * gi;
+      const float v = b * s1[i] + omb * gi * gi;
+      s0[i] = m;
+      s1[i] = v;
+      p[i] -= lr * (m / c1) / (sqrtf(v / c2) + eps);
+    }
+  }
+}
+
 struct SumSqF {
   static constexpr int kConsts = 0;
   const float* x;
@@ -818,6 +844,40 @@ extern "C" int npml_sgd_update(float* param, const float* grad, float* velocity,
                                float grad_scale, void* stream) {
   if (n <= 0) return 0;
   sgd_kernel<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(param, grad, velocity, n, lr, momentum, grad_scale);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+// hyper-parameters arrive as doubles so that 1 - decay is formed in double (1 - 0.999f is off by 5e-5 in fp32)
+extern "C" int npml_optimizer_update(int32_t kind, float* param, const float* grad, float* state0, float* state1,
+                                     int64_t n, double lr_d, double a_d, double b_d, double eps_d, double c1_d,
+                                     double c2_d, double grad_scale_d, void* stream) {
+  const float lr = (float)lr_d, a = (float)a_d, b = (float)b_d, eps = (float)eps_d, c1 = (float)c1_d, c2 = (float)c2_d;
+  const float oma = (float)(1.0 - a_d), omb = (float)(1.0 - b_d), grad_scale = (float)grad_scale_d;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  NPML_CHECK(param && grad && state0, "NULL buffer");
+  const int blocks = flat_blocks(n);
+  switch (kind) {
+    case NPML_OPT_SGD:
+      sgd_kernel<<<blocks, 256, 0, st>>>(param, grad, state0, n, lr, a, grad_scale);
+      break;
+    case NPML_OPT_ADAGRAD:
+      adaptive_opt_kernel<1><<<blocks, 256, 0, st>>>(param, grad, state0, state1, n, lr, a, oma, b, omb, eps, c1, c2,
+                                                      grad_scale);
+      break;
+    case NPML_OPT_RMSPROP:
+      adaptive_opt_kernel<2><<<blocks, 256, 0, st>>>(param, grad, state0, state1, n, lr, a, oma, b, omb, eps, c1, c2,
+                                                      grad_scale);
+      break;
+    case NPML_OPT_ADAM:
+      NPML_CHECK(state1 != nullptr, "Adam needs two state buffers");
+      adaptive_opt_kernel<3><<<blocks, 256, 0, st>>>(param, grad, state0, state1, n, lr, a, oma, b, omb, eps, c1, c2,
+                                                      grad_scale);
+      break;
+    default:
+      NPML_CHECK(false, "unknown optimizer kind");
+  }
   NPML_LAUNCH_OK();
   return 0;
 }

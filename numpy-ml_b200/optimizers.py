@@ -1,22 +1,30 @@
-"""SGD with momentum and clip-norm on device parameters (numpy_ml/neural_nets/optimizers/optimizers.py:58-148).
+"""SGD, AdaGrad, RMSProp and Adam on device parameters, with the reference's constructor arguments, string forms,
+`hyperparameters` / `cache` dicts and update rules (numpy_ml/neural_nets/optimizers/optimizers.py:58-482).
 
-The step runs on the flat fp32 parameter / gradient tensors after the gradient all-reduce
-(SURVEY.md 8f rank 1).  Only SGD with a constant learning rate is provided in this round; the other
-reference optimizers (AdaGrad / RMSProp / Adam) raise NotImplementedError."""
+The step runs in place on the fp32 parameter / gradient tensors after the gradient all-reduce:
+one elementwise kernel (`npml_optimizer_update`) per parameter; clip-norm needs one deterministic sum-of-squares
+reduction first (the reference clips each parameter tensor by its own L2 norm, after the all-reduce)."""
 import math
 import re
+from copy import deepcopy
 
 import torch
 
 from . import _lib as L
+from .schedulers import SchedulerInitializer, _eval
+
+KIND = {"SGD": 0, "AdaGrad": 1, "RMSProp": 2, "Adam": 3}
 
 
 class OptimizerBase(object):
-    def __init__(self, lr):
+    """optimizers.py:8-56."""
+    _id = None
+
+    def __init__(self, lr, scheduler=None):
         self.cache = {}
         self.cur_step = 0
         self.hyperparameters = {}
-        self.lr = lr
+        self.lr_scheduler = SchedulerInitializer(scheduler, lr=lr)()
 
     def __call__(self, param, param_grad, param_name, cur_loss=None):
         return self.update(param, param_grad, param_name, cur_loss)
@@ -27,14 +35,51 @@ class OptimizerBase(object):
     def reset_step(self):
         self.cur_step = 0
 
+    def copy(self):
+        return deepcopy(self)
+
+    def set_params(self, hparam_dict=None, cache_dict=None):
+        if hparam_dict is not None:
+            for k, v in hparam_dict.items():
+                if k in self.hyperparameters:
+                    self.hyperparameters[k] = v
+                    if k == "lr_scheduler":
+                        self.lr_scheduler = SchedulerInitializer(v, lr=None)()
+        if cache_dict is not None:
+            for k, v in cache_dict.items():
+                self.cache[k] = v
+
+    # ---- shared by the concrete optimizers -------------------------------------------------------------
+    def _grad_scale(self, grad):
+        """clip-norm factor t / ||g|| if ||g|| > t else 1 (the same lines in every reference update)."""
+        t = self.hyperparameters["clip_norm"]
+        if t is None:
+            return 1.0
+        out = torch.empty(1, dtype=torch.float64, device=grad.device)
+        ws = L.workspace(1 << 20)
+        L.check(L.load().npml_sumsq_f32(L.ptr(grad), grad.numel(), L.ptr(out), L.ptr(ws), ws.numel(), L.stream()),
+                "npml_sumsq_f32")
+        nrm = math.sqrt(float(out.item()))
+        return t / nrm if nrm > t else 1.0
+
+    def _launch(self, param, grad, s0, s1, lr, a=0.0, b=0.0, eps=0.0, c1=1.0, c2=1.0):
+        if param.dtype != torch.float32 or grad.dtype != torch.float32 or not param.is_cuda:
+            raise TypeError("optimizers update fp32 device tensors in place")
+        L.check(L.load().npml_optimizer_update(KIND[self._id], L.ptr(param), L.ptr(grad), L.ptr(s0), L.ptr(s1),
+                                               param.numel(), float(lr), float(a), float(b), float(eps), float(c1),
+                                               float(c2), float(self._grad_scale(grad)), L.stream()),
+                "npml_optimizer_update")
+        return param
+
 
 class SGD(OptimizerBase):
+    """update = momentum * cache + lr * grad; cache = update; param -= update (optimizers.py:58-148)."""
+    _id = "SGD"
+
     def __init__(self, lr=0.01, momentum=0.0, clip_norm=None, lr_scheduler=None, **kwargs):
-        super().__init__(lr)
-        if lr_scheduler not in (None, "constant") and not str(lr_scheduler).lower().startswith("constant"):
-            raise NotImplementedError("only the constant learning-rate schedule is provided")
+        super().__init__(lr, lr_scheduler)
         self.hyperparameters = {"id": "SGD", "lr": lr, "momentum": momentum, "clip_norm": clip_norm,
-                                "lr_scheduler": "ConstantScheduler(lr={})".format(lr)}
+                                "lr_scheduler": str(self.lr_scheduler)}
 
     def __str__(self):
         H = self.hyperparameters
@@ -42,35 +87,89 @@ class SGD(OptimizerBase):
                                                                              H["lr_scheduler"])
 
     def update(self, param, param_grad, param_name, cur_loss=None):
-        """u = momentum*cache + lr*g (g rescaled to `clip_norm` if longer); cache = u; param -= u
-        (optimizers.py:110-148).  Updates `param` in place and returns it."""
         H = self.hyperparameters
-        lib = L.load()
+        lr = self.lr_scheduler(self.cur_step, cur_loss)
         if param_name not in self.cache:
             self.cache[param_name] = torch.zeros_like(param_grad)
-        scale = 1.0
-        if H["clip_norm"] is not None:
-            out = torch.empty(1, dtype=torch.float64, device=param_grad.device)
-            ws = L.workspace(1 << 20)
-            L.check(lib.npml_sumsq_f32(L.ptr(param_grad), param_grad.numel(), L.ptr(out), L.ptr(ws), ws.numel(),
-                                       L.stream()), "npml_sumsq_f32")
-            nrm = math.sqrt(float(out.item()))
-            if nrm > H["clip_norm"]:
-                scale = H["clip_norm"] / nrm
-        L.check(lib.npml_sgd_update(L.ptr(param), L.ptr(param_grad), L.ptr(self.cache[param_name]), param.numel(),
-                                    float(H["lr"]), float(H["momentum"]), float(scale), L.stream()), "npml_sgd_update")
-        return param
+        return self._launch(param, param_grad, self.cache[param_name], None, lr, a=H["momentum"])
 
 
-def _eval(v):
-    try:
-        return float(v) if v not in ("none", "None") else None
-    except ValueError:
-        return v
+class AdaGrad(OptimizerBase):
+    """cache += grad**2; param -= lr * grad / (sqrt(cache) + eps) (optimizers.py:156-259)."""
+    _id = "AdaGrad"
+
+    def __init__(self, lr=0.01, eps=1e-7, clip_norm=None, lr_scheduler=None, **kwargs):
+        super().__init__(lr, lr_scheduler)
+        self.hyperparameters = {"id": "AdaGrad", "lr": lr, "eps": eps, "clip_norm": clip_norm,
+                                "lr_scheduler": str(self.lr_scheduler)}
+
+    def __str__(self):
+        H = self.hyperparameters
+        return "AdaGrad(lr={}, eps={}, clip_norm={}, lr_scheduler={})".format(H["lr"], H["eps"], H["clip_norm"],
+                                                                             H["lr_scheduler"])
+
+    def update(self, param, param_grad, param_name, cur_loss=None):
+        H = self.hyperparameters
+        lr = self.lr_scheduler(self.cur_step, cur_loss)
+        if param_name not in self.cache:
+            self.cache[param_name] = torch.zeros_like(param_grad)
+        return self._launch(param, param_grad, self.cache[param_name], None, lr, eps=H["eps"])
+
+
+class RMSProp(OptimizerBase):
+    """cache = decay*cache + (1-decay)*grad**2; param -= lr * grad / (sqrt(cache) + eps) (optimizers.py:262-361)."""
+    _id = "RMSProp"
+
+    def __init__(self, lr=0.001, decay=0.9, eps=1e-7, clip_norm=None, lr_scheduler=None, **kwargs):
+        super().__init__(lr, lr_scheduler)
+        self.hyperparameters = {"id": "RMSProp", "lr": lr, "eps": eps, "decay": decay, "clip_norm": clip_norm,
+                                "lr_scheduler": str(self.lr_scheduler)}
+
+    def __str__(self):
+        H = self.hyperparameters
+        return "RMSProp(lr={}, eps={}, decay={}, clip_norm={}, lr_scheduler={})".format(
+            H["lr"], H["eps"], H["decay"], H["clip_norm"], H["lr_scheduler"])
+
+    def update(self, param, param_grad, param_name, cur_loss=None):
+        H = self.hyperparameters
+        lr = self.lr_scheduler(self.cur_step, cur_loss)
+        if param_name not in self.cache:
+            self.cache[param_name] = torch.zeros_like(param_grad)
+        return self._launch(param, param_grad, self.cache[param_name], None, lr, a=H["decay"], eps=H["eps"])
+
+
+class Adam(OptimizerBase):
+    """Exponential moving averages of grad and grad**2 with bias correction (optimizers.py:364-482); the per-parameter
+    cache is {"t", "mean", "var"} like the reference's."""
+    _id = "Adam"
+
+    def __init__(self, lr=0.001, decay1=0.9, decay2=0.999, eps=1e-7, clip_norm=None, lr_scheduler=None, **kwargs):
+        super().__init__(lr, lr_scheduler)
+        self.hyperparameters = {"id": "Adam", "lr": lr, "eps": eps, "decay1": decay1, "decay2": decay2,
+                                "clip_norm": clip_norm, "lr_scheduler": str(self.lr_scheduler)}
+
+    def __str__(self):
+        H = self.hyperparameters
+        return "Adam(lr={}, decay1={}, decay2={}, eps={}, clip_norm={}, lr_scheduler={})".format(
+            H["lr"], H["decay1"], H["decay2"], H["eps"], H["clip_norm"], H["lr_scheduler"])
+
+    def update(self, param, param_grad, param_name, cur_loss=None):
+        H = self.hyperparameters
+        lr = self.lr_scheduler(self.cur_step, cur_loss)
+        if param_name not in self.cache:
+            self.cache[param_name] = {"t": 0, "mean": torch.zeros_like(param_grad), "var": torch.zeros_like(param_grad)}
+        C = self.cache[param_name]
+        C["t"] += 1
+        d1, d2 = H["decay1"], H["decay2"]
+        return self._launch(param, param_grad, C["mean"], C["var"], lr, a=d1, b=d2, eps=H["eps"],
+                            c1=1.0 - d1 ** C["t"], c2=1.0 - d2 ** C["t"])
+
+
+_BY_NAME = {"sgd": SGD, "adagrad": AdaGrad, "rmsprop": RMSProp, "adam": Adam}
 
 
 class OptimizerInitializer(object):
-    """None | OptimizerBase | "SGD(lr=0.01, ...)" | {"hyperparameters": ..., "cache": ...}
+    """None | OptimizerBase | "Adam(lr=0.001, ...)" | {"hyperparameters": ..., "cache": ...}
     (initializers/initializers.py:176-239)."""
 
     def __init__(self, param=None):
@@ -84,19 +183,28 @@ class OptimizerInitializer(object):
             return p
         if isinstance(p, str):
             s = p.lower()
-            kwargs = {i: _eval(j) for i, j in re.findall(r"([a-zA-Z_]*)=([^,)]*)", s)}
-            if "sgd" in s:
-                kwargs.pop("lr_scheduler", None)
-                return SGD(**kwargs)
+            # the scheduler's own "(...)" holds key=value pairs too: split it off first
+            sched = None
+            m = re.search(r"lr_scheduler=([a-z]+scheduler\([^)]*\)|[^,)]*)", s)
+            if m:
+                sched = m.group(1)
+                s_wo = s[:m.start()] + s[m.end():]
+            else:
+                s_wo = s
+            kwargs = {k: _eval(v) for k, v in re.findall(r"([a-zA-Z_0-9]*)=([^,)]*)", s_wo)}
+            if sched not in (None, "none"):
+                kwargs["lr_scheduler"] = sched
+            for name in ("adagrad", "rmsprop", "adam", "sgd"):
+                if name in s:
+                    return _BY_NAME[name](**kwargs)
             raise NotImplementedError("{}".format(s))
         if isinstance(p, dict):
             op = p.get("hyperparameters")
             if op is None:
                 raise ValueError("`param` dictionary has no `hyperparemeters` key")
-            if op["id"] != "SGD":
+            if op["id"].lower() not in _BY_NAME:
                 raise NotImplementedError("{}".format(op["id"]))
-            opt = SGD(lr=op.get("lr", 0.01), momentum=op.get("momentum", 0.0), clip_norm=op.get("clip_norm"))
-            if p.get("cache"):
-                opt.cache = dict(p["cache"])
+            opt = _BY_NAME[op["id"].lower()]()
+            opt.set_params(op, p.get("cache"))
             return opt
         raise ValueError("Unknown optimizer: {}".format(p))

@@ -296,7 +296,53 @@ def gen_module():
     save("skip_conv_module.npz", arrays, cases)
 
 
+def gen_optimizers():
+    """four steps of every reference optimizer (with and without clip-norm, and with the
+    Exponential / Noam schedules) on one (3, 3, 4, 5) parameter; every intermediate parameter and cache is stored."""
+    from numpy_ml.neural_nets.optimizers import SGD, AdaGrad, RMSProp, Adam
+    from numpy_ml.neural_nets.schedulers import ExponentialScheduler, NoamScheduler
+    rng = np.random.default_rng(9)
+    arrays, cases = {}, []
+    specs = [
+        ("sgd", SGD, dict(lr=0.05, momentum=0.9), None),
+        ("sgd_clip", SGD, dict(lr=0.05, momentum=0.5, clip_norm=1.5), None),
+        ("adagrad", AdaGrad, dict(lr=0.1, eps=1e-7), None),
+        ("adagrad_clip", AdaGrad, dict(lr=0.1, eps=1e-7, clip_norm=2.0), None),
+        ("rmsprop", RMSProp, dict(lr=0.01, decay=0.9, eps=1e-7), None),
+        ("rmsprop_exp", RMSProp, dict(lr=0.01, decay=0.8, eps=1e-7),
+         dict(kind="exponential", initial_lr=0.02, stage_length=2, staircase=True, decay=0.5)),
+        ("adam", Adam, dict(lr=0.01, decay1=0.9, decay2=0.999, eps=1e-7), None),
+        ("adam_clip_noam", Adam, dict(lr=0.01, decay1=0.8, decay2=0.99, eps=1e-7, clip_norm=3.0),
+         dict(kind="noam", model_dim=64, scale_factor=2.0, warmup_steps=3)),
+    ]
+    for cid, cls, kw, sched in specs:
+        kwargs = dict(kw)
+        if sched is not None:
+            sk = {k: v for k, v in sched.items() if k != "kind"}
+            kwargs["lr_scheduler"] = ExponentialScheduler(**sk) if sched["kind"] == "exponential" else NoamScheduler(**sk)
+        opt = cls(**kwargs)
+        param = f32(rng, (3, 3, 4, 5))
+        arrays[cid + "/param0"] = param
+        lrs = []
+        for step in range(4):
+            grad = f32(rng, (3, 3, 4, 5), 2.0)
+            arrays["{}/grad{}".format(cid, step)] = grad
+            opt.step()                                   # LayerBase.update steps the optimizer first (layers.py:82)
+            lrs.append(float(opt.lr_scheduler(opt.cur_step, None)))
+            param = opt.update(param, grad, "W")
+            arrays["{}/param{}".format(cid, step + 1)] = np.array(param)
+            c = opt.cache["W"]                           # copies: AdaGrad updates its cache in place
+            if isinstance(c, dict):
+                arrays["{}/mean{}".format(cid, step + 1)] = np.array(c["mean"])
+                arrays["{}/var{}".format(cid, step + 1)] = np.array(c["var"])
+            else:
+                arrays["{}/cache{}".format(cid, step + 1)] = np.array(c)
+        cases.append(dict(id=cid, kind=cls.__name__, kwargs=kw, sched=sched, lrs=lrs, string=str(opt)))
+    save("optimizers.npz", arrays, cases)
+
+
 if __name__ == "__main__":
+    gen_optimizers()
     gen_utils()
     gen_activations()
     gen_conv2d()

@@ -517,3 +517,58 @@ def test_full_size_adjoint_identities(cuda_device, mode, cfg):
     else:
         Yr, _ = O.conv2d_layer_fwd(Xs, Wn, bz, 1, "same", 0)
     close(Y[:2], Yr, tol, "Y[:2]")
+
+
+# ------------------------------------------------------------------------------------------------
+#  optimizer step after the path: device kernels vs the reference's golden vectors
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_optimizers_match_reference_golden(cuda_device):
+    import torch
+    pkg = npml()
+    Op, Sc = pkg.optimizers, pkg.schedulers
+    z, cases = load_golden("optimizers.npz")
+    dev = torch.device("cuda:0")
+    for c in cases:
+        cid = c["id"]
+        kwargs = dict(c["kwargs"])
+        if c["sched"] is not None:
+            sk = {k: v for k, v in c["sched"].items() if k != "kind"}
+            kwargs["lr_scheduler"] = (Sc.ExponentialScheduler if c["sched"]["kind"] == "exponential"
+                                      else Sc.NoamScheduler)(**sk)
+        opt = getattr(Op, c["kind"])(**kwargs)
+        param = torch.tensor(z[cid + "/param0"], dtype=torch.float32, device=dev)
+        for step in range(4):
+            grad = torch.tensor(z["{}/grad{}".format(cid, step)], dtype=torch.float32, device=dev)
+            opt.step()
+            out = opt.update(param, grad, "W")
+            assert out.data_ptr() == param.data_ptr()                 # in place
+            close(param, z["{}/param{}".format(cid, step + 1)], 2e-6, "{} param step {}".format(cid, step + 1))
+            cache = opt.cache["W"]
+            if c["kind"] == "Adam":
+                assert cache["t"] == step + 1
+                close(cache["mean"], z["{}/mean{}".format(cid, step + 1)], 2e-6, cid + " mean")
+                close(cache["var"], z["{}/var{}".format(cid, step + 1)], 2e-6, cid + " var")
+            else:
+                close(cache, z["{}/cache{}".format(cid, step + 1)], 2e-6, cid + " cache")
+
+
+@pytest.mark.gpu
+def test_layer_update_with_adam_matches_oracle(cuda_device):
+    """Conv2D.update(): optimizer.step(), one Adam update per parameter, gradients flushed (layers.py:76-86)."""
+    from oracle import opt_oracle as P
+    pkg = npml()
+    rng = np.random.default_rng(31)
+    X, dY = _f32(rng, (2, 6, 6, 8)), _f32(rng, (2, 6, 6, 8))
+    L = pkg.Conv2D(8, (3, 3), pad="same", optimizer="Adam(lr=0.01, decay1=0.9, decay2=0.999, eps=1e-07, clip_norm=None)")
+    L.forward(X)
+    W0, b0 = pkg.to_numpy(L.parameters["W"]), pkg.to_numpy(L.parameters["b"])
+    L.backward(dY)
+    gW, gb = pkg.to_numpy(L.gradients["W"]), pkg.to_numpy(L.gradients["b"])
+    L.update()
+    Wr, _, _, _ = P.adam_step(W0, gW, 0 * W0, 0 * W0, 0, 0.01, 0.9, 0.999, 1e-7)
+    br, _, _, _ = P.adam_step(b0, gb, 0 * b0, 0 * b0, 0, 0.01, 0.9, 0.999, 1e-7)
+    close(L.parameters["W"], Wr, 1e-5, "W after update")
+    close(L.parameters["b"], br, 1e-5, "b after update")
+    assert float(L.gradients["W"].abs().sum()) == 0.0 and L.X == []
+    assert L.hyperparameters["optimizer"]["hyperparameters"]["id"] == "Adam"

@@ -3,7 +3,7 @@ reference (tests/golden/make_golden.py).  CPU only."""
 import numpy as np
 import pytest
 
-from conftest import load_golden, to_pad, rel_err
+from conftest import load_golden, to_pad, rel_err, npml
 from oracle import conv_oracle as O
 
 TOL = 1e-12
@@ -155,3 +155,74 @@ def test_oracle_error_conventions():
         O.calc_pad_dims_2D([1, 3, 3, 1], (3, 3), (3, 3), 1)   # X_shape not a tuple   (utils.py:77-87)
     with pytest.raises(ValueError):
         O.calc_pad_dims_2D((1, 9, 9, 1), (3, 3), (3, 3), 1)   # negative pad          (utils.py:116-119)
+
+
+# ---------------------------------------------------------------------------------------------------
+#  optimizers + learning-rate schedules
+# ---------------------------------------------------------------------------------------------------
+def _sched_lr(sched, base_lr, step):
+    from oracle import opt_oracle as P
+    if sched is None:
+        return P.lr_constant(base_lr, step)
+    if sched["kind"] == "exponential":
+        return P.lr_exponential(sched["initial_lr"], sched["stage_length"], sched["staircase"], sched["decay"], step)
+    return P.lr_noam(sched["model_dim"], sched["scale_factor"], sched["warmup_steps"], step)
+
+
+def test_optimizer_oracle_matches_reference_golden():
+    from oracle import opt_oracle as P
+    z, cases = load_golden("optimizers.npz")
+    assert {c["kind"] for c in cases} == {"SGD", "AdaGrad", "RMSProp", "Adam"}
+    for c in cases:
+        cid, kw = c["id"], c["kwargs"]
+        param = z[cid + "/param0"]
+        state = {"cache": np.zeros_like(param), "mean": np.zeros_like(param), "var": np.zeros_like(param), "t": 0}
+        for step in range(4):
+            lr = _sched_lr(c["sched"], kw["lr"], step + 1)
+            assert abs(lr - c["lrs"][step]) <= 1e-15 * max(1.0, abs(lr)), (cid, step, lr, c["lrs"][step])
+            g = z["{}/grad{}".format(cid, step)]
+            cn = kw.get("clip_norm")
+            if c["kind"] == "SGD":
+                param, state["cache"] = P.sgd_step(param, g, state["cache"], lr, kw["momentum"], cn)
+            elif c["kind"] == "AdaGrad":
+                param, state["cache"] = P.adagrad_step(param, g, state["cache"], lr, kw["eps"], cn)
+            elif c["kind"] == "RMSProp":
+                param, state["cache"] = P.rmsprop_step(param, g, state["cache"], lr, kw["decay"], kw["eps"], cn)
+            else:
+                param, state["mean"], state["var"], state["t"] = P.adam_step(
+                    param, g, state["mean"], state["var"], state["t"], lr, kw["decay1"], kw["decay2"], kw["eps"], cn)
+            assert rel_err(param, z["{}/param{}".format(cid, step + 1)]) < 1e-13, (cid, step)
+            if c["kind"] == "Adam":
+                assert rel_err(state["var"], z["{}/var{}".format(cid, step + 1)]) < 1e-13
+                assert rel_err(state["mean"], z["{}/mean{}".format(cid, step + 1)]) < 1e-13
+            else:
+                assert rel_err(state["cache"], z["{}/cache{}".format(cid, step + 1)]) < 1e-13
+
+
+def test_host_optimizer_strings_and_schedules_match_reference():
+    """The product's optimizer / scheduler objects print and schedule exactly like the reference's (no GPU needed)."""
+    pkg = npml()
+    Op, Sc = pkg.optimizers, pkg.schedulers
+    _, cases = load_golden("optimizers.npz")
+    for c in cases:
+        kwargs = dict(c["kwargs"])
+        if c["sched"] is not None:
+            sk = {k: v for k, v in c["sched"].items() if k != "kind"}
+            kwargs["lr_scheduler"] = (Sc.ExponentialScheduler if c["sched"]["kind"] == "exponential"
+                                      else Sc.NoamScheduler)(**sk)
+        opt = getattr(Op, c["kind"])(**kwargs)
+        assert str(opt) == c["string"]
+        for step in range(4):
+            opt.step()
+            assert abs(opt.lr_scheduler(opt.cur_step, None) - c["lrs"][step]) <= 1e-15
+        again = Op.OptimizerInitializer(str(opt))()              # round trip through the string form
+        assert type(again) is type(opt)
+        for k, v in opt.hyperparameters.items():
+            if k != "lr_scheduler":
+                assert again.hyperparameters[k] == v, (k, again.hyperparameters[k], v)
+        assert str(again.lr_scheduler) == str(opt.lr_scheduler)
+    assert isinstance(Op.OptimizerInitializer(None)(), Op.SGD)
+    with pytest.raises(NotImplementedError):
+        Op.OptimizerInitializer("Lion(lr=0.1)")()
+    with pytest.raises(NotImplementedError):
+        Sc.SchedulerInitializer("KingScheduler(initial_lr=0.01, patience=1000, decay=0.99)")()
