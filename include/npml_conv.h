@@ -178,6 +178,17 @@ int npml_optimizer_update(int32_t kind, float* param, const float* grad, float* 
 /* sum of squares of an fp32 buffer into *out (double, device); deterministic two-stage reduction */
 int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- Pool2D (layers/layers.py:3181-3350), SURVEY.md 8f rank 3 -------------------------------
+ * Uses the desc's N,H,W,C (input), fr,fc,stride, pr1,pr2,pc1,pc2 and OH,OW = (H+pr1+pr2-fr)/stride+1; K, dil, mode, act are
+ * ignored.  pool_mode: 0 = max, 1 = average.  The zero padding takes part in the max / mean, as in the reference
+ * (layers.py:3262).  Backward is a gather over the windows covering each input pixel (no atomics); in max mode only
+ * the first maximal pixel of a window in row-major order receives its gradient (layers.py:3332-3338).
+ * dtype: NPML_F32 or NPML_BF16, the same for every tensor of a call. */
+enum { NPML_POOL_MAX = 0, NPML_POOL_AVERAGE = 1 };
+int npml_pool2d_fwd(const npml_conv_desc* d, int32_t pool_mode, const void* X, void* Y, int32_t dtype, void* stream);
+int npml_pool2d_bwd(const npml_conv_desc* d, int32_t pool_mode, const void* dY, const void* X, void* dX,
+                    int32_t dtype, void* stream);
+
 /* ---- im2col / col2im exports (utils/utils.py:486-595), API parity only; fp32 ---------------
  * X_col is (fr*fc*C, OH*OW*N) row-major with q = c*fr*fc + r*fc + t, z = (oh*OW + ow)*N + n.
  * col2im returns NCHW like the reference (utils/utils.py:595). */

@@ -1,4 +1,4 @@
-"""Conv2D / Deconv2D / BatchNorm2D / Add with the reference's layer API
+"""Conv2D / Deconv2D / Conv1D / Pool2D / Flatten / BatchNorm2D / Add with the reference's layer API
 (numpy_ml/neural_nets/layers/layers.py): same constructor arguments, lazy parameter init on the
 first forward, `parameters` / `gradients` / `hyperparameters` / `derived_variables` dicts, list-valued
 `backward`, `+=` gradient accumulation, `flush_gradients` / `update` / `freeze` / `summary`.
@@ -336,6 +336,177 @@ class Deconv2D(_ConvBase):
         fr, fc = self.kernel_shape
         p4, oh, ow = U.deconv_geometry(X_shape[1], X_shape[2], fr, fc, self.pad, self.stride)
         return p4, oh, ow, 1
+
+
+class Conv1D(_ConvBase):
+    """layers/layers.py:2603-2892.  The reference adds a unit row dimension and runs the 2-D path
+    (utils.py:668-717, layers.py:2804-2838); so does this layer, on the same kernels: X (n_ex, l_in, in_ch),
+    W (kernel_width, in_ch, out_ch), b (1, 1, out_ch), pad int | (left, right) | 'same' | 'causal'."""
+    _layer_name = "Conv2D"          # entry-point family
+    _ops = (L.OP_CONV_FPROP, L.OP_CONV_DGRAD, L.OP_CONV_WGRAD)
+
+    def __init__(self, out_ch, kernel_width, pad=0, stride=1, dilation=0, act_fn=None, init="glorot_uniform",
+                 optimizer=None, mode="fp32"):
+        super().__init__(optimizer)
+        self.pad = pad
+        self.init = init
+        self.in_ch = None
+        self.out_ch = out_ch
+        self.stride = stride
+        self.dilation = dilation
+        self.kernel_width = kernel_width
+        self.kernel_shape = (1, kernel_width)
+        self.act_fn = ActivationInitializer(act_fn)()
+        self.parameters = {"W": None, "b": None}
+        self.is_initialized = False
+        self.mode = mode
+        assert mode in L.MODES
+
+    def _init_params(self):
+        init_weights = WeightInitializer(str(self.act_fn), mode=self.init)
+        W = init_weights((self.kernel_width, self.in_ch, self.out_ch))
+        self.parameters = {"W": L.to_device(W, torch.float32),
+                           "b": torch.zeros((1, 1, self.out_ch), dtype=torch.float32, device=L.device())}
+        self.gradients = {"W": torch.zeros_like(self.parameters["W"]), "b": torch.zeros_like(self.parameters["b"])}
+        self.derived_variables = {"Z": [], "out_rows": [], "out_cols": []}
+        self.is_initialized = True
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Conv1D", "pad": self.pad, "init": self.init, "in_ch": self.in_ch, "out_ch": self.out_ch,
+                "stride": self.stride, "dilation": self.dilation, "act_fn": str(self.act_fn),
+                "kernel_width": self.kernel_width, "optimizer": self._opt_hparams()}
+
+    def _geometry(self, X_shape):
+        n, _, l_in, c = X_shape
+        p = U.resolve_pad_1D((n, l_in, c), self.pad, self.kernel_width, self.stride, self.dilation)
+        p4 = (0, 0, p[0], p[1])
+        oh, ow = U.conv_out_hw(1, l_in, 1, self.kernel_width, p4, self.stride, self.dilation)
+        return p4, oh, ow, self.dilation + 1
+
+    def forward(self, X, retain_derived=True):
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, L.torch_dtype(self.mode))
+        if Xd.dim() != 3:
+            raise ValueError("Conv1D expects (n_ex, l_in, in_ch), got {}".format(tuple(Xd.shape)))
+        Y = super().forward(Xd.unsqueeze(1), retain_derived).squeeze(1)
+        if retain_derived:                     # keep what the reference keeps: 3-D X / Z, Z.shape[1:] (layers.py:2746-2750)
+            dv = self.derived_variables
+            self.X[-1] = self.X[-1].squeeze(1)
+            dv["Z"][-1] = dv["Z"][-1].squeeze(1)
+            dv["out_rows"][-1], dv["out_cols"][-1] = dv["Z"][-1].shape[1], dv["Z"][-1].shape[2]
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdy, retain_grads=True):
+        assert self.trainable, "Layer is frozen"
+        if not isinstance(dLdy, list):
+            dLdy = [dLdy]
+        dX = []
+        for dy, x, z in zip(dLdy, self.X, self.derived_variables["Z"]):
+            as_np = isinstance(dy, np.ndarray)
+            dx = self._bwd(L.to_device(dy, L.torch_dtype(self.mode)).unsqueeze(1), x.unsqueeze(1), z.unsqueeze(1),
+                           retain_grads).squeeze(1)
+            dX.append(L.to_numpy(dx) if as_np else dx)
+        return dX[0] if len(self.X) == 1 else dX
+
+
+class Pool2D(LayerBase):
+    """layers/layers.py:3181-3350: max / average pooling over (fr, fc) windows of the zero-padded NHWC input.
+    The reference's four nested Python loops become one gather kernel per direction (npml_pool2d_fwd / _bwd)."""
+
+    def __init__(self, kernel_shape, stride=1, pad=0, mode="max", optimizer=None):
+        super().__init__(optimizer)
+        self.pad = pad
+        self.mode = mode
+        self.in_ch = None
+        self.out_ch = None
+        self.stride = stride
+        self.kernel_shape = kernel_shape
+        self.is_initialized = False
+
+    def _init_params(self):
+        self.derived_variables = {"out_rows": [], "out_cols": []}
+        self.is_initialized = True
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Pool2D", "act_fn": None, "pad": self.pad, "mode": self.mode, "in_ch": self.in_ch,
+                "out_ch": self.out_ch, "stride": self.stride, "kernel_shape": self.kernel_shape,
+                "optimizer": self._opt_hparams()}
+
+    def _desc(self, X_shape):
+        if self.mode not in ("max", "average"):
+            raise ValueError("Unrecognized pooling mode: {}".format(self.mode))
+        n, h, w, c = X_shape
+        fr, fc = self.kernel_shape
+        p4 = U.resolve_pad_2D(X_shape, self.pad, (fr, fc), self.stride)
+        oh, ow = U.conv_out_hw(h, w, fr, fc, p4, self.stride, 0)
+        return U.make_desc(n, h, w, c, c, fr, fc, self.stride, 1, p4, oh, ow), 0 if self.mode == "max" else 1
+
+    def forward(self, X, retain_derived=True):
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, torch.float32) if as_np else L.to_device(X, X.dtype if X.dtype != torch.float64
+                                                                   else torch.float32)
+        if not self.is_initialized:
+            self.in_ch = self.out_ch = Xd.shape[3]
+            self._init_params()
+        d, pm = self._desc(tuple(Xd.shape))
+        Y = torch.empty((d.N, d.OH, d.OW, d.C), dtype=Xd.dtype, device=Xd.device)
+        with L.profiled("npml_pool2d_fwd"):
+            L.check(L.load().npml_pool2d_fwd(d, pm, L.ptr(Xd), L.ptr(Y), L.code_of(Xd), L.stream()), "npml_pool2d_fwd")
+        if retain_derived:
+            self.X.append(Xd)
+            self.derived_variables["out_rows"].append(d.OH)
+            self.derived_variables["out_cols"].append(d.OW)
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdY, retain_grads=True):
+        assert self.trainable, "Layer is frozen"
+        if not isinstance(dLdY, list):
+            dLdY = [dLdY]
+        dXs = []
+        for X, dy in zip(self.X, dLdY):
+            as_np = isinstance(dy, np.ndarray)
+            dyd = L.to_device(dy, X.dtype)
+            d, pm = self._desc(tuple(X.shape))
+            dX = torch.empty_like(X)
+            with L.profiled("npml_pool2d_bwd"):
+                L.check(L.load().npml_pool2d_bwd(d, pm, L.ptr(dyd), L.ptr(X), L.ptr(dX), L.code_of(X), L.stream()),
+                        "npml_pool2d_bwd")
+            dXs.append(L.to_numpy(dX) if as_np else dX)
+        return dXs[0] if len(self.X) == 1 else dXs
+
+
+class Flatten(LayerBase):
+    """layers/layers.py:859-966: a reshape (no kernel; a view of the same device buffer)."""
+
+    def __init__(self, keep_dim="first", optimizer=None):
+        super().__init__(optimizer)
+        self.keep_dim = keep_dim
+        self._init_params()
+
+    def _init_params(self):
+        self.gradients = {}
+        self.parameters = {}
+        self.derived_variables = {"in_dims": []}
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Flatten", "keep_dim": self.keep_dim, "optimizer": self._opt_hparams()}
+
+    def forward(self, X, retain_derived=True):
+        if retain_derived:
+            self.derived_variables["in_dims"].append(tuple(X.shape))
+        if self.keep_dim == -1:
+            return X.reshape(1, -1)
+        rs = (X.shape[0], -1) if self.keep_dim == "first" else (-1, X.shape[-1])
+        return X.reshape(*rs)
+
+    def backward(self, dLdy, retain_grads=True):
+        if not isinstance(dLdy, list):
+            dLdy = [dLdy]
+        out = [dy.reshape(*dims) for dy, dims in zip(dLdy, self.derived_variables["in_dims"])]
+        return out[0] if len(dLdy) == 1 else out
 
 
 class BatchNorm2D(LayerBase):

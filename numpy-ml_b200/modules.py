@@ -1,4 +1,4 @@
-"""SkipConnectionConvModule, the reference's "ResNet-like convolution shortcut" block
+"""SkipConnectionConvModule (and SkipConnectionIdentityModule, at the end of the file), the reference's "ResNet-like convolution shortcut" block
 (numpy_ml/neural_nets/modules/modules.py:615-984): conv1 -> act -> BN1 -> conv2 -> BN2, a
 conv_skip -> BN_skip projection of the input, Add, act.  Note the order Conv -> act -> BN
 (modules.py:646), not Conv -> BN -> act."""
@@ -220,4 +220,100 @@ class SkipConnectionConvModule(ModuleBase):
         if retain_grads:
             self._dv.update({"dLdAdd3_X": dX, "dLdBn2": dBn2_out, "dLdBn1": dBn1_out, "dLdConv2": dConv2_out,
                              "dLdConv1": dConv1_out, "dLdBnSkip": dBnskip_out, "dLdConvSkip": dConvskip_out})
+        return L.to_numpy(dX) if as_np else dX
+
+
+class SkipConnectionIdentityModule(ModuleBase):
+    """modules/modules.py:360-612: conv1('same', act) -> BN1 -> conv2('same', affine, out_ch = in_ch) -> BN2 ->
+    Add([X, BN2]) -> act.  Same kernels as SkipConnectionConvModule, the input itself is the shortcut."""
+
+    def __init__(self, out_ch, kernel_shape1, kernel_shape2, stride1=1, stride2=1, act_fn=None, epsilon=1e-5,
+                 momentum=0.9, optimizer=None, init="glorot_uniform", mode="fp32", sync_bn=False):
+        super().__init__()
+        self.init = init
+        self.in_ch = None
+        self.out_ch = out_ch
+        self.epsilon = epsilon
+        self.stride1 = stride1
+        self.stride2 = stride2
+        self.optimizer = optimizer
+        self.momentum = momentum
+        self.kernel_shape1 = kernel_shape1
+        self.kernel_shape2 = kernel_shape2
+        self.act_fn = Affine(slope=1, intercept=0) if act_fn is None else ActivationInitializer(act_fn)()
+        self.mode = mode
+        self.sync_bn = sync_bn
+        self._init_params()
+
+    def _init_params(self):
+        self._dv = {}
+        self.conv1 = Conv2D(pad="same", init=self.init, out_ch=self.out_ch, act_fn=self.act_fn, stride=self.stride1,
+                            optimizer=self.optimizer, kernel_shape=self.kernel_shape1, mode=self.mode)
+        # conv2 needs the input's channel count: created on the first forward, like the reference (modules.py:445-459)
+        self.batchnorm1 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
+        self.batchnorm2 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
+        self.add3 = Add(self.act_fn)
+
+    def _init_conv2(self):
+        self.conv2 = Conv2D(pad="same", init=self.init, out_ch=self.in_ch, stride=self.stride2,
+                            optimizer=self.optimizer, kernel_shape=self.kernel_shape2,
+                            act_fn=Affine(slope=1, intercept=0), mode=self.mode)
+
+    _names = ["add3", "conv1", "conv2", "batchnorm1", "batchnorm2"]
+
+    def _by_component(self, attr):
+        return {n: (getattr(getattr(self, n), attr) if hasattr(self, n) else None) for n in self._names}
+
+    @property
+    def parameters(self):
+        return {"components": self._by_component("parameters")}
+
+    @property
+    def gradients(self):
+        return {"components": self._by_component("gradients")}
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "SkipConnectionIdentityModule", "init": self.init, "in_ch": self.in_ch, "out_ch": self.out_ch,
+                "epsilon": self.epsilon, "stride1": self.stride1, "stride2": self.stride2, "momentum": self.momentum,
+                "optimizer": self.optimizer, "act_fn": str(self.act_fn), "kernel_shape1": self.kernel_shape1,
+                "kernel_shape2": self.kernel_shape2,
+                "component_ids": ["conv1", "batchnorm1", "conv2", "batchnorm2", "add3"],
+                "components": self._by_component("hyperparameters")}
+
+    @property
+    def derived_variables(self):
+        dv = {"conv1_out": None, "conv2_out": None, "batchnorm1_out": None, "batchnorm2_out": None,
+              "components": self._by_component("derived_variables")}
+        dv.update(self._dv)
+        return dv
+
+    def forward(self, X, retain_derived=True):
+        """modules.py:574-594."""
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, L.torch_dtype(self.mode))
+        if not hasattr(self, "conv2"):
+            self.in_ch = Xd.shape[3]
+            self._init_conv2()
+        conv1_out = self.conv1.forward(Xd, retain_derived)
+        bn1_out = self.batchnorm1.forward(conv1_out, retain_derived)
+        conv2_out = self.conv2.forward(bn1_out, retain_derived)
+        bn2_out = self.batchnorm2.forward(conv2_out, retain_derived)
+        Y = self.add3.forward([Xd, bn2_out], retain_derived)
+        if retain_derived:
+            self._dv.update({"conv1_out": conv1_out, "conv2_out": conv2_out, "batchnorm1_out": bn1_out,
+                             "batchnorm2_out": bn2_out})
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdY, retain_grads=True):
+        """modules.py:596-612 (dLdAdd3_X is the returned dX: the reference accumulates into it in place)."""
+        as_np = isinstance(dLdY, np.ndarray)
+        dY = L.to_device(dLdY, L.torch_dtype(self.mode))
+        dX0, dBn2_out = self.add3.backward(dY, retain_grads)
+        dConv2_out = self.batchnorm2.backward(dBn2_out, retain_grads)
+        dBn1_out = self.conv2.backward(dConv2_out, retain_grads)
+        dConv1_out = self.batchnorm1.backward(dBn1_out, retain_grads)
+        dX = _device_add(dX0, self.conv1.backward(dConv1_out, retain_grads))
+        self._dv.update({"dLdAdd3_X": dX, "dLdBn2": dBn2_out, "dLdBn1": dBn1_out, "dLdConv2": dConv2_out,
+                         "dLdConv1": dConv1_out})
         return L.to_numpy(dX) if as_np else dX

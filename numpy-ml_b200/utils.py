@@ -1,6 +1,6 @@
 """Functional API of the convolution hot path, signature-compatible with
 numpy_ml/neural_nets/utils/utils.py (pad2D, calc_pad_dims_2D, calc_conv_out_dims, im2col, col2im,
-conv2D, deconv2D_naive, dilate).
+conv2D, deconv2D_naive, dilate) and of their 1-D forms (pad1D, calc_pad_dims_1D, conv1D).
 
 All geometry (pad resolution incl. 'same', output dims, the reference's exceptions) is resolved here
 on the host as plain ints; the arithmetic runs in libnpmlconv.so.  NumPy inputs give float64 NumPy
@@ -63,8 +63,50 @@ def resolve_pad_2D(X_shape, pad, kernel_shape=None, stride=None, dilation=0):
     return tuple(int(v) for v in p)
 
 
+def calc_pad_dims_1D(X_shape, l_out, kernel_width, stride, dilation=0, causal=False):
+    """(left, right) padding so that a 1-D conv produces length `l_out` (utils.py:123-192): half of the total on each
+    side plus one on the right if that is exactly one short; all of it on the left for a causal convolution."""
+    for name, val, typ in (("X_shape", X_shape, tuple), ("l_out", l_out, int), ("kernel_width", kernel_width, int),
+                           ("stride", stride, int)):
+        if not isinstance(val, typ):
+            raise ValueError("`{}` must be of type {}".format(name, typ.__name__))
+    _, l_in, _ = X_shape
+    _fw = kernel_width * (dilation + 1) - dilation
+    total_pad = int(stride * (l_out - 1) + _fw - l_in)
+    if causal:
+        pw1, pw2 = total_pad, 0
+        assert int(1 + (l_in + total_pad - _fw) / stride) == l_out
+    else:
+        pw1 = pw2 = total_pad // 2
+        got = int(1 + (l_in + 2 * pw1 - _fw) / stride)
+        if got == l_out - 1:
+            pw2 = pw1 + 1
+        elif got != l_out:
+            raise AssertionError
+    if pw1 < 0 or pw2 < 0:
+        raise ValueError("Padding cannot be less than 0. Got: {}".format((pw1, pw2)))
+    return (pw1, pw2)
+
+
+def resolve_pad_1D(X_shape, pad, kernel_width=None, stride=None, dilation=0):
+    """int | (left, right) | 'same' | 'causal' -> 2-tuple, as pad1D does (utils.py:229-247)."""
+    p = pad
+    if isinstance(p, int):
+        p = (p, p)
+    if p in ("same", "causal") and kernel_width and stride:
+        p = calc_pad_dims_1D(tuple(X_shape), int(X_shape[1]), kernel_width, stride, dilation=dilation,
+                             causal=(p == "causal"))
+    if not (isinstance(p, tuple) and len(p) == 2):
+        raise ValueError("Unrecognized pad: {}".format(pad))
+    return tuple(int(v) for v in p)
+
+
 def calc_conv_out_dims(X_shape, W_shape, stride=1, pad=0, dilation=0):
-    """Output volume shape of a 2D convolution (utils.py:380-439, 4-D branch)."""
+    """Output volume shape of a 1D / 2D convolution (utils.py:380-439)."""
+    if len(X_shape) == 3:
+        pw1, pw2 = resolve_pad_1D(X_shape, pad)
+        fw, _, out_ch = W_shape
+        return (X_shape[0], (X_shape[1] + pw1 + pw2 - (fw * (dilation + 1) - dilation)) // stride + 1, out_ch)
     if len(X_shape) != 4:
         raise ValueError("Unrecognized number of input dims: {}".format(len(X_shape)))
     pr1, pr2, pc1, pc2 = resolve_pad_2D(X_shape, pad)
@@ -143,6 +185,18 @@ def pad2D(X, pad, kernel_shape=None, stride=None, dilation=0):
     return _wrap(out, as_np), p
 
 
+def pad1D(X, pad, kernel_width=None, stride=None, dilation=0):
+    """Zero-pad the length axis of an (n_ex, l_in, in_ch) volume; returns (X_pad, (left, right)) (utils.py:195-249).
+    API parity only: Conv1D never materialises the padded volume."""
+    as_np = _is_np(X)
+    p = resolve_pad_1D(X.shape, pad, kernel_width, stride, dilation)
+    Xd = L.to_device(X, torch.float32) if as_np else L.to_device(X, X.dtype)
+    n, l, c = Xd.shape
+    out = torch.zeros((n, l + p[0] + p[1], c), dtype=Xd.dtype, device=Xd.device)
+    out[:, p[0]:p[0] + l, :].copy_(Xd)
+    return _wrap(out, as_np), p
+
+
 def dilate(X, d):
     """Insert `d` zero rows/cols between adjacent pixels (utils.py:309-344).  API parity only."""
     as_np = _is_np(X)
@@ -204,6 +258,17 @@ def conv2D(X, W, stride, pad, dilation=0, mode="fp32"):
     L.check(lib.npml_conv2d_fprop(d, L.ptr(Xd), L.ptr(Wd), None, L.ptr(Z), None, L.ptr(ws), ws.numel(), L.stream()),
             "npml_conv2d_fprop")
     return _wrap(Z, as_np)
+
+
+def conv1D(X, W, stride, pad, dilation=0, mode="fp32"):
+    """1D cross-correlation of (n_ex, l_in, in_ch) `X` with (kernel_width, in_ch, out_ch) `W` (utils.py:668-717): the
+    same kernels as conv2D on a volume with one row."""
+    as_np = _is_np(X)
+    Xd = L.to_device(X, L.torch_dtype(mode))
+    Wd = _weights(W)
+    p = resolve_pad_1D(Xd.shape, pad, Wd.shape[0], stride, dilation)
+    Z = conv2D(Xd.unsqueeze(1), Wd.unsqueeze(0), stride, (0, 0, p[0], p[1]), dilation, mode)
+    return _wrap(Z.squeeze(1), as_np)
 
 
 def conv2D_naive(X, W, stride, pad, dilation=0):

@@ -27,8 +27,8 @@ sys.path.insert(0, "/root/reference")
 
 from numpy_ml.neural_nets import utils as U                      # noqa: E402
 from numpy_ml.neural_nets import activations as A                # noqa: E402
-from numpy_ml.neural_nets.layers import Conv2D, Deconv2D, BatchNorm2D, Add   # noqa: E402
-from numpy_ml.neural_nets.modules import SkipConnectionConvModule            # noqa: E402
+from numpy_ml.neural_nets.layers import Conv2D, Deconv2D, BatchNorm2D, Add, Conv1D, Pool2D, Flatten   # noqa: E402
+from numpy_ml.neural_nets.modules import SkipConnectionConvModule, SkipConnectionIdentityModule     # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -341,7 +341,143 @@ def gen_optimizers():
     save("optimizers.npz", arrays, cases)
 
 
+def gen_conv1d():
+    """Conv1D through the reference's own expand-dims route, incl. 'same' / 'causal' pads."""
+    rng = np.random.default_rng(23)
+    arrays, cases = {}, []
+    confs = [
+        # xs (n, l, c), out_ch, kw, pad, s, d, act, two_calls
+        ((2, 9, 3), 4, 3, 1, 1, 0, "identity", False),
+        ((3, 12, 2), 5, 3, "same", 1, 0, "relu", False),
+        ((2, 16, 4), 3, 2, "causal", 1, 3, "tanh", False),            # Wavenet-style dilated causal conv
+        ((2, 11, 3), 2, 4, (2, 1), 2, 0, "sigmoid", False),
+        ((2, 14, 2), 6, 3, "same", 1, 2, "affine", False),
+        ((2, 10, 5), 7, 1, 0, 1, 0, "leaky_relu", False),
+        ((2, 8, 3), 3, 3, 1, 1, 0, "identity", True),
+        ((1, 13, 1), 8, 5, "causal", 1, 1, "elu", False),
+    ]
+    for i, (xs, oc, kw, pad, s, d, act, two) in enumerate(confs):
+        L = Conv1D(out_ch=oc, kernel_width=kw, pad=pad, stride=s, dilation=d, act_fn=ACTS[act]())
+        X = f32(rng, xs)
+        L.forward(X, retain_derived=False)
+        W, b = f32(rng, L.parameters["W"].shape, 0.4), f32(rng, L.parameters["b"].shape, 0.3)
+        L.parameters["W"], L.parameters["b"] = W, b
+        L.flush_gradients()
+        Y = L.forward(X)
+        out = {"X": X, "W": W, "b": b, "Y": Y, "Z": L.derived_variables["Z"][0]}
+        out["pad"] = np.asarray(U.pad1D(X, pad, kw, s, dilation=d)[1])
+        dY = f32(rng, Y.shape)
+        out["dLdy"] = dY
+        if two:
+            X2 = f32(rng, xs)
+            Y2 = L.forward(X2)
+            dY2 = f32(rng, Y2.shape)
+            dXs = L.backward([dY, dY2])
+            out.update({"X2": X2, "Y2": Y2, "dLdy2": dY2, "dX": dXs[0], "dX2": dXs[1]})
+        else:
+            out["dX"] = L.backward(dY)
+        out["dW"], out["db"] = L.gradients["W"], L.gradients["b"]
+        out["conv1D"] = U.conv1D(X, W, s, pad, d)                          # the functional form (utils.py:668-717)
+        arrays.update({f"c{i}/{k}": v for k, v in out.items()})
+        p0, p1 = ACT_PARAMS.get(act, (0.0, 0.0))
+        cases.append({"id": f"c{i}", "out_ch": oc, "kernel_width": kw, "pad": to_list(pad), "stride": s, "dilation": d,
+                      "act": act, "p0": p0, "p1": p1, "two_calls": two})
+    save("conv1d_layer.npz", arrays, cases)
+
+
+def gen_pool2d():
+    """Pool2D max / average forward + backward, Flatten.  Max-mode backward is generated only
+    for pad == 0: with padding the reference reads its windows from the unpadded input (layers.py:3326)."""
+    rng = np.random.default_rng(29)
+    arrays, cases = {}, []
+    confs = [
+        # xs, kernel, stride, pad, mode
+        ((2, 8, 8, 3), (2, 2), 2, 0, "max"),
+        ((2, 9, 7, 5), (3, 3), 2, 0, "max"),
+        ((3, 6, 6, 2), (2, 3), 1, 0, "max"),
+        ((2, 8, 8, 3), (2, 2), 2, 0, "average"),
+        ((2, 9, 7, 4), (3, 3), 1, 1, "average"),
+        ((2, 7, 10, 2), (3, 2), 2, (1, 2), "average"),
+        ((2, 6, 6, 8), (3, 3), 1, "same", "average"),
+        ((2, 7, 7, 3), (3, 3), 2, 1, "max"),          # forward only (backward outside the pinned domain)
+        ((1, 5, 5, 1), (5, 5), 1, 0, "max"),          # kernel == input
+    ]
+    for i, (xs, ks, s, pad, mode) in enumerate(confs):
+        L = Pool2D(kernel_shape=ks, stride=s, pad=pad, mode=mode)
+        X = f32(rng, xs)
+        if mode == "max":                             # ties: the first maximal pixel (row-major) takes the gradient
+            X[0, :2, :2, 0] = X.max() + 1.0
+            X = np.round(X * 4) / 4
+        Y = L.forward(X)
+        out = {"X": X, "Y": Y}
+        bwd = not (mode == "max" and pad != 0)
+        if bwd:
+            dY = f32(rng, Y.shape)
+            out["dLdY"], out["dX"] = dY, L.backward(dY)
+        arrays.update({f"p{i}/{k}": v for k, v in out.items()})
+        cases.append({"id": f"p{i}", "kernel_shape": list(ks), "stride": s, "pad": to_list(pad), "mode": mode,
+                      "backward": bwd})
+    for j, keep in enumerate(["first", "last", -1]):
+        F = Flatten(keep_dim=keep)
+        X = f32(rng, (3, 4, 5, 2))
+        Y = F.forward(X)
+        dY = f32(rng, Y.shape)
+        arrays.update({f"f{j}/X": X, f"f{j}/Y": Y, f"f{j}/dLdy": dY, f"f{j}/dX": F.backward(dY)})
+        cases.append({"id": f"f{j}", "keep_dim": keep, "flatten": True})
+    save("pool2d.npz", arrays, cases)
+
+
+def gen_identity_module():
+    """SkipConnectionIdentityModule (modules.py:360-612)."""
+    rng = np.random.default_rng(37)
+    arrays, cases = {}, []
+    confs = [((3, 8, 8, 4), 5, (3, 3), (3, 3), "relu"),
+             ((2, 7, 9, 3), 4, (3, 3), (1, 1), "identity"),
+             ((2, 6, 6, 2), 3, (3, 3), (3, 3), "tanh")]
+    for i, (xs, oc, k1, k2, act) in enumerate(confs):
+        M = SkipConnectionIdentityModule(out_ch=oc, kernel_shape1=k1, kernel_shape2=k2,
+                                         act_fn=None if act == "identity" else ACTS[act]())
+        X = f32(rng, xs)
+        M.forward(X, retain_derived=False)
+        P = {}
+        for tag, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2)):
+            conv.parameters["W"] = f32(rng, conv.parameters["W"].shape, 0.4)
+            conv.parameters["b"] = f32(rng, conv.parameters["b"].shape, 0.3)
+            bn.parameters["scaler"] = f32(rng, bn.parameters["scaler"].shape) * 0.5 + 1.0
+            bn.parameters["intercept"] = f32(rng, bn.parameters["intercept"].shape) * 0.1
+            bn.reset_running_stats()
+            P["W" + tag], P["b" + tag] = conv.parameters["W"].copy(), conv.parameters["b"].copy()
+            P["g" + tag], P["h" + tag] = bn.parameters["scaler"].copy(), bn.parameters["intercept"].copy()
+        for c in M.components:
+            c.flush_gradients()
+        Y = M.forward(X)
+        dY = f32(rng, Y.shape)
+        dX = np.array(M.backward(dY))
+        out = {"X": X, "dLdY": dY, "Y": Y, "dX": dX}
+        out.update(P)
+        dv = M.derived_variables
+        for k in ["conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2"]:
+            out[k] = np.asarray(dv[k], dtype=np.float64)
+        for tag, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2)):
+            out["dW" + tag], out["db" + tag] = conv.gradients["W"], conv.gradients["b"]
+            out["dg" + tag], out["dh" + tag] = bn.gradients["scaler"], bn.gradients["intercept"]
+            out["rm" + tag], out["rv" + tag] = bn.parameters["running_mean"], bn.parameters["running_var"]
+        arrays.update({f"m{i}/{k}": v for k, v in out.items()})
+        p0, p1 = ACT_PARAMS.get(act, (0.0, 0.0))
+        cases.append({"id": f"m{i}", "out_ch": oc, "kernel_shape1": list(k1), "kernel_shape2": list(k2), "act": act,
+                      "p0": p0, "p1": p1})
+    save("skip_identity_module.npz", arrays, cases)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:                                         # e.g. `make_golden.py conv1d pool2d`
+        for name in only:
+            globals()["gen_" + name]()
+        sys.exit(0)
+    gen_conv1d()
+    gen_pool2d()
+    gen_identity_module()
     gen_optimizers()
     gen_utils()
     gen_activations()

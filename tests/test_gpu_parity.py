@@ -572,3 +572,155 @@ def test_layer_update_with_adam_matches_oracle(cuda_device):
     close(L.parameters["b"], br, 1e-5, "b after update")
     assert float(L.gradients["W"].abs().sum()) == 0.0 and L.X == []
     assert L.hyperparameters["optimizer"]["hyperparameters"]["id"] == "Adam"
+
+
+# ------------------------------------------------------------------------------------------------
+#  callers either side of the path: Conv1D, Pool2D / Flatten, identity skip module
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", MODES)
+def test_conv1d_layer_golden(cuda_device, mode):
+    pkg = npml()
+    z, cases = load_golden("conv1d_layer.npz")
+    tol = TOL[mode]
+    for c in cases:
+        if mode != "fp32" and c["act"] in KINKED:
+            continue                                   # mask flips next to the kink, see KINKED above
+        i, pad = c["id"], to_pad(c["pad"])
+        layer = pkg.Conv1D(out_ch=c["out_ch"], kernel_width=c["kernel_width"], pad=pad, stride=c["stride"],
+                           dilation=c["dilation"], act_fn=make_act(pkg, c["act"], c["p0"], c["p1"]), mode=mode)
+        X = z[i + "/X"]
+        layer.forward(X, retain_derived=False)
+        assert tuple(layer.parameters["W"].shape) == z[i + "/W"].shape and tuple(layer.parameters["b"].shape) == z[i + "/b"].shape
+        layer.parameters["W"], layer.parameters["b"] = z[i + "/W"], z[i + "/b"]
+        Y = layer.forward(X)
+        close(Y, z[i + "/Y"], tol, i + " Y")
+        close(layer.derived_variables["Z"][0], z[i + "/Z"], tol, i + " Z")
+        assert tuple(layer.X[0].shape) == X.shape
+        assert layer.derived_variables["out_rows"][0] == z[i + "/Z"].shape[1]       # l_out (layers.py:2749)
+        assert layer.derived_variables["out_cols"][0] == z[i + "/Z"].shape[2]       # out_ch (layers.py:2750)
+        if c["two_calls"]:
+            close(layer.forward(z[i + "/X2"]), z[i + "/Y2"], tol, i + " Y2")
+            dXs = layer.backward([z[i + "/dLdy"], z[i + "/dLdy2"]])
+            close(dXs[0], z[i + "/dX"], tol, i + " dX")
+            close(dXs[1], z[i + "/dX2"], tol, i + " dX2")
+        else:
+            close(layer.backward(z[i + "/dLdy"]), z[i + "/dX"], tol, i + " dX")
+        close(layer.gradients["W"], z[i + "/dW"], tol, i + " dW")
+        close(layer.gradients["b"], z[i + "/db"], tol, i + " db")
+        if mode == "fp32":
+            close(pkg.conv1D(X, z[i + "/W"], c["stride"], pad, c["dilation"]), z[i + "/conv1D"], tol, i + " conv1D")
+            Xp, p2 = pkg.pad1D(X, pad, c["kernel_width"], c["stride"], c["dilation"])
+            assert list(p2) == list(z[i + "/pad"]) and Xp.shape[1] == X.shape[1] + sum(p2)
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", [
+    # n, l, c_in, c_out, kw, pad, stride, dilation
+    (4, 200, 64, 64, 3, "causal", 1, 3),           # Wavenet residual shape: slab kernels on a one-row volume
+    (2, 1000, 32, 48, 2, "causal", 1, 7),          # long sequence (row wider than one slab)
+    (3, 128, 64, 128, 5, "same", 2, 0),            # strided
+])
+def test_conv1d_tensor_core_vs_oracle(cuda_device, mode, case):
+    from oracle import next_oracle as NO
+    pkg = npml()
+    n, l, ci, co, kw, pad, s, d = case
+    rng = np.random.default_rng(7 + l)
+    X, W, b = _f32(rng, (n, l, ci)), _f32(rng, (kw, ci, co), (kw * ci) ** -0.5), _f32(rng, (1, 1, co), 0.1)
+    layer = pkg.Conv1D(co, kw, pad=pad, stride=s, dilation=d, act_fn="tanh", mode=mode)
+    layer.forward(X, retain_derived=False)
+    layer.parameters["W"], layer.parameters["b"] = W, b
+    Y = layer.forward(X)
+    Yr, Zr = NO.conv1d_layer_fwd(X, W, b, s, pad, d, "tanh")
+    dY = _f32(rng, Yr.shape)
+    dX = layer.backward(dY)
+    dXr, dWr, dbr = NO.conv1d_layer_bwd(dY, X, Zr, W, s, pad, d, "tanh")
+    tol = TOL[mode]
+    close(Y, Yr, tol, "Y")
+    close(dX, dXr, tol, "dX")
+    close(layer.gradients["W"], dWr, tol, "dW")
+    close(layer.gradients["b"], dbr, tol, "db")
+    assert layer._uses_tc((n, 1, l, ci))
+
+
+def test_pool2d_flatten_golden(cuda_device):
+    import torch
+    pkg = npml()
+    z, cases = load_golden("pool2d.npz")
+    for c in cases:
+        i = c["id"]
+        if c.get("flatten"):
+            F = pkg.Flatten(keep_dim=c["keep_dim"])
+            Xd = torch.tensor(z[i + "/X"], dtype=torch.float32, device="cuda")
+            Y = F.forward(Xd)
+            assert Y.data_ptr() == Xd.data_ptr() and np.array_equal(Y.cpu().numpy(), z[i + "/Y"].astype(np.float32))
+            assert np.array_equal(F.backward(z[i + "/dLdy"]), z[i + "/dX"])
+            continue
+        P = pkg.Pool2D(kernel_shape=tuple(c["kernel_shape"]), stride=c["stride"], pad=to_pad(c["pad"]), mode=c["mode"])
+        Y = P.forward(z[i + "/X"])
+        close(Y, z[i + "/Y"], 0.0 if c["mode"] == "max" else 1e-6, i + " Y")       # max is a selection: exact
+        assert P.derived_variables["out_rows"][0] == z[i + "/Y"].shape[1]
+        if c["backward"]:
+            close(P.backward(z[i + "/dLdY"]), z[i + "/dX"], 1e-6, i + " dX")
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("mode", ["max", "average"])
+def test_pool2d_vs_oracle_vae_shape(cuda_device, dtype, mode):
+    """The pooling step of the reference's VAE encoder (models/vae.py:142-189) on device tensors, both element types."""
+    import torch
+    from oracle import next_oracle as NO
+    pkg = npml()
+    rng = np.random.default_rng(41)
+    td = torch.float32 if dtype == "fp32" else torch.bfloat16
+    Xd = torch.tensor(_f32(rng, (8, 28, 28, 32)), dtype=torch.float32, device="cuda").to(td)
+    X = Xd.float().cpu().numpy().astype(np.float64)                  # the oracle sees the stored (rounded) values
+    for ks, s, pad in (((2, 2), 2, 0), ((3, 3), 2, 1), ((3, 2), 1, (1, 0))):
+        P = pkg.Pool2D(kernel_shape=ks, stride=s, pad=pad, mode=mode)
+        Y = P.forward(Xd)
+        Yr = NO.pool2d_fwd(X, ks, s, pad, mode)
+        assert Y.dtype == td
+        close(Y.float(), Yr, 0.0 if mode == "max" else (1e-6 if dtype == "fp32" else 4e-3), "Y")
+        dYd = torch.tensor(_f32(rng, Yr.shape), dtype=torch.float32, device="cuda").to(td)
+        dXr = NO.pool2d_bwd(dYd.float().cpu().numpy().astype(np.float64), X, ks, s, pad, mode)
+        close(P.backward(dYd).float(), dXr, 1e-6 if dtype == "fp32" else 4e-3, "dX")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_skip_identity_module_golden(cuda_device, mode):
+    pkg = npml()
+    z, cases = load_golden("skip_identity_module.npz")
+    tol = TOL_BN[mode]
+    for c in cases:
+        if mode != "fp32" and c["act"] in KINKED:
+            continue
+        i = c["id"]
+        act = None if c["act"] == "identity" else make_act(pkg, c["act"], c["p0"], c["p1"])
+        M = pkg.SkipConnectionIdentityModule(out_ch=c["out_ch"], kernel_shape1=tuple(c["kernel_shape1"]),
+                                             kernel_shape2=tuple(c["kernel_shape2"]), act_fn=act, mode=mode)
+        X = z[i + "/X"]
+        M.forward(X, retain_derived=False)
+        for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2)):
+            conv.parameters["W"], conv.parameters["b"] = z["{}/W{}".format(i, t)], z["{}/b{}".format(i, t)]
+            bn.parameters["scaler"], bn.parameters["intercept"] = z["{}/g{}".format(i, t)], z["{}/h{}".format(i, t)]
+            bn.reset_running_stats()
+        M.flush_gradients()
+        Y = M.forward(X)
+        dX = M.backward(z[i + "/dLdY"])
+        close(Y, z[i + "/Y"], tol, i + " Y")
+        close(dX, z[i + "/dX"], tol, i + " dX")
+        dv = M.derived_variables
+        for k in ["conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2"]:
+            close(dv[k], z["{}/{}".format(i, k)], tol, i + " " + k)
+        close(dv["dLdAdd3_X"], z[i + "/dX"], tol, i + " dLdAdd3_X")
+        for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2)):
+            close(conv.gradients["W"], z["{}/dW{}".format(i, t)], tol, i + " dW" + t)
+            close(bn.gradients["scaler"], z["{}/dg{}".format(i, t)], tol, i + " dg" + t)
+            # BN1's intercept feeds a 1x1 conv2 + BN2 in case m1: its true gradient is 0 (pure cancellation), so it is
+            # compared absolutely, on the scale of the scaler gradient
+            dh_ref = z["{}/dh{}".format(i, t)]
+            dh = pkg.to_numpy(bn.gradients["intercept"])
+            scale = max(np.linalg.norm(z["{}/dg{}".format(i, t)].ravel()), np.linalg.norm(dh_ref.ravel()), 1.0)
+            assert np.linalg.norm((dh - dh_ref).ravel()) <= tol * scale, i + " dh" + t
+            close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol, i + " rm" + t)
+            close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol, i + " rv" + t)
+        assert M.hyperparameters["component_ids"] == ["conv1", "batchnorm1", "conv2", "batchnorm2", "add3"]

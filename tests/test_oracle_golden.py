@@ -226,3 +226,66 @@ def test_host_optimizer_strings_and_schedules_match_reference():
         Op.OptimizerInitializer("Lion(lr=0.1)")()
     with pytest.raises(NotImplementedError):
         Sc.SchedulerInitializer("KingScheduler(initial_lr=0.01, patience=1000, decay=0.99)")()
+
+
+# ---------------------------------------------------------------------------------------------------
+#  callers either side of the path: Conv1D, Pool2D / Flatten, identity skip module
+# ---------------------------------------------------------------------------------------------------
+def test_conv1d_layer_golden():
+    from oracle import next_oracle as N
+    z, cases = load_golden("conv1d_layer.npz")
+    assert {"same", "causal"} <= {c["pad"] for c in cases if isinstance(c["pad"], str)}
+    for c in cases:
+        i, pad = c["id"], to_pad(c["pad"])
+        X, W, b = z[i + "/X"], z[i + "/W"], z[i + "/b"]
+        a = (c["act"], c["p0"], c["p1"])
+        assert list(N.resolve_pad_1D(X.shape, pad, c["kernel_width"], c["stride"], c["dilation"])) == list(z[i + "/pad"])
+        close(N.conv1D(X, W, c["stride"], pad, c["dilation"]), z[i + "/conv1D"])
+        Y, Z = N.conv1d_layer_fwd(X, W, b, c["stride"], pad, c["dilation"], *a)
+        close(Y, z[i + "/Y"])
+        close(Z, z[i + "/Z"])
+        dX, dW, db = N.conv1d_layer_bwd(z[i + "/dLdy"], X, Z, W, c["stride"], pad, c["dilation"], *a)
+        close(dX, z[i + "/dX"])
+        if c["two_calls"]:
+            X2 = z[i + "/X2"]
+            Y2, Z2 = N.conv1d_layer_fwd(X2, W, b, c["stride"], pad, c["dilation"], *a)
+            close(Y2, z[i + "/Y2"])
+            dX2, dW2, db2 = N.conv1d_layer_bwd(z[i + "/dLdy2"], X2, Z2, W, c["stride"], pad, c["dilation"], *a)
+            close(dX2, z[i + "/dX2"])
+            dW, db = dW + dW2, db + db2
+        close(dW, z[i + "/dW"])
+        close(db, z[i + "/db"])
+    with pytest.raises(ValueError):
+        N.calc_pad_dims_1D([2, 9, 3], 9, 3, 1)                 # X_shape not a tuple (utils.py:153-163)
+
+
+def test_pool2d_flatten_golden():
+    from oracle import next_oracle as N
+    z, cases = load_golden("pool2d.npz")
+    for c in cases:
+        i = c["id"]
+        if c.get("flatten"):
+            Y = N.flatten_fwd(z[i + "/X"], c["keep_dim"])
+            assert np.array_equal(Y, z[i + "/Y"])
+            assert np.array_equal(z[i + "/dLdy"].reshape(z[i + "/X"].shape), z[i + "/dX"])
+            continue
+        ks, pad = tuple(c["kernel_shape"]), to_pad(c["pad"])
+        close(N.pool2d_fwd(z[i + "/X"], ks, c["stride"], pad, c["mode"]), z[i + "/Y"], 1e-15)
+        if c["backward"]:
+            close(N.pool2d_bwd(z[i + "/dLdY"], z[i + "/X"], ks, c["stride"], pad, c["mode"]), z[i + "/dX"], 1e-15)
+
+
+def test_skip_identity_module_golden():
+    from oracle import next_oracle as N
+    z, cases = load_golden("skip_identity_module.npz")
+    for c in cases:
+        i = c["id"]
+        P = {k: z["{}/{}".format(i, k)] for k in ("W1", "b1", "W2", "b2", "g1", "h1", "g2", "h2")}
+        for t in "12":
+            P["rm" + t], P["rv" + t] = np.zeros_like(P["g" + t]), np.ones_like(P["g" + t])
+        o = N.skip_identity_module_fwd_bwd(z[i + "/X"], z[i + "/dLdY"], P, tuple(c["kernel_shape1"]),
+                                           tuple(c["kernel_shape2"]), 1, 1, c["act"], c["p0"], c["p1"])
+        for k in ("Y", "dX", "conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "dLdBn1", "dLdBn2",
+                  "dLdConv1", "dLdConv2", "dW1", "db1", "dW2", "db2", "dg1", "dh1", "dg2", "dh2", "rm1", "rv1", "rm2",
+                  "rv2"):
+            close(o[k], z["{}/{}".format(i, k)], 1e-10)
