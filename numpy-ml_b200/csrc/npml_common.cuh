@@ -177,6 +177,10 @@ bool slab_conv_supported(const GatherConv& g, int mode);
 size_t slab_conv_ws_bytes(const GatherConv& g, int mode);
 int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
+// row-of-taps variant for narrow outputs (fc * out_ch <= 256), tc_slab3_conv.cu; slab_gather_conv dispatches to it
+bool slab3_conv_supported(const GatherConv& g, int mode);
+int slab3_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
+                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
 // persistent slab wgrad (+ db) for stride-1 convolutions, tc_slab_wgrad.cu
 bool slab_wgrad_supported(const GatherWgrad& g, int mode);
 size_t slab_wgrad_ws_bytes(const GatherWgrad& g, int mode);

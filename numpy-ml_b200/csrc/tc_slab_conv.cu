@@ -499,17 +499,19 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
 
 bool slab_conv_supported(const GatherConv& g, int mode) {
   SlabPlan pl;
-  return plan_slab(g, mode, pl);
+  return plan_slab(g, mode, pl) || slab3_conv_supported(g, mode);
 }
 
 size_t slab_conv_ws_bytes(const GatherConv& g, int mode) {
-  SlabPlan pl;
-  if (!plan_slab(g, mode, pl)) return 0;
-  return pl.wt_bytes + 256;
+  if (!slab_conv_supported(g, mode)) return 0;
+  const int es = mode == NPML_MODE_BF16 ? 2 : 4;       // the repacked weights Wt[tap][co][ci], both slab kernels
+  return align_up((size_t)g.fr * g.fc * g.CO * g.CI * es, 256) + 256;
 }
 
 int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
                      void* ws, size_t ws_bytes, cudaStream_t st) {
+  // narrow outputs (fc * out_ch <= 256): one MMA per filter ROW, column taps folded into N (tc_slab3_conv.cu)
+  if (slab3_conv_supported(g, mode)) return slab3_gather_conv(g, mode, in, w, bias, Z, Y, ws, ws_bytes, st);
   SlabPlan pl;
   NPML_CHECK(plan_slab(g, mode, pl), "shape not supported by the slab path");
   NPML_CHECK(ws != nullptr && ws_bytes >= pl.wt_bytes, "workspace too small");

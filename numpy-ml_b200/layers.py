@@ -155,7 +155,9 @@ def _dz_prep(dY, Z, act, out_dtype, db=None, accumulate=True):
     identity = act.code == 0
     if identity and dY.dtype == out_dtype and db is None:
         return dY
-    dZ = torch.empty(dY.shape, dtype=out_dtype, device=dY.device)
+    # identity activation in the GEMMs' own dtype: dZ IS dLdy, the pass only has to produce the column sums
+    alias = identity and dY.dtype == out_dtype
+    dZ = dY if alias else torch.empty(dY.shape, dtype=out_dtype, device=dY.device)
     ws = None
     if db is not None:
         d = U.make_desc(1, 1, 1, 1, ch, 1, 1, 1, 1, (0, 0, 0, 0), 1, 1)
@@ -163,8 +165,8 @@ def _dz_prep(dY, Z, act, out_dtype, db=None, accumulate=True):
         ws = L.workspace(lib.npml_workspace_bytes(d, L.OP_DZ_PREP))
     with L.profiled("npml_dz_prep"):
         L.check(lib.npml_dz_prep(rows, ch, act.code, act.p0, act.p1, L.ptr(dY), L.code_of(dY),
-                                 None if identity else L.ptr(Z), 0 if identity else L.code_of(Z), L.ptr(dZ),
-                                 L.code_of(dZ), L.ptr(db), 1 if accumulate else 0, L.ptr(ws),
+                                 None if identity else L.ptr(Z), 0 if identity else L.code_of(Z),
+                                 None if alias else L.ptr(dZ), L.code_of(dZ), L.ptr(db), 1 if accumulate else 0, L.ptr(ws),
                                  0 if ws is None else ws.numel(), L.stream()), "npml_dz_prep")
     return dZ
 

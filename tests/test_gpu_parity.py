@@ -724,3 +724,38 @@ def test_skip_identity_module_golden(cuda_device, mode):
             close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol, i + " rm" + t)
             close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol, i + " rv" + t)
         assert M.hyperparameters["component_ids"] == ["conv1", "batchnorm1", "conv2", "batchnorm2", "add3"]
+
+
+@pytest.mark.parametrize("fold", ["2", "3"])
+@pytest.mark.parametrize("mode", ["bf16", "tf32"])
+def test_row_of_taps_slab_kernel_optin(cuda_device, monkeypatch, mode, fold):
+    """csrc/tc_slab3_conv.cu (NPML_SLAB3=2|3: column taps of a filter row folded into one MMA, epilogue row shifts):
+    forward and dX of a 3x3 / 64-channel layer, of a dilated one, and of a causal Conv1D against the oracle."""
+    from oracle import next_oracle as NO
+    monkeypatch.setenv("NPML_SLAB3", fold)
+    pkg = npml()
+    rng = np.random.default_rng(5)
+    tol = TOL[mode]
+    for (n, h, w, ci, co, pad, d) in ((3, 20, 23, 64, 64, "same", 0), (2, 17, 30, 32, 48, 2, 1)):
+        X, W = _f32(rng, (n, h, w, ci)), _f32(rng, (3, 3, ci, co), (9 * ci) ** -0.5)
+        b = _f32(rng, (1, 1, 1, co), 0.1)
+        L = pkg.Conv2D(co, (3, 3), pad=pad, dilation=d, act_fn="tanh", mode=mode)
+        L.forward(X, retain_derived=False)
+        L.parameters["W"], L.parameters["b"] = W, b
+        Y = L.forward(X)
+        Yr, Zr = O.conv2d_layer_fwd(X, W, b, 1, pad, d, "tanh")
+        dY = _f32(rng, Yr.shape)
+        dX = L.backward(dY)
+        dXr, dWr, dbr = O.conv2d_layer_bwd(dY, X, Zr, W, 1, pad, d, "tanh")
+        close(Y, Yr, tol, "Y")
+        close(dX, dXr, tol, "dX")
+        close(L.gradients["W"], dWr, tol, "dW")
+    X, W, b = _f32(rng, (2, 300, 64)), _f32(rng, (3, 64, 64), 192 ** -0.5), _f32(rng, (1, 1, 64), 0.1)
+    L = pkg.Conv1D(64, 3, pad="causal", dilation=1, mode=mode)
+    L.forward(X, retain_derived=False)
+    L.parameters["W"], L.parameters["b"] = W, b
+    Y = L.forward(X)
+    Yr, Zr = NO.conv1d_layer_fwd(X, W, b, 1, "causal", 1)
+    dY = _f32(rng, Yr.shape)
+    close(Y, Yr, tol, "conv1d Y")
+    close(L.backward(dY), NO.conv1d_layer_bwd(dY, X, Zr, W, 1, "causal", 1)[0], tol, "conv1d dX")
