@@ -119,6 +119,13 @@ int npml_cast(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, 
  * `sum` may be NULL when act is identity. */
 int npml_add_act_fwd(int32_t n_in, const void* const* xs, int32_t dtype, int64_t n, int32_t act,
                      float p0, float p1, void* sum, void* Y, void* stream);
+/* Multiply.forward / _bwd (layers/layers.py:800-856): prod = x0 * ... * x_{n_in-1}, Y = act(prod);
+ * grads[i] = dY * act'(prod) * prod_{j != i} x_j.  `prod` may be NULL in the forward when act is identity (then Y is
+ * the product) and in the backward when act is identity. */
+int npml_mul_act_fwd(int32_t n_in, const void* const* xs, int32_t dtype, int64_t n, int32_t act,
+                     float p0, float p1, void* prod, void* Y, void* stream);
+int npml_mul_act_bwd(int32_t n_in, const void* const* xs, void* const* grads, int32_t dtype, int64_t n,
+                     int32_t act, float p0, float p1, const void* dY, const void* prod, void* stream);
 /* activation fn on its own (activations/activations.py `fn`): Y = act(Z) */
 int npml_act_fwd(const void* Z, void* Y, int32_t dtype, int64_t n, int32_t act, float p0, float p1,
                  void* stream);

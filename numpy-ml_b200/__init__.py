@@ -15,7 +15,7 @@ from . import modules
 from . import dist
 from ._lib import to_numpy, launch_count
 from .build import build
-from .layers import Conv2D, Deconv2D, Conv1D, Pool2D, Flatten, BatchNorm2D, Add
-from .modules import SkipConnectionConvModule, SkipConnectionIdentityModule
+from .layers import Conv2D, Deconv2D, Conv1D, Pool2D, Flatten, BatchNorm2D, Add, Multiply, FullyConnected
+from .modules import SkipConnectionConvModule, SkipConnectionIdentityModule, WavenetResidualModule
 from .utils import (pad2D, calc_pad_dims_2D, calc_conv_out_dims, im2col, col2im, conv2D, conv2D_naive,
                     deconv2D_naive, dilate, pad1D, calc_pad_dims_1D, conv1D)

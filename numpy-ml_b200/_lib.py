@@ -43,6 +43,8 @@ SIGNATURES = {
     "npml_dz_prep": (C.c_int, [_I64, _I32, _I32, _F, _F, _P, _I32, _P, _I32, _P, _I32, _P, _I32, _P, _SZ, _P]),
     "npml_cast": (C.c_int, [_P, _I32, _P, _I32, _I64, _P]),
     "npml_add_act_fwd": (C.c_int, [_I32, C.POINTER(_P), _I32, _I64, _I32, _F, _F, _P, _P, _P]),
+    "npml_mul_act_fwd": (C.c_int, [_I32, C.POINTER(_P), _I32, _I64, _I32, _F, _F, _P, _P, _P]),
+    "npml_mul_act_bwd": (C.c_int, [_I32, C.POINTER(_P), C.POINTER(_P), _I32, _I64, _I32, _F, _F, _P, _P, _P]),
     "npml_act_fwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _F, _F, _P]),
     "npml_bn2d_fwd": (C.c_int, [_I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _F, _F, _I32, _P, _P, _P, _SZ, _P]),
     "npml_bn2d_bwd": (C.c_int, [_I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),

@@ -513,6 +513,66 @@ __global__ void add_act_kernel(AddArgs a, int dt_rt, int64_t n_vec, int act, flo
   }
 }
 
+// Multiply.forward (layers/layers.py:800-822): prod = x0 * x1 * ...; Y = act(prod)
+template <int VEC>
+__global__ void mul_act_kernel(AddArgs a, int dt, int64_t n_vec, int act, float p0, float p1, void* prod, void* Y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float s[VEC];
+    load_vec<VEC>(a.xs[0], dt, i * VEC, s);
+    for (int k = 1; k < a.n_in; ++k) {
+      float v[VEC];
+      load_vec<VEC>(a.xs[k], dt, i * VEC, v);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[j] *= v[j];
+    }
+    if (dt == NPML_BF16) {                 // later passes read the stored product
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[j] = __bfloat162float(__float2bfloat16_rn(s[j]));
+    }
+    if (prod) store_vec<VEC>(prod, dt, i * VEC, s);
+    if (Y) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s[j] = act_fn(act, s[j], p0, p1);
+      store_vec<VEC>(Y, dt, i * VEC, s);
+    }
+  }
+}
+
+struct MulBwdArgs {
+  const void* xs[8];
+  void* gs[8];
+  int n_in;
+};
+
+// Multiply._bwd (layers/layers.py:849-856): g_i = dLdY * act'(prod) * prod_{j != i} x_j
+template <int VEC>
+__global__ void mul_act_bwd_kernel(MulBwdArgs a, int dt, int64_t n_vec, int act, float p0, float p1, const void* dY,
+                                   const void* prod) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    float g[VEC];
+    load_vec<VEC>(dY, dt, i * VEC, g);
+    if (act != NPML_ACT_IDENTITY) {
+      float pr[VEC];
+      load_vec<VEC>(prod, dt, i * VEC, pr);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) g[j] *= act_grad(act, pr[j], p0, p1);
+    }
+    float x[8][VEC];
+    for (int k = 0; k < a.n_in; ++k) load_vec<VEC>(a.xs[k], dt, i * VEC, x[k]);
+    for (int k = 0; k < a.n_in; ++k) {
+      float o[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) o[j] = g[j];
+      for (int q = 0; q < a.n_in; ++q) {
+        if (q == k) continue;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] *= x[q][j];
+      }
+      store_vec<VEC>(a.gs[k], dt, i * VEC, o);
+    }
+  }
+}
+
 inline int flat_blocks(int64_t n_vec) {
   int64_t b = (n_vec + 255) / 256;
   const int64_t cap = 16LL * num_sms();
@@ -688,6 +748,48 @@ extern "C" int npml_add_act_fwd(int32_t n_in, const void* const* xs, int32_t dty
     add_act_kernel<4, -1><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, sum, Y);
   else
     add_act_kernel<1, -1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, sum, Y);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_mul_act_fwd(int32_t n_in, const void* const* xs, int32_t dtype, int64_t n, int32_t act, float p0,
+                                float p1, void* prod, void* Y, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(n_in >= 1 && n_in <= 8, "between 1 and 8 inputs are supported");
+  if (n <= 0) return 0;
+  AddArgs a;
+  a.n_in = n_in;
+  bool al = aligned_for_vec4(prod, dtype) && aligned_for_vec4(Y, dtype);
+  for (int i = 0; i < n_in; ++i) {
+    a.xs[i] = xs[i];
+    al = al && aligned_for_vec4(xs[i], dtype);
+  }
+  if (al && n % 4 == 0)
+    mul_act_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, prod, Y);
+  else
+    mul_act_kernel<1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, prod, Y);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_mul_act_bwd(int32_t n_in, const void* const* xs, void* const* grads, int32_t dtype, int64_t n,
+                                int32_t act, float p0, float p1, const void* dY, const void* prod, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(n_in >= 1 && n_in <= 8, "between 1 and 8 inputs are supported");
+  NPML_CHECK(dY != nullptr && (act == NPML_ACT_IDENTITY || prod != nullptr), "dY (and prod for an activation) required");
+  if (n <= 0) return 0;
+  MulBwdArgs a;
+  a.n_in = n_in;
+  bool al = aligned_for_vec4(dY, dtype) && aligned_for_vec4(prod, dtype);
+  for (int i = 0; i < n_in; ++i) {
+    a.xs[i] = xs[i];
+    a.gs[i] = grads[i];
+    al = al && aligned_for_vec4(xs[i], dtype) && aligned_for_vec4(grads[i], dtype);
+  }
+  if (al && n % 4 == 0)
+    mul_act_bwd_kernel<4><<<flat_blocks(n / 4), 256, 0, st>>>(a, dtype, n / 4, act, p0, p1, dY, prod);
+  else
+    mul_act_bwd_kernel<1><<<flat_blocks(n), 256, 0, st>>>(a, dtype, n, act, p0, p1, dY, prod);
   NPML_LAUNCH_OK();
   return 0;
 }

@@ -1,4 +1,4 @@
-"""Conv2D / Deconv2D / Conv1D / Pool2D / Flatten / BatchNorm2D / Add with the reference's layer API
+"""Conv2D / Deconv2D / Conv1D / Pool2D / Flatten / BatchNorm2D / Add / Multiply / FullyConnected with the reference's layer API
 (numpy_ml/neural_nets/layers/layers.py): same constructor arguments, lazy parameter init on the
 first forward, `parameters` / `gradients` / `hyperparameters` / `derived_variables` dicts, list-valued
 `backward`, `+=` gradient accumulation, `flush_gradients` / `update` / `freeze` / `summary`.
@@ -708,3 +708,130 @@ class Add(LayerBase):
     def _bwd(self, dLdY, X, _sum):
         g = _dz_prep(dLdY, _sum, self.act_fn, _sum.dtype)
         return [g for _ in X]
+
+
+class Multiply(LayerBase):
+    """Element-wise product of several inputs followed by an activation (layers/layers.py:745-856)."""
+
+    def __init__(self, act_fn=None, optimizer=None):
+        super().__init__(optimizer)
+        self.act_fn = ActivationInitializer(act_fn)()
+        self._init_params()
+
+    def _init_params(self):
+        self.gradients = {}
+        self.parameters = {}
+        self.derived_variables = {"product": []}
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "Multiply", "act_fn": str(self.act_fn), "optimizer": self._opt_hparams()}
+
+    def forward(self, X, retain_derived=True):
+        as_np = isinstance(X[0], np.ndarray)
+        first = X[0]
+        dt = torch.float32 if (as_np or first.dtype == torch.float64) else first.dtype
+        Xd = [L.to_device(x, dt) for x in X]
+        prod = torch.empty_like(Xd[0])
+        Y = prod if self.act_fn.code == 0 else torch.empty_like(prod)
+        arr = (C.c_void_p * len(Xd))(*[x.data_ptr() for x in Xd])
+        a = self.act_fn
+        with L.profiled("npml_mul_act_fwd"):
+            L.check(L.load().npml_mul_act_fwd(len(Xd), arr, L.code_of(prod), prod.numel(), a.code, a.p0, a.p1,
+                                              L.ptr(prod), None if Y is prod else L.ptr(Y), L.stream()),
+                    "npml_mul_act_fwd")
+        if retain_derived:
+            self.X.append(Xd)
+            self.derived_variables["product"].append(prod)
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdY, retain_grads=True):
+        if not isinstance(dLdY, list):
+            dLdY = [dLdY]
+        grads = []
+        for dy, x, pr in zip(dLdY, self.X, self.derived_variables["product"]):
+            as_np = isinstance(dy, np.ndarray)
+            g = self._bwd(L.to_device(dy, pr.dtype), x, pr)
+            grads.append([L.to_numpy(v) for v in g] if as_np else g)
+        return grads[0] if len(self.X) == 1 else grads
+
+    def _bwd(self, dLdY, X, prod):
+        out = [torch.empty_like(prod) for _ in X]
+        xs = (C.c_void_p * len(X))(*[x.data_ptr() for x in X])
+        gs = (C.c_void_p * len(X))(*[g.data_ptr() for g in out])
+        a = self.act_fn
+        with L.profiled("npml_mul_act_bwd"):
+            L.check(L.load().npml_mul_act_bwd(len(X), xs, gs, L.code_of(prod), prod.numel(), a.code, a.p0, a.p1,
+                                              L.ptr(dLdY), L.ptr(prod), L.stream()), "npml_mul_act_bwd")
+        return out
+
+
+class FullyConnected(_ConvBase):
+    """layers/layers.py:2010-2170: Y = act_fn(X @ W + b) with X (n_ex, n_in), W (n_in, n_out), b (1, n_out).
+    A dense layer is a 1x1 convolution over a 1x1 image, so it runs on the Conv2D entry points unchanged
+    (dX = dZ @ W.T -> dgrad, dW = X.T @ dZ and db -> wgrad_db)."""
+    _layer_name = "Conv2D"
+    _ops = (L.OP_CONV_FPROP, L.OP_CONV_DGRAD, L.OP_CONV_WGRAD)
+
+    def __init__(self, n_out, act_fn=None, init="glorot_uniform", optimizer=None, mode="fp32"):
+        super().__init__(optimizer)
+        self.init = init
+        self.n_in = None
+        self.n_out = n_out
+        self.out_ch = n_out
+        self.pad, self.stride, self.dilation, self.kernel_shape = 0, 1, 0, (1, 1)
+        self.act_fn = ActivationInitializer(act_fn)()
+        self.parameters = {"W": None, "b": None}
+        self.is_initialized = False
+        self.mode = mode
+        assert mode in L.MODES
+
+    def _init_params(self):
+        init_weights = WeightInitializer(str(self.act_fn), mode=self.init)
+        W = init_weights((self.n_in, self.n_out))
+        self.parameters = {"W": L.to_device(W, torch.float32),
+                           "b": torch.zeros((1, self.n_out), dtype=torch.float32, device=L.device())}
+        self.gradients = {"W": torch.zeros_like(self.parameters["W"]), "b": torch.zeros_like(self.parameters["b"])}
+        self.derived_variables = {"Z": []}
+        self.is_initialized = True
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "FullyConnected", "init": self.init, "n_in": self.n_in, "n_out": self.n_out,
+                "act_fn": str(self.act_fn), "optimizer": self._opt_hparams()}
+
+    def _geometry(self, X_shape):
+        return (0, 0, 0, 0), 1, 1, 1
+
+    def forward(self, X, retain_derived=True):
+        as_np = isinstance(X, np.ndarray)
+        Xd = L.to_device(X, L.torch_dtype(self.mode))
+        if Xd.dim() != 2:
+            raise ValueError("FullyConnected expects (n_ex, n_in), got {}".format(tuple(Xd.shape)))
+        if not self.is_initialized:
+            self.n_in = self.in_ch = Xd.shape[1]
+            self._init_params()
+        n, d = Xd.shape
+        if retain_derived:
+            self.derived_variables.setdefault("out_rows", [])
+            self.derived_variables.setdefault("out_cols", [])
+        Y = super().forward(Xd.view(n, 1, 1, d), retain_derived).view(n, self.n_out)
+        if retain_derived:
+            dv = self.derived_variables
+            self.X[-1] = self.X[-1].view(n, d)
+            dv["Z"][-1] = dv["Z"][-1].view(n, self.n_out)
+            dv.pop("out_rows"), dv.pop("out_cols")          # the reference keeps only Z (layers.py:2056)
+        return L.to_numpy(Y) if as_np else Y
+
+    def backward(self, dLdy, retain_grads=True):
+        assert self.trainable, "Layer is frozen"
+        if not isinstance(dLdy, list):
+            dLdy = [dLdy]
+        dX = []
+        for dy, x, z in zip(dLdy, self.X, self.derived_variables["Z"]):
+            as_np = isinstance(dy, np.ndarray)
+            n, d = x.shape
+            dx = self._bwd(L.to_device(dy, L.torch_dtype(self.mode)).view(n, 1, 1, self.n_out), x.view(n, 1, 1, d),
+                           z.view(n, 1, 1, self.n_out), retain_grads).view(n, d)
+            dX.append(L.to_numpy(dx) if as_np else dx)
+        return dX[0] if len(self.X) == 1 else dX

@@ -9,8 +9,9 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .activations import ActivationInitializer, Affine
-from .layers import Conv2D, BatchNorm2D, Add
+from .activations import ActivationInitializer, Affine, Tanh, Sigmoid
+from .layers import Conv2D, Conv1D, BatchNorm2D, Add, Multiply
+from .layers import _dz_prep
 from .utils import calc_pad_dims_2D
 
 
@@ -317,3 +318,101 @@ class SkipConnectionIdentityModule(ModuleBase):
         self._dv.update({"dLdAdd3_X": dX, "dLdBn2": dBn2_out, "dLdBn1": dBn1_out, "dLdConv2": dConv2_out,
                          "dLdConv1": dConv1_out})
         return L.to_numpy(dX) if as_np else dX
+
+
+class WavenetResidualModule(ModuleBase):
+    """modules/modules.py:119-357: causal dilated Conv1D (width 2) -> tanh * sigmoid gate -> 1x1 Conv1D, added to the
+    residual path and to the skip path.  Like the reference, `kernel_width` is stored but the dilated convolution
+    always has width 2 (modules.py:161-169).  Unlike it, `X_skip=None` on the first block means zeros (the reference
+    passes the None on to Add and fails, modules.py:297-299)."""
+
+    def __init__(self, ch_residual, ch_dilation, dilation, kernel_width, optimizer=None, init="glorot_uniform",
+                 mode="fp32"):
+        super().__init__()
+        self.init = init
+        self.dilation = dilation
+        self.optimizer = optimizer
+        self.ch_residual = ch_residual
+        self.ch_dilation = ch_dilation
+        self.kernel_width = kernel_width
+        self.mode = mode
+        self._init_params()
+
+    def _init_params(self):
+        self._dv = {}
+        ident = Affine(slope=1, intercept=0)
+        self.conv_dilation = Conv1D(stride=1, pad="causal", init=self.init, kernel_width=2, dilation=self.dilation,
+                                    out_ch=self.ch_dilation, optimizer=self.optimizer, act_fn=ident, mode=self.mode)
+        self.tanh = Tanh()
+        self.sigm = Sigmoid()
+        self.multiply_gate = Multiply(act_fn=ident)
+        self.conv_1x1 = Conv1D(stride=1, pad="same", dilation=0, init=self.init, kernel_width=1,
+                               out_ch=self.ch_residual, optimizer=self.optimizer, act_fn=ident, mode=self.mode)
+        self.add_residual = Add(act_fn=ident)
+        self.add_skip = Add(act_fn=ident)
+
+    _names = ["conv_1x1", "add_skip", "add_residual", "conv_dilation", "multiply_gate"]
+
+    def _by_component(self, attr):
+        return {n: getattr(getattr(self, n), attr) for n in self._names}
+
+    @property
+    def parameters(self):
+        return {"components": self._by_component("parameters")}
+
+    @property
+    def gradients(self):
+        return {"components": self._by_component("gradients")}
+
+    @property
+    def hyperparameters(self):
+        return {"layer": "WavenetResidualModule", "init": self.init, "dilation": self.dilation,
+                "optimizer": self.optimizer, "ch_residual": self.ch_residual, "ch_dilation": self.ch_dilation,
+                "kernel_width": self.kernel_width, "component_ids": list(self._names),
+                "components": self._by_component("hyperparameters")}
+
+    @property
+    def derived_variables(self):
+        dv = {"conv_1x1_out": None, "conv_dilation_out": None, "multiply_gate_out": None,
+              "components": self._by_component("derived_variables")}
+        dv.update(self._dv)
+        return dv
+
+    def forward(self, X_main, X_skip=None):
+        """modules.py:283-318.  Returns (Y_main, Y_skip)."""
+        as_np = isinstance(X_main, np.ndarray)
+        dt = L.torch_dtype(self.mode)
+        Xm = L.to_device(X_main, dt)
+        conv_dilation_out = self.conv_dilation.forward(Xm)
+        tanh_gate = self.tanh.fn(conv_dilation_out)
+        sigm_gate = self.sigm.fn(conv_dilation_out)
+        multiply_gate_out = self.multiply_gate.forward([tanh_gate, sigm_gate])
+        conv_1x1_out = self.conv_1x1.forward(multiply_gate_out)
+        Xs = torch.zeros_like(conv_1x1_out) if X_skip is None else L.to_device(X_skip, dt)
+        self.X_main, self.X_skip = Xm, Xs
+        Y_skip = self.add_skip.forward([Xs, conv_1x1_out])
+        Y_main = self.add_residual.forward([Xm, conv_1x1_out])
+        self._dv.update({"tanh_out": tanh_gate, "sigm_out": sigm_gate, "conv_dilation_out": conv_dilation_out,
+                         "multiply_gate_out": multiply_gate_out, "conv_1x1_out": conv_1x1_out})
+        return (L.to_numpy(Y_main), L.to_numpy(Y_skip)) if as_np else (Y_main, Y_skip)
+
+    def backward(self, dY_skip, dY_main=None):
+        """modules.py:320-357.  Returns (dX_main, dX_skip)."""
+        as_np = isinstance(dY_skip, np.ndarray)
+        dt = L.torch_dtype(self.mode)
+        dX_skip, dConv_1x1_out = self.add_skip.backward(L.to_device(dY_skip, dt))
+        dX_main = None
+        if dY_main is not None:
+            dX_main, dConv_1x1_main = self.add_residual.backward(L.to_device(dY_main, dt))
+            dConv_1x1_out = _device_add(dConv_1x1_out, dConv_1x1_main)
+        dMultiply_out = self.conv_1x1.backward(dConv_1x1_out)
+        dTanh_out, dSigm_out = self.multiply_gate.backward(dMultiply_out)
+        z = self._dv["conv_dilation_out"]
+        dTanh_in = _dz_prep(dTanh_out, z, self.tanh, z.dtype)
+        dSigm_in = _dz_prep(dSigm_out, z, self.sigm, z.dtype)
+        dDilation_out = _device_add(dTanh_in, dSigm_in)
+        conv_back = self.conv_dilation.backward(dDilation_out)
+        dX_main = conv_back if dX_main is None else _device_add(dX_main, conv_back)
+        self._dv.update({"dLdTanh": dTanh_out, "dLdSigmoid": dSigm_out, "dLdConv_1x1": dConv_1x1_out,
+                         "dLdMultiply": dMultiply_out, "dLdConv_dilation": dDilation_out})
+        return (L.to_numpy(dX_main), L.to_numpy(dX_skip)) if as_np else (dX_main, dX_skip)

@@ -155,3 +155,67 @@ def skip_identity_module_fwd_bwd(X, dLdY, P, k1, k2, s1=1, s2=1, act="identity",
     dX1, o["dW1"], o["db1"] = O.conv2d_layer_bwd(o["dLdConv1"], X, z1, P["W1"], s1, "same", 0, act, p0, p1)
     o["dX"] = dX0 + dX1
     return o
+
+
+# --------------------------------------------------------------------------- #
+#  Multiply / FullyConnected / WavenetResidualModule / the VAE encoder chain    #
+# --------------------------------------------------------------------------- #
+def multiply_fwd(Xs, act="identity", p0=0.0, p1=0.0):
+    """Multiply.forward (layers.py:800-822).  Returns (Y, product)."""
+    prod = Xs[0].copy()
+    for x in Xs[1:]:
+        prod = prod * x
+    return O.act_fn(act, prod, p0, p1), prod
+
+
+def multiply_bwd(dLdY, Xs, prod, act="identity", p0=0.0, p1=0.0):
+    """Multiply._bwd (layers.py:849-856): input i receives dLdY * act'(prod) * prod_{j != i} x_j."""
+    g = dLdY * O.act_grad(act, prod, p0, p1)
+    out = []
+    for i in range(len(Xs)):
+        gi = g.copy()
+        for j, x in enumerate(Xs):
+            if j != i:
+                gi = gi * x
+        out.append(gi)
+    return out
+
+
+def fc_fwd(X, W, b, act="identity", p0=0.0, p1=0.0):
+    """FullyConnected._fwd (layers.py:2100-2106): Z = X @ W + b."""
+    Z = X @ W + b
+    return O.act_fn(act, Z, p0, p1), Z
+
+
+def fc_bwd(dLdy, X, W, b, act="identity", p0=0.0, p1=0.0):
+    """FullyConnected._bwd (layers.py:2144-2155)."""
+    Z = X @ W + b
+    dZ = dLdy * O.act_grad(act, Z, p0, p1)
+    return dZ @ W.T, X.T @ dZ, dZ.sum(axis=0, keepdims=True)
+
+
+def wavenet_module_fwd_bwd(X_main, X_skip, dY_skip, dY_main, P, dilation):
+    """WavenetResidualModule.forward / backward (modules.py:283-357).  conv_dilation is a causal Conv1D of width 2
+    (the constructor's kernel_width is stored but not used, modules.py:161-169), conv_1x1 a 'same' Conv1D of width 1.
+    P: Wd, bd, W1, b1."""
+    o = {}
+    o["conv_dilation_out"], zd = conv1d_layer_fwd(X_main, P["Wd"], P["bd"], 1, "causal", dilation)
+    o["tanh_out"], o["sigm_out"] = np.tanh(zd), 1.0 / (1.0 + np.exp(-zd))
+    o["multiply_gate_out"], prod = multiply_fwd([o["tanh_out"], o["sigm_out"]])
+    o["conv_1x1_out"], z1 = conv1d_layer_fwd(o["multiply_gate_out"], P["W1"], P["b1"], 1, "same", 0)
+    o["Y_skip"] = X_skip + o["conv_1x1_out"]
+    o["Y_main"] = X_main + o["conv_1x1_out"]
+    d1 = dY_skip.copy()
+    o["dX_skip"] = dY_skip.copy()
+    dX_main = np.zeros_like(X_main)
+    if dY_main is not None:
+        dX_main = dY_main.copy()
+        d1 = d1 + dY_main
+    o["dLdConv_1x1"] = d1
+    o["dLdMultiply"], o["dW1"], o["db1"] = conv1d_layer_bwd(d1, o["multiply_gate_out"], z1, P["W1"], 1, "same", 0)
+    o["dLdTanh"], o["dLdSigmoid"] = multiply_bwd(o["dLdMultiply"], [o["tanh_out"], o["sigm_out"]], prod)
+    dd = o["dLdTanh"] * O.act_grad("tanh", zd) + o["dLdSigmoid"] * O.act_grad("sigmoid", zd)
+    o["dLdConv_dilation"] = dd
+    back, o["dWd"], o["dbd"] = conv1d_layer_bwd(dd, X_main, zd, P["Wd"], 1, "causal", dilation)
+    o["dX_main"] = dX_main + back
+    return o

@@ -27,8 +27,10 @@ sys.path.insert(0, "/root/reference")
 
 from numpy_ml.neural_nets import utils as U                      # noqa: E402
 from numpy_ml.neural_nets import activations as A                # noqa: E402
-from numpy_ml.neural_nets.layers import Conv2D, Deconv2D, BatchNorm2D, Add, Conv1D, Pool2D, Flatten   # noqa: E402
-from numpy_ml.neural_nets.modules import SkipConnectionConvModule, SkipConnectionIdentityModule     # noqa: E402
+from numpy_ml.neural_nets.layers import (Conv2D, Deconv2D, BatchNorm2D, Add, Conv1D, Pool2D, Flatten,   # noqa: E402
+                                         Multiply, FullyConnected)
+from numpy_ml.neural_nets.modules import (SkipConnectionConvModule, SkipConnectionIdentityModule,    # noqa: E402
+                                          WavenetResidualModule)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -469,12 +471,107 @@ def gen_identity_module():
     save("skip_identity_module.npz", arrays, cases)
 
 
+def gen_wavenet_vae():
+    """SURVEY.md 8f ranks 2-3, the models either side of the path: Multiply, FullyConnected, WavenetResidualModule
+    (modules.py:119-357) and the BernoulliVAE encoder chain Conv -> MaxPool -> Conv -> MaxPool -> Flatten -> FC -> FC
+    (models/vae.py:142-189) built from the reference's own layers."""
+    rng = np.random.default_rng(43)
+    arrays, cases = {}, []
+    # Multiply
+    for i, (shape, n_in, act) in enumerate([((3, 5, 4), 2, "identity"), ((2, 4, 4, 3), 3, "tanh")]):
+        M = Multiply(act_fn=ACTS[act]())
+        Xs = [f32(rng, shape) for _ in range(n_in)]
+        Y = M.forward(Xs)
+        dY = f32(rng, Y.shape)
+        g = M.backward(dY)
+        for j in range(n_in):
+            arrays[f"mul{i}/X{j}"], arrays[f"mul{i}/dX{j}"] = Xs[j], g[j]
+        arrays[f"mul{i}/Y"], arrays[f"mul{i}/dLdY"] = Y, dY
+        cases.append({"id": f"mul{i}", "kind": "multiply", "n_in": n_in, "act": act})
+    # FullyConnected
+    for i, (n, din, dout, act) in enumerate([(5, 12, 7, "relu"), (64, 32, 16, "identity"), (3, 9, 4, "sigmoid")]):
+        F = FullyConnected(n_out=dout, act_fn=ACTS[act]())
+        X = f32(rng, (n, din))
+        F.forward(X, retain_derived=False)
+        W, b = f32(rng, (din, dout), 0.4), f32(rng, (1, dout), 0.3)
+        F.parameters["W"], F.parameters["b"] = W, b
+        F.flush_gradients()
+        Y = F.forward(X)
+        dY = f32(rng, Y.shape)
+        dX = F.backward(dY)
+        arrays.update({f"fc{i}/X": X, f"fc{i}/W": W, f"fc{i}/b": b, f"fc{i}/Y": Y, f"fc{i}/dLdy": dY, f"fc{i}/dX": dX,
+                       f"fc{i}/dW": F.gradients["W"], f"fc{i}/db": F.gradients["b"]})
+        cases.append({"id": f"fc{i}", "kind": "fc", "n_out": dout, "act": act})
+    # WavenetResidualModule
+    for i, (n, l, chr_, chd, dil, with_main) in enumerate([(2, 16, 4, 6, 1, True), (3, 24, 8, 8, 3, True), (2, 12, 3, 5, 0, False)]):
+        M = WavenetResidualModule(ch_residual=chr_, ch_dilation=chd, dilation=dil, kernel_width=2)
+        Xm, Xs = f32(rng, (n, l, chr_)), f32(rng, (n, l, chr_))
+        M.forward(Xm, Xs)
+        P = {}
+        for tag, conv in (("d", M.conv_dilation), ("1", M.conv_1x1)):
+            conv.parameters["W"] = f32(rng, conv.parameters["W"].shape, 0.5)
+            conv.parameters["b"] = f32(rng, conv.parameters["b"].shape, 0.3)
+            P["W" + tag], P["b" + tag] = conv.parameters["W"].copy(), conv.parameters["b"].copy()
+        for c in M.components:
+            c.flush_gradients()
+        Ym, Ys = M.forward(Xm, Xs)
+        dYs, dYm = f32(rng, Ys.shape), (f32(rng, Ym.shape) if with_main else None)
+        dXm, dXs = M.backward(dYs.copy(), None if dYm is None else dYm.copy())
+        out = {"X_main": Xm, "X_skip": Xs, "Y_main": Ym, "Y_skip": Ys, "dY_skip": dYs, "dX_main": np.array(dXm), "dX_skip": np.array(dXs)}
+        if dYm is not None:
+            out["dY_main"] = dYm
+        out.update(P)
+        dv = M.derived_variables
+        for k in ["conv_dilation_out", "tanh_out", "sigm_out", "multiply_gate_out", "conv_1x1_out", "dLdTanh", "dLdSigmoid",
+                  "dLdConv_1x1", "dLdMultiply", "dLdConv_dilation"]:
+            out[k] = np.asarray(dv[k], dtype=np.float64)
+        out["dWd"], out["dbd"] = M.conv_dilation.gradients["W"], M.conv_dilation.gradients["b"]
+        out["dW1"], out["db1"] = M.conv_1x1.gradients["W"], M.conv_1x1.gradients["b"]
+        arrays.update({f"wn{i}/{k}": v for k, v in out.items()})
+        cases.append({"id": f"wn{i}", "kind": "wavenet", "ch_residual": chr_, "ch_dilation": chd, "dilation": dil,
+                      "with_main": with_main})
+    # VAE encoder chain (defaults of models/vae.py at a small size): 5x5 'same' conv, 2x2 max pools, two dense layers
+    enc = [Conv2D(act_fn=A.ReLU(), pad="same", out_ch=8, stride=1, kernel_shape=(5, 5)),
+           Pool2D(mode="max", pad=0, stride=2, kernel_shape=(2, 2)),
+           Conv2D(act_fn=A.ReLU(), pad="same", out_ch=16, stride=1, kernel_shape=(5, 5)),
+           Pool2D(mode="max", pad=0, stride=2, kernel_shape=(2, 2)),
+           Flatten(), FullyConnected(n_out=24, act_fn=A.ReLU()), FullyConnected(n_out=10, act_fn=A.Identity())]
+    X = np.round(f32(rng, (4, 12, 12, 1)) * 8) / 8
+    out = X
+    for L in enc:
+        out = L.forward(out)
+    k = 0
+    for L in enc:                       # non-trivial parameters (biases are zero at init)
+        if L.parameters:
+            L.parameters["W"] = np.round(f32(rng, L.parameters["W"].shape, 0.3) * 64) / 64
+            L.parameters["b"] = f32(rng, L.parameters["b"].shape, 0.2)
+            arrays[f"vae/W{k}"], arrays[f"vae/b{k}"] = L.parameters["W"].copy(), L.parameters["b"].copy()
+            k += 1
+        L.flush_gradients()
+    out = X
+    for L in enc:
+        out = L.forward(out)
+    dY = f32(rng, out.shape)
+    g = dY
+    for L in reversed(enc):
+        g = L.backward(g)
+    arrays.update({"vae/X": X, "vae/Y": out, "vae/dLdY": dY, "vae/dX": np.array(g)})
+    k = 0
+    for L in enc:
+        if L.parameters:
+            arrays[f"vae/dW{k}"], arrays[f"vae/db{k}"] = L.gradients["W"], L.gradients["b"]
+            k += 1
+    cases.append({"id": "vae", "kind": "vae_encoder"})
+    save("wavenet_vae.npz", arrays, cases)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:                                         # e.g. `make_golden.py conv1d pool2d`
         for name in only:
             globals()["gen_" + name]()
         sys.exit(0)
+    gen_wavenet_vae()
     gen_conv1d()
     gen_pool2d()
     gen_identity_module()

@@ -759,3 +759,97 @@ def test_row_of_taps_slab_kernel_optin(cuda_device, monkeypatch, mode, fold):
     dY = _f32(rng, Yr.shape)
     close(Y, Yr, tol, "conv1d Y")
     close(L.backward(dY), NO.conv1d_layer_bwd(dY, X, Zr, W, 1, "causal", 1)[0], tol, "conv1d dX")
+
+
+def test_multiply_fc_golden(cuda_device):
+    pkg = npml()
+    z, cases = load_golden("wavenet_vae.npz")
+    for c in cases:
+        i = c["id"]
+        if c["kind"] == "multiply":
+            M = pkg.Multiply(act_fn=make_act(pkg, c["act"], 0, 0))
+            Xs = [z["{}/X{}".format(i, j)] for j in range(c["n_in"])]
+            close(M.forward(Xs), z[i + "/Y"], 2e-6, i + " Y")
+            g = M.backward(z[i + "/dLdY"])
+            assert len(g) == c["n_in"]
+            for j in range(c["n_in"]):
+                close(g[j], z["{}/dX{}".format(i, j)], 2e-6, "{} dX{}".format(i, j))
+        elif c["kind"] == "fc":
+            F = pkg.FullyConnected(n_out=c["n_out"], act_fn=make_act(pkg, c["act"], 0, 0))
+            X = z[i + "/X"]
+            F.forward(X, retain_derived=False)
+            assert tuple(F.parameters["W"].shape) == z[i + "/W"].shape and tuple(F.parameters["b"].shape) == z[i + "/b"].shape
+            F.parameters["W"], F.parameters["b"] = z[i + "/W"], z[i + "/b"]
+            close(F.forward(X), z[i + "/Y"], TOL["fp32"], i + " Y")
+            assert list(F.derived_variables) == ["Z"] and tuple(F.X[0].shape) == X.shape
+            close(F.backward(z[i + "/dLdy"]), z[i + "/dX"], TOL["fp32"], i + " dX")
+            close(F.gradients["W"], z[i + "/dW"], TOL["fp32"], i + " dW")
+            close(F.gradients["b"], z[i + "/db"], TOL["fp32"], i + " db")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_wavenet_module_golden(cuda_device, mode):
+    pkg = npml()
+    z, cases = load_golden("wavenet_vae.npz")
+    tol = TOL[mode] * (1 if mode == "fp32" else 2)     # two chained convolutions and a gate product
+    for c in cases:
+        if c["kind"] != "wavenet":
+            continue
+        i = c["id"]
+        M = pkg.WavenetResidualModule(ch_residual=c["ch_residual"], ch_dilation=c["ch_dilation"], dilation=c["dilation"],
+                                      kernel_width=2, mode=mode)
+        M.forward(z[i + "/X_main"], z[i + "/X_skip"])
+        for t, conv in (("d", M.conv_dilation), ("1", M.conv_1x1)):
+            conv.parameters["W"], conv.parameters["b"] = z["{}/W{}".format(i, t)], z["{}/b{}".format(i, t)]
+        M.flush_gradients()
+        Ym, Ys = M.forward(z[i + "/X_main"], z[i + "/X_skip"])
+        close(Ym, z[i + "/Y_main"], tol, i + " Y_main")
+        close(Ys, z[i + "/Y_skip"], tol, i + " Y_skip")
+        dXm, dXs = M.backward(z[i + "/dY_skip"], z[i + "/dY_main"] if c["with_main"] else None)
+        close(dXm, z[i + "/dX_main"], tol, i + " dX_main")
+        close(dXs, z[i + "/dX_skip"], tol, i + " dX_skip")
+        dv = M.derived_variables
+        for k in ("conv_dilation_out", "tanh_out", "sigm_out", "multiply_gate_out", "conv_1x1_out", "dLdTanh", "dLdSigmoid",
+                  "dLdConv_1x1", "dLdMultiply", "dLdConv_dilation"):
+            close(dv[k], z["{}/{}".format(i, k)], tol, i + " " + k)
+        close(M.conv_dilation.gradients["W"], z[i + "/dWd"], tol, i + " dWd")
+        close(M.conv_dilation.gradients["b"], z[i + "/dbd"], tol, i + " dbd")
+        close(M.conv_1x1.gradients["W"], z[i + "/dW1"], tol, i + " dW1")
+        close(M.conv_1x1.gradients["b"], z[i + "/db1"], tol, i + " db1")
+
+
+def test_vae_encoder_chain_golden(cuda_device):
+    """Conv -> MaxPool -> Conv -> MaxPool -> Flatten -> FC -> FC (models/vae.py:142-189) end to end on the device,
+    forward and backward, against the reference's own layers (fixture) -- device tensors flow between the layers."""
+    import torch
+    pkg = npml()
+    z, _ = load_golden("wavenet_vae.npz")
+    enc = [pkg.Conv2D(act_fn="relu", pad="same", out_ch=8, stride=1, kernel_shape=(5, 5)),
+           pkg.Pool2D(mode="max", pad=0, stride=2, kernel_shape=(2, 2)),
+           pkg.Conv2D(act_fn="relu", pad="same", out_ch=16, stride=1, kernel_shape=(5, 5)),
+           pkg.Pool2D(mode="max", pad=0, stride=2, kernel_shape=(2, 2)),
+           pkg.Flatten(), pkg.FullyConnected(n_out=24, act_fn="relu"), pkg.FullyConnected(n_out=10)]
+    X = torch.tensor(z["vae/X"], dtype=torch.float32, device="cuda")
+    out = X
+    for L in enc:
+        out = L.forward(out, retain_derived=False)
+    k = 0
+    for L in enc:
+        if L.parameters:
+            L.parameters["W"], L.parameters["b"] = z["vae/W{}".format(k)], z["vae/b{}".format(k)]
+            k += 1
+    out = X
+    for L in enc:
+        out = L.forward(out)
+    assert out.is_cuda
+    close(out, z["vae/Y"], 1e-5, "Y")
+    g = torch.tensor(z["vae/dLdY"], dtype=torch.float32, device="cuda")
+    for L in reversed(enc):
+        g = L.backward(g)
+    close(g, z["vae/dX"], 1e-5, "dX")
+    k = 0
+    for L in enc:
+        if L.parameters:
+            close(L.gradients["W"], z["vae/dW{}".format(k)], 1e-5, "dW{}".format(k))
+            close(L.gradients["b"], z["vae/db{}".format(k)], 1e-5, "db{}".format(k))
+            k += 1

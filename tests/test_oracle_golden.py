@@ -289,3 +289,59 @@ def test_skip_identity_module_golden():
                   "dLdConv1", "dLdConv2", "dW1", "db1", "dW2", "db2", "dg1", "dh1", "dg2", "dh2", "rm1", "rv1", "rm2",
                   "rv2"):
             close(o[k], z["{}/{}".format(i, k)], 1e-10)
+
+
+def _vae_encoder_oracle(z):
+    """Conv(5x5,'same',ReLU) -> MaxPool 2x2/2 -> Conv(5x5,'same',ReLU) -> MaxPool 2x2/2 -> Flatten -> FC(ReLU) -> FC
+    (models/vae.py:142-189), forward + backward with the oracle's functions."""
+    from oracle import next_oracle as N
+    W = [z["vae/W{}".format(k)] for k in range(4)]
+    b = [z["vae/b{}".format(k)] for k in range(4)]
+    X = z["vae/X"]
+    a1, z1 = O.conv2d_layer_fwd(X, W[0], b[0], 1, "same", 0, "relu")
+    p1 = N.pool2d_fwd(a1, (2, 2), 2, 0, "max")
+    a2, z2 = O.conv2d_layer_fwd(p1, W[1], b[1], 1, "same", 0, "relu")
+    p2 = N.pool2d_fwd(a2, (2, 2), 2, 0, "max")
+    f = N.flatten_fwd(p2)
+    h, _ = N.fc_fwd(f, W[2], b[2], "relu")
+    y, _ = N.fc_fwd(h, W[3], b[3])
+    g, dW3, db3 = N.fc_bwd(z["vae/dLdY"], h, W[3], b[3])
+    g, dW2, db2 = N.fc_bwd(g, f, W[2], b[2], "relu")
+    g = N.pool2d_bwd(g.reshape(p2.shape), a2, (2, 2), 2, 0, "max")
+    g, dW1, db1 = O.conv2d_layer_bwd(g, p1, z2, W[1], 1, "same", 0, "relu")
+    g = N.pool2d_bwd(g, a1, (2, 2), 2, 0, "max")
+    dX, dW0, db0 = O.conv2d_layer_bwd(g, X, z1, W[0], 1, "same", 0, "relu")
+    return y, dX, [dW0, dW1, dW2, dW3], [db0, db1, db2, db3]
+
+
+def test_multiply_fc_wavenet_vae_golden():
+    from oracle import next_oracle as N
+    z, cases = load_golden("wavenet_vae.npz")
+    for c in cases:
+        i = c["id"]
+        if c["kind"] == "multiply":
+            Xs = [z["{}/X{}".format(i, j)] for j in range(c["n_in"])]
+            Y, prod = N.multiply_fwd(Xs, c["act"])
+            close(Y, z[i + "/Y"])
+            for j, g in enumerate(N.multiply_bwd(z[i + "/dLdY"], Xs, prod, c["act"])):
+                close(g, z["{}/dX{}".format(i, j)])
+        elif c["kind"] == "fc":
+            X, W, b = z[i + "/X"], z[i + "/W"], z[i + "/b"]
+            close(N.fc_fwd(X, W, b, c["act"])[0], z[i + "/Y"])
+            dX, dW, db = N.fc_bwd(z[i + "/dLdy"], X, W, b, c["act"])
+            close(dX, z[i + "/dX"]); close(dW, z[i + "/dW"]); close(db, z[i + "/db"])
+        elif c["kind"] == "wavenet":
+            P = {k: z["{}/{}".format(i, k)] for k in ("Wd", "bd", "W1", "b1")}
+            o = N.wavenet_module_fwd_bwd(z[i + "/X_main"], z[i + "/X_skip"], z[i + "/dY_skip"],
+                                         z[i + "/dY_main"] if c["with_main"] else None, P, c["dilation"])
+            for k in ("Y_main", "Y_skip", "dX_main", "dX_skip", "conv_dilation_out", "tanh_out", "sigm_out",
+                      "multiply_gate_out", "conv_1x1_out", "dLdTanh", "dLdSigmoid", "dLdConv_1x1", "dLdMultiply",
+                      "dLdConv_dilation", "dWd", "dbd", "dW1", "db1"):
+                close(o[k], z["{}/{}".format(i, k)], 1e-11)
+        else:
+            y, dX, dWs, dbs = _vae_encoder_oracle(z)
+            close(y, z["vae/Y"], 1e-11)
+            close(dX, z["vae/dX"], 1e-11)
+            for k in range(4):
+                close(dWs[k], z["vae/dW{}".format(k)], 1e-11)
+                close(dbs[k], z["vae/db{}".format(k)], 1e-11)
