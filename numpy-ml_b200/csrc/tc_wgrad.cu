@@ -289,10 +289,23 @@ bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl, bool want_db = false)
   if (P.stages < 2) return false;
   pl.smem = (size_t)P.stages * stage_bytes + 1024 + 256;
   const int mt = ceildiv(P.nblocks, P.mb), nt = ceildiv(g.CO, bn);
-  int splits = ceildiv(2 * num_sms(), mt * nt);
-  const int max_splits = ceildiv(P.ntiles, 4);              // at least 4 pixel tiles per CTA
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  // Split the pixel range so that the CTAs fill WHOLE waves: the kernel takes waves x (pixel tiles per CTA + a fixed
+  // prologue / epilogue), and one CTA more than a multiple of the resident slots costs a full extra wave (cfg5 used
+  // to launch 320 CTAs on 148 slots: three waves for 2.16 waves of work).  Every split also adds one partial to the
+  // fixed-order reduction.  Costs are in units of one pixel tile (8 or 16 MMAs).
+  const int per_sm = (int)((227 * 1024) / pl.smem) < 1 ? 1 : (int)((227 * 1024) / pl.smem);
+  const int slots = per_sm * num_sms();
+  const int max_splits = P.ntiles < 4 ? 1 : ceildiv(P.ntiles, 4);   // at least 4 pixel tiles per CTA
+  int splits = 1;
+  double best = -1.0;
+  for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+    const int tps = ceildiv(P.ntiles, sp);
+    const int eff = ceildiv(P.ntiles, tps);
+    if (eff != sp) continue;                                  // same launch as a smaller sp
+    const int waves = ceildiv(mt * nt * eff, slots);
+    const double cost = (double)waves * (tps + 2.0) + 1.2 * eff;
+    if (best < 0.0 || cost < best) { best = cost; splits = sp; }
+  }
   P.tiles_per_split = ceildiv(P.ntiles, splits);
   splits = ceildiv(P.ntiles, P.tiles_per_split);
   pl.splits = splits;
