@@ -33,6 +33,7 @@ int launch_repack_weights(const GatherConv& g, bool bf16, const float* w, void* 
 namespace {
 
 constexpr int kMaxTaps = 64;
+constexpr int kMaxCls = 9;
 constexpr int kRowBytes = 128;
 constexpr int kThreads = 256;
 constexpr int kSlabStages = 2;
@@ -46,6 +47,13 @@ struct SlabParams {
   int16_t tap_w[kMaxTaps];     // index of the tap in Wt
   int ntaps, nkb, kelems;
   int N, OH, OW, CO, Hp, Wp, pady, padx;
+  // Output parity classes (form 1 with stride s > 1: Deconv2D.forward, strided Conv2D dX).  Class c owns the output
+  // pixels (y0 + s*i, x0 + s*j); on those the transposed convolution is an ordinary stride-1 gather of the input
+  // with the class's own taps, so every class is a slab problem of its own on a common (Hp, Wp) slot grid and the
+  // work units are numbered class-major.  ncls == 1 (so = 1, y0 = x0 = 0) is the plain stride-1 convolution.
+  int ncls, units_per_cls, so, OHf, OWf;
+  int16_t cls_tap0[kMaxCls], cls_ntaps[kMaxCls];       // the class's slice of tap_off16 / tap_w
+  int16_t cls_pady[kMaxCls], cls_padx[kMaxCls], cls_y0[kMaxCls], cls_x0[kMaxCls], cls_oh[kMaxCls], cls_ow[kMaxCls];
   int UT, SR, BN, n_acc;
   int plane_bytes, w_block_bytes, w_resident, w_stages;
   int total_tiles, num_units;
@@ -117,7 +125,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
       uint32_t p = 0;
       for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
-        const int rho0 = (unit * UT * 128) / P.Wp;
+        const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
+        const int rho0 = ((unit - cls * P.units_per_cls) * UT * 128) / P.Wp;
+        const int padx = P.cls_padx[cls], pady = P.cls_pady[cls];
         for (int kb = 0; kb < P.nkb; ++kb, ++p) {
           const int st = p & 1;
           ptx::mbar_wait(&slab_empty[st], ((p >> 1) & 1u) ^ 1u);
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
           uint8_t* dst = smem + (size_t)st * P.plane_bytes;
           int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
           for (int i = 0; i < P.SR; ++i) {
-            ptx::tma_load_4d(dst + (size_t)i * row_bytes, &P.amap, &slab_full[st], kb * P.kelems, -P.padx, yp - P.pady, n);
+            ptx::tma_load_4d(dst + (size_t)i * row_bytes, &P.amap, &slab_full[st], kb * P.kelems, -padx, yp - pady, n);
             if (++yp == P.Hp) { yp = 0; ++n; }
           }
         }
@@ -143,14 +153,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
                              P.tap_w[t]);
       } else {
         uint32_t ws = 0, wph = 0;
-        for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x)
+        for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
+          const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
+          const int tap0 = P.cls_tap0[cls], nt = P.cls_ntaps[cls];
           for (int kb = 0; kb < P.nkb; ++kb)
-            for (int t = 0; t < P.ntaps; ++t) {
+            for (int t = 0; t < nt; ++t) {
               ptx::mbar_wait(&w_empty[ws], wph ^ 1u);
               ptx::mbar_expect_tx(&w_full[ws], (uint32_t)P.w_block_bytes);
-              ptx::tma_load_3d(w_area + (size_t)ws * P.w_block_bytes, &P.wmap, &w_full[ws], kb * P.kelems, co0, P.tap_w[t]);
+              ptx::tma_load_3d(w_area + (size_t)ws * P.w_block_bytes, &P.wmap, &w_full[ws], kb * P.kelems, co0,
+                               P.tap_w[tap0 + t]);
               if (++ws == (uint32_t)P.w_stages) { ws = 0; wph ^= 1u; }
             }
+        }
       }
     }
   } else if (warp == 1) {
@@ -161,7 +175,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     // straight-line code with immediate constant-bank offsets.  Ring positions are counters (no division).
     const bool leader = ptx::elect_one();
     const uint32_t BN = (uint32_t)P.BN, n_acc = (uint32_t)P.n_acc, idesc = P.idesc;
-    const int ntaps = NT > 0 ? NT : P.ntaps;
     const int nkb = P.nkb, Wp = P.Wp, total_tiles = P.total_tiles, num_units = P.num_units;
     const bool w_res = P.w_resident != 0;
     const uint32_t w_stages = (uint32_t)P.w_stages, wbb16 = (uint32_t)P.w_block_bytes >> 4;
@@ -176,8 +189,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       ptx::tc_fence_after();
     }
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int s0 = unit * UT * 128;
-      const int ntile = min(UT, total_tiles - unit * UT);
+      // class of the unit (NT > 0 instantiations are single-class with compile-time taps)
+      const int cls = (NT == 0 && P.ncls > 1) ? unit / P.units_per_cls : 0;
+      const int lu = unit - cls * P.units_per_cls;          // unit index inside the class (total_tiles is per class)
+      const int ntaps = NT > 0 ? NT : P.cls_ntaps[cls];
+      const int tap0 = NT > 0 ? 0 : P.cls_tap0[cls];
+      const int s0 = lu * UT * 128;
+      const int ntile = min(UT, total_tiles - lu * UT);
       const uint32_t a_off16 = (uint32_t)(s0 % Wp) * (kRowBytes >> 4);
       uint32_t sl[UT], ph[UT], dt[UT];
 #pragma unroll
@@ -195,10 +213,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
           const uint64_t a_base = slab_d + (st * plane16 + a_off16);
 #pragma unroll
           for (int t = 0; t < ntaps; ++t) {
-            const uint64_t ad = a_base + P.tap_off16[t];
+            const uint64_t ad = a_base + P.tap_off16[tap0 + t];
             uint64_t bd;
             if (kRes) {
-              bd = w_d + (uint32_t)(t * nkb + kb) * wbb16;
+              bd = w_d + (uint32_t)((tap0 + t) * nkb + kb) * wbb16;
             } else {
               ptx::mbar_wait(&w_full[ws], wph);
               ptx::tc_fence_after();
@@ -318,14 +336,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     const bool direct = P.epi_direct != 0;
 
     for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
-      const int ntile = min(UT, P.total_tiles - unit * UT);
+      const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
+      const int lu = unit - cls * P.units_per_cls;
+      const int ntile = min(UT, P.total_tiles - lu * UT);
       for (int j = 0; j < ntile; ++j) {
-        const int s = (unit * UT + j) * 128 + m;
+        const int s = (lu * UT + j) * 128 + m;
         const int n = s / img_slots;
         const int rem = s - n * img_slots;
         const int yp = rem / Wp, xp = rem - yp * Wp;
-        const bool row_ok = n < P.N && yp < P.OH && xp < P.OW;
-        const int my_pix = row_ok ? (n * P.OH + yp) * P.OW + xp : -1;
+        const bool row_ok = n < P.N && yp < P.cls_oh[cls] && xp < P.cls_ow[cls];
+        // pixel of the FULL output tensor: (y0 + so*yp, x0 + so*xp)
+        const int my_pix = row_ok ? (n * P.OHf + P.cls_y0[cls] + P.so * yp) * P.OWf + P.cls_x0[cls] + P.so * xp : -1;
         ptx::mbar_wait(&acc_full[slot], sph);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + slot * (uint32_t)BN;
@@ -380,33 +401,82 @@ struct SlabPlan {
   size_t smem = 0, wt_bytes = 0;
 };
 
+inline int posmod(int a, int b) { return ((a % b) + b) % b; }
+
 bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   if (mode != NPML_MODE_BF16 && mode != NPML_MODE_TF32) return false;
   if (std::getenv("NPML_DISABLE_SLAB")) return false;
   const bool bf16 = mode == NPML_MODE_BF16;
   const int es = bf16 ? 2 : 4, vec = 16 / es;
-  if (g.s != 1 || g.N < 1) return false;
+  if (g.N < 1 || g.s < 1) return false;
+  // stride 1 (both forms), or the transposed form with stride 2 / 3 split into output parity classes
+  const bool classes = g.s > 1;
+  if (classes && (g.form != 1 || g.s > 3 || std::getenv("NPML_DISABLE_SLAB_CLASSES"))) return false;
   if (g.CI % vec || g.CO % vec) return false;
   if (g.fr * g.fc > kMaxTaps) return false;
-  const int Hp = g.OH + (g.fr - 1) * g.D, Wp = g.OW + (g.fc - 1) * g.D;
+  SlabParams& P = pl.P;
+  memset(&P, 0, sizeof(P));
+  P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.CO = g.CO;
+  P.OHf = g.OH; P.OWf = g.OW; P.so = g.s;
+  // per class: the taps that reach it, as (dy, dx) offsets into the UNSTRIDED input
+  struct TapOff { int dy, dx, w; };
+  TapOff taps[kMaxTaps];
+  int ncls = 0, nt = 0, span_y = 0, span_x = 0, max_oh = 0, max_ow = 0;
+  int dymin[kMaxCls], dxmin[kMaxCls];
+  for (int qy = 0; qy < g.s; ++qy)
+    for (int qx = 0; qx < g.s; ++qx) {
+      int y0 = 0, x0 = 0, oh = g.OH, ow = g.OW;
+      if (classes) {
+        y0 = posmod(qy - g.pr, g.s); x0 = posmod(qx - g.pc, g.s);
+        if (y0 >= g.OH || x0 >= g.OW) continue;
+        oh = ceildiv(g.OH - y0, g.s); ow = ceildiv(g.OW - x0, g.s);
+      }
+      const int c = ncls;
+      int lo_y = 1 << 30, hi_y = -(1 << 30), lo_x = 1 << 30, hi_x = -(1 << 30);
+      P.cls_tap0[c] = (int16_t)nt;
+      for (int r = 0; r < g.fr; ++r)
+        for (int t = 0; t < g.fc; ++t) {
+          int dy, dx;
+          if (g.form == 0) {                       // in[y + r*D - pr]
+            dy = r * g.D - g.pr; dx = t * g.D - g.pc;
+          } else {                                 // in[(y + pr - r*D) / s], only the taps whose parity matches
+            if (posmod(r * g.D, g.s) != qy || posmod(t * g.D, g.s) != qx) continue;
+            dy = (y0 + g.pr - r * g.D) / g.s; dx = (x0 + g.pc - t * g.D) / g.s;      // exact by construction
+          }
+          taps[nt++] = TapOff{dy, dx, r * g.fc + t};
+          lo_y = dy < lo_y ? dy : lo_y; hi_y = dy > hi_y ? dy : hi_y;
+          lo_x = dx < lo_x ? dx : lo_x; hi_x = dx > hi_x ? dx : hi_x;
+        }
+      P.cls_ntaps[c] = (int16_t)(nt - P.cls_tap0[c]);
+      if (P.cls_ntaps[c] == 0) return false;       // a class no tap reaches (bias only): left to the per-tile kernel
+      dymin[c] = lo_y; dxmin[c] = lo_x;
+      span_y = hi_y - lo_y > span_y ? hi_y - lo_y : span_y;
+      span_x = hi_x - lo_x > span_x ? hi_x - lo_x : span_x;
+      max_oh = oh > max_oh ? oh : max_oh; max_ow = ow > max_ow ? ow : max_ow;
+      P.cls_y0[c] = (int16_t)y0; P.cls_x0[c] = (int16_t)x0; P.cls_oh[c] = (int16_t)oh; P.cls_ow[c] = (int16_t)ow;
+      P.cls_pady[c] = (int16_t)(-lo_y); P.cls_padx[c] = (int16_t)(-lo_x);
+      ++ncls;
+      if (!classes) { qy = g.s; break; }
+    }
+  if (ncls == 0) return false;
+  const int Hp = max_oh + span_y, Wp = max_ow + span_x;
   if (Wp > 256) return false;
+  // the flat slot grid computes Hp*Wp slots per max_oh*max_ow outputs: not worth it when the taps span much more
+  // than the outputs (small strided planes); the per-tile kernel takes those.  Measured: cfg5 forward (17x17 slots
+  // per 16x16 outputs) 61 -> 45 us on the slab, cfg3 dX (17x17 per 14x14) 32 -> 36 us.
+  if (classes && (double)Hp * Wp > 1.3 * max_oh * max_ow) return false;
+  P.Hp = Hp; P.Wp = Wp; P.ncls = ncls;
   const int64_t slots = (int64_t)g.N * Hp * Wp;
   if (slots + 128 * 8 >= (1LL << 31) / 2) return false;
   if ((int64_t)g.N * g.IH * g.IW * g.CI >= (1LL << 31) || (int64_t)g.N * g.OH * g.OW * g.CO >= (1LL << 31)) return false;
-  SlabParams& P = pl.P;
-  memset(&P, 0, sizeof(P));
-  P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.CO = g.CO; P.Hp = Hp; P.Wp = Wp;
-  // both forms reduce to out[y, x] = sum in[y + offy - pady, x + offx - padx] * W[wtap]
-  P.pady = g.form == 0 ? g.pr : (g.fr - 1) * g.D - g.pr;
-  P.padx = g.form == 0 ? g.pc : (g.fc - 1) * g.D - g.pc;
-  int nt = 0;
-  for (int r = 0; r < g.fr; ++r)
-    for (int t = 0; t < g.fc; ++t) {
-      const int offy = g.form == 0 ? r * g.D : (g.fr - 1 - r) * g.D;
-      const int offx = g.form == 0 ? t * g.D : (g.fc - 1 - t) * g.D;
-      P.tap_off16[nt] = (uint32_t)(offy * Wp + offx) * (kRowBytes >> 4);
-      P.tap_w[nt] = (int16_t)(r * g.fc + t);
-      ++nt;
+  P.pady = P.cls_pady[0]; P.padx = P.cls_padx[0];
+  int halo = 0;
+  for (int c = 0; c < ncls; ++c)
+    for (int i = P.cls_tap0[c]; i < P.cls_tap0[c] + P.cls_ntaps[c]; ++i) {
+      const int off = (taps[i].dy - dymin[c]) * Wp + (taps[i].dx - dxmin[c]);
+      P.tap_off16[i] = (uint32_t)off * (kRowBytes >> 4);
+      P.tap_w[i] = (int16_t)taps[i].w;
+      halo = off > halo ? off : halo;
     }
   P.ntaps = nt;
   P.kelems = kRowBytes / es;
@@ -420,8 +490,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   if (P.n_acc > kMaxAcc) P.n_acc = kMaxAcc;
   P.idesc = ptx::instr_desc(bf16 ? 1 : 2, 0, 0, 128, bn);
   P.w_block_bytes = bn * kRowBytes;
-  const int halo = (g.fr - 1) * g.D * Wp + (g.fc - 1) * g.D;
-  const int total_tiles = (int)((slots + 127) / 128);
+  const int total_tiles = (int)((slots + 127) / 128);         // per class
   P.total_tiles = total_tiles;
   const int fixed = 4 * 32 * 32 * es /*epilogue staging*/ + 512 /*bias*/ + 512 /*barriers*/;
   const int w_res_bytes = nt * P.nkb * P.w_block_bytes;
@@ -442,7 +511,8 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
     }
   }
   if (!found) return false;
-  P.num_units = ceildiv(total_tiles, P.UT);
+  P.units_per_cls = ceildiv(total_tiles, P.UT);
+  P.num_units = P.units_per_cls * ncls;
   {
     const char* e = std::getenv("NPML_SLAB_EPI");
     P.epi_direct = (e && e[0] == 'd' && (g.CO * es) % 32 == 0) ? 1 : 0;
@@ -485,8 +555,8 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
     case 3: kern = tc_slab_conv_kernel<T, NTV, 3>; break;                          \
     default: kern = tc_slab_conv_kernel<T, NTV, 4>; break;                         \
   }
-  if (P.ntaps == 9) { NPML_SLAB_UT(9) }
-  else if (P.ntaps == 1) { NPML_SLAB_UT(1) }
+  if (P.ncls == 1 && P.ntaps == 9) { NPML_SLAB_UT(9) }
+  else if (P.ncls == 1 && P.ntaps == 1) { NPML_SLAB_UT(1) }
   else { NPML_SLAB_UT(0) }
 #undef NPML_SLAB_UT
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));

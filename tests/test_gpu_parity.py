@@ -221,6 +221,8 @@ CONV_CASES = [
     ((1, 2, 260, 8), 8, (3, 3), "same", 1, 0, "identity"),          # padded row wider than a TMA box: per-tile path
     ((9, 5, 5, 64), 64, (3, 3), "same", 1, 3, "identity"),          # dilation 3 at stride 1, units span images
     # thin shapes (cfg1): in_ch = 1 and out_ch <= 4 take the CUDA-core thin kernels in every mode
+    ((3, 32, 32, 64), 128, (3, 3), 1, 2, 0, "identity"),            # strided conv: dX by output-parity classes on the slab
+    ((2, 30, 30, 64), 64, (4, 4), 1, 2, 0, "tanh"),                 # 4x4 s2 (the Deconv2D adjoint shape)
     ((4, 12, 12, 1), 32, (3, 3), "same", 1, 0, "identity"),         # cfg1 miniature
     ((3, 7, 9, 24), 2, (3, 3), 1, 1, 0, "sigmoid"),                 # out_ch = 2 forward
 ]
@@ -262,6 +264,11 @@ DECONV_CASES = [
     ((2, 7, 7, 16), 8, (3, 3), "same", 1, "identity"),
     ((2, 4, 4, 64), 32, (5, 5), 2, 2, "identity"),
     ((2, 5, 5, 3), 6, (4, 4), 1, 2, "identity"),                     # odd channels -> CUDA-core path
+    # output-parity classes on the slab kernel (forward): classes with 4/2/2/1 taps, unequal class sizes, units that
+    # span images and classes
+    ((3, 16, 16, 64), 64, (3, 3), 1, 2, "relu"),                     # 3x3 s2: classes of 16x16 / 16x15 / 15x16 / 15x15
+    ((5, 12, 9, 128), 32, (4, 4), 1, 2, "tanh"),                     # two channel blocks, non-square
+    ((2, 20, 20, 32), 160, (2, 2), 0, 2, "identity"),                # one tap per class, two N tiles
 ]
 
 
