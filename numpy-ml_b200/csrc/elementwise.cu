@@ -139,10 +139,31 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
     // a thread keeps the same VEC channels for all of its rows: per-channel constants are loaded once
     float kc[F::kConsts > 0 ? F::kConsts : 1][VEC];
     f.template init<VEC>(c0, cg.ch, kc);
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += cg.TY) {
+    // kBatch rows per trip: ALL their loads are issued before the first store.  The output of a pass may alias an
+    // input (dZ on dY), so the compiler will not move a load above an earlier row's store by itself, and one row of
+    // loads in flight per thread leaves these passes at ~3.8 TB/s on 67 MB tensors.
+    constexpr int kBatch = F::kBatch;
+    int64_t r = r0 + ty;
+#pragma unroll(kBatch == 1 ? 4 : 1)
+    for (; r + (int64_t)(kBatch - 1) * cg.TY < r1; r += (int64_t)kBatch * cg.TY) {
+      float in[kBatch][F::kIn][VEC];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) f.template load<VEC, DT>((r + (int64_t)u * cg.TY) * cg.ch + c0, in[u]);
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        float out[NV > 0 ? NV : 1][VEC];
+        f.template finish<VEC, DT>((r + (int64_t)u * cg.TY) * cg.ch + c0, kc, in[u], out);
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[a][j] += out[a][j];
+      }
+    }
+    for (; r < r1; r += cg.TY) {
+      float in[F::kIn][VEC];
       float out[NV > 0 ? NV : 1][VEC];
-      f.template run<VEC, DT>(r * cg.ch + c0, kc, out);
+      f.template load<VEC, DT>(r * cg.ch + c0, in);
+      f.template finish<VEC, DT>(r * cg.ch + c0, kc, in, out);
 #pragma unroll
       for (int a = 0; a < NV; ++a)
 #pragma unroll
@@ -268,23 +289,34 @@ int launch_col_final(const Acc* part, int nblk, int width, double* sums, cudaStr
 template <int DT>
 __device__ __forceinline__ int sel(int runtime_dt) { return DT >= 0 ? DT : runtime_dt; }
 
-// Functor protocol: kConsts per-channel constants are fetched once per thread by init(c0, ch, kc); run(i, kc, out)
-// handles the VEC elements at flat index i and returns the NV values to be column-summed.
+// Functor protocol: kConsts per-channel constants are fetched once per thread by init(c0, ch, kc); load(i, in) reads
+// the kIn input vectors at flat index i, finish(i, kc, in, out) does the arithmetic and the store and returns the NV
+// values to be column-summed.
+static __device__ __noinline__ float act_grad_ool(int act, float x, float p0, float p1) { return act_grad(act, x, p0, p1); }
+
 struct DzPrepF {
   static constexpr int kConsts = 0;
+  static constexpr int kIn = 2;
+  static constexpr int kBatch = 2;      // rows whose loads are issued together (registers: kBatch*kIn*VEC)
   const void* dY; const void* Z; void* dZ;
   int dy_dt, z_dt, dz_dt, act;
   float p0, p1;
   template <int VEC>
   __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
   template <int VEC, int DT>
-  __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[1][VEC]) const {
-    float g[VEC], z[VEC];
-    load_vec<VEC>(dY, sel<DT>(dy_dt), i, g);
-    if (act != NPML_ACT_IDENTITY) {
-      load_vec<VEC>(Z, sel<DT>(z_dt), i, z);
+  __device__ __forceinline__ void load(int64_t i, float (&in)[2][VEC]) const {
+    load_vec<VEC>(dY, sel<DT>(dy_dt), i, in[0]);
+    if (act != NPML_ACT_IDENTITY) load_vec<VEC>(Z, sel<DT>(z_dt), i, in[1]);
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t i, const float (&)[1][VEC], float (&in)[2][VEC], float (&out)[1][VEC]) const {
+    float (&g)[VEC] = in[0];
+    if (act == NPML_ACT_RELU) {                 // the common case stays inline; one copy of the 12-way switch otherwise
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) g[j] *= act_grad(act, z[j], p0, p1);
+      for (int j = 0; j < VEC; ++j) g[j] = in[1][j] > 0.f ? g[j] : 0.f;
+    } else if (act != NPML_ACT_IDENTITY) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) g[j] *= act_grad_ool(act, in[1][j], p0, p1);
     }
     // the sum is taken over the values the GEMMs will see (after rounding to the dZ dtype)
     if (sel<DT>(dz_dt) == NPML_BF16) {
@@ -299,21 +331,25 @@ struct DzPrepF {
 
 struct BnStatsF {
   static constexpr int kConsts = 0;
+  static constexpr int kIn = 1;
+  static constexpr int kBatch = 4;
   const void* x; int dt;
   template <int VEC>
   __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
   template <int VEC, int DT>
-  __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[2][VEC]) const {
-    float v[VEC];
-    load_vec<VEC>(x, sel<DT>(dt), i, v);
+  __device__ __forceinline__ void load(int64_t i, float (&in)[1][VEC]) const { load_vec<VEC>(x, sel<DT>(dt), i, in[0]); }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t, const float (&)[1][VEC], float (&in)[1][VEC], float (&out)[2][VEC]) const {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) { out[0][j] = v[j]; out[1][j] = v[j] * v[j]; }
+    for (int j = 0; j < VEC; ++j) { out[0][j] = in[0][j]; out[1][j] = in[0][j] * in[0][j]; }
   }
 };
 
 // y = a*(x - mean) + h with a = scaler*rstd (coef: [3][ch] = mean, a, h, written by the finalize kernels)
 struct BnNormF {
   static constexpr int kConsts = 3;
+  static constexpr int kIn = 1;
+  static constexpr int kBatch = 4;
   const void* x; void* y; int dt;
   const float* coef;
   template <int VEC>
@@ -324,9 +360,10 @@ struct BnNormF {
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void run(int64_t i, const float (&kc)[3][VEC], float (&)[1][VEC]) const {
-    float v[VEC];
-    load_vec<VEC>(x, sel<DT>(dt), i, v);
+  __device__ __forceinline__ void load(int64_t i, float (&in)[1][VEC]) const { load_vec<VEC>(x, sel<DT>(dt), i, in[0]); }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[3][VEC], float (&in)[1][VEC], float (&)[1][VEC]) const {
+    float (&v)[VEC] = in[0];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) v[j] = fmaf(kc[1][j], v[j] - kc[0][j], kc[2][j]);
     store_vec<VEC>(y, sel<DT>(dt), i, v);
@@ -335,6 +372,8 @@ struct BnNormF {
 
 struct BnBwdStatsF {
   static constexpr int kConsts = 2;
+  static constexpr int kIn = 2;
+  static constexpr int kBatch = 1;      // measured: batching the two-input BatchNorm backward passes is slower (95 vs 88 us)
   const void* dy; const void* x; int dt;
   const float* mean; const float* rstd;
   template <int VEC>
@@ -346,14 +385,16 @@ struct BnBwdStatsF {
     }
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void run(int64_t i, const float (&kc)[2][VEC], float (&out)[2][VEC]) const {
-    float d[VEC], v[VEC];
-    load_vec<VEC>(dy, sel<DT>(dt), i, d);
-    load_vec<VEC>(x, sel<DT>(dt), i, v);
+  __device__ __forceinline__ void load(int64_t i, float (&in)[2][VEC]) const {
+    load_vec<VEC>(dy, sel<DT>(dt), i, in[0]);
+    load_vec<VEC>(x, sel<DT>(dt), i, in[1]);
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t, const float (&kc)[2][VEC], float (&in)[2][VEC], float (&out)[2][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      out[0][j] = d[j];
-      out[1][j] = d[j] * ((v[j] - kc[0][j]) * kc[1][j]);
+      out[0][j] = in[0][j];
+      out[1][j] = in[0][j] * ((in[1][j] - kc[0][j]) * kc[1][j]);
     }
   }
 };
@@ -361,6 +402,8 @@ struct BnBwdStatsF {
 // dx = g*rstd*(dy - m1 - nhat*m2), nhat = (x - mean)*rstd; coef: [5][ch] = mean, rstd, g*rstd, m1, m2
 struct BnBwdDxF {
   static constexpr int kConsts = 5;
+  static constexpr int kIn = 2;
+  static constexpr int kBatch = 1;      // measured: batching the two-input BatchNorm backward passes is slower (95 vs 88 us)
   const void* dy; const void* x; void* dx; int dt;
   const float* coef;
   template <int VEC>
@@ -371,14 +414,17 @@ struct BnBwdDxF {
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void run(int64_t i, const float (&kc)[5][VEC], float (&)[1][VEC]) const {
-    float d[VEC], v[VEC];
-    load_vec<VEC>(dy, sel<DT>(dt), i, d);
-    load_vec<VEC>(x, sel<DT>(dt), i, v);
+  __device__ __forceinline__ void load(int64_t i, float (&in)[2][VEC]) const {
+    load_vec<VEC>(dy, sel<DT>(dt), i, in[0]);
+    load_vec<VEC>(x, sel<DT>(dt), i, in[1]);
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[5][VEC], float (&in)[2][VEC], float (&)[1][VEC]) const {
+    float (&v)[VEC] = in[1];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float nh = (v[j] - kc[0][j]) * kc[1][j];
-      v[j] = kc[2][j] * (d[j] - kc[3][j] - nh * kc[4][j]);
+      v[j] = kc[2][j] * (in[0][j] - kc[3][j] - nh * kc[4][j]);
     }
     store_vec<VEC>(dx, sel<DT>(dt), i, v);
   }
@@ -489,26 +535,35 @@ struct AddArgs {
 template <int VEC, int DT>
 __global__ void add_act_kernel(AddArgs a, int dt_rt, int64_t n_vec, int act, float p0, float p1, void* sum, void* Y) {
   const int dt = sel<DT>(dt_rt);
-#pragma unroll 2
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    float s[VEC];
-    load_vec<VEC>(a.xs[0], dt, i * VEC, s);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // two positions per trip, all loads before the first store (the outputs may alias an input for the compiler)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += 2 * stride) {
+    const bool two = i + stride < n_vec;
+    float s[2][VEC];
+    load_vec<VEC>(a.xs[0], dt, i * VEC, s[0]);
+    if (two) load_vec<VEC>(a.xs[0], dt, (i + stride) * VEC, s[1]);
     for (int k = 1; k < a.n_in; ++k) {
-      float v[VEC];
-      load_vec<VEC>(a.xs[k], dt, i * VEC, v);
+      float v[2][VEC];
+      load_vec<VEC>(a.xs[k], dt, i * VEC, v[0]);
+      if (two) load_vec<VEC>(a.xs[k], dt, (i + stride) * VEC, v[1]);
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) s[j] += v[j];
+      for (int j = 0; j < VEC; ++j) { s[0][j] += v[0][j]; s[1][j] += two ? v[1][j] : 0.f; }
     }
-    // later passes read the stored sum, so activations see the stored (rounded) value
-    if (dt == NPML_BF16) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) s[j] = __bfloat162float(__float2bfloat16_rn(s[j]));
-    }
-    if (sum) store_vec<VEC>(sum, dt, i * VEC, s);
-    if (Y) {
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const int64_t pos = (i + u * stride) * VEC;
+      // later passes read the stored sum, so activations see the stored (rounded) value
+      if (dt == NPML_BF16) {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) s[j] = act_fn(act, s[j], p0, p1);
-      store_vec<VEC>(Y, dt, i * VEC, s);
+        for (int j = 0; j < VEC; ++j) s[u][j] = __bfloat162float(__float2bfloat16_rn(s[u][j]));
+      }
+      if (sum) store_vec<VEC>(sum, dt, pos, s[u]);
+      if (Y) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) s[u][j] = act_fn(act, s[u][j], p0, p1);
+        store_vec<VEC>(Y, dt, pos, s[u]);
+      }
     }
   }
 }
@@ -618,13 +673,20 @@ __global__ void adaptive_opt_kernel(float* __restrict__ p, const float* __restri
 
 struct SumSqF {
   static constexpr int kConsts = 0;
+  static constexpr int kIn = 1;
+  static constexpr int kBatch = 4;
   const float* x;
   template <int VEC>
   __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
   template <int VEC, int DT>
-  __device__ __forceinline__ void run(int64_t i, const float (&)[1][VEC], float (&out)[1][VEC]) const {
+  __device__ __forceinline__ void load(int64_t i, float (&in)[1][VEC]) const {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) out[0][j] = x[i + j] * x[i + j];
+    for (int j = 0; j < VEC; ++j) in[0][j] = x[i + j];
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t, const float (&)[1][VEC], float (&in)[1][VEC], float (&out)[1][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[0][j] = in[0][j] * in[0][j];
   }
 };
 
