@@ -329,6 +329,23 @@ struct DzPrepF {
   }
 };
 
+// column sums of one tensor (db of an identity-activation layer whose dZ is dLdy itself)
+struct ColSumF {
+  static constexpr int kConsts = 0;
+  static constexpr int kIn = 1;
+  static constexpr int kBatch = 4;
+  const void* x; int dt;
+  template <int VEC>
+  __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
+  template <int VEC, int DT>
+  __device__ __forceinline__ void load(int64_t i, float (&in)[1][VEC]) const { load_vec<VEC>(x, sel<DT>(dt), i, in[0]); }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t, const float (&)[1][VEC], float (&in)[1][VEC], float (&out)[1][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) out[0][j] = in[0][j];
+  }
+};
+
 struct BnStatsF {
   static constexpr int kConsts = 0;
   static constexpr int kIn = 1;
@@ -764,7 +781,12 @@ extern "C" int npml_dz_prep(int64_t rows, int32_t ch, int32_t act, float p0, flo
   const size_t part_bytes = align_up((size_t)p.grid.x * ch * sizeof(float), 256);
   NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + (size_t)ch * sizeof(double), "workspace too small");
   float* part = (float*)ws;
-  if (int e = launch_col_pass<1, float>(p, f, part, st, same_dt)) return e;
+  if (act == NPML_ACT_IDENTITY && dZ == nullptr) {          // nothing to write: a plain column sum of dLdy
+    ColSumF cs{dY, dy_dtype};
+    if (int e = launch_col_pass<1, float>(p, cs, part, st, dy_dtype == NPML_F64 ? -1 : dy_dtype)) return e;
+  } else if (int e = launch_col_pass<1, float>(p, f, part, st, same_dt)) {
+    return e;
+  }
   db_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, db);
   NPML_LAUNCH_OK();
   return 0;
