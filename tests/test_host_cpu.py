@@ -140,3 +140,43 @@ def test_shard_batch():
         spans = [D.shard_batch(n, g, r) for r in range(g)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_1d_geometry_and_next_layer_host_logic():
+    """Host side of the SURVEY 8f rows: 1-D pads against the reference's values, Pool2D / FullyConnected / Flatten
+    bookkeeping that needs no kernel, and that the drop-ins fail loudly without a GPU."""
+    import torch
+    pkg = npml()
+    U = pkg.utils
+    z, cases = load_golden("conv1d_layer.npz")
+    for c in cases:
+        X = z[c["id"] + "/X"]
+        p = U.resolve_pad_1D(X.shape, to_pad(c["pad"]), c["kernel_width"], c["stride"], c["dilation"])
+        assert list(p) == list(z[c["id"] + "/pad"])
+        assert U.calc_conv_out_dims(X.shape, z[c["id"] + "/W"].shape, c["stride"], p, c["dilation"]) == z[c["id"] + "/Z"].shape
+    assert U.calc_pad_dims_1D((2, 16, 4), 16, 2, 1, dilation=3, causal=True) == (4, 0)       # all of it on the left
+    with pytest.raises(ValueError):
+        U.calc_pad_dims_1D([2, 16, 4], 16, 2, 1)                                            # utils.py:153-163
+    with pytest.raises(ValueError):
+        U.calc_pad_dims_1D((2, 16, 4), 3, 2, 1)                                             # negative pad
+    P = pkg.Pool2D(kernel_shape=(3, 3), stride=2, pad=1, mode="average")
+    d, pm = P._desc((4, 9, 7, 5))
+    assert (d.OH, d.OW, d.pr1, d.pc2, pm) == (5, 4, 1, 1, 1)
+    assert P.hyperparameters["layer"] == "Pool2D" and P.hyperparameters["mode"] == "average"
+    with pytest.raises(ValueError):
+        pkg.Pool2D(kernel_shape=(2, 2), mode="median")._desc((1, 4, 4, 1))
+    F = pkg.Flatten(keep_dim="first")
+    Y = F.forward(np.zeros((3, 4, 5, 2)))
+    assert Y.shape == (3, 40) and F.backward(np.ones((3, 40))).shape == (3, 4, 5, 2)
+    assert pkg.Flatten(keep_dim=-1).forward(np.zeros((2, 3))).shape == (1, 6)
+    fc = pkg.FullyConnected(n_out=7, act_fn="relu")
+    assert fc.hyperparameters == {"layer": "FullyConnected", "init": "glorot_uniform", "n_in": None, "n_out": 7,
+                                  "act_fn": "ReLU", "optimizer": fc._opt_hparams()}
+    W = pkg.WavenetResidualModule(ch_residual=4, ch_dilation=6, dilation=2, kernel_width=3)
+    assert W.conv_dilation.kernel_width == 2 and W.conv_dilation.pad == "causal"            # modules.py:161-169
+    assert W.hyperparameters["component_ids"] == ["conv_1x1", "add_skip", "add_residual", "conv_dilation", "multiply_gate"]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            pkg.Conv1D(4, 3).forward(np.zeros((1, 8, 2)))
+        with pytest.raises(RuntimeError):
+            P.forward(np.zeros((1, 4, 4, 1)))
