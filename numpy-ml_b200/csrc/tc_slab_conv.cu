@@ -42,7 +42,7 @@ constexpr int kMaxAcc = 16;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct SlabParams {
-  CUtensorMap amap, wmap;
+  CUtensorMap amap[kMaxCls], wmap;  // one activation map per input parity plane (a single one unless form 0, s > 1)
   uint32_t tap_off16[kMaxTaps];  // (offy*Wp + offx) slots * 128 B >> 4: descriptor start-address advance of the tap
   int16_t tap_w[kMaxTaps];     // index of the tap in Wt
   int ntaps, nkb, kelems;
@@ -52,6 +52,11 @@ struct SlabParams {
   // with the class's own taps, so every class is a slab problem of its own on a common (Hp, Wp) slot grid and the
   // work units are numbered class-major.  ncls == 1 (so = 1, y0 = x0 = 0) is the plain stride-1 convolution.
   int ncls, units_per_cls, so, OHf, OWf;
+  // Input parity planes (form 0 with stride s > 1: strided Conv2D.forward, Deconv2D dX).  Plane (py, px) is the
+  // strided view in[:, py::s, px::s, :]; on it the taps with that parity are stride-1 taps, so the K loop simply
+  // runs over (plane, channel block) pairs, each with its own tensor map and tap slice (the cls_* tables are then
+  // indexed by plane).  nplanes == 1 otherwise.  nkg = nplanes * nkb K groups per unit.
+  int nplanes, nkg;
   int16_t cls_tap0[kMaxCls], cls_ntaps[kMaxCls];       // the class's slice of tap_off16 / tap_w
   int16_t cls_pady[kMaxCls], cls_padx[kMaxCls], cls_y0[kMaxCls], cls_x0[kMaxCls], cls_oh[kMaxCls], cls_ow[kMaxCls];
   int UT, SR, BN, n_acc;
@@ -121,21 +126,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
   if (warp == 0) {
     // ===== slab producer: whole padded rows [rho0, rho0 + SR) of channel block kb, one TMA box per row =====
     if (ptx::elect_one()) {
-      ptx::prefetch_tmap(&P.amap);
+      for (int i = 0; i < P.nplanes; ++i) ptx::prefetch_tmap(&P.amap[i]);
       const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
       uint32_t p = 0;
       for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
         const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
         const int rho0 = ((unit - cls * P.units_per_cls) * UT * 128) / P.Wp;
-        const int padx = P.cls_padx[cls], pady = P.cls_pady[cls];
-        for (int kb = 0; kb < P.nkb; ++kb, ++p) {
+        for (int kg = 0; kg < P.nkg; ++kg, ++p) {
+          const int plane = P.nplanes > 1 ? kg / P.nkb : 0;
+          const int kb = kg - plane * P.nkb;
+          const int tg = P.nplanes > 1 ? plane : cls;
+          const int padx = P.cls_padx[tg], pady = P.cls_pady[tg];
           const int st = p & 1;
           ptx::mbar_wait(&slab_empty[st], ((p >> 1) & 1u) ^ 1u);
           ptx::mbar_expect_tx(&slab_full[st], (uint32_t)P.SR * row_bytes);
           uint8_t* dst = smem + (size_t)st * P.plane_bytes;
           int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
           for (int i = 0; i < P.SR; ++i) {
-            ptx::tma_load_4d(dst + (size_t)i * row_bytes, &P.amap, &slab_full[st], kb * P.kelems, -padx, yp - pady, n);
+            ptx::tma_load_4d(dst + (size_t)i * row_bytes, &P.amap[plane], &slab_full[st], kb * P.kelems, -padx, yp - pady, n);
             if (++yp == P.Hp) { yp = 0; ++n; }
           }
         }
@@ -155,8 +163,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
         uint32_t ws = 0, wph = 0;
         for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
           const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
-          const int tap0 = P.cls_tap0[cls], nt = P.cls_ntaps[cls];
-          for (int kb = 0; kb < P.nkb; ++kb)
+          for (int kg = 0; kg < P.nkg; ++kg) {
+            const int plane = P.nplanes > 1 ? kg / P.nkb : 0;
+            const int kb = kg - plane * P.nkb;
+            const int tg = P.nplanes > 1 ? plane : cls;
+            const int tap0 = P.cls_tap0[tg], nt = P.cls_ntaps[tg];
             for (int t = 0; t < nt; ++t) {
               ptx::mbar_wait(&w_empty[ws], wph ^ 1u);
               ptx::mbar_expect_tx(&w_full[ws], (uint32_t)P.w_block_bytes);
@@ -164,6 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
                                P.tap_w[tap0 + t]);
               if (++ws == (uint32_t)P.w_stages) { ws = 0; wph ^= 1u; }
             }
+          }
         }
       }
     }
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     // straight-line code with immediate constant-bank offsets.  Ring positions are counters (no division).
     const bool leader = ptx::elect_one();
     const uint32_t BN = (uint32_t)P.BN, n_acc = (uint32_t)P.n_acc, idesc = P.idesc;
-    const int nkb = P.nkb, Wp = P.Wp, total_tiles = P.total_tiles, num_units = P.num_units;
+    const int nkb = P.nkb, nkg = P.nkg, Wp = P.Wp, total_tiles = P.total_tiles, num_units = P.num_units;
     const bool w_res = P.w_resident != 0;
     const uint32_t w_stages = (uint32_t)P.w_stages, wbb16 = (uint32_t)P.w_block_bytes >> 4;
     const uint32_t plane16 = (uint32_t)P.plane_bytes >> 4;
@@ -192,8 +204,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       // class of the unit (NT > 0 instantiations are single-class with compile-time taps)
       const int cls = (NT == 0 && P.ncls > 1) ? unit / P.units_per_cls : 0;
       const int lu = unit - cls * P.units_per_cls;          // unit index inside the class (total_tiles is per class)
-      const int ntaps = NT > 0 ? NT : P.cls_ntaps[cls];
-      const int tap0 = NT > 0 ? 0 : P.cls_tap0[cls];
       const int s0 = lu * UT * 128;
       const int ntile = min(UT, total_tiles - lu * UT);
       const uint32_t a_off16 = (uint32_t)(s0 % Wp) * (kRowBytes >> 4);
@@ -206,7 +216,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
       auto run_unit = [&](auto full_tag, auto res_tag) {
         constexpr bool kFull = decltype(full_tag)::value;     // every tile of the unit exists
         constexpr bool kRes = decltype(res_tag)::value;       // weights resident in smem (no ring waits)
-        for (int kb = 0; kb < nkb; ++kb, ++p) {
+        for (int kg = 0; kg < nkg; ++kg, ++p) {
+          // tap slice of this K group: the unit's class (form 1), the group's input plane (form 0, s > 1), or all
+          // NT compile-time taps
+          const int plane = (NT == 0 && P.nplanes > 1) ? kg / nkb : 0;
+          const int kb = kg - plane * nkb;
+          const int tg = (NT == 0 && P.nplanes > 1) ? plane : cls;
+          const int ntaps = NT > 0 ? NT : P.cls_ntaps[tg];
+          const int tap0 = NT > 0 ? 0 : P.cls_tap0[tg];
           const uint32_t st = p & 1u;
           ptx::mbar_wait(&slab_full[st], (p >> 1) & 1u);
           ptx::tc_fence_after();
@@ -222,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
               ptx::tc_fence_after();
               bd = w_d + ws * wbb16;
             }
-            const bool first = (kb == 0 && t == 0), last = (kb == nkb - 1 && t == ntaps - 1);
+            const bool first = (kg == 0 && t == 0), last = (kg == nkg - 1 && t == ntaps - 1);
             if (first) {
 #pragma unroll
               for (int j = 0; j < UT; ++j)
@@ -399,7 +416,10 @@ struct SlabPlan {
   SlabParams P;
   dim3 grid;
   size_t smem = 0, wt_bytes = 0;
+  int plane_py[kMaxCls], plane_px[kMaxCls];      // input parity of each plane (form 0, s > 1)
 };
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 inline int posmod(int a, int b) { return ((a % b) + b) % b; }
 
@@ -409,15 +429,18 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   const bool bf16 = mode == NPML_MODE_BF16;
   const int es = bf16 ? 2 : 4, vec = 16 / es;
   if (g.N < 1 || g.s < 1) return false;
-  // stride 1 (both forms), or the transposed form with stride 2 / 3 split into output parity classes
-  const bool classes = g.s > 1;
-  if (classes && (g.form != 1 || g.s > 3 || std::getenv("NPML_DISABLE_SLAB_CLASSES"))) return false;
+  // stride 1 (both forms); stride 2 / 3: the transposed form split into output parity classes, the forward form
+  // split into input parity planes
+  const bool classes = g.s > 1 && g.form == 1, planes = g.s > 1 && g.form == 0;
+  if (g.s > 3) return false;
+  if (classes && std::getenv("NPML_DISABLE_SLAB_CLASSES")) return false;
+  if (planes && std::getenv("NPML_DISABLE_SLAB_PLANES")) return false;
   if (g.CI % vec || g.CO % vec) return false;
   if (g.fr * g.fc > kMaxTaps) return false;
   SlabParams& P = pl.P;
   memset(&P, 0, sizeof(P));
   P.N = g.N; P.OH = g.OH; P.OW = g.OW; P.CO = g.CO;
-  P.OHf = g.OH; P.OWf = g.OW; P.so = g.s;
+  P.OHf = g.OH; P.OWf = g.OW; P.so = classes ? g.s : 1;
   // per class: the taps that reach it, as (dy, dx) offsets into the UNSTRIDED input
   struct TapOff { int dy, dx, w; };
   TapOff taps[kMaxTaps];
@@ -431,14 +454,17 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
         if (y0 >= g.OH || x0 >= g.OW) continue;
         oh = ceildiv(g.OH - y0, g.s); ow = ceildiv(g.OW - x0, g.s);
       }
-      const int c = ncls;
+      if (planes && (qy >= g.IH || qx >= g.IW)) continue;      // empty parity plane
+      const int c = ncls;                                       // group index: class (form 1) or plane (form 0)
       int lo_y = 1 << 30, hi_y = -(1 << 30), lo_x = 1 << 30, hi_x = -(1 << 30);
       P.cls_tap0[c] = (int16_t)nt;
       for (int r = 0; r < g.fr; ++r)
         for (int t = 0; t < g.fc; ++t) {
           int dy, dx;
-          if (g.form == 0) {                       // in[y + r*D - pr]
-            dy = r * g.D - g.pr; dx = t * g.D - g.pc;
+          if (g.form == 0) {                       // in[y*s + r*D - pr]: row (y + dy) of the plane with parity py
+            const int offy = r * g.D - g.pr, offx = t * g.D - g.pc;
+            if (planes && (posmod(offy, g.s) != qy || posmod(offx, g.s) != qx)) continue;
+            dy = floordiv(offy, g.s); dx = floordiv(offx, g.s);
           } else {                                 // in[(y + pr - r*D) / s], only the taps whose parity matches
             if (posmod(r * g.D, g.s) != qy || posmod(t * g.D, g.s) != qx) continue;
             dy = (y0 + g.pr - r * g.D) / g.s; dx = (x0 + g.pc - t * g.D) / g.s;      // exact by construction
@@ -448,7 +474,11 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
           lo_x = dx < lo_x ? dx : lo_x; hi_x = dx > hi_x ? dx : hi_x;
         }
       P.cls_ntaps[c] = (int16_t)(nt - P.cls_tap0[c]);
-      if (P.cls_ntaps[c] == 0) return false;       // a class no tap reaches (bias only): left to the per-tile kernel
+      if (P.cls_ntaps[c] == 0) {
+        if (planes) continue;                      // a plane no tap reads
+        return false;                              // a class no tap reaches (bias only): left to the per-tile kernel
+      }
+      pl.plane_py[c] = qy; pl.plane_px[c] = qx;
       dymin[c] = lo_y; dxmin[c] = lo_x;
       span_y = hi_y - lo_y > span_y ? hi_y - lo_y : span_y;
       span_x = hi_x - lo_x > span_x ? hi_x - lo_x : span_x;
@@ -456,22 +486,24 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
       P.cls_y0[c] = (int16_t)y0; P.cls_x0[c] = (int16_t)x0; P.cls_oh[c] = (int16_t)oh; P.cls_ow[c] = (int16_t)ow;
       P.cls_pady[c] = (int16_t)(-lo_y); P.cls_padx[c] = (int16_t)(-lo_x);
       ++ncls;
-      if (!classes) { qy = g.s; break; }
+      if (g.s == 1) { qy = g.s; break; }
     }
   if (ncls == 0) return false;
+  const int ngroups = ncls;
+  if (planes) ncls = 1;
   const int Hp = max_oh + span_y, Wp = max_ow + span_x;
   if (Wp > 256) return false;
   // the flat slot grid computes Hp*Wp slots per max_oh*max_ow outputs: not worth it when the taps span much more
   // than the outputs (small strided planes); the per-tile kernel takes those.  Measured: cfg5 forward (17x17 slots
   // per 16x16 outputs) 61 -> 45 us on the slab, cfg3 dX (17x17 per 14x14) 32 -> 36 us.
-  if (classes && (double)Hp * Wp > 1.3 * max_oh * max_ow) return false;
-  P.Hp = Hp; P.Wp = Wp; P.ncls = ncls;
+  if ((classes || planes) && (double)Hp * Wp > 1.3 * max_oh * max_ow) return false;
+  P.Hp = Hp; P.Wp = Wp; P.ncls = ncls; P.nplanes = planes ? ngroups : 1;
   const int64_t slots = (int64_t)g.N * Hp * Wp;
   if (slots + 128 * 8 >= (1LL << 31) / 2) return false;
   if ((int64_t)g.N * g.IH * g.IW * g.CI >= (1LL << 31) || (int64_t)g.N * g.OH * g.OW * g.CO >= (1LL << 31)) return false;
   P.pady = P.cls_pady[0]; P.padx = P.cls_padx[0];
   int halo = 0;
-  for (int c = 0; c < ncls; ++c)
+  for (int c = 0; c < ngroups; ++c)
     for (int i = P.cls_tap0[c]; i < P.cls_tap0[c] + P.cls_ntaps[c]; ++i) {
       const int off = (taps[i].dy - dymin[c]) * Wp + (taps[i].dx - dxmin[c]);
       P.tap_off16[i] = (uint32_t)off * (kRowBytes >> 4);
@@ -481,6 +513,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   P.ntaps = nt;
   P.kelems = kRowBytes / es;
   P.nkb = ceildiv(g.CI, P.kelems);
+  P.nkg = P.nkb * P.nplanes;
   P.act = g.act; P.p0 = g.p0; P.p1 = g.p1;
   int bn = (g.CO + 15) / 16 * 16;
   if (bn > 128) bn = 128;
@@ -540,11 +573,17 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
     if (int e = make_tmap(&P.wmap, bf16, ws, 3, dims, strides, box, false)) return e;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
-    const uint64_t strides[4] = {(uint64_t)es, (uint64_t)g.CI * es, (uint64_t)g.IW * g.CI * es,
-                                 (uint64_t)g.IH * g.IW * g.CI * es};
     const uint32_t box[4] = {(uint32_t)P.kelems, (uint32_t)P.Wp, 1, 1};
-    if (int e = make_tmap(&P.amap, bf16, const_cast<void*>(in), 4, dims, strides, box, false)) return e;
+    const int sp = P.nplanes > 1 ? g.s : 1;           // plane (py, px) = in[:, py::sp, px::sp, :]
+    for (int i = 0; i < P.nplanes; ++i) {
+      const int py = sp > 1 ? pl.plane_py[i] : 0, px = sp > 1 ? pl.plane_px[i] : 0;
+      const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)ceildiv(g.IW - px, sp), (uint64_t)ceildiv(g.IH - py, sp),
+                                (uint64_t)g.N};
+      const uint64_t strides[4] = {(uint64_t)es, (uint64_t)sp * g.CI * es, (uint64_t)sp * g.IW * g.CI * es,
+                                   (uint64_t)g.IH * g.IW * g.CI * es};
+      char* base = (char*)const_cast<void*>(in) + ((size_t)py * g.IW + px) * g.CI * es;
+      if (int e = make_tmap(&P.amap[i], bf16, base, 4, dims, strides, box, false)) return e;
+    }
   }
   typedef void (*Kern)(const SlabParams, const float*, T*, T*);
   Kern kern = nullptr;
@@ -555,8 +594,8 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
     case 3: kern = tc_slab_conv_kernel<T, NTV, 3>; break;                          \
     default: kern = tc_slab_conv_kernel<T, NTV, 4>; break;                         \
   }
-  if (P.ncls == 1 && P.ntaps == 9) { NPML_SLAB_UT(9) }
-  else if (P.ncls == 1 && P.ntaps == 1) { NPML_SLAB_UT(1) }
+  if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 9) { NPML_SLAB_UT(9) }
+  else if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 1) { NPML_SLAB_UT(1) }
   else { NPML_SLAB_UT(0) }
 #undef NPML_SLAB_UT
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
