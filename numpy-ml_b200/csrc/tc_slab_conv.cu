@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
   uint8_t* smem = w_area + w_bytes;                                     // slab planes
   uint8_t* staging = smem + (size_t)kSlabStages * P.plane_bytes;         // 4 warps x 32 rows x (32 columns of T)
   float* bias_s = reinterpret_cast<float*>(staging + 4 * 32 * 32 * sizeof(T));
-  uint64_t* slab_full = reinterpret_cast<uint64_t*>(bias_s + 128);
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(bias_s + 256);
   uint64_t* slab_empty = slab_full + kSlabStages;
   uint64_t* w_full = slab_empty + kSlabStages;
   uint64_t* w_empty = w_full + kMaxWStages;
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     ptx::tmem_relinquish();
   }
   if (warp >= 4) {
-    const int i = threadIdx.x - 128;            // BN <= 128
-    bias_s[i] = (bias != nullptr && i < P.BN && co0 + i < P.CO) ? bias[co0 + i] : 0.f;
+    for (int i = threadIdx.x - 128; i < 256; i += 128)      // BN <= 256
+      bias_s[i] = (bias != nullptr && i < P.BN && co0 + i < P.CO) ? bias[co0 + i] : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -516,7 +516,10 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   P.nkg = P.nkb * P.nplanes;
   P.act = g.act; P.p0 = g.p0; P.p1 = g.p1;
   int bn = (g.CO + 15) / 16 * 16;
-  if (bn > 128) bn = 128;
+  // wide outputs: one N = 192..256 tile (two accumulators) instead of two N = 128 tiles -- the A slab is fetched once
+  // per MMA for twice the math, and the CTAs of the second N tile do not reload the same slabs
+  if (bn > 256) bn = (g.CO % 256 == 0 || g.CO > 512) ? 256 : 128;
+  if (std::getenv("NPML_SLAB_BN128") && bn > 128) bn = 128;
   if (bn < 32) bn = 32;
   P.BN = bn;
   P.n_acc = 512 / bn;
@@ -525,7 +528,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   P.w_block_bytes = bn * kRowBytes;
   const int total_tiles = (int)((slots + 127) / 128);         // per class
   P.total_tiles = total_tiles;
-  const int fixed = 4 * 32 * 32 * es /*epilogue staging*/ + 512 /*bias*/ + 512 /*barriers*/;
+  const int fixed = 4 * 32 * 32 * es /*epilogue staging*/ + 1024 /*bias*/ + 512 /*barriers*/;
   const int w_res_bytes = nt * P.nkb * P.w_block_bytes;
   bool found = false;
   // weights resident first (no re-streaming), largest unit that fits; then streamed weights
