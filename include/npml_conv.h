@@ -75,6 +75,14 @@ typedef struct npml_conv_desc {
  * layers/layers.py:3037-3038).  Z (pre-activation) and/or Y (= act(Z)) may be NULL. */
 int npml_conv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b,
                       void* Z, void* Y, void* ws, size_t ws_bytes, void* stream);
+/* fprop with a FROZEN BatchNorm2D folded into the same epilogue (north_star: "the BatchNorm2D affine [is a] fused
+ * epilogue"; modules/modules.py:905-937 runs conv -> BatchNorm2D back to back, and with retain_derived=False or a frozen
+ * layer BatchNorm2D.forward is the per-channel affine of its running statistics, layers/layers.py:1141-1156):
+ *   Y = bn_scale[k] * act_fn(conv(X, W) + b) + bn_shift[k]        (Z, if given, still receives conv(X, W) + b)
+ * bn_scale / bn_shift: fp32 device vectors of K entries, produced on the device by npml_bn2d_fold.  Y is required. */
+int npml_conv2d_fprop_bn(const npml_conv_desc* d, const void* X, const float* W, const float* b,
+                         const float* bn_scale, const float* bn_shift, void* Z, void* Y, void* ws, size_t ws_bytes,
+                         void* stream);
 /* dgrad replaces W_col @ dLdZ_col + col2im / np.add.at  (layers/layers.py:3113-3114,
  * utils/utils.py:546-595); gather form, no atomics.  dZ already holds dLdy * act'(Z). */
 int npml_conv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX,
@@ -96,6 +104,9 @@ int npml_conv2d_wgrad_db(const npml_conv_desc* d, const void* X, const void* dZ,
  * wgrad: dW[r,t,c,k]  = sum X[n,iy,ix,c] * dZ[n, iy*s + r - pr1, ix*s + t - pc1, k] */
 int npml_deconv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b,
                         void* Z, void* Y, void* ws, size_t ws_bytes, void* stream);
+int npml_deconv2d_fprop_bn(const npml_conv_desc* d, const void* X, const float* W, const float* b,
+                           const float* bn_scale, const float* bn_shift, void* Z, void* Y, void* ws, size_t ws_bytes,
+                           void* stream);
 int npml_deconv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX,
                         void* ws, size_t ws_bytes, void* stream);
 int npml_deconv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, float* dW,
@@ -141,6 +152,11 @@ int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, int32_t dtyp
                   const float* scaler, const float* intercept, float* running_mean,
                   float* running_var, float momentum, float eps, int32_t use_batch_stats,
                   float* save_mean, float* save_rstd, void* ws, size_t ws_bytes, void* stream);
+/* frozen BatchNorm2D as a per-channel affine (layers/layers.py:1141-1156 with the running statistics):
+ *   scale = scaler / sqrt(running_var + eps), shift = intercept - running_mean * scale
+ * for npml_conv2d_fprop_bn / npml_deconv2d_fprop_bn; everything stays on the device. */
+int npml_bn2d_fold(int32_t ch, const float* scaler, const float* intercept, const float* running_mean,
+                   const float* running_var, float eps, float* scale, float* shift, void* stream);
 int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const void* x, void* dx, int32_t dtype,
                   const float* scaler, const float* save_mean, const float* save_rstd,
                   float* d_scaler, float* d_intercept, int32_t accumulate, void* ws,

@@ -33,10 +33,12 @@ _DESC = C.POINTER(ConvDesc)
 # name -> (restype, argtypes); kept in step with include/npml_conv.h (tests check every symbol)
 SIGNATURES = {
     "npml_conv2d_fprop": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "npml_conv2d_fprop_bn": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_wgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_wgrad_db": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_fprop": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "npml_deconv2d_fprop_bn": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_wgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_workspace_bytes": (_SZ, [_DESC, C.c_int]),
@@ -47,6 +49,7 @@ SIGNATURES = {
     "npml_mul_act_bwd": (C.c_int, [_I32, C.POINTER(_P), C.POINTER(_P), _I32, _I64, _I32, _F, _F, _P, _P, _P]),
     "npml_act_fwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _F, _F, _P]),
     "npml_bn2d_fwd": (C.c_int, [_I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _F, _F, _I32, _P, _P, _P, _SZ, _P]),
+    "npml_bn2d_fold": (C.c_int, [_I32, _P, _P, _P, _P, _F, _P, _P, _P]),
     "npml_bn2d_bwd": (C.c_int, [_I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
     "npml_bn2d_stats": (C.c_int, [_I64, _I32, _P, _I32, _P, _P, _SZ, _P]),
     "npml_bn2d_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _SZ, _P]),

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(NT) gather_conv_kernel(GatherConv g, const TIn
       if (co >= g.CO) continue;
       float z = acc[i][j] + (bias ? bias[co] : 0.f);
       if (Z) st_f(Z, p * g.CO + co, z);
-      if (Y) st_f(Y, p * g.CO + co, act_fn(g.act, z, g.p0, g.p1));
+      if (Y) st_f(Y, p * g.CO + co, post_affine(g, co, act_fn(g.act, z, g.p0, g.p1)));
     }
   }
 }
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128) thin_co_conv_kernel(GatherConv g, const T
     for (int co = 0; co < CO_T; ++co) {
       const float z = acc[co] + (bias ? bias[co] : 0.f);
       if (Z) st_f(Z, p * CO_T + co, z);
-      if (Y) st_f(Y, p * CO_T + co, act_fn(g.act, z, g.p0, g.p1));
+      if (Y) st_f(Y, p * CO_T + co, post_affine(g, co, act_fn(g.act, z, g.p0, g.p1)));
     }
   }
 }
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256) thin_ci_conv_kernel(GatherConv g, const T
   for (int j = 0; j < 4; ++j) {
     const float z = acc[j] + (bias ? bias[c4 + j] : 0.f);
     if (Z) st_f(Z, o + j, z);
-    if (Y) st_f(Y, o + j, act_fn(g.act, z, g.p0, g.p1));
+    if (Y) st_f(Y, o + j, post_affine(g, c4 + j, act_fn(g.act, z, g.p0, g.p1)));
   }
 }
 

@@ -505,6 +505,18 @@ __global__ void bn_running_to_saved_kernel(int ch, float eps, const float* runni
   coef[2 * ch + c] = intercept[c];
 }
 
+// Frozen BatchNorm2D as a per-channel affine y = scale * x + shift (layers/layers.py:1141-1156 with the running statistics):
+// scale = scaler / sqrt(running_var + eps), shift = intercept - running_mean * scale.  Feeds the convolution epilogues.
+__global__ void bn_fold_kernel(int ch, float eps, const float* running_mean, const float* running_var, const float* scaler,
+                               const float* intercept, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  const float rs = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  const float sc = scaler[c] * rs;
+  scale[c] = sc;
+  shift[c] = fmaf(-running_mean[c], sc, intercept[c]);
+}
+
 // sums_local / sums_global != nullptr (sync-BN): the parameter gradients accumulate this rank's sums (the gradient
 // bucket is all-reduced later), the dX coefficients use the sums over all ranks
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, int ch, int accumulate,
@@ -938,6 +950,16 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   NPML_LAUNCH_OK();
   BnBwdDxF fd{dy, x, dx, dtype, coef};
   return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st, dtype);
+}
+
+extern "C" int npml_bn2d_fold(int32_t ch, const float* scaler, const float* intercept, const float* running_mean,
+                              const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  if (ch <= 0) return 0;
+  NPML_CHECK(scaler && intercept && running_mean && running_var && scale && shift, "NULL pointer");
+  bn_fold_kernel<<<(ch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ch, eps, running_mean, running_var, scaler, intercept,
+                                                                     scale, shift);
+  NPML_LAUNCH_OK();
+  return 0;
 }
 
 // ---- sync-BN: the same passes split at the point where the per-channel sums cross ranks ---------------------

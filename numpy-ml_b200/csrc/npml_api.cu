@@ -71,13 +71,17 @@ static GatherWgrad make_wgrad(const npml_conv_desc* d, int op) {
 }
 
 static int run_gather(const npml_conv_desc* d, int op, const void* in, const float* W, const float* b, void* Z,
-                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st, const float* post_scale = nullptr,
+                      const float* post_shift = nullptr) {
   if (check_desc(d, op == NPML_OP_DECONV_FPROP || op == NPML_OP_DECONV_DGRAD)) return 1;
   if (d->N == 0) return 0;
   NPML_CHECK(in && W, "NULL input");
   NPML_CHECK(Z || Y, "no output buffer");
   GatherConv g = make_gather(d, op);
-  if (g.act == NPML_ACT_IDENTITY && Z == nullptr) { Z = Y; Y = nullptr; }
+  NPML_CHECK((post_scale == nullptr) == (post_shift == nullptr), "bn_scale and bn_shift go together");
+  NPML_CHECK(post_scale == nullptr || Y != nullptr, "the folded BatchNorm2D needs the Y output");
+  g.post_scale = post_scale; g.post_shift = post_shift;
+  if (g.act == NPML_ACT_IDENTITY && Z == nullptr && post_scale == nullptr) { Z = Y; Y = nullptr; }
   if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode))
     return slab_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode))
@@ -124,6 +128,14 @@ extern "C" {
 int npml_conv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
                       void* ws, size_t ws_bytes, void* stream) {
   return run_gather(d, NPML_OP_CONV_FPROP, X, W, b, Z, Y, ws, ws_bytes, (cudaStream_t)stream);
+}
+int npml_conv2d_fprop_bn(const npml_conv_desc* d, const void* X, const float* W, const float* b, const float* bn_scale,
+                         const float* bn_shift, void* Z, void* Y, void* ws, size_t ws_bytes, void* stream) {
+  return run_gather(d, NPML_OP_CONV_FPROP, X, W, b, Z, Y, ws, ws_bytes, (cudaStream_t)stream, bn_scale, bn_shift);
+}
+int npml_deconv2d_fprop_bn(const npml_conv_desc* d, const void* X, const float* W, const float* b, const float* bn_scale,
+                           const float* bn_shift, void* Z, void* Y, void* ws, size_t ws_bytes, void* stream) {
+  return run_gather(d, NPML_OP_DECONV_FPROP, X, W, b, Z, Y, ws, ws_bytes, (cudaStream_t)stream, bn_scale, bn_shift);
 }
 int npml_conv2d_dgrad(const npml_conv_desc* d, const void* dZ, const float* W, void* dX, void* ws, size_t ws_bytes,
                       void* stream) {

@@ -147,7 +147,16 @@ struct GatherConv {
   int64_t w_tap, w_ci, w_co;
   int act;
   float p0, p1;
+  // optional per-channel affine applied AFTER the activation: Y = post_scale[co] * act(z + b) + post_shift[co]
+  // (a frozen BatchNorm2D that follows the convolution, layers/layers.py:1141-1156, folded into the epilogue);
+  // device pointers, CO entries each, both NULL when unused.  Z (the pre-activation) is never affected.
+  const float* post_scale;
+  const float* post_shift;
 };
+
+__device__ __forceinline__ float post_affine(const GatherConv& g, int co, float y) {
+  return g.post_scale ? fmaf(y, g.post_scale[co], g.post_shift[co]) : y;
+}
 
 // wgrad:  dW[(r*fc+t)*o_tap + ci*o_ci + co*o_co] (+)= sum_{n,y,x} in[n, y*s + r*D - pr, x*s + t*D - pc, ci]
 //                                                                * g[n, y, x, co]

@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256) repack_weights_t_kernel(const float* __re
 // ---- the kernel ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_constant__ TcConvParams P,
-                                                                  const float* __restrict__ bias, T* __restrict__ Z,
+                                                                  const float* __restrict__ bias,
+                                                                  const float* __restrict__ post_scale,
+                                                                  const float* __restrict__ post_shift, T* __restrict__ Z,
                                                                   T* __restrict__ Y) {
   constexpr bool kTf32 = sizeof(T) == 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -263,6 +265,11 @@ __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_c
         if (Z) store_row_chunk<T>(Z + pix * P.CO + co, v, n_valid);
         if (Y) {
           act_apply32(P.act, P.p0, P.p1, v);
+          if (post_scale) {                       // frozen BatchNorm2D folded into the epilogue
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < n_valid) v[j] = fmaf(v[j], post_scale[co + j], post_shift[co + j]);
+          }
           store_row_chunk<T>(Y + pix * P.CO + co, v, n_valid);
         }
       }
@@ -461,7 +468,7 @@ static int launch_tc(const GatherConv& g, Plan& pl, const void* in, const float*
     NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[bf16 ? 0 : 1] = true;
   }
-  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, (T*)Z, (T*)Y);
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, g.post_scale, g.post_shift, (T*)Z, (T*)Y);
   NPML_LAUNCH_OK();
   return 0;
 }

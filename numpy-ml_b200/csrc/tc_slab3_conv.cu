@@ -340,6 +340,7 @@ bool plan_slab3(const GatherConv& g, int mode, Slab3Plan& pl) {
   // amount), so tc_slab_conv.cu stays the default.  See DESIGN.md section 4, finding 5.
   const char* opt = std::getenv("NPML_SLAB3");
   if (opt == nullptr || (opt[0] != '2' && opt[0] != '3')) return false;
+  if (g.post_scale != nullptr) return false;        // the folded BatchNorm2D epilogue lives in tc_slab_conv.cu
   const bool bf16 = mode == NPML_MODE_BF16;
   const int es = bf16 ? 2 : 4, vec = 16 / es;
   if (g.s != 1 || g.N < 1) return false;

@@ -68,6 +68,7 @@ struct SlabParams {
                                 // bound by the MMA operand fetch, not by the epilogue)
   int act;
   float p0, p1;
+  int affine;                   // 1: Y = scale[co] * act(z + b) + shift[co] (frozen BatchNorm2D folded into the epilogue)
 };
 
 // Measured on B200: the 128B swizzle of both the TMA write and the UMMA read is a function of the ABSOLUTE
@@ -80,17 +81,21 @@ constexpr uint64_t kDesc64 = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29))
 
 template <typename T, int NT, int UT>
 __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_constant__ SlabParams P,
-                                                                   const float* __restrict__ bias, T* __restrict__ Z,
+                                                                   const float* __restrict__ bias,
+                                                                   const float* __restrict__ post_scale,
+                                                                   const float* __restrict__ post_shift, T* __restrict__ Z,
                                                                    T* __restrict__ Y) {
   constexpr bool kTf32 = sizeof(T) == 4;
-  // [weights (1024-aligned base)] [2 slab planes (128-aligned)] [epilogue staging] [bias] [barriers]
+  // [weights (1024-aligned base)] [2 slab planes (128-aligned)] [epilogue staging] [bias | scale | shift] [barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* w_area = smem_raw;
   const int w_bytes = (P.w_resident ? P.ntaps * P.nkb : P.w_stages) * P.w_block_bytes;
   uint8_t* smem = w_area + w_bytes;                                     // slab planes
   uint8_t* staging = smem + (size_t)kSlabStages * P.plane_bytes;         // 4 warps x 32 rows x (32 columns of T)
   float* bias_s = reinterpret_cast<float*>(staging + 4 * 32 * 32 * sizeof(T));
-  uint64_t* slab_full = reinterpret_cast<uint64_t*>(bias_s + 256);
+  float* scale_s = bias_s + 256;
+  float* shift_s = scale_s + 256;
+  uint64_t* slab_full = reinterpret_cast<uint64_t*>(bias_s + (P.affine ? 768 : 256));   // scale / shift only when used
   uint64_t* slab_empty = slab_full + kSlabStages;
   uint64_t* w_full = slab_empty + kSlabStages;
   uint64_t* w_empty = w_full + kMaxWStages;
@@ -115,8 +120,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     ptx::tmem_relinquish();
   }
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 256; i += 128)      // BN <= 256
-      bias_s[i] = (bias != nullptr && i < P.BN && co0 + i < P.CO) ? bias[co0 + i] : 0.f;
+    for (int i = threadIdx.x - 128; i < 256; i += 128) {    // BN <= 256
+      const bool ok = i < P.BN && co0 + i < P.CO;
+      bias_s[i] = (bias != nullptr && ok) ? bias[co0 + i] : 0.f;
+      if (P.affine) {
+        scale_s[i] = ok ? post_scale[co0 + i] : 1.f;
+        shift_s[i] = ok ? post_shift[co0 + i] : 0.f;
+      }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -384,18 +395,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
             v[i + 2] = __uint_as_float(r[i + 2]) + bb.z; v[i + 3] = __uint_as_float(r[i + 3]) + bb.w;
           }
           const int co = co0 + c;
-          if (direct) {
-            if (Z) emit_direct(Z, v, my_pix, co);
-            if (Y) {
-              act_apply32(P.act, P.p0, P.p1, v);
-              emit_direct(Y, v, my_pix, co);
+          if (Z) {
+            if (direct) emit_direct(Z, v, my_pix, co);
+            else emit(Z, v, my_pix, co);
+          }
+          if (Y) {
+            act_apply32(P.act, P.p0, P.p1, v);
+            if (P.affine) {                         // frozen BatchNorm2D: per-channel scale / shift after the activation
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 sc = *reinterpret_cast<const float4*>(scale_s + c + i);
+                const float4 sh = *reinterpret_cast<const float4*>(shift_s + c + i);
+                v[i] = fmaf(v[i], sc.x, sh.x); v[i + 1] = fmaf(v[i + 1], sc.y, sh.y);
+                v[i + 2] = fmaf(v[i + 2], sc.z, sh.z); v[i + 3] = fmaf(v[i + 3], sc.w, sh.w);
+              }
             }
-          } else {
-            if (Z) emit(Z, v, my_pix, co);
-            if (Y) {
-              act_apply32(P.act, P.p0, P.p1, v);
-              emit(Y, v, my_pix, co);
-            }
+            if (direct) emit_direct(Y, v, my_pix, co);
+            else emit(Y, v, my_pix, co);
           }
         }
         if (++slot == (uint32_t)n_acc) { slot = 0; sph ^= 1u; }
@@ -515,6 +531,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   P.nkb = ceildiv(g.CI, P.kelems);
   P.nkg = P.nkb * P.nplanes;
   P.act = g.act; P.p0 = g.p0; P.p1 = g.p1;
+  P.affine = g.post_scale != nullptr ? 1 : 0;
   int bn = (g.CO + 15) / 16 * 16;
   // wide outputs: one N = 192..256 tile (two accumulators) instead of two N = 128 tiles -- the A slab is fetched once
   // per MMA for twice the math, and the CTAs of the second N tile do not reload the same slabs
@@ -528,7 +545,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   P.w_block_bytes = bn * kRowBytes;
   const int total_tiles = (int)((slots + 127) / 128);         // per class
   P.total_tiles = total_tiles;
-  const int fixed = 4 * 32 * 32 * es /*epilogue staging*/ + 1024 /*bias*/ + 512 /*barriers*/;
+  const int fixed = 4 * 32 * 32 * es /*epilogue staging*/ + (P.affine ? 3072 : 1024) /*bias (, scale, shift)*/ + 512 /*barriers*/;
   const int w_res_bytes = nt * P.nkb * P.w_block_bytes;
   bool found = false;
   // weights resident first (no re-streaming), largest unit that fits; then streamed weights
@@ -588,7 +605,7 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
       if (int e = make_tmap(&P.amap[i], bf16, base, 4, dims, strides, box, false)) return e;
     }
   }
-  typedef void (*Kern)(const SlabParams, const float*, T*, T*);
+  typedef void (*Kern)(const SlabParams, const float*, const float*, const float*, T*, T*);
   Kern kern = nullptr;
 #define NPML_SLAB_UT(NTV)                                                          \
   switch (P.UT) {                                                                  \
@@ -602,7 +619,7 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
   else { NPML_SLAB_UT(0) }
 #undef NPML_SLAB_UT
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, (T*)Z, (T*)Y);
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, g.post_scale, g.post_shift, (T*)Z, (T*)Y);
   NPML_LAUNCH_OK();
   return 0;
 }

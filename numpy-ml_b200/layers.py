@@ -208,9 +208,14 @@ class _ConvBase(LayerBase):
             X_shape = tuple(self.X[-1].shape) if self.X else self._last_shape
         return bool(L.load().npml_uses_tensor_cores(self._desc(tuple(X_shape)), self._ops[0]))
 
-    def forward(self, X, retain_derived=True):
+    def forward(self, X, retain_derived=True, fused_bn=None):
         """Y = act_fn(conv(X, W) + b); bias and activation are the kernel's epilogue
-        (layers.py:3006-3046 / 3438-3478)."""
+        (layers.py:3006-3046 / 3438-3478).
+
+        `fused_bn` (an extension): a BatchNorm2D that directly follows this layer and is in inference mode for this
+        call (frozen, or `retain_derived=False`: layers.py:1141-1146 then normalises with the running statistics).
+        Its per-channel affine becomes part of the same epilogue and the return value is BatchNorm2D(Y) -- exactly
+        what `fused_bn.forward(self.forward(X))` would give, without the intermediate tensor."""
         as_np = isinstance(X, np.ndarray)
         Xd = L.to_device(X, L.torch_dtype(self.mode))
         if not self.is_initialized:
@@ -221,11 +226,20 @@ class _ConvBase(LayerBase):
         d = self._desc(tuple(Xd.shape))
         self._last_shape = tuple(Xd.shape)
         out_shape = (d.N, d.OH, d.OW, d.K)
-        Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
-        Y = Z if self.act_fn.code == 0 else torch.empty_like(Z)
         pre = "npml_conv2d_" if self._layer_name == "Conv2D" else "npml_deconv2d_"
-        self._call(pre + "fprop", d, self._ops[0], L.ptr(Xd), L.ptr(W), L.ptr(b),
-                   L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
+        if fused_bn is not None:
+            if fused_bn.trainable and retain_derived:
+                raise ValueError("fused_bn needs a BatchNorm2D in inference mode (frozen or retain_derived=False)")
+            scale, shift = fused_bn.folded_affine(d.K)
+            Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device) if retain_derived else None
+            Y = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
+            self._call(pre + "fprop_bn", d, self._ops[0], L.ptr(Xd), L.ptr(W), L.ptr(b), L.ptr(scale), L.ptr(shift),
+                       L.ptr(Z), L.ptr(Y))
+        else:
+            Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
+            Y = Z if self.act_fn.code == 0 else torch.empty_like(Z)
+            self._call(pre + "fprop", d, self._ops[0], L.ptr(Xd), L.ptr(W), L.ptr(b),
+                       L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
         if retain_derived:
             self.X.append(Xd)
             self.derived_variables["Z"].append(Z)
@@ -543,6 +557,22 @@ class BatchNorm2D(LayerBase):
     def hyperparameters(self):
         return {"layer": "BatchNorm2D", "act_fn": None, "in_ch": self.in_ch, "out_ch": self.out_ch,
                 "epsilon": self.epsilon, "momentum": self.momentum, "optimizer": self._opt_hparams()}
+
+    def folded_affine(self, in_ch=None):
+        """(scale, shift) device vectors with BatchNorm2D_inference(x) = scale * x + shift (layers.py:1141-1156 on the
+        running statistics), for the convolution's fused epilogue (npml_conv2d_fprop_bn)."""
+        if not self.is_initialized:
+            self.in_ch = self.out_ch = int(in_ch)
+            self._init_params()
+        P = self.parameters
+        for k in P:
+            P[k] = _as_param(P[k])
+        ch = self.in_ch
+        out = torch.empty(2, ch, dtype=torch.float32, device=L.device())
+        L.check(L.load().npml_bn2d_fold(ch, L.ptr(P["scaler"]), L.ptr(P["intercept"]), L.ptr(P["running_mean"]),
+                                        L.ptr(P["running_var"]), float(self.epsilon), L.ptr(out[0]), L.ptr(out[1]),
+                                        L.stream()), "npml_bn2d_fold")
+        return out[0], out[1]
 
     def reset_running_stats(self):
         assert self.trainable, "Layer is frozen"

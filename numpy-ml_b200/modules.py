@@ -92,6 +92,10 @@ class ModuleBase(ABC):
 
 
 class SkipConnectionConvModule(ModuleBase):
+    # inference (retain_derived=False) forwards fold each BatchNorm2D into the epilogue of the convolution before it;
+    # set to False to run the seven layers one by one as in training
+    fuse_inference = True
+
     def __init__(self, out_ch1, out_ch2, kernel_shape1, kernel_shape2, kernel_shape_skip, pad1=0, pad2=0, stride1=1,
                  stride2=1, act_fn=None, epsilon=1e-5, momentum=0.9, stride_skip=1, optimizer=None,
                  init="glorot_uniform", mode="fp32", sync_bn=False):
@@ -194,6 +198,14 @@ class SkipConnectionConvModule(ModuleBase):
         if not hasattr(self, "conv_skip"):
             self._init_conv_skip(tuple(Xd.shape))
             self.in_ch = Xd.shape[3]
+        if not retain_derived and self.fuse_inference:
+            # inference: every BatchNorm2D is the affine of its running statistics (layers.py:1141-1146) and nothing is
+            # retained, so each conv -> BN pair is ONE kernel (bias, activation and BN affine in the epilogue)
+            bn1_out = self.conv1.forward(Xd, False, fused_bn=self.batchnorm1)
+            bn2_out = self.conv2.forward(bn1_out, False, fused_bn=self.batchnorm2)
+            bn_skip_out = self.conv_skip.forward(Xd, False, fused_bn=self.batchnorm_skip)
+            Y = self.add3.forward([bn_skip_out, bn2_out], False)
+            return L.to_numpy(Y) if as_np else Y
         conv1_out = self.conv1.forward(Xd, retain_derived)
         bn1_out = self.batchnorm1.forward(conv1_out, retain_derived)
         conv2_out = self.conv2.forward(bn1_out, retain_derived)
@@ -227,6 +239,7 @@ class SkipConnectionConvModule(ModuleBase):
 class SkipConnectionIdentityModule(ModuleBase):
     """modules/modules.py:360-612: conv1('same', act) -> BN1 -> conv2('same', affine, out_ch = in_ch) -> BN2 ->
     Add([X, BN2]) -> act.  Same kernels as SkipConnectionConvModule, the input itself is the shortcut."""
+    fuse_inference = True
 
     def __init__(self, out_ch, kernel_shape1, kernel_shape2, stride1=1, stride2=1, act_fn=None, epsilon=1e-5,
                  momentum=0.9, optimizer=None, init="glorot_uniform", mode="fp32", sync_bn=False):
@@ -296,6 +309,11 @@ class SkipConnectionIdentityModule(ModuleBase):
         if not hasattr(self, "conv2"):
             self.in_ch = Xd.shape[3]
             self._init_conv2()
+        if not retain_derived and self.fuse_inference:      # see SkipConnectionConvModule.forward
+            bn1_out = self.conv1.forward(Xd, False, fused_bn=self.batchnorm1)
+            bn2_out = self.conv2.forward(bn1_out, False, fused_bn=self.batchnorm2)
+            Y = self.add3.forward([Xd, bn2_out], False)
+            return L.to_numpy(Y) if as_np else Y
         conv1_out = self.conv1.forward(Xd, retain_derived)
         bn1_out = self.batchnorm1.forward(conv1_out, retain_derived)
         conv2_out = self.conv2.forward(bn1_out, retain_derived)

@@ -225,6 +225,10 @@ CONV_CASES = [
     ((2, 30, 30, 64), 64, (4, 4), 1, 2, 0, "tanh"),                 # 4x4 s2 (the Deconv2D adjoint shape)
     ((4, 12, 12, 1), 32, (3, 3), "same", 1, 0, "identity"),         # cfg1 miniature
     ((3, 7, 9, 24), 2, (3, 3), 1, 1, 0, "sigmoid"),                 # out_ch = 2 forward
+    # wide outputs on the slab kernel: one N = 144 / 256 tile spanning two TMEM accumulators, 320 = 128 + 128 + 64
+    ((2, 8, 8, 64), 144, (3, 3), 1, 1, 0, "relu"),
+    ((3, 9, 9, 64), 256, (3, 3), 1, 1, 0, "identity"),
+    ((2, 8, 8, 32), 320, (3, 3), 1, 1, 0, "tanh"),
 ]
 
 
@@ -297,6 +301,132 @@ def test_deconv2d_vs_oracle(cuda_device, mode, case):
     close(dX, dXr, tol, "dX")
     close(L.gradients["W"], dWr, tol, "dW")
     close(L.gradients["b"], dbr, tol, "db")
+
+
+# ------------------------------------------------------------------------------------------------
+#  frozen BatchNorm2D folded into the convolution epilogue (npml_conv2d_fprop_bn / npml_deconv2d_fprop_bn)
+# ------------------------------------------------------------------------------------------------
+def _random_bn(pkg, rng, ch):
+    bn = pkg.BatchNorm2D()
+    P = {"scaler": rng.uniform(0.5, 1.5, ch), "intercept": 0.1 * rng.standard_normal(ch),
+         "running_mean": 0.2 * rng.standard_normal(ch), "running_var": rng.uniform(0.5, 2.0, ch)}
+    P = {k: v.astype(np.float32).astype(np.float64) for k, v in P.items()}
+    bn.in_ch = bn.out_ch = ch
+    bn._init_params()
+    for k, v in P.items():
+        bn.parameters[k] = v
+    return bn, P
+
+
+# (kind, index into CONV_CASES / DECONV_CASES): slab (resident / streamed weights, Z and Y both written, N = 144 / 256
+# tiles), per-tile gather kernel, CUDA-core and thin kernels, Deconv2D on the class slab and on the CUDA cores
+FUSED_BN_CASES = [("conv", 0), ("conv", 1), ("conv", 4), ("conv", 8), ("conv", 9), ("conv", 10), ("conv", 11),
+                  ("conv", 19), ("conv", 20), ("conv", 21), ("conv", 22), ("deconv", 0), ("deconv", 5), ("deconv", 6)]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", range(len(FUSED_BN_CASES)))
+def test_conv_fused_frozen_bn_epilogue(cuda_device, mode, case):
+    """Y = BN_running(act(conv(X) + b)) from ONE kernel equals the oracle's conv -> BatchNorm2D(inference) chain
+    (layers.py:3037-3038 then 1141-1156), and the retained Z is still the pre-activation."""
+    pkg = npml()
+    kind, idx = FUSED_BN_CASES[case]
+    rng = np.random.default_rng(700 + case)
+    if kind == "conv":
+        xs, oc, ks, pad, s, d, act = CONV_CASES[idx]
+        p0 = 0.25 if act == "leaky_relu" else 0.0
+        L = pkg.Conv2D(out_ch=oc, kernel_shape=ks, pad=pad, stride=s, dilation=d, act_fn=make_act(pkg, act, p0, 0.0),
+                       mode=mode)
+    else:
+        xs, oc, ks, pad, s, act = DECONV_CASES[idx]
+        p0, d = 0.0, 0
+        L = pkg.Deconv2D(out_ch=oc, kernel_shape=ks, pad=pad, stride=s, act_fn=make_act(pkg, act, 0, 0), mode=mode)
+    X = _f32(rng, xs)
+    W = _f32(rng, ks + (xs[3], oc), 1.0 / np.sqrt(ks[0] * ks[1] * xs[3]))
+    b = _f32(rng, (1, 1, 1, oc), 0.1)
+    L.forward(X, retain_derived=False)
+    L.parameters["W"], L.parameters["b"] = W, b
+    bn, P = _random_bn(pkg, rng, oc)
+    if kind == "conv":
+        Yr, Zr = O.conv2d_layer_fwd(X, W, b, s, pad, d, act, p0, 0.0)
+    else:
+        Yr, Zr = O.deconv2d_layer_fwd(X, W, b, s, pad, act)
+    ref, _, _ = O.bn2d_fwd(Yr, P["scaler"], P["intercept"], P["running_mean"], P["running_var"], use_batch_stats=False)
+    tol = TOL[mode]
+    # inference call: nothing retained
+    close(L.forward(X, retain_derived=False, fused_bn=bn), ref, tol, "fused Y")
+    assert len(L.X) == 0 and len(L.derived_variables["Z"]) == 0
+    # the two-kernel chain gives the same numbers (same arithmetic, one rounding more in bf16)
+    close(bn.forward(L.forward(X, retain_derived=False), retain_derived=False), ref, tol, "unfused Y")
+    # frozen BatchNorm2D with a retaining forward: Z is kept and is the pre-activation
+    bn.freeze()
+    close(L.forward(X, retain_derived=True, fused_bn=bn), ref, tol, "fused Y (frozen)")
+    close(L.derived_variables["Z"][0], Zr, tol, "Z")
+    bn.unfreeze()
+    with pytest.raises(ValueError):
+        L.forward(X, retain_derived=True, fused_bn=bn)                # a training-mode BatchNorm2D cannot be folded
+    for k in ("running_mean", "running_var"):                         # inference never touches the running statistics
+        assert np.array_equal(pkg.to_numpy(bn.parameters[k]), P[k])
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("module", ["conv", "identity"])
+def test_skip_modules_fused_inference(cuda_device, mode, module):
+    """retain_derived=False forward of the two skip-connection modules: each conv -> BatchNorm2D pair is one kernel;
+    equals the oracle's layer-by-layer chain on the running statistics and the unfused product path."""
+    pkg = npml()
+    rng = np.random.default_rng(800)
+    act = "relu"
+    if module == "conv":
+        cin, c1, c2 = 64, 128, 128
+        M = pkg.SkipConnectionConvModule(out_ch1=c1, out_ch2=c2, kernel_shape1=(3, 3), kernel_shape2=(3, 3),
+                                         kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn=make_act(pkg, act, 0, 0),
+                                         mode=mode)
+    else:
+        cin = c1 = c2 = 64
+        M = pkg.SkipConnectionIdentityModule(out_ch=c1, kernel_shape1=(3, 3), kernel_shape2=(3, 3),
+                                             act_fn=make_act(pkg, act, 0, 0), mode=mode)
+    X = _f32(rng, (3, 12, 12, cin))
+    M.forward(X, retain_derived=False)
+    triples = [("1", M.conv1, M.batchnorm1, cin, c1), ("2", M.conv2, M.batchnorm2, c1, c2)]
+    if module == "conv":
+        triples.append(("s", M.conv_skip, M.batchnorm_skip, cin, c2))
+    P = {}
+    for t, conv, bn, ci, co in triples:
+        k = conv.kernel_shape
+        P["W" + t] = _f32(rng, k + (ci, co), 1.0 / np.sqrt(k[0] * k[1] * ci))
+        P["b" + t] = _f32(rng, (1, 1, 1, co), 0.1)
+        conv.parameters["W"], conv.parameters["b"] = P["W" + t], P["b" + t]
+        _, q = _random_bn(pkg, rng, co)
+        for name, v in q.items():
+            bn.parameters[name] = v
+        P["bn" + t] = q
+
+    def bn_ref(x, q):
+        return O.bn2d_fwd(x, q["scaler"], q["intercept"], q["running_mean"], q["running_var"], use_batch_stats=False)[0]
+
+    pad1 = 1 if module == "conv" else "same"
+    a1, _ = O.conv2d_layer_fwd(X, P["W1"], P["b1"], 1, pad1, 0, act)
+    h1 = bn_ref(a1, P["bn1"])
+    a2, _ = O.conv2d_layer_fwd(h1, P["W2"], P["b2"], 1, pad1, 0, "identity")
+    h2 = bn_ref(a2, P["bn2"])
+    if module == "conv":
+        a_s, _ = O.conv2d_layer_fwd(X, P["Ws"], P["bs"], 1, 0, 0, "identity")
+        short = bn_ref(a_s, P["bns"])
+    else:
+        short = X
+    ref, _ = O.add_fwd([short, h2], act)
+    tol = TOL_BN[mode]
+    pkg.launch_count(reset=True)
+    Y = M.forward(X, retain_derived=False)
+    fused_launches = pkg.launch_count(reset=True)
+    close(Y, ref, tol, "fused module Y")
+    M.fuse_inference = False
+    Y2 = M.forward(X, retain_derived=False)
+    plain_launches = pkg.launch_count(reset=True)
+    close(Y2, ref, tol, "layer-by-layer module Y")
+    assert fused_launches < plain_launches
+    assert M.derived_variables["conv1_out"] is None and len(M.conv1.X) == 0
 
 
 @pytest.mark.parametrize("act", ["relu", "tanh"])
