@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 #include "../../include/npml_conv.h"
@@ -50,6 +51,19 @@ inline int num_sms() {
     if (n <= 0) n = 148;
   }
   return n;
+}
+
+// nanoseconds the long-waiting warps of the tcgen05 kernels sleep between two polls of an mbarrier
+// (ptx::mbar_wait_sleep); NPML_WAIT_NS overrides, 0 = spin
+inline int wait_ns() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NPML_WAIT_NS");
+    v = e ? atoi(e) : 0;       // measured on B200 (cfg2..cfg5, 0 / 128 / 512 ns): failed polls are rare (try_wait suspends in hardware), sleeping only adds wake-up latency
+    if (v < 0) v = 0;
+    if (v > 10000) v = 10000;
+  }
+  return v;
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -98,6 +98,7 @@ struct TcConvParams {
   int BN, stages, nkb;  // N tile, pipeline depth, K blocks per tap
   int kelems;           // elements per K block (64 bf16 / 32 fp32)
   uint32_t idesc, tmem_cols;
+  int wait_ns;                 // sleep between polls of the epilogue warps (npml::wait_ns())
   int act;
   float p0, p1;
 };
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) tc_gather_conv_kernel(const __grid_c
     const bool row_ok = (m < P.TW * P.TH * P.TN) && n < P.N && oy < C.oh && ox < C.ow;
     const int64_t pix = ((int64_t)n * P.OH + (C.y0 + (int64_t)C.so * oy)) * P.OW + (C.x0 + (int64_t)C.so * ox);
     if (nk > 0) {
-      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::mbar_wait_sleep(tmem_full_bar, 0, (uint32_t)P.wait_ns);
       ptx::tc_fence_after();
     }
     for (int c = 0; c < P.BN; c += 32) {
@@ -335,6 +336,7 @@ bool plan_geometry(const GatherConv& g, int mode, Plan& pl) {
   while ((int)cols < bn) cols <<= 1;
   P.tmem_cols = cols;
   P.idesc = ptx::instr_desc(bf16 ? 1 : 2, 0, 0, 128, bn);
+  P.wait_ns = wait_ns();
   const int stage_bytes = kATileBytes + bn * kRowBytes;
   P.stages = bn <= 64 ? 4 : (bn <= 128 ? 3 : 4);
   pl.smem = (size_t)P.stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;

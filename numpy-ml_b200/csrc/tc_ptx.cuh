@@ -49,6 +49,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Waiting without hammering shared memory: every mbarrier.try_wait that fails is a shared-memory access, and on
+// sm_100a the tensor core fetches its operands through the same shared-memory banks (48 wavefronts per 128x64x16
+// MMA).  Warps that wait for a long time by design (epilogue warps while a tile is being accumulated, producers
+// while their ring is full) therefore sleep between polls; ns == 0 is the plain spin loop.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  if (ns == 0) { mbar_wait(bar, parity); return; }
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -18,6 +18,10 @@
 //   warp 2  weight producer (TMA; all taps resident in smem when they fit, else a streamed ring shared by
 //           the UT tiles of the unit) and TMEM allocator
 //   warps 4..7  epilogue (tcgen05.ld -> +bias -> act -> global), overlapped with the next tiles' MMAs
+//   warps 8..11 second epilogue group: the tiles of a CTA alternate between the two groups.  Measured (ncu source
+//               page of cfg2): with one group the MMA warp spent ~25 % of the kernel waiting for accumulator slots --
+//               a tile's epilogue is one long dependent chain (tcgen05.ld -> math -> st.shared -> ld.shared ->
+//               st.global) and four warps cannot hide it
 #include <cstdlib>
 #include <type_traits>
 
@@ -35,7 +39,7 @@ namespace {
 constexpr int kMaxTaps = 64;
 constexpr int kMaxCls = 9;
 constexpr int kRowBytes = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;      // warps 0..3 producers / MMA, 4..7 epilogue group 0, 8..11 epilogue group 1
 constexpr int kSlabStages = 2;
 constexpr int kMaxWStages = 8;
 constexpr int kMaxAcc = 16;
@@ -68,6 +72,8 @@ struct SlabParams {
                                 // bound by the MMA operand fetch, not by the epilogue)
   int act;
   float p0, p1;
+  int epi2;                     // 1: warps 8..11 take every other tile (their rows go straight to global memory)
+  int wait_ns;                  // sleep between mbarrier polls of the producer / epilogue warps (npml::wait_ns())
   int affine;                   // 1: Y = scale[co] * act(z + b) + shift[co] (frozen BatchNorm2D folded into the epilogue)
 };
 
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     ptx::tmem_relinquish();
   }
   if (warp >= 4) {
-    for (int i = threadIdx.x - 128; i < 256; i += 128) {    // BN <= 256
+    for (int i = threadIdx.x - 128; i < 256; i += kThreads - 128) {    // BN <= 256
       const bool ok = i < P.BN && co0 + i < P.CO;
       bias_s[i] = (bias != nullptr && ok) ? bias[co0 + i] : 0.f;
       if (P.affine) {
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
           const int tg = P.nplanes > 1 ? plane : cls;
           const int padx = P.cls_padx[tg], pady = P.cls_pady[tg];
           const int st = p & 1;
-          ptx::mbar_wait(&slab_empty[st], ((p >> 1) & 1u) ^ 1u);
+          ptx::mbar_wait_sleep(&slab_empty[st], ((p >> 1) & 1u) ^ 1u, (uint32_t)P.wait_ns);
           ptx::mbar_expect_tx(&slab_full[st], (uint32_t)P.SR * row_bytes);
           uint8_t* dst = smem + (size_t)st * P.plane_bytes;
           int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
             const int tg = P.nplanes > 1 ? plane : cls;
             const int tap0 = P.cls_tap0[tg], nt = P.cls_ntaps[tg];
             for (int t = 0; t < nt; ++t) {
-              ptx::mbar_wait(&w_empty[ws], wph ^ 1u);
+              ptx::mbar_wait_sleep(&w_empty[ws], wph ^ 1u, (uint32_t)P.wait_ns >> 2);
               ptx::mbar_expect_tx(&w_full[ws], (uint32_t)P.w_block_bytes);
               ptx::tma_load_3d(w_area + (size_t)ws * P.w_block_bytes, &P.wmap, &w_full[ws], kb * P.kelems, co0,
                                P.tap_w[tap0 + t]);
@@ -251,16 +257,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
               bd = w_d + ws * wbb16;
             }
             const bool first = (kg == 0 && t == 0), last = (kg == nkg - 1 && t == ntaps - 1);
-            if (first) {
 #pragma unroll
-              for (int j = 0; j < UT; ++j)
-                if (kFull || j < ntile) ptx::mbar_wait(&acc_empty[sl[j]], ph[j] ^ 1u);
-              ptx::tc_fence_after();
-            }
-            if (leader) {
-#pragma unroll
-              for (int j = 0; j < UT; ++j) {
-                if (kFull || j < ntile) {
+            for (int j = 0; j < UT; ++j) {
+              if (kFull || j < ntile) {
+                if (first) {            // the accumulator slot of tile j is waited for right before its first MMA
+                  ptx::mbar_wait(&acc_empty[sl[j]], ph[j] ^ 1u);
+                  ptx::tc_fence_after();
+                }
+                if (leader) {
 #pragma unroll
                   for (int ks = 0; ks < 4; ++ks)
                     ptx::mma_ss<kTf32>(dt[j], ad + (uint64_t)(j * (128 * kRowBytes >> 4) + 2 * ks), bd + (uint64_t)(2 * ks), idesc,
@@ -268,8 +272,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
                   if (last) ptx::tc_commit(&acc_full[sl[j]]);
                 }
               }
-              if (!kRes) ptx::tc_commit(&w_empty[ws]);
             }
+            if (leader && !kRes) ptx::tc_commit(&w_empty[ws]);
             if (!kRes && ++ws == w_stages) { ws = 0; wph ^= 1u; }
           }
           if (leader) ptx::tc_commit(&slab_empty[st]);
@@ -293,10 +297,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     constexpr int kRPI = 32 / kCPR;               // rows written per store instruction
     constexpr int kVec = 16 / (int)sizeof(T);     // elements per 16-byte piece
     const int qd = warp & 3;                      // TMEM lane quadrant of this warp
+    const int grp = (warp - 4) >> 2;              // epilogue group: tiles alternate between the groups when P.epi2
+    const uint32_t ngrp = P.epi2 ? 2u : 1u;
     const int m = qd * 32 + lane;                 // row of the M tile
     const int img_slots = P.Hp * P.Wp;
     const int BN = P.BN, CO = P.CO, Wp = P.Wp, n_acc = P.n_acc;
-    uint8_t* stg = staging + (size_t)(warp - 4) * 32 * kRB;
+    uint8_t* stg = staging + (size_t)((warp - 4) & 3) * 32 * kRB;      // group 1 never stages
     const uint32_t stg_u32 = ptx::smem_u32(stg);
     const int my_swz = kCPR == 4 ? ((lane >> 1) & 3) : (lane & 7);
     const int rd_row0 = lane / kCPR, rd_cc = lane % kCPR;
@@ -361,13 +367,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
                        : "memory");
       }
     };
-    const bool direct = P.epi_direct != 0;
+    const bool direct = P.epi_direct != 0 || grp == 1;
+    uint32_t tseq = 0;                            // running tile number of this CTA
 
-    for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x) {
+    for (int unit = (grp == 0 || P.epi2) ? (int)blockIdx.x : P.num_units; unit < P.num_units; unit += gridDim.x) {
       const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
       const int lu = unit - cls * P.units_per_cls;
       const int ntile = min(UT, P.total_tiles - lu * UT);
-      for (int j = 0; j < ntile; ++j) {
+      for (int j = 0; j < ntile; ++j, ++tseq) {
+        if ((tseq & (ngrp - 1u)) != (uint32_t)grp) {          // the other group's tile: only the ring position moves
+          if (++slot == (uint32_t)n_acc) { slot = 0; sph ^= 1u; }
+          continue;
+        }
         const int s = (lu * UT + j) * 128 + m;
         const int n = s / img_slots;
         const int rem = s - n * img_slots;
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
         const bool row_ok = n < P.N && yp < P.cls_oh[cls] && xp < P.cls_ow[cls];
         // pixel of the FULL output tensor: (y0 + so*yp, x0 + so*xp)
         const int my_pix = row_ok ? (n * P.OHf + P.cls_y0[cls] + P.so * yp) * P.OWf + P.cls_x0[cls] + P.so * xp : -1;
-        ptx::mbar_wait(&acc_full[slot], sph);
+        ptx::mbar_wait_sleep(&acc_full[slot], sph, (uint32_t)P.wait_ns);
         ptx::tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(qd * 32) << 16) + slot * (uint32_t)BN;
         for (int c = 0; c < BN; c += 32) {
@@ -532,6 +543,7 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   P.nkg = P.nkb * P.nplanes;
   P.act = g.act; P.p0 = g.p0; P.p1 = g.p1;
   P.affine = g.post_scale != nullptr ? 1 : 0;
+  P.wait_ns = wait_ns();
   int bn = (g.CO + 15) / 16 * 16;
   // wide outputs: one N = 192..256 tile (two accumulators) instead of two N = 128 tiles -- the A slab is fetched once
   // per MMA for twice the math, and the CTAs of the second N tile do not reload the same slabs
@@ -569,6 +581,8 @@ bool plan_slab(const GatherConv& g, int mode, SlabPlan& pl) {
   {
     const char* e = std::getenv("NPML_SLAB_EPI");
     P.epi_direct = (e && e[0] == 'd' && (g.CO * es) % 32 == 0) ? 1 : 0;
+    // second epilogue group (32-byte row stores straight from registers: needs 32-byte aligned rows)
+    P.epi2 = ((g.CO * es) % 32 == 0 && !std::getenv("NPML_SLAB_EPI1")) ? 1 : 0;
   }
   const int nty = ceildiv(g.CO, bn);
   int ctas = num_sms() / nty;

@@ -48,6 +48,7 @@ struct SlabWgradParams {
   int R, SRX, KS, num_units;
   int xplane_bytes, xstage_bytes, gplane_bytes, gstage_bytes;
   uint32_t idesc;
+  int wait_ns;                 // sleep between mbarrier polls of the producer / epilogue warps (npml::wait_ns())
 };
 
 // The MMA issue loop for a group of NT accumulator tiles.  The whole warp walks the loops in convergent control
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
       uint32_t uc = 0;
       for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x, ++uc) {
         const uint32_t st = uc & 1u;
-        ptx::mbar_wait(&empty_bar[st], ((uc >> 1) & 1u) ^ 1u);
+        ptx::mbar_wait_sleep(&empty_bar[st], ((uc >> 1) & 1u) ^ 1u, (uint32_t)P.wait_ns);
         ptx::mbar_expect_tx(&full_bar[st], tx);
         const int rho0 = unit * P.R;
         int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
     const int qd = warp & 3;
     const int l = qd * 32 + lane;                 // accumulator row
     const int w = l >> 6, cl = l & 63;            // window of the pair, channel inside the window
-    ptx::mbar_wait(acc_bar, 0);
+    ptx::mbar_wait_sleep(acc_bar, 0, (uint32_t)P.wait_ns * 4u);      // these warps wait for the whole reduction
     ptx::tc_fence_after();
     for (int i = 0; i < nmt; ++i) {
       const int gi = mt0 + i;
@@ -269,6 +270,7 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   P.nb = bn / 64;
   const int ncot = ceildiv(g.CO, bn);
   P.idesc = ptx::instr_desc(1, 1, 1, 128, bn);
+  P.wait_ns = wait_ns();
   const int halo = (g.fr - 1) * g.D * Wp + (g.fc - 1) * g.D;
   // largest unit (R padded rows) whose two stages fit
   int R = 0;

@@ -47,6 +47,7 @@ struct TcWgradParams {
   int tiles_per_split;
   int stages, rows_used, kinstr_bytes, mmas_per_tile;
   uint32_t idesc, tmem_cols;
+  int wait_ns;                 // sleep between polls of the epilogue warps (npml::wait_ns())
 };
 
 template <typename T>
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) tc_wgrad_kernel(const __grid_constan
     }
     float* out = is_db ? part_db + (int64_t)blockIdx.z * P.CO : part + ((int64_t)blockIdx.z * P.Mrows + row) * P.CO;
     if (nk > 0) {
-      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::mbar_wait_sleep(tmem_full_bar, 0, (uint32_t)P.wait_ns);
       ptx::tc_fence_after();
     }
     const int BN = P.nb * P.kelems;
@@ -256,6 +257,7 @@ bool plan_wgrad(const GatherWgrad& g, int mode, WPlan& pl, bool want_db = false)
   while ((int)cols < bn) cols <<= 1;
   P.tmem_cols = cols;
   P.idesc = ptx::instr_desc(bf16 ? 1 : 2, 1, 1, 128, bn);
+  P.wait_ns = wait_ns();
   P.kinstr_bytes = (bf16 ? 16 : 8) * kRowBytes;             // K pixels per MMA x 128 B
   P.mmas_per_tile = 128 / (bf16 ? 16 : 8);
   int nb = 0;
