@@ -200,6 +200,11 @@ bool slab_conv_supported(const GatherConv& g, int mode);
 size_t slab_conv_ws_bytes(const GatherConv& g, int mode);
 int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
+// weight-stationary variant (weights in tensor memory, pixels along N) for out_ch <= 128, tc_ws_conv.cu
+bool ws_conv_supported(const GatherConv& g, int mode);
+size_t ws_conv_ws_bytes(const GatherConv& g, int mode);
+int ws_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
+                   void* ws, size_t ws_bytes, cudaStream_t st);
 // row-of-taps variant for narrow outputs (fc * out_ch <= 256), tc_slab3_conv.cu; slab_gather_conv dispatches to it
 bool slab3_conv_supported(const GatherConv& g, int mode);
 int slab3_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,

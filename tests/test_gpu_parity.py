@@ -898,6 +898,44 @@ def test_row_of_taps_slab_kernel_optin(cuda_device, monkeypatch, mode, fold):
     close(L.backward(dY), NO.conv1d_layer_bwd(dY, X, Zr, W, 1, "causal", 1)[0], tol, "conv1d dX")
 
 
+# stride-1 shapes csrc/tc_ws_conv.cu takes in bf16 mode: pair mode (out_ch <= 64: two taps per MMA, even slot distance),
+# single mode (out_ch in 65..128), two K blocks, all-paired 4x4 rows, 25 taps, dilation 3 (delta = 4), 1x1, channel tails
+WS_CASES = [0, 3, 4, 5, 7, 9, 10, 12, 13, 15, 21]
+
+
+@pytest.mark.parametrize("case", WS_CASES)
+def test_weight_stationary_kernel_optin(cuda_device, monkeypatch, case):
+    """csrc/tc_ws_conv.cu (NPML_WS=1: weights resident in tensor memory, pixels along N, tap pairs stacked along M):
+    forward (with the folded frozen BatchNorm2D too) and dX against the oracle, and bit-for-bit the same dW path."""
+    monkeypatch.setenv("NPML_WS", "1")
+    pkg = npml()
+    xs, oc, ks, pad, s, d, act = CONV_CASES[case]
+    assert s == 1
+    rng = np.random.default_rng(900 + case)
+    p0 = 0.25 if act == "leaky_relu" else 0.0
+    L = pkg.Conv2D(out_ch=oc, kernel_shape=ks, pad=pad, stride=s, dilation=d, act_fn=make_act(pkg, act, p0, 0.0),
+                   mode="bf16")
+    X = _f32(rng, xs)
+    W = _f32(rng, ks + (xs[3], oc), 1.0 / np.sqrt(ks[0] * ks[1] * xs[3]))
+    b = _f32(rng, (1, 1, 1, oc), 0.1)
+    L.forward(X, retain_derived=False)
+    L.parameters["W"], L.parameters["b"] = W, b
+    tol = TOL["bf16"]
+    Y = L.forward(X)
+    Yr, Zr = O.conv2d_layer_fwd(X, W, b, s, pad, d, act, p0, 0.0)
+    close(Y, Yr, tol, "Y")
+    close(L.derived_variables["Z"][0], Zr, tol, "Z")
+    dY = _f32(rng, Yr.shape)
+    dX = L.backward(dY)
+    Zd = pkg.to_numpy(L.derived_variables["Z"][0]) if act in KINKED else Zr
+    dXr, dWr, dbr = O.conv2d_layer_bwd(dY, X, Zd, W, s, pad, d, act, p0, 0.0)
+    close(dX, dXr, tol, "dX")
+    close(L.gradients["W"], dWr, tol, "dW")
+    bn, P = _random_bn(pkg, rng, oc)
+    ref, _, _ = O.bn2d_fwd(Yr, P["scaler"], P["intercept"], P["running_mean"], P["running_var"], use_batch_stats=False)
+    close(L.forward(X, retain_derived=False, fused_bn=bn), ref, tol, "fused BN")
+
+
 def test_multiply_fc_golden(cuda_device):
     pkg = npml()
     z, cases = load_golden("wavenet_vae.npz")
