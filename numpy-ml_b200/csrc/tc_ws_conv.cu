@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
                                                                  const float* __restrict__ post_scale,
                                                                  const float* __restrict__ post_shift,
                                                                  __nv_bfloat16* __restrict__ Z, __nv_bfloat16* __restrict__ Y) {
-  // [2 slab planes] [2 epilogue staging tiles: NT pixels x (128 | 256) bytes] [barriers]
+  // [2 slab planes] [2 x (epilogue staging tile: NT pixels x (128 | 256) bytes, pixel table: NT ints)] [barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   uint8_t* stage = smem + (size_t)kSlabStages * P.plane_bytes;
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
     const bool pair = P.pair != 0;
     const int RB = pair ? 128 : 256, cpr_shift = pair ? 3 : 4;      // staging row bytes, log2(16-byte pieces per row)
     const uint32_t stg_u32 = ptx::smem_u32(stage + (size_t)grp * P.stage_bytes);
+    const uint32_t ptab_u32 = stg_u32 + (uint32_t)(P.NT * RB);           // pixel table behind the staging tile
     const int bar_id = 1 + grp;
     int cos[4];
     float bvs[4], scs[4], shs[4];
@@ -272,15 +273,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
           ptx::mbar_wait(&acc_full[slot], sph);
           ptx::tc_fence_after();
           const uint32_t t_addr = acc_col0 + ((uint32_t)(qd * 32) << 16) + slot * NC;
+          // output pixel of every slot of the tile, once per tile: ptab[p] = pixel index or -1 (junk slot)
+          if (tid_g < NT) {
+            const unsigned sidx = (unsigned)(s_tile + tid_g);
+            const unsigned n = sidx / (unsigned)img_slots;
+            const unsigned rem = sidx - n * (unsigned)img_slots;
+            const unsigned yp = rem / (unsigned)Wp, xp = rem - yp * (unsigned)Wp;
+            const int pix = (n < (unsigned)P.N && yp < (unsigned)P.OH && xp < (unsigned)P.OW)
+                                ? (int)((n * (unsigned)P.OH + yp) * (unsigned)P.OW + xp) : -1;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(ptab_u32 + 4u * (uint32_t)tid_g), "r"(pix) : "memory");
+          }
           for (int pass = 0; pass < npass; ++pass) {
             const bool is_y = (Z == nullptr) || pass == 1;
+            const bool last_pass = pass == npass - 1;
             __nv_bfloat16* __restrict__ out = is_y ? Y : Z;
-            for (int cb = 0; cb < NT; cb += 32) {
-              uint32_t ra[16], rb[16];
+            auto load_chunk = [&](int cb, uint32_t (&ra)[16], uint32_t (&rb)[16]) {
               tmem_ld_16x256b_x4(t_addr + (uint32_t)cb, ra);
               tmem_ld_16x256b_x4(t_addr + (16u << 16) + (uint32_t)(cb + (pair ? P.delta : 0)), rb);
+            };
+            // chunk cb is in (ra, rb); the loads of chunk cb + 32 go into (na, nb) before cb is converted
+            auto process = [&](int cb, uint32_t (&ra)[16], uint32_t (&rb)[16], uint32_t (&na)[16], uint32_t (&nb)[16]) {
               ptx::tmem_ld_wait();
-              if (pass == npass - 1 && cb + 32 >= NT) {          // accumulator fully read: hand the slot back
+              if (cb + 32 < NT) {
+                load_chunk(cb + 32, na, nb);
+              } else if (last_pass) {                         // accumulator fully read: hand the slot back
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[slot]);
@@ -326,30 +342,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
                   asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
                 }
               }
+            };
+            {
+              uint32_t a0[16], b0[16], a1[16], b1[16];
+              load_chunk(0, a0, b0);
+              for (int cb = 0; cb < NT; cb += 64) {
+                process(cb, a0, b0, a1, b1);
+                if (cb + 32 < NT) process(cb + 32, a1, b1, a0, b0);
+              }
             }
             bar_sync(bar_id, 128);
-            // staging -> global: 16 bytes per lane, a pixel's channels contiguous.  A thread keeps its 16-byte column
-            // k and walks the pixels in steps of 128 / (pieces per row); the pixel coordinates are advanced by carries
-            // (two divisions per tile instead of two per piece).
+            // staging -> global: 16 bytes per lane, a pixel's channels contiguous; a thread keeps its 16-byte column k
             {
               const unsigned k = (unsigned)tid_g & ((1u << cpr_shift) - 1u), pstep = 128u >> cpr_shift;
-              unsigned pp = (unsigned)tid_g >> cpr_shift;
-              const unsigned sidx = (unsigned)s_tile + pp;
-              unsigned n = sidx / (unsigned)img_slots;
-              const unsigned rem = sidx - n * (unsigned)img_slots;
-              unsigned yp = rem / (unsigned)Wp, xp = rem - yp * (unsigned)Wp;
-              const bool k_ok = 8u * k < (unsigned)CO;
-              for (; pp < (unsigned)NT; pp += pstep) {
-                if (k_ok && n < (unsigned)P.N && yp < (unsigned)P.OH && xp < (unsigned)P.OW) {
-                  uint4 u;
-                  const uint32_t addr = stg_u32 + pp * (uint32_t)RB + ((k ^ ((pp >> 1) & 3u)) << 4);
-                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
-                  *reinterpret_cast<uint4*>(out + ((int64_t)((n * (unsigned)P.OH + yp) * (unsigned)P.OW + xp) * CO + 8 * k)) = u;
-                }
-                xp += pstep;
-                while (xp >= (unsigned)Wp) {
-                  xp -= (unsigned)Wp;
-                  if (++yp == (unsigned)P.Hp) { yp = 0; ++n; }
+              if (8u * k < (unsigned)CO) {
+                for (unsigned pp = (unsigned)tid_g >> cpr_shift; pp < (unsigned)NT; pp += pstep) {
+                  int pix;
+                  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pix) : "r"(ptab_u32 + 4u * pp) : "memory");
+                  if (pix >= 0) {
+                    uint4 u;
+                    const uint32_t addr = stg_u32 + pp * (uint32_t)RB + ((k ^ ((pp >> 1) & 3u)) << 4);
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+                    *reinterpret_cast<uint4*>(out + ((int64_t)pix * CO + 8 * k)) = u;
+                  }
                 }
               }
             }
@@ -463,7 +478,7 @@ bool plan_ws(const GatherConv& g, int mode, WsPlan& pl) {
   if (P.n_acc > kMaxAcc) P.n_acc = kMaxAcc;
   P.idesc = ptx::instr_desc(1, 0, 0, 128, P.NC);
   P.total_tiles = (int)((slots + NT - 1) / NT);
-  P.stage_bytes = NT * (P.pair ? 128 : 256);
+  P.stage_bytes = NT * (P.pair ? 128 : 256) + NT * 4;        // staging tile + pixel table
   const int fixed = 1024 /*barriers*/ + 2 * P.stage_bytes;
   bool found = false;
   for (int ut = P.n_acc < 4 ? P.n_acc : 4; ut >= 1 && !found; --ut) {
