@@ -82,6 +82,8 @@ static int run_gather(const npml_conv_desc* d, int op, const void* in, const flo
   NPML_CHECK(post_scale == nullptr || Y != nullptr, "the folded BatchNorm2D needs the Y output");
   g.post_scale = post_scale; g.post_shift = post_shift;
   if (g.act == NPML_ACT_IDENTITY && Z == nullptr && post_scale == nullptr) { Z = Y; Y = nullptr; }
+  if (d->mode == NPML_MODE_BF16 && ws2_conv_supported(g, d->mode))
+    return ws2_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode))
     return ws_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode))
@@ -171,7 +173,8 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
   switch (op) {
     case NPML_OP_CONV_FPROP: case NPML_OP_CONV_DGRAD: case NPML_OP_DECONV_FPROP: case NPML_OP_DECONV_DGRAD: {
       GatherConv g = make_gather(d, op);
-      if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode)) bytes += ws_conv_ws_bytes(g, d->mode);
+      if (d->mode == NPML_MODE_BF16 && ws2_conv_supported(g, d->mode)) bytes += ws2_conv_ws_bytes(g, d->mode);
+      else if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode)) bytes += ws_conv_ws_bytes(g, d->mode);
       else if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode)) bytes += slab_conv_ws_bytes(g, d->mode);
       else if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode)) bytes += tc_conv_ws_bytes(g, d->mode);
       break;

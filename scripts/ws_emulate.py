@@ -83,20 +83,27 @@ def emulate(inp, Wt, OH, OW, fr, fc, D, pr, pc, form, NT=32):
     return out
 
 
-def check(xs, oc, ks, pad, d, rng):
+def check(xs, oc, ks, pad, d, rng, rows_per_tile=0):
     X = rng.standard_normal(xs)
     W = rng.standard_normal(ks + (xs[3], oc))
     Z = O.conv2D(X, W, 1, pad, d)
     p4 = O.resolve_pad(X.shape, pad, ks, 1, d)
     D = d + 1
     Wt = W.reshape(ks[0] * ks[1], xs[3], oc).transpose(0, 2, 1)           # [tap][co][ci], forward
-    got = emulate(X, Wt, Z.shape[1], Z.shape[2], ks[0], ks[1], D, p4[0], p4[2], 0)
+    kw = {}
+    if rows_per_tile:              # the NPML_WS=2 tiling: a tile is a whole number of padded rows (NT = R * Wp)
+        kw["NT"] = rows_per_tile * plan(xs[0], xs[1], xs[2], xs[3], Z.shape[1], Z.shape[2], oc, ks[0], ks[1], D, p4[0],
+                                        p4[2], 0)["Wp"]
+    got = emulate(X, Wt, Z.shape[1], Z.shape[2], ks[0], ks[1], D, p4[0], p4[2], 0, **kw)
     e1 = np.abs(got - Z).max()
     # dX = transposed form: gathers dZ with W[r, t, c, k] read as [tap][co = c][ci = k]
     dZ = rng.standard_normal(Z.shape)
     dXr, _, _ = O.conv2d_layer_bwd(dZ, X, Z, W, 1, pad, d)
     Wt2 = W.reshape(ks[0] * ks[1], xs[3], oc)                             # [tap][c][k]
-    got2 = emulate(dZ, Wt2, xs[1], xs[2], ks[0], ks[1], D, p4[0], p4[2], 1)
+    if rows_per_tile:
+        kw["NT"] = rows_per_tile * plan(xs[0], Z.shape[1], Z.shape[2], oc, xs[1], xs[2], xs[3], ks[0], ks[1], D, p4[0],
+                                        p4[2], 1)["Wp"]
+    got2 = emulate(dZ, Wt2, xs[1], xs[2], ks[0], ks[1], D, p4[0], p4[2], 1, **kw)
     e2 = np.abs(got2 - dXr).max()
     print(xs, oc, ks, pad, d, "fwd err %.2e  dX err %.2e" % (e1, e2))
     assert e1 < 1e-9 and e2 < 1e-9

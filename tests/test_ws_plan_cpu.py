@@ -29,6 +29,13 @@ def test_ws_decomposition_matches_oracle(case):
     E.check(xs, oc, ks, pad, d, np.random.default_rng(case))
 
 
+@pytest.mark.parametrize("rows", [1, 2, 3])
+def test_ws_row_aligned_tiles(rows):
+    """The tiling of the experimental NPML_WS=2 variant (csrc/tc_ws2_conv.cu): NT = rows * Wp, not a multiple of 32."""
+    E.check((2, 7, 6, 8), 16, (3, 3), "same", 0, np.random.default_rng(40 + rows), rows_per_tile=rows)
+    E.check((2, 6, 6, 8), 72, (3, 3), 1, 0, np.random.default_rng(50 + rows), rows_per_tile=rows)
+
+
 def test_pairs_are_at_even_slot_distance():
     """tcgen05.ld.16x256b needs an even column offset (scripts/ts_probe2.cu): delta = D or 2D, never odd, at most 8."""
     for D in (1, 2, 3, 4):
