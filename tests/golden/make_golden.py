@@ -565,6 +565,50 @@ def gen_wavenet_vae():
     save("wavenet_vae.npz", arrays, cases)
 
 
+def gen_module_inference():
+    """retain_derived=False forwards of the two skip-connection modules AFTER a training forward, so that the running
+    statistics every BatchNorm2D normalises with (layers/layers.py:1141-1146) are non-trivial.  Pins the oracle chain the
+    fused conv -> BatchNorm2D epilogue (npml_conv2d_fprop_bn) is tested against."""
+    rng = np.random.default_rng(23)
+    arrays, cases = {}, []
+    confs = [("conv", (3, 8, 8, 3), 4, 5, "relu"), ("conv", (2, 9, 9, 2), 3, 3, "tanh"), ("identity", (3, 7, 7, 4), 4, 4, "relu")]
+    for i, (kind, xs, oc1, oc2, act) in enumerate(confs):
+        if kind == "conv":
+            M = SkipConnectionConvModule(out_ch1=oc1, out_ch2=oc2, kernel_shape1=(3, 3), kernel_shape2=(3, 3),
+                                         kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn=ACTS[act]())
+        else:
+            M = SkipConnectionIdentityModule(out_ch=oc1, kernel_shape1=(3, 3), kernel_shape2=(3, 3), act_fn=ACTS[act]())
+        X = f32(rng, xs)
+        M.forward(X, retain_derived=False)
+        triples = [("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2)]
+        if kind == "conv":
+            triples.append(("s", M.conv_skip, M.batchnorm_skip))
+        out = {}
+        for tag, conv, bn in triples:
+            conv.parameters["W"] = f32(rng, conv.parameters["W"].shape, 0.4)
+            conv.parameters["b"] = f32(rng, conv.parameters["b"].shape, 0.3)
+            bn.parameters["scaler"] = f32(rng, bn.parameters["scaler"].shape) * 0.5 + 1.0
+            bn.parameters["intercept"] = f32(rng, bn.parameters["intercept"].shape) * 0.1
+            bn.reset_running_stats()
+        for c in M.components:
+            c.flush_gradients()
+        M.forward(f32(rng, xs))                     # a training forward moves the running statistics
+        for c in M.components:
+            c.flush_gradients()
+        for tag, conv, bn in triples:
+            out["W" + tag], out["b" + tag] = conv.parameters["W"].copy(), conv.parameters["b"].copy()
+            out["g" + tag], out["h" + tag] = bn.parameters["scaler"].copy(), bn.parameters["intercept"].copy()
+            out["rm" + tag] = np.asarray(bn.parameters["running_mean"], dtype=np.float64).copy()
+            out["rv" + tag] = np.asarray(bn.parameters["running_var"], dtype=np.float64).copy()
+        Y = M.forward(X, retain_derived=False)
+        for tag, conv, bn in triples:               # inference must not move them
+            assert np.array_equal(out["rm" + tag], bn.parameters["running_mean"])
+        out.update({"X": X, "Y": np.asarray(Y, dtype=np.float64)})
+        arrays.update({f"i{i}/{k}": v for k, v in out.items()})
+        cases.append({"id": f"i{i}", "kind": kind, "out_ch1": oc1, "out_ch2": oc2, "act": act})
+    save("skip_modules_inference.npz", arrays, cases)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only:                                         # e.g. `make_golden.py conv1d pool2d`
@@ -582,3 +626,4 @@ if __name__ == "__main__":
     gen_deconv2d()
     gen_bn_add()
     gen_module()
+    gen_module_inference()

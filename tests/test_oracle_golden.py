@@ -345,3 +345,31 @@ def test_multiply_fc_wavenet_vae_golden():
             for k in range(4):
                 close(dWs[k], z["vae/dW{}".format(k)], 1e-11)
                 close(dbs[k], z["vae/db{}".format(k)], 1e-11)
+
+
+def test_skip_modules_inference_golden():
+    """retain_derived=False forwards of the skip-connection modules (every BatchNorm2D on its running statistics,
+    layers/layers.py:1141-1146; modules/modules.py:905-937, 574-594) as produced by the unmodified reference: the
+    layer-by-layer oracle chain that the fused conv -> BatchNorm2D epilogue is tested against on the GPU
+    (tests/test_gpu_parity.py::test_skip_modules_fused_inference) must reproduce them."""
+    z, cases = load_golden("skip_modules_inference.npz")
+
+    def bn(x, i, t):
+        return O.bn2d_fwd(x, z[f"{i}/g{t}"], z[f"{i}/h{t}"], z[f"{i}/rm{t}"], z[f"{i}/rv{t}"], use_batch_stats=False)[0]
+
+    for c in cases:
+        i, act = c["id"], c["act"]
+        X = z[i + "/X"]
+        pad1 = 1 if c["kind"] == "conv" else "same"
+        a1, _ = O.conv2d_layer_fwd(X, z[i + "/W1"], z[i + "/b1"], 1, pad1, 0, act)
+        a2, _ = O.conv2d_layer_fwd(bn(a1, i, "1"), z[i + "/W2"], z[i + "/b2"], 1, pad1, 0, "identity")
+        h2 = bn(a2, i, "2")
+        if c["kind"] == "conv":
+            a_s, _ = O.conv2d_layer_fwd(X, z[i + "/Ws"], z[i + "/bs"], 1, 0, 0, "identity")
+            short = bn(a_s, i, "s")
+        else:
+            short = X
+        Y, _ = O.add_fwd([short, h2], act)
+        assert rel_err(Y, z[i + "/Y"]) < 1e-12, i
+        # a training forward moved the running statistics away from their initial (0, 1)
+        assert np.abs(z[i + "/rm1"]).max() > 1e-3 and np.abs(z[i + "/rv1"] - 1.0).max() > 1e-3
