@@ -213,6 +213,12 @@ int npml_uses_tensor_cores(const npml_conv_desc* d, int op) {
   return 0;
 }
 
+int npml_debug_ws_plan(const npml_conv_desc* d, int op, int variant, int32_t* out, int32_t cap) {
+  if (!d || !out || op < NPML_OP_CONV_FPROP || op > NPML_OP_DECONV_DGRAD) return -1;
+  const GatherConv g = make_gather(d, op);
+  return variant == 2 ? ws2_plan_debug(g, d->mode, out, cap) : ws_plan_debug(g, d->mode, out, cap);
+}
+
 const char* npml_last_error(void) { return g_err.c_str(); }
 
 int64_t npml_launch_count(int32_t reset) {

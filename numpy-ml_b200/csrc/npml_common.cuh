@@ -210,6 +210,8 @@ bool ws2_conv_supported(const GatherConv& g, int mode);
 size_t ws2_conv_ws_bytes(const GatherConv& g, int mode);
 int ws2_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
                     void* ws, size_t ws_bytes, cudaStream_t st);
+int ws_plan_debug(const GatherConv& g, int mode, int32_t* out, int32_t cap);      // host-only test hooks
+int ws2_plan_debug(const GatherConv& g, int mode, int32_t* out, int32_t cap);
 // row-of-taps variant for narrow outputs (fc * out_ch <= 256), tc_slab3_conv.cu; slab_gather_conv dispatches to it
 bool slab3_conv_supported(const GatherConv& g, int mode);
 int slab3_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,

@@ -538,4 +538,27 @@ int ws_gather_conv(const GatherConv& g, int mode, const void* in, const float* w
   return 0;
 }
 
+// Host-only test hook (npml_debug_ws_plan): what the planner decided, as plain integers.
+//   out[0..15] = supported, pair, delta, NT, NC, n_acc, UT, SR, Hp, Wp, pady, padx, ngroups, wcols, total_tiles, smem bytes
+//   then ngroups triples (tap offset in slots, tap_a, tap_b)
+int ws_plan_debug(const GatherConv& g, int mode, int32_t* out, int32_t cap) {
+  WsPlan pl;
+  const bool ok = plan_ws(g, mode, pl);
+  if (cap < 16) return -1;
+  for (int i = 0; i < cap; ++i) out[i] = 0;
+  out[0] = ok ? 1 : 0;
+  if (!ok) return 16;
+  const WsParams& P = pl.P;
+  const int32_t head[16] = {1, P.pair, P.delta, P.NT, P.NC, P.n_acc, P.UT, P.SR, P.Hp, P.Wp, P.pady, P.padx, P.ngroups,
+                            P.wcols, P.total_tiles, (int32_t)pl.smem};
+  for (int i = 0; i < 16; ++i) out[i] = head[i];
+  int n = 16;
+  for (int gi = 0; gi < P.ngroups && n + 3 <= cap; ++gi) {
+    out[n++] = (int32_t)(P.tap_off16[gi] / (kRowBytes >> 4));
+    out[n++] = P.tap_a[gi];
+    out[n++] = P.tap_b[gi];
+  }
+  return n;
+}
+
 }  // namespace npml

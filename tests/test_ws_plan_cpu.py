@@ -53,3 +53,87 @@ def test_pairs_are_at_even_slot_distance():
                     assert dya == dyb and abs(dxa - dxb) * D == P["delta"]
             taps = sorted([g[1] for g in P["groups"]] + [g[2] for g in P["groups"] if g[2] >= 0])
             assert taps == list(range(9))          # every tap exactly once
+
+
+# ---------------------------------------------------------------------------------------------------
+#  the C++ planners themselves (npml_debug_ws_plan: host only, no device) against the NumPy mirror above
+# ---------------------------------------------------------------------------------------------------
+def _cpp_plan(pkg, monkeypatch, variant, N, H, W, C, K, ks, pad, dil, op):
+    import ctypes as C_
+    from oracle import conv_oracle as O
+    lib = pkg._lib.load()
+    monkeypatch.setenv("NPML_WS", str(variant))
+    p4 = O.resolve_pad((N, H, W, C), pad, ks, 1, dil)
+    _, oh, ow, _ = O.calc_conv_out_dims((N, H, W, C), ks + (C, K), 1, p4, dil)
+    d = pkg.utils.make_desc(N, H, W, C, K, ks[0], ks[1], 1, dil + 1, p4, oh, ow, "bf16")
+    out = (C_.c_int32 * 256)()
+    n = lib.npml_debug_ws_plan(d, op, variant, C_.cast(out, C_.c_void_p), 256)
+    assert n >= 16
+    return list(out[:n]), p4, oh, ow
+
+
+PLAN_SHAPES = [
+    # N, H, W, C, K, kernel, pad, dilation
+    (256, 56, 56, 64, 64, (3, 3), "same", 0),       # cfg2
+    (256, 32, 32, 64, 128, (3, 3), 1, 0),           # cfg4 conv1
+    (8, 20, 24, 32, 48, (4, 4), 1, 0),
+    (4, 17, 19, 16, 16, (5, 5), 2, 0),
+    (4, 30, 30, 64, 64, (3, 3), "same", 1),         # D = 2
+    (4, 30, 30, 64, 64, (3, 3), "same", 2),         # D = 3 -> delta 6
+    (2, 12, 12, 64, 128, (1, 1), 0, 0),
+]
+
+
+@pytest.mark.parametrize("shape", range(len(PLAN_SHAPES)))
+@pytest.mark.parametrize("op", [0, 1])               # NPML_OP_CONV_FPROP, NPML_OP_CONV_DGRAD
+def test_cpp_planner_matches_numpy_mirror(monkeypatch, shape, op):
+    from conftest import npml
+    pkg = npml()
+    N, H, W, C, K, ks, pad, dil = PLAN_SHAPES[shape]
+    got, p4, oh, ow = _cpp_plan(pkg, monkeypatch, 1, N, H, W, C, K, ks, pad, dil, op)
+    D = dil + 1
+    if op == 0:     # forward: gathers X (N, H, W, C) into (N, OH, OW, K)
+        ref = E.plan(N, H, W, C, oh, ow, K, ks[0], ks[1], D, p4[0], p4[2], 0)
+        co, ci = K, C
+    else:           # dX: gathers dZ (N, OH, OW, K) into (N, H, W, C)
+        ref = E.plan(N, oh, ow, K, H, W, C, ks[0], ks[1], D, p4[0], p4[2], 1)
+        co, ci = C, K
+    nkb = (ci + 63) // 64
+    ngroups_ref = len(ref["groups"])
+    if ngroups_ref * nkb * 32 + 2 * (64 + (8 if ref["pair"] else 0)) > 512:
+        assert got[0] == 0                          # the weights do not fit in tensor memory next to two accumulators
+        return
+    assert got[0] == 1
+    sup, pair, delta, NT, NC, n_acc, UT, SR, Hp, Wp, pady, padx, ngroups, wcols, tiles, smem = got[:16]
+    assert (Hp, Wp, pady, padx) == (ref["Hp"], ref["Wp"], ref["pady"], ref["padx"])
+    assert bool(pair) == ref["pair"] and (not pair or delta == ref["delta"])
+    groups = [tuple(got[16 + 3 * i:19 + 3 * i]) for i in range(ngroups)]
+    assert groups == [tuple(g) for g in ref["groups"]]
+    # resources: TMEM columns, shared memory, the tile covers what the epilogue walks, every slot is in some tile
+    assert wcols == ngroups * nkb * 32 and wcols + n_acc * NC <= 512 and n_acc >= 2
+    assert NT % 32 == 0 and NC == NT + (8 if pair else 0) and 1 <= UT <= n_acc
+    assert smem <= 227 * 1024
+    assert tiles * NT >= N * Hp * Wp
+    halo = max(g[0] for g in groups)
+    assert SR * Wp >= (Wp - 1) + UT * NT + (NC - NT) + halo       # the slab holds every slot a unit's MMAs read
+
+
+@pytest.mark.parametrize("shape", [0, 1])
+def test_cpp_planner_row_tiles_variant(monkeypatch, shape):
+    """tc_ws2_conv.cu (NPML_WS=2, not yet run on a GPU): tiles are whole padded rows; same taps as variant 1."""
+    from conftest import npml
+    pkg = npml()
+    N, H, W, C, K, ks, pad, dil = PLAN_SHAPES[shape]
+    v1, _, _, _ = _cpp_plan(pkg, monkeypatch, 1, N, H, W, C, K, ks, pad, dil, 0)
+    v2, _, _, _ = _cpp_plan(pkg, monkeypatch, 2, N, H, W, C, K, ks, pad, dil, 0)
+    assert v2[0] == 1
+    sup, pair, delta, NT, NC, n_acc, UT, SR, Hp, Wp, pady, padx, ngroups, wcols, tiles, smem = v2[:16]
+    assert v2[16:] == v1[16:] and (Hp, Wp, pady, padx, pair, delta) == tuple(v1[i] for i in (8, 9, 10, 11, 1, 2))
+    assert NT % Wp == 0 and NT <= 128                         # whole rows
+    rows = NT // Wp
+    assert tiles * rows >= N * Hp
+    assert NC % 8 == 0 and NC >= NT + (delta if pair else 0) and NC <= 256
+    stride = (NT + 31) // 32 * 32 + (8 if pair else 0)        # TMEM columns between accumulators
+    assert wcols + n_acc * stride <= 512 and n_acc >= 2 and 1 <= UT <= n_acc
+    halo = max(v2[16 + 3 * i] for i in range(ngroups))
+    assert SR * Wp >= (UT - 1) * NT + NC + halo and smem <= 227 * 1024
