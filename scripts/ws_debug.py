@@ -1,5 +1,5 @@
 """GPU diagnostic for csrc/tc_ws_conv.cu: the same Conv2D forward / backward with NPML_WS=1 (weight-stationary kernel)
-and NPML_WS=0 (slab kernel) in one process, per-tap so that a wrong tap / half / shift shows up by name."""
+(or the variant given on the command line, `ws_debug.py 2`) and NPML_WS=0 (slab kernel) in one process, per-tap so that a wrong tap / half / shift shows up by name."""
 import importlib
 import os
 import sys
@@ -10,10 +10,11 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("numpy-ml_b200")
+VARIANT = sys.argv[1] if len(sys.argv) > 1 else "1"      # "2": the experimental row-tile / TMA-store variant
 
 
 def run(layer, X, dY, ws):
-    os.environ["NPML_WS"] = "1" if ws else "0"
+    os.environ["NPML_WS"] = VARIANT if ws else "0"
     layer.flush_gradients()
     Y = layer.forward(X)
     dX = layer.backward(dY)
