@@ -19,6 +19,8 @@
  *     desc.mode: NPML_MODE_FP32 and NPML_MODE_TF32 -> float, NPML_MODE_BF16 -> bfloat16.
  *   - "dil" is the tap spacing D = dilation + 1 (numpy-ml's `dilation` counts inserted zeros,
  *     utils/utils.py:95).
+ *   - alignment: activation tensors and the workspace 16 / 128 bytes (the tensor-core paths report an error
+ *     otherwise); outputs that are also 32-byte aligned let the epilogues use 32-byte stores.
  */
 #ifndef NPML_CONV_H_
 #define NPML_CONV_H_

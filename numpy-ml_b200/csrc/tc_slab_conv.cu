@@ -660,6 +660,10 @@ int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float*
   NPML_CHECK(ws != nullptr && ws_bytes >= pl.wt_bytes, "workspace too small");
   NPML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(ws) & 127) == 0,
              "activation / workspace pointers must be 16 / 128 byte aligned");
+  // rows stored straight from registers use 32-byte stores: outputs that are not 32-byte aligned (a caller's own view)
+  // keep the staged 16-byte path
+  if (((reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(Y)) & 31) != 0) { pl.P.epi2 = 0; pl.P.epi_direct = 0; }
+  NPML_CHECK(((reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0, "Z / Y must be 16-byte aligned");
   if (mode == NPML_MODE_BF16) return launch_slab<__nv_bfloat16>(g, pl, in, w, bias, Z, Y, ws, st);
   return launch_slab<float>(g, pl, in, w, bias, Z, Y, ws, st);
 }
