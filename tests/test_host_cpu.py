@@ -180,3 +180,20 @@ def test_1d_geometry_and_next_layer_host_logic():
             pkg.Conv1D(4, 3).forward(np.zeros((1, 8, 2)))
         with pytest.raises(RuntimeError):
             P.forward(np.zeros((1, 4, 4, 1)))
+
+
+def test_bench_algorithmic_work_matches_survey_table():
+    """bench.py's roofline numerator (fwd + bwd = 3 passes of 2 * MACs, padded taps counted) against SURVEY.md 8d:
+    cfg1 0.0434, cfg2 177.57, cfg3 27.41, cfg4 360.78 (convolutions only), cfg5 103.08 GFLOP per step."""
+    import importlib
+    bench = importlib.import_module("bench")
+    want = {"cfg1": 0.0434, "cfg2": 177.57, "cfg3": 27.41, "cfg4": 360.78, "cfg5": 103.08}
+    for name, gf in want.items():
+        cfg = dict(bench.CONFIGS[name])
+        got = 3.0 * bench.flops_per_pass(cfg, cfg["N"]) / 1e9
+        assert abs(got - gf) / gf < 2e-3, (name, got, gf)
+    # the CPU sample of the reference arm never exceeds the batch and shrinks with the number of steps
+    cfg = dict(bench.CONFIGS["cfg2"])
+    cfg.setdefault("_id", "cfg2")
+    n1, n25 = bench.cpu_sample_size(cfg, 100.0, 1), bench.cpu_sample_size(cfg, 100.0, 25)
+    assert 1 <= n25 <= n1 <= cfg["N"]
