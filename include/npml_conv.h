@@ -233,8 +233,8 @@ int npml_comm_destroy(void);
 const char* npml_last_error(void);
 /* 1 if the tcgen05 tensor-core path will be used for (desc, op), 0 if the CUDA-core path. */
 int npml_uses_tensor_cores(const npml_conv_desc* d, int op);
-/* Test hook (host only, no device work): the decisions of the weight-stationary planner (csrc/tc_ws_conv.cu, variant 1;
- * csrc/tc_ws2_conv.cu, variant 2) for a forward / dX call, honouring NPML_WS like a real call.  out[0..15] = supported,
+/* Test hook (host only, no device work): the decisions of the weight-stationary planner (csrc/tc_ws_conv.cu; variant must
+ * be 1) for a forward / dX call, honouring NPML_WS like a real call.  out[0..15] = supported,
  * pair, delta, NT, NC, n_acc, UT, SR, Hp, Wp, pady, padx, ngroups, weight TMEM columns, tiles, dynamic smem bytes, then
  * one (tap offset in slots, tap_a, tap_b) triple per MMA group.  Returns the number of ints written, < 0 on bad arguments.
  * tests/test_ws_plan_cpu.py checks it against the NumPy mirror that is itself checked against the oracle. */

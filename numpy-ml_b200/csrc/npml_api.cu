@@ -82,8 +82,6 @@ static int run_gather(const npml_conv_desc* d, int op, const void* in, const flo
   NPML_CHECK(post_scale == nullptr || Y != nullptr, "the folded BatchNorm2D needs the Y output");
   g.post_scale = post_scale; g.post_shift = post_shift;
   if (g.act == NPML_ACT_IDENTITY && Z == nullptr && post_scale == nullptr) { Z = Y; Y = nullptr; }
-  if (d->mode == NPML_MODE_BF16 && ws2_conv_supported(g, d->mode))
-    return ws2_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode))
     return ws_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
   if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode))
@@ -173,8 +171,7 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
   switch (op) {
     case NPML_OP_CONV_FPROP: case NPML_OP_CONV_DGRAD: case NPML_OP_DECONV_FPROP: case NPML_OP_DECONV_DGRAD: {
       GatherConv g = make_gather(d, op);
-      if (d->mode == NPML_MODE_BF16 && ws2_conv_supported(g, d->mode)) bytes += ws2_conv_ws_bytes(g, d->mode);
-      else if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode)) bytes += ws_conv_ws_bytes(g, d->mode);
+      if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode)) bytes += ws_conv_ws_bytes(g, d->mode);
       else if (d->mode != NPML_MODE_FP32 && slab_conv_supported(g, d->mode)) bytes += slab_conv_ws_bytes(g, d->mode);
       else if (d->mode != NPML_MODE_FP32 && tc_conv_supported(g, d->mode)) bytes += tc_conv_ws_bytes(g, d->mode);
       break;
@@ -216,7 +213,8 @@ int npml_uses_tensor_cores(const npml_conv_desc* d, int op) {
 int npml_debug_ws_plan(const npml_conv_desc* d, int op, int variant, int32_t* out, int32_t cap) {
   if (!d || !out || op < NPML_OP_CONV_FPROP || op > NPML_OP_DECONV_DGRAD) return -1;
   const GatherConv g = make_gather(d, op);
-  return variant == 2 ? ws2_plan_debug(g, d->mode, out, cap) : ws_plan_debug(g, d->mode, out, cap);
+  NPML_CHECK(variant == 1, "only variant 1 exists");
+  return ws_plan_debug(g, d->mode, out, cap);
 }
 
 const char* npml_last_error(void) { return g_err.c_str(); }

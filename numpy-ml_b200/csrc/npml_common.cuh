@@ -50,6 +50,12 @@ inline int num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
+  // test hook: NPML_MAX_CTAS caps every persistent grid, so that a miniature problem walks a CTA through many work
+  // units (ring wrap-arounds, phase flips, the partial last unit) -- tests/test_gpu_parity.py, steady-state cases
+  if (const char* e = getenv("NPML_MAX_CTAS")) {
+    const int cap = atoi(e);
+    if (cap > 0 && cap < n) return cap;
+  }
   return n;
 }
 
@@ -205,13 +211,7 @@ bool ws_conv_supported(const GatherConv& g, int mode);
 size_t ws_conv_ws_bytes(const GatherConv& g, int mode);
 int ws_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
                    void* ws, size_t ws_bytes, cudaStream_t st);
-// experimental NPML_WS=2 variant of the above (row-aligned tiles, TMA-store epilogue), tc_ws2_conv.cu
-bool ws2_conv_supported(const GatherConv& g, int mode);
-size_t ws2_conv_ws_bytes(const GatherConv& g, int mode);
-int ws2_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
-                    void* ws, size_t ws_bytes, cudaStream_t st);
 int ws_plan_debug(const GatherConv& g, int mode, int32_t* out, int32_t cap);      // host-only test hooks
-int ws2_plan_debug(const GatherConv& g, int mode, int32_t* out, int32_t cap);
 // row-of-taps variant for narrow outputs (fc * out_ch <= 256), tc_slab3_conv.cu; slab_gather_conv dispatches to it
 bool slab3_conv_supported(const GatherConv& g, int mode);
 int slab3_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,

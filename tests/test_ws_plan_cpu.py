@@ -29,13 +29,6 @@ def test_ws_decomposition_matches_oracle(case):
     E.check(xs, oc, ks, pad, d, np.random.default_rng(case))
 
 
-@pytest.mark.parametrize("rows", [1, 2, 3])
-def test_ws_row_aligned_tiles(rows):
-    """The tiling of the experimental NPML_WS=2 variant (csrc/tc_ws2_conv.cu): NT = rows * Wp, not a multiple of 32."""
-    E.check((2, 7, 6, 8), 16, (3, 3), "same", 0, np.random.default_rng(40 + rows), rows_per_tile=rows)
-    E.check((2, 6, 6, 8), 72, (3, 3), 1, 0, np.random.default_rng(50 + rows), rows_per_tile=rows)
-
-
 def test_pairs_are_at_even_slot_distance():
     """tcgen05.ld.16x256b needs an even column offset (scripts/ts_probe2.cu): delta = D or 2D, never odd, at most 8."""
     for D in (1, 2, 3, 4):
@@ -116,24 +109,3 @@ def test_cpp_planner_matches_numpy_mirror(monkeypatch, shape, op):
     assert tiles * NT >= N * Hp * Wp
     halo = max(g[0] for g in groups)
     assert SR * Wp >= (Wp - 1) + UT * NT + (NC - NT) + halo       # the slab holds every slot a unit's MMAs read
-
-
-@pytest.mark.parametrize("shape", [0, 1])
-def test_cpp_planner_row_tiles_variant(monkeypatch, shape):
-    """tc_ws2_conv.cu (NPML_WS=2, not yet run on a GPU): tiles are whole padded rows; same taps as variant 1."""
-    from conftest import npml
-    pkg = npml()
-    N, H, W, C, K, ks, pad, dil = PLAN_SHAPES[shape]
-    v1, _, _, _ = _cpp_plan(pkg, monkeypatch, 1, N, H, W, C, K, ks, pad, dil, 0)
-    v2, _, _, _ = _cpp_plan(pkg, monkeypatch, 2, N, H, W, C, K, ks, pad, dil, 0)
-    assert v2[0] == 1
-    sup, pair, delta, NT, NC, n_acc, UT, SR, Hp, Wp, pady, padx, ngroups, wcols, tiles, smem = v2[:16]
-    assert v2[16:] == v1[16:] and (Hp, Wp, pady, padx, pair, delta) == tuple(v1[i] for i in (8, 9, 10, 11, 1, 2))
-    assert NT % Wp == 0 and NT <= 128                         # whole rows
-    rows = NT // Wp
-    assert tiles * rows >= N * Hp
-    assert NC % 8 == 0 and NC >= NT + (delta if pair else 0) and NC <= 256
-    stride = (NT + 31) // 32 * 32 + (8 if pair else 0)        # TMEM columns between accumulators
-    assert wcols + n_acc * stride <= 512 and n_acc >= 2 and 1 <= UT <= n_acc
-    halo = max(v2[16 + 3 * i] for i in range(ngroups))
-    assert SR * Wp >= (UT - 1) * NT + NC + halo and smem <= 227 * 1024
