@@ -200,6 +200,12 @@ enum { NPML_OPT_SGD = 0, NPML_OPT_ADAGRAD = 1, NPML_OPT_RMSPROP = 2, NPML_OPT_AD
 int npml_optimizer_update(int32_t kind, float* param, const float* grad, float* state0, float* state1, int64_t n,
                           double lr, double a, double b, double eps, double c1, double c2, double grad_scale,
                           void* stream);
+/* The same step with the clip-norm factor formed ON THE DEVICE: grad_sumsq points at ||grad||^2 (double, device, from
+ * npml_sumsq_f32 on the same stream); g' = grad * (clip_norm / ||grad|| if ||grad|| > clip_norm else 1)
+ * (optimizers/optimizers.py:136-139, 246-249, 348-351, 457-460).  No host read-back, so update() never synchronises. */
+int npml_optimizer_update_clipped(int32_t kind, float* param, const float* grad, float* state0, float* state1, int64_t n,
+                                  double lr, double a, double b, double eps, double c1, double c2,
+                                  const double* grad_sumsq, double clip_norm, void* stream);
 /* sum of squares of an fp32 buffer into *out (double, device); deterministic two-stage reduction */
 int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream);
 

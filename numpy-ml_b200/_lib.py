@@ -57,6 +57,7 @@ SIGNATURES = {
     "npml_bn2d_bwd_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
     "npml_sgd_update": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P]),
     "npml_optimizer_update": (C.c_int, [_I32, _P, _P, _P, _P, _I64] + [C.c_double] * 7 + [_P]),
+    "npml_optimizer_update_clipped": (C.c_int, [_I32, _P, _P, _P, _P, _I64] + [C.c_double] * 6 + [_P, C.c_double, _P]),
     "npml_sumsq_f32": (C.c_int, [_P, _I64, _P, _P, _SZ, _P]),
     "npml_pool2d_fwd": (C.c_int, [_DESC, _I32, _P, _P, _I32, _P]),
     "npml_pool2d_bwd": (C.c_int, [_DESC, _I32, _P, _P, _P, _I32, _P]),

@@ -665,8 +665,17 @@ inline int flat_blocks(int64_t n_vec) {
   return (int)b;
 }
 
+// clip-norm factor formed on the device (no host read-back of ||g||): t / ||g|| if ||g|| > t else 1
+// (optimizers/optimizers.py:136-139), ||g||^2 from npml_sumsq_f32
+__device__ __forceinline__ float clip_scale(const double* __restrict__ sumsq, float clip, float gscale) {
+  if (sumsq == nullptr) return gscale;
+  const double nrm = sqrt(*sumsq);
+  return nrm > (double)clip ? (float)((double)clip / nrm) : 1.f;
+}
+
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ v, int64_t n, float lr,
-                           float momentum, float gscale) {
+                           float momentum, float gscale, const double* __restrict__ sumsq = nullptr, float clip = 0.f) {
+  gscale = clip_scale(sumsq, clip, gscale);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float u = momentum * v[i] + lr * (g[i] * gscale);
     v[i] = u;
@@ -679,7 +688,9 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 template <int KIND>
 __global__ void adaptive_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ s0,
                                     float* __restrict__ s1, int64_t n, float lr, float a, float oma, float b, float omb,
-                                    float eps, float c1, float c2, float gscale) {
+                                    float eps, float c1, float c2, float gscale,
+                                    const double* __restrict__ sumsq = nullptr, float clip = 0.f) {
+  gscale = clip_scale(sumsq, clip, gscale);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     if (KIND == 1) {                       // cache += g^2 ; p -= lr * g / (sqrt(cache) + eps)
@@ -1057,37 +1068,50 @@ extern "C" int npml_sgd_update(float* param, const float* grad, float* velocity,
 }
 
 // hyper-parameters arrive as doubles so that 1 - decay is formed in double (1 - 0.999f is off by 5e-5 in fp32)
-extern "C" int npml_optimizer_update(int32_t kind, float* param, const float* grad, float* state0, float* state1,
-                                     int64_t n, double lr_d, double a_d, double b_d, double eps_d, double c1_d,
-                                     double c2_d, double grad_scale_d, void* stream) {
+static int optimizer_update(int32_t kind, float* param, const float* grad, float* state0, float* state1, int64_t n,
+                            double lr_d, double a_d, double b_d, double eps_d, double c1_d, double c2_d,
+                            double grad_scale_d, const double* sumsq, double clip_d, void* stream) {
   const float lr = (float)lr_d, a = (float)a_d, b = (float)b_d, eps = (float)eps_d, c1 = (float)c1_d, c2 = (float)c2_d;
-  const float oma = (float)(1.0 - a_d), omb = (float)(1.0 - b_d), grad_scale = (float)grad_scale_d;
+  const float oma = (float)(1.0 - a_d), omb = (float)(1.0 - b_d), grad_scale = (float)grad_scale_d, clip = (float)clip_d;
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) return 0;
   NPML_CHECK(param && grad && state0, "NULL buffer");
   const int blocks = flat_blocks(n);
   switch (kind) {
     case NPML_OPT_SGD:
-      sgd_kernel<<<blocks, 256, 0, st>>>(param, grad, state0, n, lr, a, grad_scale);
+      sgd_kernel<<<blocks, 256, 0, st>>>(param, grad, state0, n, lr, a, grad_scale, sumsq, clip);
       break;
     case NPML_OPT_ADAGRAD:
       adaptive_opt_kernel<1><<<blocks, 256, 0, st>>>(param, grad, state0, state1, n, lr, a, oma, b, omb, eps, c1, c2,
-                                                      grad_scale);
+                                                      grad_scale, sumsq, clip);
       break;
     case NPML_OPT_RMSPROP:
       adaptive_opt_kernel<2><<<blocks, 256, 0, st>>>(param, grad, state0, state1, n, lr, a, oma, b, omb, eps, c1, c2,
-                                                      grad_scale);
+                                                      grad_scale, sumsq, clip);
       break;
     case NPML_OPT_ADAM:
       NPML_CHECK(state1 != nullptr, "Adam needs two state buffers");
       adaptive_opt_kernel<3><<<blocks, 256, 0, st>>>(param, grad, state0, state1, n, lr, a, oma, b, omb, eps, c1, c2,
-                                                      grad_scale);
+                                                      grad_scale, sumsq, clip);
       break;
     default:
       NPML_CHECK(false, "unknown optimizer kind");
   }
   NPML_LAUNCH_OK();
   return 0;
+}
+
+extern "C" int npml_optimizer_update(int32_t kind, float* param, const float* grad, float* state0, float* state1,
+                                     int64_t n, double lr, double a, double b, double eps, double c1, double c2,
+                                     double grad_scale, void* stream) {
+  return optimizer_update(kind, param, grad, state0, state1, n, lr, a, b, eps, c1, c2, grad_scale, nullptr, 0.0, stream);
+}
+
+extern "C" int npml_optimizer_update_clipped(int32_t kind, float* param, const float* grad, float* state0, float* state1,
+                                             int64_t n, double lr, double a, double b, double eps, double c1, double c2,
+                                             const double* grad_sumsq, double clip_norm, void* stream) {
+  NPML_CHECK(grad_sumsq != nullptr && clip_norm > 0.0, "clip-norm needs ||g||^2 on the device and a positive threshold");
+  return optimizer_update(kind, param, grad, state0, state1, n, lr, a, b, eps, c1, c2, 1.0, grad_sumsq, clip_norm, stream);
 }
 
 extern "C" int npml_sumsq_f32(const float* buf, int64_t n, double* out, void* ws, size_t ws_bytes, void* stream) {

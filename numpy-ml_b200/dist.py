@@ -55,12 +55,34 @@ def rank():
     return _state["rank"]
 
 
-def shard_batch(n_ex, world=None, r=None):
-    """Contiguous [start, stop) slice of the batch axis owned by rank `r`."""
+def shard_batch(n_ex, world=None, r=None, even=False):
+    """Contiguous [start, stop) slice of the batch axis owned by rank `r`.  `even=True` (what sync-BN needs: it
+    forms the global row count as rows * world) raises unless every rank gets the same number of examples."""
     world = _state["world"] if world is None else world
     r = _state["rank"] if r is None else r
+    if even and n_ex % world != 0:
+        raise ValueError("batch of {} examples does not split evenly over {} ranks".format(n_ex, world))
     per = (n_ex + world - 1) // world
     return min(r * per, n_ex), min((r + 1) * per, n_ex)
+
+
+_equal_rows_checked = set()
+
+
+def require_equal_shards(rows):
+    """Sync-BN normalises with `rows * world` as the global count, so every rank must hold the same number of rows
+    (an empty or ragged shard would silently skew mean / variance / dX, and an empty one deadlocks the collective).
+    Checked with one host-side exchange the first time a row count is seen, never again for that count (so a
+    captured CUDA graph replays without it)."""
+    if _state["world"] == 1 or rows in _equal_rows_checked:
+        return
+    import torch.distributed as dist
+    t = torch.tensor([rows, -rows], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if int(t[0]) != -int(t[1]):
+        raise ValueError("sync BatchNorm2D needs equal shards on every rank: this rank has {} rows, the job has "
+                         "between {} and {}".format(rows, -int(t[1]), int(t[0])))
+    _equal_rows_checked.add(rows)
 
 
 class GradBucket(object):
@@ -95,7 +117,7 @@ class GradBucket(object):
         for l in self.layers:
             l._bucket = self
         self.overlap = bool(overlap) and _state["world"] > 1 and self.flat.is_cuda
-        self._done = set()
+        self._done, self._dirty = set(), set()
         self._side = torch.cuda.Stream() if self.overlap else None
         if self.overlap:
             for l in self.layers:
@@ -124,6 +146,11 @@ class GradBucket(object):
 
     def _on_ready(self, layer):
         """dW / db of `layer` are enqueued on the current stream: reduce that slice on the side stream."""
+        if id(layer) in self._done or len(layer.X) > 1:
+            # a second backward into the same slice (list-valued backward, index=): an early reduce would mix reduced
+            # and local contributions -- leave this layer to the deferred reduce in allreduce()
+            self._dirty.add(id(layer))
+            return
         off, n = self.slices[id(layer)]
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
@@ -137,13 +164,18 @@ class GradBucket(object):
         if not self.overlap:
             self._reduce(0, self.flat.numel())
             return self.flat
+        both = self._done & self._dirty
+        if both:
+            raise RuntimeError("GradBucket(overlap=True): a layer's gradients were reduced early and then accumulated "
+                               "into again in the same step; use overlap=False when one step runs several backward "
+                               "calls per layer")
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             for l in self.layers:
                 if id(l) not in self._done:
                     self._reduce(*self.slices[id(l)])
         torch.cuda.current_stream().wait_stream(self._side)
-        self._done = set()
+        self._done, self._dirty = set(), set()
         return self.flat
 
 

@@ -171,6 +171,14 @@ def _dz_prep(dY, Z, act, out_dtype, db=None, accumulate=True):
     return dZ
 
 
+def _same_shapes(Xs, who):
+    """The element-wise kernels index every input with the first one's element count: unequal shapes would read out
+    of bounds (the reference's `out += X[i]` raises or broadcasts)."""
+    for i, x in enumerate(Xs[1:], 1):
+        if tuple(x.shape) != tuple(Xs[0].shape):
+            raise ValueError("{}: input {} has shape {}, expected {}".format(who, i, tuple(x.shape), tuple(Xs[0].shape)))
+
+
 class _ConvBase(LayerBase):
     """State handling shared by Conv2D and Deconv2D (they differ only in geometry and entry points)."""
     _layer_name = None
@@ -320,6 +328,25 @@ class Conv2D(_ConvBase):
         p4 = U.resolve_pad_2D(X_shape, self.pad, (fr, fc), self.stride, self.dilation)
         oh, ow = U.conv_out_hw(X_shape[1], X_shape[2], fr, fc, p4, self.stride, self.dilation)
         return p4, oh, ow, self.dilation + 1
+
+    def _backward_naive(self, dLdy, retain_grads=True):
+        """The reference keeps a second, loop-form definition of the backward pass next to the vectorised one
+        (layers.py:3118-3178) as an in-repo cross-check.  Its counterpart here: the same gradients from the fp32
+        CUDA-core gather kernels (direct_fp32.cu -- one thread per output element, plain loops over taps and
+        channels, no tensor cores, no TMA), whatever `mode` the layer runs in.  Same contract as `backward`."""
+        assert self.trainable, "Layer is frozen"
+        if not isinstance(dLdy, list):
+            dLdy = [dLdy]
+        mode, self.mode = self.mode, "fp32"
+        try:
+            dXs = []
+            for dy, x, z in zip(dLdy, self.X, self.derived_variables["Z"]):
+                as_np = isinstance(dy, np.ndarray)
+                dx = self._bwd(L.to_device(dy, torch.float32), x.float(), z.float(), retain_grads)
+                dXs.append(L.to_numpy(dx) if as_np else dx.to(x.dtype))
+        finally:
+            self.mode = mode
+        return dXs[0] if len(self.X) == 1 else dXs
 
 
 class Deconv2D(_ConvBase):
@@ -607,6 +634,7 @@ class BatchNorm2D(LayerBase):
         if use_batch and self.sync:
             from . import dist as D
             lib = L.load()
+            D.require_equal_shards(rows)       # total = rows * world below; raises on ragged / empty shards
             sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
             with L.profiled("npml_bn2d_fwd"):
                 L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(),
@@ -712,6 +740,7 @@ class Add(LayerBase):
         first = X[0]
         dt = torch.float32 if (as_np or first.dtype == torch.float64) else first.dtype
         Xd = [L.to_device(x, dt) for x in X]
+        _same_shapes(Xd, "Add")
         n = Xd[0].numel()
         total = torch.empty_like(Xd[0])
         Y = total if self.act_fn.code == 0 else torch.empty_like(total)
@@ -736,8 +765,14 @@ class Add(LayerBase):
         return grads[0] if len(self.X) == 1 else grads
 
     def _bwd(self, dLdY, X, _sum):
+        """Every input receives dLdY * act'(sum) (layers.py:739-742).  The reference returns one NEW array per input;
+        so does this layer (a caller's in-place `dX +=` must not reach the sibling gradients or its own dLdY), unless
+        the owner promises to only read them (`_share_grads`, set by the skip-connection modules)."""
         g = _dz_prep(dLdY, _sum, self.act_fn, _sum.dtype)
-        return [g for _ in X]
+        if getattr(self, "_share_grads", False):
+            return [g for _ in X]
+        first = g.clone() if g is dLdY else g
+        return [first] + [g.clone() for _ in X[1:]]
 
 
 class Multiply(LayerBase):
@@ -762,6 +797,7 @@ class Multiply(LayerBase):
         first = X[0]
         dt = torch.float32 if (as_np or first.dtype == torch.float64) else first.dtype
         Xd = [L.to_device(x, dt) for x in X]
+        _same_shapes(Xd, "Multiply")
         prod = torch.empty_like(Xd[0])
         Y = prod if self.act_fn.code == 0 else torch.empty_like(prod)
         arr = (C.c_void_p * len(Xd))(*[x.data_ptr() for x in Xd])

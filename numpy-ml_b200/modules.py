@@ -132,6 +132,7 @@ class SkipConnectionConvModule(ModuleBase):
         self.batchnorm2 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
         self.batchnorm_skip = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
         self.add3 = Add(self.act_fn)
+        self.add3._share_grads = True       # the module only reads the branch gradients (no in-place update)
 
     def _calc_skip_padding(self, X_shape):
         """Padding of the skip conv so that it matches conv2's output dims (modules.py:755-788).
@@ -267,6 +268,7 @@ class SkipConnectionIdentityModule(ModuleBase):
         self.batchnorm1 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
         self.batchnorm2 = BatchNorm2D(epsilon=self.epsilon, momentum=self.momentum, sync=self.sync_bn)
         self.add3 = Add(self.act_fn)
+        self.add3._share_grads = True       # the module only reads the branch gradients (no in-place update)
 
     def _init_conv2(self):
         self.conv2 = Conv2D(pad="same", init=self.init, out_ch=self.in_ch, stride=self.stride2,

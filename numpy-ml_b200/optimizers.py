@@ -50,25 +50,25 @@ class OptimizerBase(object):
                 self.cache[k] = v
 
     # ---- shared by the concrete optimizers -------------------------------------------------------------
-    def _grad_scale(self, grad):
-        """clip-norm factor t / ||g|| if ||g|| > t else 1 (the same lines in every reference update)."""
-        t = self.hyperparameters["clip_norm"]
-        if t is None:
-            return 1.0
-        out = torch.empty(1, dtype=torch.float64, device=grad.device)
-        ws = L.workspace(1 << 20)
-        L.check(L.load().npml_sumsq_f32(L.ptr(grad), grad.numel(), L.ptr(out), L.ptr(ws), ws.numel(), L.stream()),
-                "npml_sumsq_f32")
-        nrm = math.sqrt(float(out.item()))
-        return t / nrm if nrm > t else 1.0
-
     def _launch(self, param, grad, s0, s1, lr, a=0.0, b=0.0, eps=0.0, c1=1.0, c2=1.0):
+        """One elementwise kernel.  With clip_norm set, ||grad||^2 is reduced on the device and the factor
+        t / ||g|| (if ||g|| > t, optimizers.py:136-139) is formed inside the update kernel: no host read-back."""
         if param.dtype != torch.float32 or grad.dtype != torch.float32 or not param.is_cuda:
             raise TypeError("optimizers update fp32 device tensors in place")
-        L.check(L.load().npml_optimizer_update(KIND[self._id], L.ptr(param), L.ptr(grad), L.ptr(s0), L.ptr(s1),
-                                               param.numel(), float(lr), float(a), float(b), float(eps), float(c1),
-                                               float(c2), float(self._grad_scale(grad)), L.stream()),
-                "npml_optimizer_update")
+        lib, t = L.load(), self.hyperparameters["clip_norm"]
+        if t is None:
+            L.check(lib.npml_optimizer_update(KIND[self._id], L.ptr(param), L.ptr(grad), L.ptr(s0), L.ptr(s1),
+                                              param.numel(), float(lr), float(a), float(b), float(eps), float(c1),
+                                              float(c2), 1.0, L.stream()), "npml_optimizer_update")
+            return param
+        ssq = torch.empty(1, dtype=torch.float64, device=grad.device)
+        ws = L.workspace(1 << 20)
+        L.check(lib.npml_sumsq_f32(L.ptr(grad), grad.numel(), L.ptr(ssq), L.ptr(ws), ws.numel(), L.stream()),
+                "npml_sumsq_f32")
+        L.check(lib.npml_optimizer_update_clipped(KIND[self._id], L.ptr(param), L.ptr(grad), L.ptr(s0), L.ptr(s1),
+                                                  param.numel(), float(lr), float(a), float(b), float(eps), float(c1),
+                                                  float(c2), L.ptr(ssq), float(t), L.stream()),
+                "npml_optimizer_update_clipped")
         return param
 
 

@@ -132,14 +132,29 @@ def deconv2d_layer_bwd(dLdY, X, Z, W, stride, pad, act="identity", p0=0.0, p1=0.
     return dX, dW, db
 
 
-def skip_conv_module_fwd_bwd(X, dLdY, P, k1, k2, k_skip, pad1, pad2, s1=1, s2=1, s_skip=1,
-                             act="identity", p0=0.0, p1=0.0, momentum=0.9, epsilon=1e-5):
-    """SkipConnectionConvModule forward + backward (modules/modules.py:905-984): conv_oracle's wiring with the
-    tap-wise convolutions above."""
-    saved = O.conv2d_layer_fwd, O.conv2d_layer_bwd
-    O.conv2d_layer_fwd, O.conv2d_layer_bwd = conv2d_layer_fwd, conv2d_layer_bwd
-    try:
-        return O.skip_conv_module_fwd_bwd(X, dLdY, P, k1, k2, k_skip, pad1, pad2, s1, s2, s_skip, act, p0, p1,
-                                          momentum, epsilon)
-    finally:
-        O.conv2d_layer_fwd, O.conv2d_layer_bwd = saved
+class _tapwise(object):
+    """conv_oracle's module wiring with the tap-wise convolutions above (swapped in for the duration of a call)."""
+
+    def __enter__(self):
+        self.saved = O.conv2d_layer_fwd, O.conv2d_layer_bwd
+        O.conv2d_layer_fwd, O.conv2d_layer_bwd = conv2d_layer_fwd, conv2d_layer_bwd
+
+    def __exit__(self, *exc):
+        O.conv2d_layer_fwd, O.conv2d_layer_bwd = self.saved
+
+
+def skip_conv_module_fwd(*args, **kw):
+    """SkipConnectionConvModule forward (modules/modules.py:905-937)."""
+    with _tapwise():
+        return O.skip_conv_module_fwd(*args, **kw)
+
+
+def skip_conv_module_bwd(*args, **kw):
+    """SkipConnectionConvModule backward (modules/modules.py:939-984)."""
+    with _tapwise():
+        return O.skip_conv_module_bwd(*args, **kw)
+
+
+def skip_conv_module_fwd_bwd(*args, **kw):
+    with _tapwise():
+        return O.skip_conv_module_fwd_bwd(*args, **kw)
