@@ -2,19 +2,26 @@
 """Headline benchmark of the numpy-ml convolution hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--mode bf16] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = Conv2D.forward + Conv2D.backward (dX, dW, db) over one batch of synthetic input
-(SURVEY.md 8d); under N > 1 every rank owns one batch shard (weak scaling: 256 images per GPU for cfg2)
-and the step ends with ONE all-reduce (SUM) of the flat dW||db bucket.  Rank 0 prints one JSON line.
+One "step" = forward + backward (dX, dW, db) of the config's layer over one batch of synthetic input.
+Under N > 1 every rank owns one batch shard and the step ends with the all-reduce (SUM) of the flat dW||db bucket.
+Rank 0 prints ONE JSON line: the headline config (cfg2 unless --config says otherwise) at the top level and, under
+"configs", the same measurements for every BASELINE.json config (cfg1..cfg5).
 
-  value          images/s, whole job, inputs resident in HBM in the mode's storage dtype
-  e2e            the same step through the public layer API with HOST (pinned) buffers: X and dLdy are
-                 copied host->device and Y, dX, dW, db device->host inside the timed region
-  roofline       the dominant kernel (largest share of the step), timed live with CUDA events on the
-                 launching stream inside the timed region
-  cpu_baseline   the CPU oracle (a restatement of the reference's im2col + GEMM + np.add.at algorithm,
-                 oracle/conv_oracle.py) timed on this box's host cores on a bounded sample
-  --impl reference  times that CPU path alone (the reference is pure Python/NumPy)
+  value          images/s, whole job, inputs resident in HBM in the mode's storage dtype (CUDA-graph replays of the
+                 step captured through the public layer API)
+  scaling        "weak": per-GPU batch fixed (the headline).  "strong" (sub-object, N > 1): the config's batch split
+                 N/g per GPU as SURVEY.md 8e words it
+  roofline       the dominant call (largest share of the step): median of >= 30 synchronised replays, timed with CUDA
+                 events recorded on the launching stream inside the captured step
+  e2e            the same step through numpy-ml_b200/pipeline.py:HostPipeline with PINNED HOST buffers: host->device
+                 copies of X and dLdy and device->host copies of Y, dX, dW||db inside the timed region
+  e2e_dropin     the plain reference call pair: float64 NumPy in, float64 NumPy out (pageable memory)
+  cpu_baseline   the UNMODIFIED reference (baseline/_ref, staged by baseline/stage_ref.sh) timed on this box's host
+                 cores on a bounded sample; the oracle port only when the reference copy is absent
+  dp_parity      (N > 1) all-reduced dW||db of the sharded step against rank 0 running the GLOBAL batch alone
+  --impl reference  times that CPU path alone, on the same config dict
 """
 import argparse
 import importlib
@@ -44,6 +51,7 @@ CONFIGS = {
     "cfg5": dict(kind="deconv", N=128, H=16, W=16, C=256, K=128, k=(4, 4), pad=1, stride=2, dilation=0,
                  name="Deconv2D 4x4 s2 pad1, N=128, 16x16x256->128"),
 }
+L2_BYTES = 126e6
 
 
 def peaks():
@@ -55,19 +63,40 @@ def peaks():
             p["source"] = "measured"
         except Exception:
             pass
+    # TF32 dense peak measured the same way (scripts/measure_tf32_peak.py -> profiles/tf32_peak.json)
+    f = os.path.join(ROOT, "profiles", "tf32_peak.json")
+    p["tf32_tflops_sustained"], p["tf32_source"] = p["bf16_tflops_sustained"] / 2.0, "assumed bf16 sustained / 2"
+    if os.path.exists(f):
+        try:
+            t = json.load(open(f))
+            p["tf32_tflops_sustained"], p["tf32_source"] = float(t["tf32_tflops_sustained"]), "measured (profiles/tf32_peak.json)"
+        except Exception:
+            pass
     return p
 
 
-def out_hw(cfg):
-    pkg_u = importlib.import_module("numpy-ml_b200").utils
-    if cfg["kind"] == "skip":
-        return cfg["H"], cfg["W"]
-    if cfg["kind"] == "conv":
-        p4 = pkg_u.resolve_pad_2D((cfg["N"], cfg["H"], cfg["W"], cfg["C"]), cfg["pad"], cfg["k"], cfg["stride"],
-                                  cfg["dilation"])
-        return pkg_u.conv_out_hw(cfg["H"], cfg["W"], cfg["k"][0], cfg["k"][1], p4, cfg["stride"], cfg["dilation"])
-    _, oh, ow = pkg_u.deconv_geometry(cfg["H"], cfg["W"], cfg["k"][0], cfg["k"][1], cfg["pad"], cfg["stride"])
-    return oh, ow
+def _geom():
+    """Geometry helpers restated here so that the reference arm never imports the product package."""
+    def eff(k, d):
+        return k * (d + 1) - d
+
+    def out_hw(cfg):
+        if cfg["kind"] == "skip":
+            return cfg["H"], cfg["W"]
+        fr, fc = cfg["k"]
+        if cfg["kind"] == "deconv":
+            s, p = cfg["stride"], cfg["pad"]
+            return s * (cfg["H"] - 1) + fr - 2 * p, s * (cfg["W"] - 1) + fc - 2 * p
+        if cfg["pad"] == "same":
+            if cfg["stride"] == 1:
+                return cfg["H"], cfg["W"]
+            raise ValueError("'same' with stride > 1 is not a bench config")
+        p, s, d = cfg["pad"], cfg["stride"], cfg["dilation"]
+        return (cfg["H"] + 2 * p - eff(fr, d)) // s + 1, (cfg["W"] + 2 * p - eff(fc, d)) // s + 1
+    return out_hw
+
+
+out_hw = _geom()
 
 
 def flops_per_pass(cfg, n):
@@ -89,51 +118,17 @@ def min_bytes_per_pass(cfg, n, esize):
     return float(x + y + w)
 
 
-# ---------------------------------------------------------------------------------------------------
-#  CPU arm: the oracle port of the reference algorithm
-# ---------------------------------------------------------------------------------------------------
-def make_inputs(cfg, n, seed):
-    rng = np.random.default_rng(seed)
+def config_dict(cfg, mode, world, n):
+    """The `config` object of the JSON line; identical for both arms (nothing in it depends on the implementation)."""
+    esize = 2 if mode == "bf16" else 4
     oh, ow = out_hw(cfg)
-    X = rng.standard_normal((n, cfg["H"], cfg["W"], cfg["C"]), dtype=np.float32)
-    dY = rng.standard_normal((n, oh, ow, cfg["K"]), dtype=np.float32)
-    from oracle import conv_oracle as O
-    if cfg["kind"] == "skip":
-        return X, dY, skip_params(cfg, seed), None
-    np.random.seed(seed)
-    W = O.glorot_uniform(cfg["k"] + (cfg["C"], cfg["K"])).astype(np.float32)
-    b = (0.1 * rng.standard_normal((1, 1, 1, cfg["K"]))).astype(np.float32)
-    return X, dY, W, b
-
-
-def skip_params(cfg, seed):
-    """Parameters of the cfg4 module (same on every rank): glorot conv weights, small biases, BN affine."""
-    from oracle import conv_oracle as O
-    rng = np.random.default_rng(seed)
-    np.random.seed(seed)
-    C, K = cfg["C"], cfg["K"]
-    P = {}
-    for t, shape in (("1", (3, 3, C, K)), ("2", (3, 3, K, K)), ("s", (1, 1, C, K))):
-        P["W" + t] = O.glorot_uniform(shape).astype(np.float32).astype(np.float64)
-        P["b" + t] = (0.1 * rng.standard_normal((1, 1, 1, K))).astype(np.float32).astype(np.float64)
-        P["g" + t] = rng.uniform(0.5, 1.5, K).astype(np.float32).astype(np.float64)
-        P["h" + t] = (0.1 * rng.standard_normal(K)).astype(np.float32).astype(np.float64)
-        P["rm" + t], P["rv" + t] = np.zeros(K), np.ones(K)
-    return P
-
-
-def cpu_step(cfg, X, dY, W, b):
-    """forward + backward of the reference algorithm in float64 (oracle port)."""
-    from oracle import conv_oracle as O
-    if cfg["kind"] == "skip":
-        return O.skip_conv_module_fwd_bwd(X.astype(np.float64), dY.astype(np.float64), W, (3, 3), (3, 3), (1, 1), 1, 1,
-                                          1, 1, 1, "relu")
-    X, dY, W, b = (a.astype(np.float64) for a in (X, dY, W, b))
-    if cfg["kind"] == "conv":
-        Y, Z = O.conv2d_layer_fwd(X, W, b, cfg["stride"], cfg["pad"], cfg["dilation"])
-        return O.conv2d_layer_bwd(dY, X, Z, W, cfg["stride"], cfg["pad"], cfg["dilation"])
-    Y, Z = O.deconv2d_layer_fwd(X, W, b, cfg["stride"], cfg["pad"])
-    return O.deconv2d_layer_bwd(dY, X, Z, W, cfg["stride"], cfg["pad"])
+    work = (n * cfg["H"] * cfg["W"] * cfg["C"] + n * oh * ow * cfg["K"]) * esize
+    if work >= L2_BYTES:
+        l2 = "inputs X + dLdy are {:.0f} MB per step (L2 is 126 MB); no explicit flush".format(work / 1e6)
+    else:
+        l2 = "inputs X + dLdy are {:.0f} MB per step (< 126 MB L2): a 256 MB buffer is written between timed steps".format(work / 1e6)
+    return {"workload": cfg["name"], "mode": mode, "per_gpu_batch": n, "global_batch": n * world,
+            "parallelism": "dp{}".format(world) + ("+syncbn" if (cfg["kind"] == "skip" and world > 1) else ""), "l2": l2}
 
 
 def host_threads():
@@ -143,41 +138,98 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def time_cpu(cfg, n_sample, reps, warmup, seed):
-    X, dY, W, b = make_inputs(cfg, n_sample, seed)
-    for _ in range(warmup):
-        cpu_step(cfg, X, dY, W, b)
-    ts = []
-    for _ in range(reps):
+# ---------------------------------------------------------------------------------------------------
+#  CPU arm: the unmodified reference (baseline/_ref) on this box's host cores; oracle port as the labelled fallback
+# ---------------------------------------------------------------------------------------------------
+class CpuArm(object):
+    def __init__(self, cfg, seed):
+        from baseline import reference_arm as R
+        self.cfg, self.seed = cfg, seed
+        self.threads = host_threads()
+        try:       # torchrun exports OMP_NUM_THREADS=1: give the BLAS the same cores at every --gpus N
+            from threadpoolctl import threadpool_limits
+            self._limit = threadpool_limits(limits=self.threads)
+        except Exception:
+            self._limit = None
+        if R.available():
+            self.kind, self.R = "reference", R
+            self.ref = R.load()
+            self.obj = R.build(self.ref, cfg, seed)
+            self.what = "unmodified numpy-ml {} forward+backward, float64".format(
+                {"conv": "Conv2D", "deconv": "Deconv2D", "skip": "SkipConnectionConvModule"}[cfg["kind"]])
+        else:
+            self.kind = "port"
+            self.what = "float64 oracle port of im2col+GEMM+np.add.at (baseline/_ref not staged)"
+
+    def inputs(self, n):
+        rng = np.random.default_rng(self.seed)
+        oh, ow = out_hw(self.cfg)
+        X = rng.standard_normal((n, self.cfg["H"], self.cfg["W"], self.cfg["C"]), dtype=np.float32).astype(np.float64)
+        dY = rng.standard_normal((n, oh, ow, self.cfg["K"]), dtype=np.float32).astype(np.float64)
+        return X, dY
+
+    def step(self, X, dY):
+        cfg = self.cfg
+        if self.kind == "reference":
+            return self.R.step(self.obj, X, dY)
+        from oracle import conv_oracle as O
+        if not hasattr(self, "_P"):
+            self._P = port_params(cfg, self.seed)
+        if cfg["kind"] == "skip":
+            return O.skip_conv_module_fwd_bwd(X, dY, self._P, (3, 3), (3, 3), (1, 1), 1, 1, 1, 1, 1, "relu")
+        W, b = self._P
+        if cfg["kind"] == "conv":
+            Y, Z = O.conv2d_layer_fwd(X, W, b, cfg["stride"], cfg["pad"], cfg["dilation"])
+            return O.conv2d_layer_bwd(dY, X, Z, W, cfg["stride"], cfg["pad"], cfg["dilation"])
+        Y, Z = O.deconv2d_layer_fwd(X, W, b, cfg["stride"], cfg["pad"])
+        return O.deconv2d_layer_bwd(dY, X, Z, W, cfg["stride"], cfg["pad"])
+
+    def time(self, budget_s, reps, warmup):
+        """images/s on a sample of the config's batch sized so that (reps + warmup) steps fit `budget_s`."""
+        n_full = self.cfg["N"]
+        probe = min(n_full, 2)
+        X, dY = self.inputs(probe)
+        self.step(X, dY)                                   # first call initialises the layer (lazy init)
         t0 = time.perf_counter()
-        cpu_step(cfg, X, dY, W, b)
-        ts.append(time.perf_counter() - t0)
-    return ts
+        self.step(X, dY)
+        rate = probe / max(time.perf_counter() - t0, 1e-6)
+        n = int(max(probe, min(n_full, rate * budget_s / max(reps + warmup, 1))))
+        X, dY = self.inputs(n)
+        for _ in range(warmup):
+            self.step(X, dY)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            self.step(X, dY)
+            ts.append(time.perf_counter() - t0)
+        sample = "{} of {} images per step, {}, {} host threads".format(n, n_full, self.what, self.threads)
+        return n, ts, sample
 
 
-def cpu_sample_size(cfg, budget_s, steps):
-    # survey-time throughput of the reference on 8 vCPU, images/s
-    rate = {"cfg1": 1250.0, "cfg2": 6.9, "cfg3": 110.0, "cfg4": 4.8, "cfg5": 2.75}[cfg["_id"]]
-    n = int(max(2, min(cfg["N"], budget_s * rate / max(steps, 1))))
-    return n
+def port_params(cfg, seed):
+    from oracle import conv_oracle as O
+    rng = np.random.default_rng(seed)
+    rs = np.random.RandomState(seed)
+    if cfg["kind"] == "skip":
+        return skip_params(cfg, seed)
+    W = O.glorot_uniform(cfg["k"] + (cfg["C"], cfg["K"]), rng=rs)
+    return W, 0.1 * rng.standard_normal((1, 1, 1, cfg["K"]))
 
 
 def run_reference(args, cfg):
-    """--impl reference: the reference's CPU implementation of the path on this box's host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    n = cpu_sample_size(cfg, 100.0, args.steps + args.warmup)
-    ts = time_cpu(cfg, n, args.steps, args.warmup, 1000 + int(cfg["_id"][3:]))
+    seed = 1000 + int(cfg["_id"][3:])
+    arm = CpuArm(cfg, seed)
+    n, ts, sample = arm.time(100.0, args.steps, args.warmup)
     total = sum(ts)
     value = n * len(ts) / total
-    sample = "{} of {} images per step, float64, oracle port of im2col+GEMM+np.add.at".format(n, cfg["N"])
+    cpu = {"value": value, "unit": "images/s", "cores": arm.threads, "kind": arm.kind, "sample": sample}
     line = {"impl": "reference", "metric": "Conv2D fwd+bwd images/s", "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": cfg["name"], "mode": "reference-cpu", "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": host_threads(), "kind": "port",
-                             "sample": sample},
+            "config": config_dict(cfg, args.mode, args.gpus, cfg["N"]), "cpu_baseline": cpu,
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -236,7 +288,9 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------------
 #  GPU arm
 # ---------------------------------------------------------------------------------------------------
-ELEMENTWISE = ("npml_bn2d_fwd", "npml_bn2d_bwd", "npml_add_act_fwd", "npml_dz_prep")
+# algorithmic HBM traffic of the element-wise entry points, in tensors of the layer's output size read + written once
+ELEMENTWISE_PASSES = {"npml_bn2d_fwd": 2, "npml_bn2d_apply": 2, "npml_bn2d_bwd": 3, "npml_add_act_fwd": 3, "npml_dz_prep": 3,
+                      "npml_bn2d_add_act_fwd": 3, "npml_bn2d_pair_bwd": 5, "npml_bn2d_bwd_act": 3}
 
 
 def measured_traffic(cfg_id, mode, kernel):
@@ -248,24 +302,32 @@ def measured_traffic(cfg_id, mode, kernel):
         return None
 
 
-def run_gpu(args, cfg):
-    import torch
-    pkg = importlib.import_module("numpy-ml_b200")
-    L, D = pkg._lib, pkg.dist
-    st = D.init()
-    world, rank = st["world"], st["rank"]
-    if world == 1:
-        torch.cuda.set_device(0)
-    dev = torch.device("cuda", torch.cuda.current_device())
-    mode = args.mode
-    n = cfg["N"]
-    kind = cfg["kind"]
-    seed = 1000 + int(cfg["_id"][3:])
-    X, dY, W, b = make_inputs(cfg, n, seed + 17 * rank)
-    _, _, W, b = make_inputs(cfg, 2, seed)          # identical parameters on every rank
-    act_dt = L.torch_dtype(mode)
-    esize = 2 if mode == "bf16" else 4
+def skip_params(cfg, seed):
+    """Parameters of the cfg4 module (same on every rank): glorot conv weights, small biases, BN affine."""
+    from oracle import conv_oracle as O
+    rng = np.random.default_rng(seed)
+    rs = np.random.RandomState(seed)
+    C, K = cfg["C"], cfg["K"]
+    P = {}
+    for t, shape in (("1", (3, 3, C, K)), ("2", (3, 3, K, K)), ("s", (1, 1, C, K))):
+        P["W" + t] = O.glorot_uniform(shape, rng=rs).astype(np.float32).astype(np.float64)
+        P["b" + t] = (0.1 * rng.standard_normal((1, 1, 1, K))).astype(np.float32).astype(np.float64)
+        P["g" + t] = rng.uniform(0.5, 1.5, K).astype(np.float32).astype(np.float64)
+        P["h" + t] = (0.1 * rng.standard_normal(K)).astype(np.float32).astype(np.float64)
+        P["rm" + t], P["rv" + t] = np.zeros(K), np.ones(K)
+    return P
 
+
+class Ctx(object):
+    pass
+
+
+def build_model(ctx, cfg, mode, sync_bn):
+    """The product object of a config with the benchmark's parameters (identical on every rank)."""
+    import torch
+    pkg, L = ctx.pkg, ctx.pkg._lib
+    seed = 1000 + int(cfg["_id"][3:])
+    kind = cfg["kind"]
     if kind == "conv":
         model = pkg.Conv2D(cfg["K"], cfg["k"], pad=cfg["pad"], stride=cfg["stride"], dilation=cfg["dilation"], mode=mode)
     elif kind == "deconv":
@@ -273,45 +335,43 @@ def run_gpu(args, cfg):
     else:
         model = pkg.SkipConnectionConvModule(out_ch1=cfg["K"], out_ch2=cfg["K"], kernel_shape1=(3, 3), kernel_shape2=(3, 3),
                                              kernel_shape_skip=(1, 1), pad1=1, pad2=1, act_fn="relu", mode=mode,
-                                             sync_bn=(world > 1))
-    Xh = torch.from_numpy(X).pin_memory()
-    dYh = torch.from_numpy(dY).pin_memory()
-    Xd = L.to_device(Xh.to(dev), act_dt)
-    dYd = L.to_device(dYh.to(dev), act_dt)
-    model.forward(Xd, retain_derived=False)
+                                             sync_bn=sync_bn)
+    probe = torch.zeros((2, cfg["H"], cfg["W"], cfg["C"]), dtype=L.torch_dtype(mode), device=ctx.dev)
+    model.forward(probe, retain_derived=False)
     if kind == "skip":
+        P = skip_params(cfg, seed)
         layers = [model.conv1, model.conv2, model.conv_skip, model.batchnorm1, model.batchnorm2, model.batchnorm_skip]
         for t, conv, bn in (("1", model.conv1, model.batchnorm1), ("2", model.conv2, model.batchnorm2),
                             ("s", model.conv_skip, model.batchnorm_skip)):
-            conv.parameters["W"], conv.parameters["b"] = (L.to_device(W["W" + t], torch.float32),
-                                                          L.to_device(W["b" + t], torch.float32))
-            bn.parameters["scaler"], bn.parameters["intercept"] = (L.to_device(W["g" + t], torch.float32),
-                                                                   L.to_device(W["h" + t], torch.float32))
-        conv_layers = layers[:3]
+            conv.parameters["W"], conv.parameters["b"] = (L.to_device(P["W" + t], torch.float32),
+                                                          L.to_device(P["b" + t], torch.float32))
+            bn.parameters["scaler"], bn.parameters["intercept"] = (L.to_device(P["g" + t], torch.float32),
+                                                                   L.to_device(P["h" + t], torch.float32))
+        convs = layers[:3]
     else:
-        layers = conv_layers = [model]
+        W, b = port_params(cfg, seed)
+        layers = convs = [model]
         model.parameters["W"], model.parameters["b"] = L.to_device(W, torch.float32), L.to_device(b, torch.float32)
-    # dW / db of a layer are all-reduced on a side stream while its dX is still being computed
-    bucket = D.GradBucket(layers, overlap=True)
+    return model, layers, convs
 
-    def step():
-        model.flush_gradients()
-        Y = model.forward(Xd)
-        dX = model.backward(dYd)
-        if world > 1:
-            bucket.allreduce()
-        return Y, dX
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
+def synth(ctx, cfg, n, rank):
+    """This rank's shard of the synthetic batch, generated on the device (any rank's shard can be re-created anywhere)."""
+    import torch
+    g = torch.Generator(device=ctx.dev)
+    g.manual_seed(1000 + int(cfg["_id"][3:]) + 17 * rank)
+    oh, ow = out_hw(cfg)
+    X = torch.randn((n, cfg["H"], cfg["W"], cfg["C"]), generator=g, device=ctx.dev, dtype=torch.float32)
+    dY = torch.randn((n, oh, ow, cfg["K"]), generator=g, device=ctx.dev, dtype=torch.float32)
+    return X, dY
 
-    # ---- CUDA graph of one step (launch-bound configs: the host needs ~0.18 ms to enqueue a step) -------------
-    # forward + backward (+ all-reduce) are captured ONCE through the public layer API; the timed region replays the
-    # graph.  The per-call CUDA events are captured as external event-record nodes, so the per-call durations are
-    # still measured inside the timed region (those of the last replay).
-    graph = None
-    if not args.no_graph:
+
+def timed_graph(ctx, step, steps, flush_l2):
+    """Capture `step` once, replay it `steps` times; returns (ms_total max over ranks, launches/step, profile, host ms)."""
+    import torch
+    L, D = ctx.pkg._lib, ctx.pkg.dist
+    graph, prof, launches = None, None, 0
+    if not ctx.args.no_graph:
         try:
             torch.cuda.synchronize()
             L.PROFILE, L.PROFILE_EXTERNAL = [], True
@@ -319,9 +379,9 @@ def run_gpu(args, cfg):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 step()
-            graph, graph_prof, graph_launches = g, L.PROFILE, L.launch_count()
-        except Exception as e:      # capture not possible (e.g. torch without external events): eager timed region
-            if rank == 0:
+            graph, prof, launches = g, L.PROFILE, L.launch_count()
+        except Exception as e:      # capture not possible: eager timed region
+            if ctx.rank == 0:
                 print("bench: CUDA graph capture failed ({}); timing eagerly".format(str(e).splitlines()[0]), file=sys.stderr)
             graph = None
             try:
@@ -329,23 +389,39 @@ def run_gpu(args, cfg):
             except Exception:
                 pass
         L.PROFILE, L.PROFILE_EXTERNAL = None, False
-        if graph is not None:
-            for _ in range(3):
-                graph.replay()
-            torch.cuda.synchronize()
 
-    # ---- timed region: K steps, CUDA events on the launching stream, per-call events inside ----------
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
-    # pre-roll: keep the GPU under the same load for ~0.4 s so that nvidia-smi (50 ms period) samples the clocks of
-    # a loaded device; these steps are extra warm-up, not part of the timed region.  The number of steps is derived
-    # from a max-over-ranks estimate so that every rank issues the same number of collectives.
     def one():
         if graph is not None:
             graph.replay()
         else:
             step()
 
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize()
+    # per-call durations: median over >= 30 synchronised replays (external events inside the captured step)
+    per_call = {}
+    if graph is not None:
+        for _ in range(max(30, ctx.args.kernel_reps)):
+            D.barrier() if ctx.world > 1 else None
+            graph.replay()
+            torch.cuda.synchronize()
+            acc = {}
+            for name, a, z in prof:
+                acc.setdefault(name, []).append(a.elapsed_time(z))
+            for name, v in acc.items():
+                per_call.setdefault(name, []).append(v)
+    else:
+        L.PROFILE = []
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+        acc = {}
+        for name, a, z in L.PROFILE:
+            acc.setdefault(name, []).append(a.elapsed_time(z))
+        L.PROFILE = None
+        per_call = {k: [v] for k, v in acc.items()}
+    # pre-roll under load so that nvidia-smi samples the clocks of a busy device (not timed)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
     for _ in range(5):
@@ -353,182 +429,291 @@ def run_gpu(args, cfg):
     p1.record()
     torch.cuda.synchronize()
     est_ms = max(D.all_reduce_max(p0.elapsed_time(p1)) / 5.0, 1e-3)
-    for _ in range(int(min(5000, max(10, 400.0 / est_ms)))):
+    for _ in range(int(min(3000, max(10, ctx.preroll_ms / est_ms)))):
         one()
     torch.cuda.synchronize()
     if graph is None:
-        L.PROFILE = []
-    L.launch_count(reset=True)
+        L.launch_count(reset=True)
     D.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
     t_host = time.perf_counter()
-    for _ in range(args.steps):
-        if graph is not None:
-            graph.replay()
-        else:
-            step()
-    host_ms = 1e3 * (time.perf_counter() - t_host) / args.steps      # time the host needs to ENQUEUE one step
-    e1.record()
-    torch.cuda.synchronize()
-    D.barrier()
-    if graph is not None:
-        launches = graph_launches * args.steps
-        prof, prof_steps = graph_prof, 1
+    if not flush_l2:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        host_ms = 1e3 * (time.perf_counter() - t_host) / steps
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
     else:
-        launches = L.launch_count()
-        prof, L.PROFILE = L.PROFILE, None
-        prof_steps = args.steps
-    clocks = sampler.stop()
-    ms_total = D.all_reduce_max(e0.elapsed_time(e1))
-    ms_step = ms_total / args.steps
-    value = world * n * args.steps / (ms_total * 1e-3)
+        evs = []
+        for _ in range(steps):
+            ctx.flush_buf.zero_()                        # 256 MB write: evicts the step's tensors from the 126 MB L2
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            one()
+            z.record()
+            evs.append((a, z))
+        host_ms = 1e3 * (time.perf_counter() - t_host) / steps
+        torch.cuda.synchronize()
+        ms_total = sum(a.elapsed_time(z) for a, z in evs)
+    D.barrier()
+    if graph is None:
+        launches = L.launch_count() / float(steps)
+    ms_total = D.all_reduce_max(ms_total)
+    return ms_total, launches, per_call, host_ms, graph
+
+
+def measure(ctx, cfg, headline):
+    import torch
+    args, pkg, world, rank = ctx.args, ctx.pkg, ctx.world, ctx.rank
+    L, D, PL = pkg._lib, pkg.dist, pkg.pipeline
+    mode, kind, n = args.mode, cfg["kind"], cfg["N"]
+    steps = args.steps if headline else min(args.steps, 20)
+    act_dt = L.torch_dtype(mode)
+    esize = 2 if mode == "bf16" else 4
+    oh, ow = out_hw(cfg)
+    X32, dY32 = synth(ctx, cfg, n, rank)
+    Xd, dYd = L.cast(X32, act_dt), L.cast(dY32, act_dt)
+    model, layers, convs = build_model(ctx, cfg, mode, sync_bn=(world > 1))
+    bucket = D.GradBucket(layers, overlap=True)
+    work_bytes = (Xd.numel() + dYd.numel()) * esize
+    flush_l2 = work_bytes < L2_BYTES
+
+    def make_step(x, dy, reduce=True):
+        def step():
+            model.flush_gradients()
+            Y = model.forward(x)
+            dX = model.backward(dy)
+            if world > 1 and reduce:
+                bucket.allreduce()
+            return Y, dX
+        return step
+
+    step = make_step(Xd, dYd)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device()) if headline else None
+    if sampler:
+        sampler.start()
+    ms_total, launches, per_call, host_ms, graph = timed_graph(ctx, step, steps, flush_l2)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / steps
+    value = world * n * steps / (ms_total * 1e-3)
+    out = {"value": value, "ms_per_step": ms_step, "steps": steps, "config": config_dict(cfg, mode, world, n),
+           "host_enqueue_ms_per_step": host_ms, "cuda_graph": graph is not None, "gpu_launches": int(round(launches * steps))}
 
     # ---- per-call shares and the roofline of the dominant call ----------------------------------------
-    per, count = {}, {}
-    for name, a, z in prof:
-        per[name] = per.get(name, 0.0) + a.elapsed_time(z)
-        count[name] = count.get(name, 0) + 1
-    step_ms = {k: v / prof_steps for k, v in per.items()}          # time per step spent in each entry point
-    call_ms = {k: per[k] / count[k] for k in per}                   # mean duration of one call
+    call_ms = {k: float(np.median([np.mean(r) for r in v])) for k, v in per_call.items()}      # one call, median over replays
+    step_ms = {k: float(np.median([np.sum(r) for r in v])) for k, v in per_call.items()}       # all calls of a step
+    count = {k: len(v[0]) for k, v in per_call.items()}
     fl = flops_per_pass(cfg, n)
     pk = peaks()
-    dominant = max(step_ms, key=step_ms.get)
-    tc = all(bool(l._uses_tc()) for l in conv_layers)
-    calls_per_step = count[dominant] / prof_steps
-    if dominant in ELEMENTWISE:
-        oh, ow = out_hw(cfg)
-        elems = n * oh * ow * cfg["K"]
-        passes = {"npml_bn2d_fwd": 2, "npml_bn2d_bwd": 3, "npml_add_act_fwd": 3, "npml_dz_prep": 3}[dominant]
-        byt = float(elems * esize * passes)
-        achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
-    elif tc:
-        peak = pk["bf16_tflops_sustained"] if mode == "bf16" else pk["bf16_tflops_sustained"] / 2.0
-        achieved = fl / calls_per_step / (call_ms[dominant] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak,
-                "peak_source": pk["source"] + (" bf16 sustained" if mode == "bf16" else " bf16 sustained / 2 (tf32)")}
-    else:
-        byt = min_bytes_per_pass(cfg, n, esize)
-        achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
-    roof["traffic"] = measured_traffic(cfg["_id"], mode, dominant)
-    roof["kernel_ms"] = {k: round(v, 4) for k, v in call_ms.items()}
-    roof["step_ms_by_call"] = {k: round(v, 4) for k, v in step_ms.items()}
-    roof["share_of_step"] = round(step_ms[dominant] / ms_step, 3)
-    tflops_step = 3.0 * fl * world / (ms_step * 1e-3) / 1e12
+    tc = all(bool(l._uses_tc()) for l in convs)
+    out["tensor_cores"] = tc
+    if step_ms:
+        dominant = max(step_ms, key=step_ms.get)
+        if dominant in ELEMENTWISE_PASSES:
+            byt = float(n * oh * ow * cfg["K"] * esize * ELEMENTWISE_PASSES[dominant])
+            achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
+        elif tc:
+            peak = pk["bf16_tflops_sustained"] if mode == "bf16" else pk["tf32_tflops_sustained"]
+            achieved = fl / count[dominant] / (call_ms[dominant] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak,
+                    "peak_source": pk["source"] + " bf16 sustained" if mode == "bf16" else "tf32: " + pk["tf32_source"]}
+        else:
+            byt = min_bytes_per_pass(cfg, n, esize)
+            achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
+        roof["traffic"] = measured_traffic(cfg["_id"], mode, dominant)
+        roof["kernel_ms"] = {k: round(v, 4) for k, v in call_ms.items()}
+        roof["kernel_ms_stat"] = "median of {} synchronised replays".format(len(next(iter(per_call.values()))))
+        roof["step_ms_by_call"] = {k: round(v, 4) for k, v in step_ms.items()}
+        roof["share_of_step"] = round(step_ms[dominant] / ms_step, 3)
+        out["roofline"] = roof
+    out["tflops"] = 3.0 * fl * world / (ms_step * 1e-3) / 1e12
+    out["frac_of_tensor_peak"] = out["tflops"] / (world * (pk["bf16_tflops_sustained"] if mode == "bf16" else pk["tf32_tflops_sustained"]))
 
-    # ---- end to end through the public API with HOST buffers ----------------------------------------------
-    # X and dLdy start in pinned host memory (fp32); Y, dX, dW, db end in pinned host memory.  Host->device and
-    # device->host copies run on their own streams so the two PCIe directions overlap; Conv2D / Deconv2D batches
-    # are pipelined in chunks (forward / backward of chunk i while chunk i+1 is in flight).  The module of cfg4
-    # needs whole-batch BatchNorm statistics, so it is not chunked.
-    e2e_steps = max(1, min(args.steps, 5))
-    oh, ow = out_hw(cfg)
-    Yh = torch.empty((n, oh, ow, cfg["K"]), dtype=act_dt).pin_memory()
-    dXh = torch.empty(X.shape, dtype=act_dt).pin_memory()
-    gradh = torch.empty(bucket.flat.numel(), dtype=torch.float32).pin_memory()
-    chunks = 1 if kind == "skip" else 4
-    bounds = [(i * n // chunks, (i + 1) * n // chunks) for i in range(chunks)]
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    xs32 = [torch.empty((hi - lo,) + X.shape[1:], dtype=torch.float32, device=dev) for lo, hi in bounds]
-    dys32 = [torch.empty((hi - lo, oh, ow, cfg["K"]), dtype=torch.float32, device=dev) for lo, hi in bounds]
+    # ---- N > 1: exposed all-reduce time, strong scaling, data-parallel parity ---------------------------
+    if world > 1:
+        if graph is not None:
+            graph.reset()
+        ms_nored, _, _, _, g2 = timed_graph(ctx, make_step(Xd, dYd, reduce=False), steps, flush_l2)
+        if g2 is not None:
+            g2.reset()
+        out["allreduce"] = {"bytes": int(bucket.flat.numel() * 4), "exposed_ms_per_step": max(0.0, (ms_total - ms_nored) / steps),
+                            "step_ms_without": ms_nored / steps, "collective": "one fused local-reduce + all-reduce of the flat dW||db bucket"
+                            if getattr(D, "FUSED_ALLREDUCE", False) else "ncclAllReduce(SUM, fp32) per layer slice on a side stream, overlapped with dgrad"}
+        if n % world == 0 and n // world >= 1:
+            ns = n // world
+            xs, dys = Xd[:ns].contiguous(), dYd[:ns].contiguous()
+            st = make_step(xs, dys)
+            for _ in range(3):
+                st()
+            torch.cuda.synchronize()
+            ms_s, _, _, _, g3 = timed_graph(ctx, st, steps, True)
+            if g3 is not None:
+                g3.reset()
+            out["strong"] = {"scaling": "strong", "global_batch": n, "per_gpu_batch": ns, "value": n * steps / (ms_s * 1e-3),
+                             "ms_per_step": ms_s / steps}
+        out["dp_parity"] = dp_parity(ctx, cfg, model, layers, bucket, make_step(Xd, dYd))
+    elif graph is not None:
+        graph.reset()
 
-    def e2e_step():
-        cur = torch.cuda.current_stream()
-        s_in.wait_stream(cur)
-        s_out.wait_stream(cur)
-        ev_x, ev_dy = [], []
-        with torch.cuda.stream(s_in):
-            for i, (lo, hi) in enumerate(bounds):
-                xs32[i].copy_(Xh[lo:hi], non_blocking=True)
-                ev_x.append(torch.cuda.Event()); ev_x[-1].record()
-            for i, (lo, hi) in enumerate(bounds):
-                dys32[i].copy_(dYh[lo:hi], non_blocking=True)
-                ev_dy.append(torch.cuda.Event()); ev_dy[-1].record()
-        model.flush_gradients()
-        outs = []
-        for i, (lo, hi) in enumerate(bounds):
-            cur.wait_event(ev_x[i])
-            Y = model.forward(L.cast(xs32[i], act_dt))
-            outs.append(Y)
-            ev = torch.cuda.Event(); ev.record()
-            s_out.wait_event(ev)
-            with torch.cuda.stream(s_out):
-                Yh[lo:hi].copy_(Y, non_blocking=True)
-        for i, (lo, hi) in enumerate(bounds):
-            cur.wait_event(ev_dy[i])
-            dyd = L.cast(dys32[i], act_dt)
-            dX = model.backward(dyd) if chunks == 1 else model.backward(dyd, index=i)
-            outs.append(dX)
-            ev = torch.cuda.Event(); ev.record()
-            s_out.wait_event(ev)
-            with torch.cuda.stream(s_out):
-                dXh[lo:hi].copy_(dX, non_blocking=True)
-        if world > 1:
-            bucket.allreduce()
-        ev = torch.cuda.Event(); ev.record()
-        s_out.wait_event(ev)
-        with torch.cuda.stream(s_out):
-            gradh.copy_(bucket.flat, non_blocking=True)
-        cur.wait_stream(s_out)
-        return outs
-
-    e2e_step()
-    torch.cuda.synchronize()
-    D.barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    f1.record()
-    torch.cuda.synchronize()
-    D.barrier()
-    e2e_ms = D.all_reduce_max(f0.elapsed_time(f1))
-    e2e = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
-           "h2d_bytes_per_step": int(Xh.numel() * 4 + dYh.numel() * 4),
-           "d2h_bytes_per_step": int(Yh.numel() * esize + dXh.numel() * esize + gradh.numel() * 4),
-           "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "chunks": chunks,
-           "host_dtype_in": "f32", "host_dtype_out": "bf16" if mode == "bf16" else "f32"}
+    # ---- end to end through the public API with HOST buffers (numpy-ml_b200/pipeline.py) ----------------
+    if not args.no_e2e:
+        e2e_steps = max(1, min(steps, 5 if headline else 3))
+        host_in = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.host_dtype]
+        host_out = act_dt if args.host_out == "mode" else torch.float32
+        Xh, dYh = PL.pinned(X32.shape, host_in), PL.pinned(dY32.shape, host_in)
+        Xh.copy_(X32.to(host_in)); dYh.copy_(dY32.to(host_in))
+        Yh, dXh = PL.pinned((n, oh, ow, cfg["K"]), host_out), PL.pinned(X32.shape, host_out)
+        gradh = PL.pinned((bucket.flat.numel(),), torch.float32)
+        pipe = PL.HostPipeline(model, chunks=args.chunks, flat=bucket.flat, reduce=(bucket.allreduce if world > 1 else None))
+        pipe.step(Xh, dYh, Yh, dXh, gradh)
+        torch.cuda.synchronize()
+        D.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(e2e_steps):
+            pipe.step(Xh, dYh, Yh, dXh, gradh)
+        f1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        e2e_ms = D.all_reduce_max(f0.elapsed_time(f1))
+        h2d, d2h = pipe.bytes_per_step(Xh, dYh, Yh, dXh, gradh)
+        out["e2e"] = {"value": world * n * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps, "chunks": pipe.chunks,
+                      "host_dtype_in": args.host_dtype, "host_dtype_out": str(host_out).replace("torch.", ""),
+                      "api": "numpy-ml_b200.pipeline.HostPipeline.step (pinned host buffers)", "numa_cpus": ctx.numa}
+        del Xh, dYh, Yh, dXh, pipe
+        if headline and world == 1 and not args.no_dropin:
+            # the plain drop-in: float64 NumPy in, float64 NumPy out, pageable memory (one warm-up + one timed step)
+            Xn, dYn = X32.double().cpu().numpy(), dY32.double().cpu().numpy()
+            PL.dropin_step(model, Xn[:2], dYn[:2])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            Yn, dXn = PL.dropin_step(model, Xn, dYn)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["e2e_dropin"] = {"value": n / dt, "unit": "images/s", "ms_per_step": 1e3 * dt,
+                                 "h2d_bytes_per_step": int((Xn.size + dYn.size) * 4), "d2h_bytes_per_step": int((Yn.size + dXn.size) * 4),
+                                 "api": "layer.forward(np.float64) / layer.backward(np.float64) -> np.float64 (wall clock)"}
+            del Xn, dYn, Yn, dXn
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------------
-    cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        ns = cpu_sample_size(cfg, 20.0, 1)
-        ts = time_cpu(cfg, ns, 1, 0, seed)
-        cpu = {"value": ns / ts[0], "unit": "images/s", "cores": host_threads(), "kind": "port",
-               "sample": "{} of {} images, one fwd+bwd, float64, oracle port of im2col+GEMM+np.add.at".format(ns, n)}
+        arm = CpuArm(cfg, 1000 + int(cfg["_id"][3:]))
+        ns, ts, sample = arm.time(15.0 if headline else 4.0, 1, 0)
+        out["cpu_baseline"] = {"value": ns / ts[0], "unit": "images/s", "cores": arm.threads, "kind": arm.kind, "sample": sample}
+    else:
+        out["cpu_baseline"] = None
+    if clocks is not None:
+        out["clocks"] = clocks
+    for l in layers:
+        l._bucket = None
+    del model, bucket, Xd, dYd, X32, dY32
+    torch.cuda.empty_cache()
+    return out
 
+
+def dp_parity(ctx, cfg, model, layers, bucket, step):
+    """One sharded step + all-reduce on every rank; rank 0 then runs the GLOBAL batch alone (every rank's shard
+    re-created from its seed) and compares: dW||db (and the BatchNorm gradients) of the bucket, and for the module
+    with sync-BN also rank 0's slice of Y.  Normwise relative errors; fp32 summation-order noise is expected."""
+    import torch
+    L, D = ctx.pkg._lib, ctx.pkg.dist
+    world, rank, mode, n = ctx.world, ctx.rank, ctx.args.mode, cfg["N"]
+    act_dt = L.torch_dtype(mode)
+    Y, _ = step()
+    torch.cuda.synchronize()
+    got = bucket.flat.clone()
+    y0 = Y.float().clone()
+    D.barrier()
+    res = None
     if rank == 0:
-        line = {"metric": "Conv2D fwd+bwd images/s", "value": value, "unit": "images/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[mode],
-                "data": "synthetic",
-                "config": {"workload": cfg["name"], "mode": mode, "per_gpu_batch": n, "global_batch": n * world,
-                           "parallelism": "dp{}".format(world) + ("+syncbn" if (kind == "skip" and world > 1) else ""),
-                           "tensor_cores": tc,
-                           "l2": "inputs X + dLdy are {:.0f} MB per step (L2 is 126 MB); no explicit flush".format(
-                               (Xd.numel() + dYd.numel()) * esize / 1e6)},
-                "host_enqueue_ms_per_step": host_ms, "cuda_graph": graph is not None, "tflops": tflops_step, "frac_of_bf16_peak": tflops_step / (world * pk["bf16_tflops_sustained"]),
-                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        ref_model, ref_layers, _ = build_model(ctx, cfg, mode, sync_bn=False)
+        shards = [synth(ctx, cfg, n, r) for r in range(world)]
+        if cfg["kind"] == "skip":          # whole-batch BatchNorm statistics: one forward over the concatenated batch
+            Xg = L.cast(torch.cat([s[0] for s in shards]), act_dt)
+            dYg = L.cast(torch.cat([s[1] for s in shards]), act_dt)
+            Yg = ref_model.forward(Xg)
+            ref_model.backward(dYg)
+            y_err = float(((Yg[:n].float() - y0).norm() / Yg[:n].float().norm()).item())
+        else:                              # gradients accumulate over the shards (+=), like one full-batch backward
+            y_err = None
+            for xs, dys in shards:
+                ref_model.forward(L.cast(xs, act_dt))
+                ref_model.backward(L.cast(dys, act_dt))
+                ref_model.X, ref_model.derived_variables["Z"] = [], []
+                ref_model.derived_variables["out_rows"], ref_model.derived_variables["out_cols"] = [], []
+        ref = torch.cat([l.gradients[k].reshape(-1) for l in ref_layers for k in sorted(l.gradients)])
+        err = float(((got - ref).norm() / ref.norm()).item())
+        res = {"grad_bucket_rel_err": err, "elements": int(ref.numel()), "global_batch": n * world}
+        if y_err is not None:
+            res["syncbn_Y_rel_err"] = y_err
+        del ref_model
+    D.barrier()
+    return res
+
+
+def run_gpu(args):
+    import torch
+    pkg = importlib.import_module("numpy-ml_b200")
+    ctx = Ctx()
+    ctx.args, ctx.pkg = args, pkg
+    st = pkg.dist.init()
+    ctx.world, ctx.rank = st["world"], st["rank"]
+    if ctx.world == 1:
+        torch.cuda.set_device(0)
+    ctx.dev = torch.device("cuda", torch.cuda.current_device())
+    ctx.numa = None if args.no_numa else pkg.pipeline.bind_to_gpu_numa_node()
+    ctx.numa = None if ctx.numa is None else "{} cpus".format(len(ctx.numa))
+    ctx.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=ctx.dev)
+    ctx.preroll_ms = 400.0
+    head_id = args.config
+    cfg = dict(CONFIGS[head_id]); cfg["_id"] = head_id
+    head = measure(ctx, cfg, True)
+    configs = {}
+    ctx.preroll_ms = 100.0
+    if not args.single:
+        for cid in sorted(CONFIGS):
+            if cid == head_id:
+                configs[cid] = {k: head[k] for k in head if k != "clocks"}
+                continue
+            c = dict(CONFIGS[cid]); c["_id"] = cid
+            try:
+                configs[cid] = measure(ctx, c, False)
+            except Exception as e:                              # one config must not take the headline down
+                configs[cid] = {"error": "{}: {}".format(type(e).__name__, str(e).splitlines()[0] if str(e) else "")}
+    if ctx.rank == 0:
+        mode = args.mode
+        line = {"metric": "Conv2D fwd+bwd images/s", "value": head["value"], "unit": "images/s", "n_gpus": ctx.world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[mode], "data": "synthetic"}
+        for k in ("config", "tensor_cores", "host_enqueue_ms_per_step", "cuda_graph", "tflops", "frac_of_tensor_peak", "roofline",
+                  "cpu_baseline", "e2e", "e2e_dropin", "allreduce", "strong", "dp_parity", "gpu_launches", "clocks"):
+            if k in head:
+                line[k] = head[k]
+        if configs:
+            line["configs"] = configs
+            line["gpu_launches"] = int(sum(c.get("gpu_launches", 0) for c in configs.values()))
         print(json.dumps(line), flush=True)
-    # teardown must never hang the job: a captured graph that contains NCCL kernels has to be destroyed before the
-    # communicator, and a watchdog forces the exit if the clean shutdown still blocks
+    # teardown must never hang the job: a watchdog forces the exit if the clean shutdown blocks
     watchdog = threading.Timer(30.0, lambda: os._exit(0))
     watchdog.daemon = True
     watchdog.start()
     sys.stdout.flush()
-    if graph is not None:
-        graph_prof = None
-        graph.reset()
-        graph = None
     torch.cuda.synchronize()
-    D.barrier()
-    D.destroy()
+    pkg.dist.barrier()
+    pkg.dist.destroy()
     watchdog.cancel()
 
 
@@ -540,15 +725,22 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--single", action="store_true", help="only the --config workload (no \"configs\" object)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the float64 NumPy drop-in leg")
     ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU's NUMA node")
+    ap.add_argument("--chunks", type=int, default=4, help="chunks of the host pipeline")
+    ap.add_argument("--host-dtype", default="f32", choices=["f32", "bf16", "f16"], help="dtype of the pinned host inputs")
+    ap.add_argument("--host-out", default="mode", choices=["mode", "f32"], help="dtype of the pinned host outputs")
+    ap.add_argument("--kernel-reps", type=int, default=30, help="synchronised replays behind roofline.kernel_ms")
     args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
-    cfg["_id"] = args.config
     if args.impl == "reference":
+        cfg = dict(CONFIGS[args.config]); cfg["_id"] = args.config
         run_reference(args, cfg)
     else:
-        run_gpu(args, cfg)
+        run_gpu(args)
 
 
 if __name__ == "__main__":

@@ -809,8 +809,16 @@ def test_full_size_skip_conv_module_against_oracle(cuda_device, mode):
     for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
         chk("dW" + t, conv.gradients["W"], ref["dW" + t])
         chk("dg" + t, bn.gradients["scaler"], ref["dg" + t])
-        chk("dh" + t, bn.gradients["intercept"], ref["dh" + t])
+    chk("dh2", M.batchnorm2.gradients["intercept"], ref["dh2"])
+    chk("dhs", M.batchnorm_skip.gradients["intercept"], ref["dhs"])
     chk("db1", M.conv1.gradients["b"], ref["db1"])
+    # dIntercept of batchnorm1 = sum over 262 144 pixels of dLdBn1 = dgrad(conv2) of a BatchNorm backward, whose
+    # per-channel sums are zero by construction: only the image borders survive, the rest is cancellation.  The sum's
+    # rounding noise scales with the norm of the SUMMANDS (eps * ||dLdBn1||_F for independent element errors), so
+    # that is the yardstick; eps = 4 x the storage rounding of the mode (bf16 2^-9, tf32 products 2^-11, fp32 2^-24)
+    eps = {"fp32": 2.4e-7, "tf32": 2e-3, "bf16": 8e-3}[mode]
+    dh1 = M.batchnorm1.gradients["intercept"].double().cpu().numpy().ravel()
+    assert np.linalg.norm(dh1 - ref["dh1"].ravel()) <= eps * np.linalg.norm(ref["dLdBn1"].ravel()), (mode, "dh1")
     assert not bad, (mode, bad)
 
 

@@ -192,8 +192,29 @@ def test_bench_algorithmic_work_matches_survey_table():
         cfg = dict(bench.CONFIGS[name])
         got = 3.0 * bench.flops_per_pass(cfg, cfg["N"]) / 1e9
         assert abs(got - gf) / gf < 2e-3, (name, got, gf)
-    # the CPU sample of the reference arm never exceeds the batch and shrinks with the number of steps
-    cfg = dict(bench.CONFIGS["cfg2"])
-    cfg.setdefault("_id", "cfg2")
-    n1, n25 = bench.cpu_sample_size(cfg, 100.0, 1), bench.cpu_sample_size(cfg, 100.0, 25)
-    assert 1 <= n25 <= n1 <= cfg["N"]
+    # both arms print the same `config` object (the driver compares them), and bench.py's own geometry agrees with the package
+    pkg = npml()
+    for name in want:
+        cfg = dict(bench.CONFIGS[name]); cfg["_id"] = name
+        assert bench.config_dict(cfg, "bf16", 2, cfg["N"])["global_batch"] == 2 * cfg["N"]
+        if cfg["kind"] == "conv":
+            p4 = pkg.utils.resolve_pad_2D((1, cfg["H"], cfg["W"], cfg["C"]), cfg["pad"], cfg["k"], cfg["stride"], cfg["dilation"])
+            assert bench.out_hw(cfg) == tuple(pkg.utils.conv_out_hw(cfg["H"], cfg["W"], cfg["k"][0], cfg["k"][1], p4, cfg["stride"], cfg["dilation"]))
+        elif cfg["kind"] == "deconv":
+            assert bench.out_hw(cfg) == tuple(pkg.utils.deconv_geometry(cfg["H"], cfg["W"], cfg["k"][0], cfg["k"][1], cfg["pad"], cfg["stride"])[1:])
+
+
+def test_reference_arm_runs_the_unmodified_reference():
+    """bench.py --impl reference: the CPU arm is the reference itself when baseline/_ref is staged (kind "reference"),
+    the oracle port otherwise (kind "port"); one tiny timed step of cfg1 through it."""
+    import importlib
+    bench = importlib.import_module("bench")
+    cfg = dict(bench.CONFIGS["cfg1"]); cfg["_id"] = "cfg1"
+    arm = bench.CpuArm(cfg, 1001)
+    from baseline import reference_arm as R
+    assert arm.kind == ("reference" if R.available() else "port")
+    X, dY = arm.inputs(2)
+    out = arm.step(X, dY)
+    assert out[0].shape[0] == 2
+    n, ts, sample = arm.time(0.5, 1, 0)
+    assert 2 <= n <= cfg["N"] and len(ts) == 1 and "host threads" in sample
