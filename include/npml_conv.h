@@ -69,8 +69,14 @@ typedef struct npml_conv_desc {
   int32_t act;                 /* NPML_ACT_* applied in the forward epilogue           */
   float act_p0, act_p1;
   int32_t accumulate;          /* wgrad: dW += result (layers/layers.py:3087-3089)      */
-  int32_t reserved;
+  int32_t flags;               /* NPML_FLAG_*                                           */
 } npml_conv_desc;
+
+/* fprop / dgrad: the workspace handed to this call ALREADY holds the operand-type copy of the weights that an
+ * earlier call with the same (desc, op) and the same W wrote there -- skip the repack kernel.  The host layer keeps one
+ * such workspace per (layer, op) and drops it whenever W changes (assignment, optimizer step), so weights are
+ * repacked once per update(), not once per call.  Never set it on a workspace the library has not filled. */
+enum { NPML_FLAG_WEIGHTS_PACKED = 1 };
 
 /* ---- Conv2D (layers/layers.py:2895-3178) --------------------------------------------------
  * fprop replaces pad2D + im2col + W_col @ X_col + b + act_fn  (utils/utils.py:603-665,

@@ -18,13 +18,14 @@ F32, BF16, F64 = 0, 1, 2
 OP_CONV_FPROP, OP_CONV_DGRAD, OP_CONV_WGRAD = 0, 1, 2
 OP_DECONV_FPROP, OP_DECONV_DGRAD, OP_DECONV_WGRAD = 3, 4, 5
 OP_DZ_PREP, OP_BN = 6, 7
+FLAG_WEIGHTS_PACKED = 1
 
 
 class ConvDesc(C.Structure):
     """Mirror of `npml_conv_desc` (include/npml_conv.h)."""
     _fields_ = [(n, C.c_int32) for n in ("N", "H", "W", "C", "K", "fr", "fc", "stride", "dil", "pr1", "pr2", "pc1",
                                          "pc2", "OH", "OW", "mode", "act")] + \
-               [("act_p0", C.c_float), ("act_p1", C.c_float), ("accumulate", C.c_int32), ("reserved", C.c_int32)]
+               [("act_p0", C.c_float), ("act_p1", C.c_float), ("accumulate", C.c_int32), ("flags", C.c_int32)]
 
 
 _P, _I32, _I64, _F, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
@@ -76,6 +77,9 @@ SIGNATURES = {
 }
 
 _lib = None
+# True: a packed-weights workspace may be reused by calls recorded into a CUDA graph (layers._ConvBase._call_w); only
+# for captures whose weights stay constant across replays (bench.py's forward + backward step has no optimizer update)
+GRAPH_REUSE_PACKED = False
 # when a list, the layers append (entry point, start event, end event) around every C-ABI call
 PROFILE = None
 # True while a step is being captured into a CUDA graph: the events must be "external" so that they become

@@ -37,6 +37,7 @@ static GatherConv make_gather(const npml_conv_desc* d, int op) {
   g.N = d->N; g.fr = d->fr; g.fc = d->fc; g.s = d->stride; g.D = d->dil; g.pr = d->pr1; g.pc = d->pc1;
   g.w_tap = (int64_t)d->C * d->K;
   g.act = NPML_ACT_IDENTITY; g.p0 = 0.f; g.p1 = 0.f;
+  g.weights_packed = (d->flags & NPML_FLAG_WEIGHTS_PACKED) != 0;
   switch (op) {
     case NPML_OP_CONV_FPROP:    // Z[n,oh,ow,k] = sum X[n, oh*s + r*D - pr1, ow*s + t*D - pc1, c] W[r,t,c,k]
     case NPML_OP_DECONV_FPROP:  // Z[n,y,x,k]   = sum X[n, (y + pr1 - r)/s, (x + pc1 - t)/s, c] W[r,t,c,k]

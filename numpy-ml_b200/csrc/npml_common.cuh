@@ -172,6 +172,8 @@ struct GatherConv {
   // device pointers, CO entries each, both NULL when unused.  Z (the pre-activation) is never affected.
   const float* post_scale;
   const float* post_shift;
+  // NPML_FLAG_WEIGHTS_PACKED: the workspace already holds Wt for these weights; launch_repack_weights is a no-op
+  bool weights_packed;
 };
 
 __device__ __forceinline__ float post_affine(const GatherConv& g, int co, float y) {

@@ -415,6 +415,7 @@ size_t tc_conv_ws_bytes(const GatherConv& g, int mode) {
 
 // w (strided fp32) -> Wt[tap][co][ci] in the operand type (also used by tc_slab_conv.cu)
 int launch_repack_weights(const GatherConv& g, bool bf16, const float* w, void* wt, cudaStream_t st) {
+  if (g.weights_packed) return 0;      // the caller kept the packed copy of an earlier call (NPML_FLAG_WEIGHTS_PACKED)
   const int64_t total = (int64_t)g.fr * g.fc * g.CO * g.CI;
   if (g.w_co == 1 && g.CI >= 16 && g.fr * g.fc <= 65535) {            // source contiguous along co: tiled transpose
     const dim3 grid((unsigned)((g.CO + 31) / 32), (unsigned)((g.CI + 31) / 32), (unsigned)(g.fr * g.fc));

@@ -84,6 +84,7 @@ class LayerBase(ABC):
         for k, v in self.gradients.items():
             if k in self.parameters:
                 self.parameters[k] = self.optimizer(_as_param(self.parameters[k]), v, k, cur_loss)
+        self._wgen = self.__dict__.get("_wgen", 0) + 1      # the kernels' packed copies of W are stale now
         self.flush_gradients()
 
     def set_params(self, summary_dict):
@@ -210,6 +211,34 @@ class _ConvBase(LayerBase):
         with L.profiled(name):
             L.check(getattr(lib, name)(d, *args, L.ptr(ws), ws.numel(), L.stream()), name)
 
+    _DESC_KEY = ("N", "H", "W", "C", "K", "fr", "fc", "stride", "dil", "pr1", "pr2", "pc1", "pc2", "OH", "OW", "mode")
+
+    def _call_w(self, name, d, op, W, *args):
+        """fprop / dgrad: the operand-type copy of the weights that the kernels read (Wt[tap][co][ci], bf16 / tf32) lives
+        in a workspace this layer keeps per op, and is rebuilt only when W changed -- a new tensor, an in-place torch
+        op (`_version`), or an optimizer step (`update()` bumps `_wgen`) -- instead of in front of every call
+        (NPML_FLAG_WEIGHTS_PACKED).  While a CUDA graph is being captured the packed copy is reused only if the caller
+        declared the weights constant across replays (`_lib.GRAPH_REUSE_PACKED`): a captured step that contains its own
+        optimizer update must repack inside the graph."""
+        lib = L.load()
+        cache = self.__dict__.setdefault("_wpack", {})
+        key = tuple(getattr(d, f) for f in self._DESC_KEY)
+        gen = self.__dict__.get("_wgen", 0)
+        ent = cache.get(op)
+        hit = (ent is not None and ent[1] is W and ent[2] == W._version and ent[3] == gen and ent[4] == key)
+        if hit and not L.GRAPH_REUSE_PACKED and torch.cuda.is_current_stream_capturing():
+            hit = False
+        if hit:
+            ws = ent[0]
+            d.flags |= L.FLAG_WEIGHTS_PACKED
+        else:
+            nbytes = int(lib.npml_workspace_bytes(d, op))
+            ws = ent[0] if (ent is not None and ent[0].numel() >= nbytes) else \
+                torch.empty(max(nbytes, 256), dtype=torch.uint8, device=W.device)
+            cache[op] = (ws, W, W._version, gen, key)
+        with L.profiled(name):
+            L.check(getattr(lib, name)(d, *args, L.ptr(ws), ws.numel(), L.stream()), name)
+
     def _uses_tc(self, X_shape=None):
         """True if the forward of this layer runs on the tcgen05 kernels for the last (or given) input shape."""
         if X_shape is None:
@@ -241,13 +270,13 @@ class _ConvBase(LayerBase):
             scale, shift = fused_bn.folded_affine(d.K)
             Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device) if retain_derived else None
             Y = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
-            self._call(pre + "fprop_bn", d, self._ops[0], L.ptr(Xd), L.ptr(W), L.ptr(b), L.ptr(scale), L.ptr(shift),
-                       L.ptr(Z), L.ptr(Y))
+            self._call_w(pre + "fprop_bn", d, self._ops[0], W, L.ptr(Xd), L.ptr(W), L.ptr(b), L.ptr(scale), L.ptr(shift),
+                         L.ptr(Z), L.ptr(Y))
         else:
             Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
             Y = Z if self.act_fn.code == 0 else torch.empty_like(Z)
-            self._call(pre + "fprop", d, self._ops[0], L.ptr(Xd), L.ptr(W), L.ptr(b),
-                       L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
+            self._call_w(pre + "fprop", d, self._ops[0], W, L.ptr(Xd), L.ptr(W), L.ptr(b),
+                         L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
         if retain_derived:
             self.X.append(Xd)
             self.derived_variables["Z"].append(Z)
@@ -292,7 +321,8 @@ class _ConvBase(LayerBase):
         if retain_grads and hook is not None:
             hook(self)
         dX = torch.empty_like(X)
-        self._call(pre + "dgrad", d, self._ops[1], L.ptr(dZ), L.ptr(W), L.ptr(dX))
+        d.accumulate = 0
+        self._call_w(pre + "dgrad", d, self._ops[1], W, L.ptr(dZ), L.ptr(W), L.ptr(dX))
         return dX
 
 

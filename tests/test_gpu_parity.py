@@ -813,10 +813,10 @@ def test_full_size_skip_conv_module_against_oracle(cuda_device, mode):
     chk("dhs", M.batchnorm_skip.gradients["intercept"], ref["dhs"])
     chk("db1", M.conv1.gradients["b"], ref["db1"])
     # dIntercept of batchnorm1 = sum over 262 144 pixels of dLdBn1 = dgrad(conv2) of a BatchNorm backward, whose
-    # per-channel sums are zero by construction: only the image borders survive, the rest is cancellation.  The sum's
-    # rounding noise scales with the norm of the SUMMANDS (eps * ||dLdBn1||_F for independent element errors), so
-    # that is the yardstick; eps = 4 x the storage rounding of the mode (bf16 2^-9, tf32 products 2^-11, fp32 2^-24)
-    eps = {"fp32": 2.4e-7, "tf32": 2e-3, "bf16": 8e-3}[mode]
+    # per-channel sums are zero by construction: only the image borders survive, the rest is cancellation (measured:
+    # |dh1| is 0.2 of the summands' norm).  The rounding noise of such a sum scales with the norm of the SUMMANDS, so
+    # the mode's tolerance is applied relative to ||dLdBn1||_F; a zeroed dh1 is still 10x over that bound in bf16.
+    eps = TOL[mode]
     dh1 = M.batchnorm1.gradients["intercept"].double().cpu().numpy().ravel()
     assert np.linalg.norm(dh1 - ref["dh1"].ravel()) <= eps * np.linalg.norm(ref["dLdBn1"].ravel()), (mode, "dh1")
     assert not bad, (mode, bad)
