@@ -399,12 +399,23 @@ def timed_graph(ctx, step, steps, flush_l2):
     for _ in range(3):
         one()
     torch.cuda.synchronize()
-    # per-call durations: median over >= 30 synchronised replays (external events inside the captured step)
+    # per-call durations: external events inside the captured step, read after the LAST of a burst of back-to-back
+    # replays (so that every sample is taken under the sustained clocks / power state of a long run, which is what the
+    # "sustained" tensor peak describes); median over >= 30 such samples
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    for _ in range(5):
+        one()
+    q1.record()
+    torch.cuda.synchronize()
+    burst = int(min(64, max(4, 3.0 / max(q0.elapsed_time(q1) / 5.0, 1e-3))))
     per_call = {}
     if graph is not None:
         for _ in range(max(30, ctx.args.kernel_reps)):
-            D.barrier() if ctx.world > 1 else None
-            graph.replay()
+            for i in range(burst):
+                if flush_l2 and i == burst - 1:
+                    ctx.flush_buf.zero_()           # the sampled replay starts with a cold L2, like the timed steps
+                graph.replay()
             torch.cuda.synchronize()
             acc = {}
             for name, a, z in prof:
@@ -533,7 +544,7 @@ def measure(ctx, cfg, headline):
                     "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}
         roof["traffic"] = measured_traffic(cfg["_id"], mode, dominant)
         roof["kernel_ms"] = {k: round(v, 4) for k, v in call_ms.items()}
-        roof["kernel_ms_stat"] = "median of {} synchronised replays".format(len(next(iter(per_call.values()))))
+        roof["kernel_ms_stat"] = "median of {} samples, each the last of a burst of back-to-back replays".format(len(next(iter(per_call.values()))))
         roof["step_ms_by_call"] = {k: round(v, 4) for k, v in step_ms.items()}
         roof["share_of_step"] = round(step_ms[dominant] / ms_step, 3)
         out["roofline"] = roof

@@ -189,6 +189,47 @@ int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch, const void
                         const double* sums_local, const double* sums_global, float* d_scaler,
                         float* d_intercept, int32_t accumulate, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- fused passes of the skip-connection modules (modules/modules.py:905-984) ------------------------------------
+ * The residual tail Y = act(BatchNorm2D_a(xa) + BatchNorm2D_b(xb)) (modules.py:931-937: batchnorm2, batchnorm_skip,
+ * add3; layers.py:1146-1156, 705-711) and its backward (modules.py:941-953; layers.py:739-742, 1192-1215) read and
+ * write every tensor ONCE instead of once per layer.  All tensors are (rows, ch) views of NHWC volumes in `dtype`.
+ *
+ * npml_bn2d_finalize: (mean, rstd) and the running-statistics update from per-channel sums = [sum x, sum x^2]
+ *   (npml_bn2d_stats, all-reduced by the host under sync-BN); nothing is normalised here.
+ * npml_bn2d_pair_add_act_fwd: sum = BN_a(xa) + BN_b(xb), Y = act(sum) in one pass.  scaler_b == NULL: xb is added as
+ *   it is (SkipConnectionIdentityModule, modules.py:560-590).  `sum` and/or `Y` may be NULL.
+ * npml_bn2d_pair_bwd_stats: g = dY * act'(s) is formed on the fly (s = the stored sum; for ReLU the output Y works
+ *   as well, for identity s is ignored); sums[3*ch] = [sum g, sum g*nhat_a, sum g*nhat_b].  mean_b == NULL: no second
+ *   BatchNorm2D (third block zero).
+ * npml_bn2d_pair_bwd_apply: dxa = BN_a'(g), dxb = BN_b'(g) (dxb = g without a second BatchNorm2D, may be NULL then);
+ *   dScaler / dIntercept of both accumulate `sums_local`, dX uses `sums_global` (pass the same buffer twice without
+ *   sync-BN) and rows_total.
+ * npml_bn2d_bwd_act: BatchNorm2D backward whose dX pass also applies the activation derivative of the layer in FRONT
+ *   of it (x = act(z)): dz = BN'(dy) * act'(z) -- the prologue of that layer's own backward (layers.py:3103) without a
+ *   pass of its own.  zm = z, or NULL for ReLU (x > 0 <=> z > 0) / identity.  sums_local/global: NULL (statistics are
+ *   computed here) or the split sync-BN form of npml_bn2d_bwd_stats. */
+int npml_bn2d_finalize(int64_t rows_total, int32_t ch, const double* sums, float* running_mean, float* running_var,
+                       float momentum, float eps, float* save_mean, float* save_rstd, void* stream);
+int npml_bn2d_pair_add_act_fwd(int64_t rows, int32_t ch, const void* xa, const void* xb, int32_t dtype,
+                               const float* scaler_a, const float* intercept_a, const float* mean_a, const float* rstd_a,
+                               const float* scaler_b, const float* intercept_b, const float* mean_b, const float* rstd_b,
+                               int32_t act, float p0, float p1, void* sum, void* Y, void* stream);
+int npml_bn2d_pair_bwd_stats(int64_t rows, int32_t ch, const void* dY, const void* s, int32_t act, float p0, float p1,
+                             const void* xa, const void* xb, int32_t dtype, const float* mean_a, const float* rstd_a,
+                             const float* mean_b, const float* rstd_b, double* sums, void* ws, size_t ws_bytes,
+                             void* stream);
+int npml_bn2d_pair_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch, const void* dY, const void* s, int32_t act,
+                             float p0, float p1, const void* xa, const void* xb, int32_t dtype, const float* scaler_a,
+                             const float* mean_a, const float* rstd_a, const float* scaler_b, const float* mean_b,
+                             const float* rstd_b, const double* sums_local, const double* sums_global, void* dxa,
+                             void* dxb, float* d_scaler_a, float* d_intercept_a, float* d_scaler_b, float* d_intercept_b,
+                             int32_t accumulate, void* ws, size_t ws_bytes, void* stream);
+int npml_bn2d_bwd_act(int64_t rows, int64_t rows_total, int32_t ch, const void* dy, const void* x, void* dz,
+                      int32_t dtype, const float* scaler, const float* save_mean, const float* save_rstd,
+                      const double* sums_local, const double* sums_global, float* d_scaler, float* d_intercept,
+                      int32_t accumulate, int32_t act, float p0, float p1, const void* zm, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ---- SGD step on the (all-reduced) gradient (optimizers/optimizers.py:110-148) ----------------
  * g' = grad * grad_scale (grad_scale carries the clip-norm factor t/||g||, 1 when not clipping);
  * u = momentum*velocity + lr*g'; velocity = u; param -= u.  All fp32, n elements. */

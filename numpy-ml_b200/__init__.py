@@ -13,6 +13,7 @@ from . import optimizers
 from . import layers
 from . import modules
 from . import dist
+from . import pipeline
 from ._lib import to_numpy, launch_count
 from .build import build
 from .layers import Conv2D, Deconv2D, Conv1D, Pool2D, Flatten, BatchNorm2D, Add, Multiply, FullyConnected

@@ -56,6 +56,13 @@ SIGNATURES = {
     "npml_bn2d_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _SZ, _P]),
     "npml_bn2d_bwd_stats": (C.c_int, [_I64, _I32, _P, _P, _I32, _P, _P, _P, _P, _SZ, _P]),
     "npml_bn2d_bwd_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "npml_bn2d_finalize": (C.c_int, [_I64, _I32, _P, _P, _P, _F, _F, _P, _P, _P]),
+    "npml_bn2d_pair_add_act_fwd": (C.c_int, [_I64, _I32, _P, _P, _I32] + [_P] * 8 + [_I32, _F, _F, _P, _P, _P]),
+    "npml_bn2d_pair_bwd_stats": (C.c_int, [_I64, _I32, _P, _P, _I32, _F, _F, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "npml_bn2d_pair_bwd_apply": (C.c_int, [_I64, _I64, _I32, _P, _P, _I32, _F, _F, _P, _P, _I32] + [_P] * 6 + [_P, _P, _P, _P]
+                                 + [_P] * 4 + [_I32, _P, _SZ, _P]),
+    "npml_bn2d_bwd_act": (C.c_int, [_I64, _I64, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _F, _F, _P,
+                                    _P, _SZ, _P]),
     "npml_sgd_update": (C.c_int, [_P, _P, _P, _I64, _F, _F, _F, _P]),
     "npml_optimizer_update": (C.c_int, [_I32, _P, _P, _P, _P, _I64] + [C.c_double] * 7 + [_P]),
     "npml_optimizer_update_clipped": (C.c_int, [_I32, _P, _P, _P, _P, _I64] + [C.c_double] * 6 + [_P, C.c_double, _P]),

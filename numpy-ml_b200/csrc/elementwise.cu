@@ -416,13 +416,19 @@ struct BnBwdStatsF {
   }
 };
 
-// dx = g*rstd*(dy - m1 - nhat*m2), nhat = (x - mean)*rstd; coef: [5][ch] = mean, rstd, g*rstd, m1, m2
+// dx = g*rstd*(dy - m1 - nhat*m2), nhat = (x - mean)*rstd; coef: [5][ch] = mean, rstd, g*rstd, m1, m2.
+// act != identity: the layer in front of this BatchNorm2D ends in an activation (x = act(z)); its backward prologue
+// dZ = dx * act'(z) (layers/layers.py:3103) is applied here, in the same pass, instead of in a pass of its own.  ReLU
+// needs no extra tensor (x > 0 <=> z > 0); every other activation reads z from `zm`.
 struct BnBwdDxF {
   static constexpr int kConsts = 5;
-  static constexpr int kIn = 2;
+  static constexpr int kIn = 3;
   static constexpr int kBatch = 1;      // measured: batching the two-input BatchNorm backward passes is slower (95 vs 88 us)
   const void* dy; const void* x; void* dx; int dt;
   const float* coef;
+  int act = NPML_ACT_IDENTITY;
+  float p0 = 0.f, p1 = 0.f;
+  const void* zm = nullptr;
   template <int VEC>
   __device__ __forceinline__ void init(int c0, int ch, float (&kc)[5][VEC]) const {
 #pragma unroll
@@ -431,21 +437,196 @@ struct BnBwdDxF {
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void load(int64_t i, float (&in)[2][VEC]) const {
+  __device__ __forceinline__ void load(int64_t i, float (&in)[3][VEC]) const {
     load_vec<VEC>(dy, sel<DT>(dt), i, in[0]);
     load_vec<VEC>(x, sel<DT>(dt), i, in[1]);
+    if (zm != nullptr) load_vec<VEC>(zm, sel<DT>(dt), i, in[2]);
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[5][VEC], float (&in)[2][VEC], float (&)[1][VEC]) const {
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[5][VEC], float (&in)[3][VEC], float (&)[1][VEC]) const {
     float (&v)[VEC] = in[1];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const float nh = (v[j] - kc[0][j]) * kc[1][j];
-      v[j] = kc[2][j] * (in[0][j] - kc[3][j] - nh * kc[4][j]);
+      const float xv = v[j];
+      const float nh = (xv - kc[0][j]) * kc[1][j];
+      float d = kc[2][j] * (in[0][j] - kc[3][j] - nh * kc[4][j]);
+      if (act == NPML_ACT_RELU) {
+        d = (zm != nullptr ? in[2][j] : xv) > 0.f ? d : 0.f;
+      } else if (act != NPML_ACT_IDENTITY) {
+        // the unfused path rounds dx to the storage type before the prologue multiplies it
+        if (sel<DT>(dt) == NPML_BF16) d = __bfloat162float(__float2bfloat16_rn(d));
+        d *= act_grad_ool(act, in[2][j], p0, p1);
+      }
+      v[j] = d;
     }
     store_vec<VEC>(dx, sel<DT>(dt), i, v);
   }
 };
+
+// ---- the residual tail of the skip-connection modules, fused (modules/modules.py:931-937, 941-953) -----------------
+// Forward: Y = act(BN_a(xa) + BN_b(xb)) in ONE pass over (xa, xb) instead of two BatchNorm2D passes and an Add pass.
+// `b` may be a plain tensor (identity shortcut: scaler_b == nullptr -> xb is added as it is).
+struct BnPairAddActF {
+  static constexpr int kConsts = 6;
+  static constexpr int kIn = 2;
+  static constexpr int kBatch = 2;
+  const void* xa; const void* xb; void* sum; void* Y; int dt;
+  const float* scaler_a; const float* intercept_a; const float* mean_a; const float* rstd_a;
+  const float* scaler_b; const float* intercept_b; const float* mean_b; const float* rstd_b;
+  int act; float p0, p1;
+  template <int VEC>
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[6][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = c0 + j < ch ? c0 + j : ch - 1;
+      kc[0][j] = mean_a[c]; kc[1][j] = scaler_a[c] * rstd_a[c]; kc[2][j] = intercept_a[c];
+      if (scaler_b != nullptr) { kc[3][j] = mean_b[c]; kc[4][j] = scaler_b[c] * rstd_b[c]; kc[5][j] = intercept_b[c]; }
+      else { kc[3][j] = 0.f; kc[4][j] = 1.f; kc[5][j] = 0.f; }
+    }
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void load(int64_t i, float (&in)[2][VEC]) const {
+    load_vec<VEC>(xa, sel<DT>(dt), i, in[0]);
+    load_vec<VEC>(xb, sel<DT>(dt), i, in[1]);
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[6][VEC], float (&in)[2][VEC], float (&)[1][VEC]) const {
+    float (&v)[VEC] = in[0];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float ya = fmaf(kc[1][j], v[j] - kc[0][j], kc[2][j]);
+      const float yb = fmaf(kc[4][j], in[1][j] - kc[3][j], kc[5][j]);
+      float t = ya + yb;
+      if (sel<DT>(dt) == NPML_BF16) t = __bfloat162float(__float2bfloat16_rn(t));   // activations see the stored sum
+      v[j] = t;
+    }
+    if (sum) store_vec<VEC>(sum, sel<DT>(dt), i, v);
+    if (Y) {
+      if (act == NPML_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+      } else if (act != NPML_ACT_IDENTITY) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) v[j] = act_fn(act, v[j], p0, p1);
+      }
+      store_vec<VEC>(Y, sel<DT>(dt), i, v);
+    }
+  }
+};
+
+// Backward, pass 1: g = dY * act'(s) is never written; its three column sums are all the two BatchNorm backwards
+// need: [sum g, sum g * nhat_a, sum g * nhat_b] (dIntercept of both, dScaler_a, dScaler_b; layers/layers.py:1207-1213).
+// For ReLU `s` may be the OUTPUT Y (Y > 0 <=> sum > 0); identity reads no s at all.
+struct BnPairBwdStatsF {
+  static constexpr int kConsts = 4;
+  static constexpr int kIn = 4;
+  static constexpr int kBatch = 1;
+  const void* dY; const void* s; const void* xa; const void* xb; int dt;
+  const float* mean_a; const float* rstd_a; const float* mean_b; const float* rstd_b;
+  int act; float p0, p1;
+  template <int VEC>
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[4][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const int c = c0 + j < ch ? c0 + j : ch - 1;
+      kc[0][j] = mean_a[c]; kc[1][j] = rstd_a[c];
+      kc[2][j] = mean_b ? mean_b[c] : 0.f; kc[3][j] = rstd_b ? rstd_b[c] : 0.f;
+    }
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void load(int64_t i, float (&in)[4][VEC]) const {
+    load_vec<VEC>(dY, sel<DT>(dt), i, in[0]);
+    if (act != NPML_ACT_IDENTITY) load_vec<VEC>(s, sel<DT>(dt), i, in[1]);
+    load_vec<VEC>(xa, sel<DT>(dt), i, in[2]);
+    if (mean_b != nullptr) load_vec<VEC>(xb, sel<DT>(dt), i, in[3]);
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t, const float (&kc)[4][VEC], float (&in)[4][VEC], float (&out)[3][VEC]) const {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float g = in[0][j];
+      if (act == NPML_ACT_RELU) g = in[1][j] > 0.f ? g : 0.f;
+      else if (act != NPML_ACT_IDENTITY) g *= act_grad_ool(act, in[1][j], p0, p1);
+      if (sel<DT>(dt) == NPML_BF16) g = __bfloat162float(__float2bfloat16_rn(g));      // the value the unfused path stores
+      out[0][j] = g;
+      out[1][j] = g * ((in[2][j] - kc[0][j]) * kc[1][j]);
+      out[2][j] = mean_b != nullptr ? g * ((in[3][j] - kc[2][j]) * kc[3][j]) : 0.f;
+    }
+  }
+};
+
+// Backward, pass 2: dxa = BN_a'(g), dxb = BN_b'(g) (or dxb = g for an identity shortcut), both from one read of
+// (dY, s, xa, xb).  coef: [8][ch] = mean_a, rstd_a, scaler_a*rstd_a, m2a, mean_b, rstd_b, scaler_b*rstd_b, m2b; m1 (shared).
+struct BnPairBwdDxF {
+  static constexpr int kConsts = 9;
+  static constexpr int kIn = 4;
+  static constexpr int kBatch = 1;
+  const void* dY; const void* s; const void* xa; const void* xb; void* dxa; void* dxb; int dt;
+  const float* coef;
+  int has_b;
+  int act; float p0, p1;
+  template <int VEC>
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[9][VEC]) const {
+#pragma unroll
+    for (int a = 0; a < 9; ++a)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void load(int64_t i, float (&in)[4][VEC]) const {
+    load_vec<VEC>(dY, sel<DT>(dt), i, in[0]);
+    if (act != NPML_ACT_IDENTITY) load_vec<VEC>(s, sel<DT>(dt), i, in[1]);
+    load_vec<VEC>(xa, sel<DT>(dt), i, in[2]);
+    if (has_b) load_vec<VEC>(xb, sel<DT>(dt), i, in[3]);
+  }
+  template <int VEC, int DT>
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[9][VEC], float (&in)[4][VEC], float (&)[1][VEC]) const {
+    float da[VEC], db[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float g = in[0][j];
+      if (act == NPML_ACT_RELU) g = in[1][j] > 0.f ? g : 0.f;
+      else if (act != NPML_ACT_IDENTITY) g *= act_grad_ool(act, in[1][j], p0, p1);
+      if (sel<DT>(dt) == NPML_BF16) g = __bfloat162float(__float2bfloat16_rn(g));
+      const float na = (in[2][j] - kc[0][j]) * kc[1][j];
+      da[j] = kc[2][j] * (g - kc[8][j] - na * kc[3][j]);
+      if (has_b) {
+        const float nb = (in[3][j] - kc[4][j]) * kc[5][j];
+        db[j] = kc[6][j] * (g - kc[8][j] - nb * kc[7][j]);
+      } else {
+        db[j] = g;
+      }
+    }
+    store_vec<VEC>(dxa, sel<DT>(dt), i, da);
+    if (dxb) store_vec<VEC>(dxb, sel<DT>(dt), i, db);
+  }
+};
+
+// per-channel epilogue of the pair backward: parameter gradients from this rank's sums, dX coefficients from the
+// sums over all ranks (sync-BN; the same buffer otherwise)
+__global__ void bn_pair_bwd_finalize_kernel(int ch, int accumulate, double inv_m, const double* __restrict__ local,
+                                            const double* __restrict__ global, const float* scaler_a, const float* mean_a,
+                                            const float* rstd_a, const float* scaler_b, const float* mean_b,
+                                            const float* rstd_b, float* d_scaler_a, float* d_intercept_a,
+                                            float* d_scaler_b, float* d_intercept_b, float* coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  const float l0 = (float)local[c], la = (float)local[ch + c], lb = (float)local[2 * ch + c];
+  if (d_intercept_a) d_intercept_a[c] = accumulate ? d_intercept_a[c] + l0 : l0;
+  if (d_scaler_a) d_scaler_a[c] = accumulate ? d_scaler_a[c] + la : la;
+  if (d_intercept_b) d_intercept_b[c] = accumulate ? d_intercept_b[c] + l0 : l0;
+  if (d_scaler_b) d_scaler_b[c] = accumulate ? d_scaler_b[c] + lb : lb;
+  coef[c] = mean_a[c];
+  coef[ch + c] = rstd_a[c];
+  coef[2 * ch + c] = scaler_a[c] * rstd_a[c];
+  coef[3 * ch + c] = (float)(global[ch + c] * inv_m);
+  const bool has_b = scaler_b != nullptr;
+  coef[4 * ch + c] = has_b ? mean_b[c] : 0.f;
+  coef[5 * ch + c] = has_b ? rstd_b[c] : 0.f;
+  coef[6 * ch + c] = has_b ? scaler_b[c] * rstd_b[c] : 0.f;
+  coef[7 * ch + c] = has_b ? (float)(global[2 * ch + c] * inv_m) : 0.f;
+  coef[8 * ch + c] = (float)(global[c] * inv_m);
+}
 
 // part [nblk][width] -> sums[width] (double), fixed order
 __global__ void col_sums_kernel(const double* __restrict__ part, int nblk, int width, double* __restrict__ sums) {
@@ -487,6 +668,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, in
   const float rs = (float)(1.0 / sqrt(var + (double)eps));
   save_mean[c] = (float)mean;
   save_rstd[c] = rs;
+  if (coef == nullptr) return;
   coef[c] = (float)mean;
   coef[ch + c] = scaler[c] * rs;
   coef[2 * ch + c] = intercept[c];
@@ -782,7 +964,7 @@ __global__ void col2im_kernel(npml_conv_desc d, const float* __restrict__ Xc, fl
 size_t colpass_ws_bytes(int64_t rows, int ch, int nv) {
   ColPlan p = plan_cols(rows, ch, 1);     // vec = 1 gives the largest grid.x any plan for this shape can have
   return align_up((size_t)p.grid.x * nv * ch * sizeof(double), 256) + align_up((size_t)nv * ch * sizeof(double), 256) +
-         align_up((size_t)5 * ch * sizeof(float), 256);   // partials, sums, per-channel coefficient table
+         align_up((size_t)9 * ch * sizeof(float), 256);   // partials, sums, per-channel coefficient table
 }
 
 }  // namespace npml
@@ -1041,6 +1223,121 @@ extern "C" int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch,
   const int vec = pick_vec(ch, vec_ok, aligned16(x) && aligned16(dy) && aligned16(dx));
   BnBwdDxF fd{dy, x, dx, dtype, coef};
   return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st, dtype);
+}
+
+// BatchNorm2D backward with the activation derivative of the layer in front of it folded into the dX pass
+// (BnBwdDxF): dZ = BN'(dy) * act'(z).  zm == nullptr with ReLU: the sign of x itself is the mask.
+extern "C" int npml_bn2d_bwd_act(int64_t rows, int64_t rows_total, int32_t ch, const void* dy, const void* x, void* dz,
+                                 int32_t dtype, const float* scaler, const float* save_mean, const float* save_rstd,
+                                 const double* sums_local, const double* sums_global, float* d_scaler, float* d_intercept,
+                                 int32_t accumulate, int32_t act, float p0, float p1, const void* zm, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(rows_total >= rows, "rows_total < rows");
+  NPML_CHECK((sums_local == nullptr) == (sums_global == nullptr), "sums_local and sums_global go together");
+  NPML_CHECK(act == NPML_ACT_IDENTITY || act == NPML_ACT_RELU || zm != nullptr, "the pre-activation is required");
+  const bool vec_ok = aligned_for_vec4(x, dtype) && aligned_for_vec4(dy, dtype) && aligned_for_vec4(dz, dtype) &&
+                      aligned_for_vec4(zm, dtype);
+  const int vec = pick_vec(ch, vec_ok, aligned16(x) && aligned16(dy) && aligned16(dz) && aligned16(zm));
+  ColPlan p = plan_cols(rows, ch, vec, true);
+  const size_t part_bytes = align_up((size_t)p.grid.x * 2 * ch * sizeof(double), 256);
+  const size_t sums_bytes = align_up((size_t)2 * ch * sizeof(double), 256);
+  NPML_CHECK(ws != nullptr && ws_bytes >= part_bytes + sums_bytes + (size_t)5 * ch * sizeof(float), "workspace too small");
+  double* part = (double*)ws;
+  float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
+  if (sums_global == nullptr) {
+    BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
+    if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
+  }
+  bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
+                                                                  1.0 / (double)rows_total, save_mean, save_rstd, scaler, coef,
+                                                                  sums_local, sums_global);
+  NPML_LAUNCH_OK();
+  BnBwdDxF fd{dy, x, dz, dtype, coef, act, p0, p1, zm};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), fd, (float*)nullptr, st, dtype);
+}
+
+// per-channel statistics -> (mean, rstd) + running-statistics update, without touching the tensor (the normalisation
+// itself happens in a fused consumer, e.g. npml_bn2d_pair_add_act_fwd)
+extern "C" int npml_bn2d_finalize(int64_t rows_total, int32_t ch, const double* sums, float* running_mean,
+                                  float* running_var, float momentum, float eps, float* save_mean, float* save_rstd,
+                                  void* stream) {
+  if (ch <= 0) return 0;
+  NPML_CHECK(sums && running_mean && running_var && save_mean && save_rstd && rows_total > 0, "bad arguments");
+  bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(nullptr, 0, ch, 1.0 / (double)rows_total,
+                                                                               momentum, eps, running_mean, running_var,
+                                                                               save_mean, save_rstd, nullptr, nullptr,
+                                                                               nullptr, sums);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_bn2d_pair_add_act_fwd(int64_t rows, int32_t ch, const void* xa, const void* xb, int32_t dtype,
+                                          const float* scaler_a, const float* intercept_a, const float* mean_a,
+                                          const float* rstd_a, const float* scaler_b, const float* intercept_b,
+                                          const float* mean_b, const float* rstd_b, int32_t act, float p0, float p1,
+                                          void* sum, void* Y, void* stream) {
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(xa && xb && scaler_a && intercept_a && mean_a && rstd_a && (sum || Y), "NULL argument");
+  NPML_CHECK(scaler_b == nullptr || (intercept_b && mean_b && rstd_b), "incomplete second BatchNorm2D");
+  const bool vec_ok = aligned_for_vec4(xa, dtype) && aligned_for_vec4(xb, dtype) && aligned_for_vec4(sum, dtype) &&
+                      aligned_for_vec4(Y, dtype);
+  const int vec = pick_vec(ch, vec_ok, aligned16(xa) && aligned16(xb) && aligned16(sum) && aligned16(Y));
+  BnPairAddActF f{xa, xb, sum, Y, dtype, scaler_a, intercept_a, mean_a, rstd_a, scaler_b, intercept_b, mean_b, rstd_b,
+                  act, p0, p1};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), f, (float*)nullptr, (cudaStream_t)stream, dtype);
+}
+
+extern "C" int npml_bn2d_pair_bwd_stats(int64_t rows, int32_t ch, const void* dY, const void* s, int32_t act, float p0,
+                                        float p1, const void* xa, const void* xb, int32_t dtype, const float* mean_a,
+                                        const float* rstd_a, const float* mean_b, const float* rstd_b, double* sums,
+                                        void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NPML_CHECK(sums != nullptr, "sums is NULL");
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(dY && xa && mean_a && rstd_a && (act == NPML_ACT_IDENTITY || s), "NULL argument");
+  NPML_CHECK((mean_b == nullptr) == (rstd_b == nullptr) && (mean_b == nullptr || xb), "incomplete second BatchNorm2D");
+  const bool vec_ok = aligned_for_vec4(dY, dtype) && aligned_for_vec4(s, dtype) && aligned_for_vec4(xa, dtype) &&
+                      aligned_for_vec4(xb, dtype);
+  const int vec = pick_vec(ch, vec_ok, aligned16(dY) && aligned16(s) && aligned16(xa) && aligned16(xb));
+  ColPlan p = plan_cols(rows, ch, vec, true);
+  NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 3 * ch * sizeof(double), "workspace too small");
+  double* part = (double*)ws;
+  BnPairBwdStatsF f{dY, s, xa, xb, dtype, mean_a, rstd_a, mean_b, rstd_b, act, p0, p1};
+  if (int e = launch_col_pass<3, double>(p, f, part, st, dtype)) return e;
+  col_sums_kernel<<<(3 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 3 * ch, sums);
+  NPML_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int npml_bn2d_pair_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch, const void* dY, const void* s,
+                                        int32_t act, float p0, float p1, const void* xa, const void* xb, int32_t dtype,
+                                        const float* scaler_a, const float* mean_a, const float* rstd_a,
+                                        const float* scaler_b, const float* mean_b, const float* rstd_b,
+                                        const double* sums_local, const double* sums_global, void* dxa, void* dxb,
+                                        float* d_scaler_a, float* d_intercept_a, float* d_scaler_b, float* d_intercept_b,
+                                        int32_t accumulate, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (rows <= 0 || ch <= 0) return 0;
+  NPML_CHECK(dY && xa && dxa && scaler_a && mean_a && rstd_a && sums_local && sums_global && rows_total >= rows,
+             "bad arguments");
+  NPML_CHECK(act == NPML_ACT_IDENTITY || s != nullptr, "the activation needs its argument");
+  const bool has_b = scaler_b != nullptr;
+  NPML_CHECK(!has_b || (xb && mean_b && rstd_b && dxb), "incomplete second BatchNorm2D");
+  NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)9 * ch * sizeof(float), "workspace too small");
+  float* coef = (float*)ws;
+  bn_pair_bwd_finalize_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, accumulate, 1.0 / (double)rows_total, sums_local,
+                                                                sums_global, scaler_a, mean_a, rstd_a, scaler_b, mean_b,
+                                                                rstd_b, d_scaler_a, d_intercept_a, d_scaler_b,
+                                                                d_intercept_b, coef);
+  NPML_LAUNCH_OK();
+  const bool vec_ok = aligned_for_vec4(dY, dtype) && aligned_for_vec4(s, dtype) && aligned_for_vec4(xa, dtype) &&
+                      aligned_for_vec4(xb, dtype) && aligned_for_vec4(dxa, dtype) && aligned_for_vec4(dxb, dtype);
+  const int vec = pick_vec(ch, vec_ok, aligned16(dY) && aligned16(s) && aligned16(xa) && aligned16(xb) && aligned16(dxa) &&
+                                           aligned16(dxb));
+  BnPairBwdDxF f{dY, s, xa, xb, dxa, dxb, dtype, coef, has_b ? 1 : 0, act, p0, p1};
+  return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), f, (float*)nullptr, st, dtype);
 }
 
 extern "C" int npml_im2col(const npml_conv_desc* d, const float* X, float* X_col, void* stream) {

@@ -303,12 +303,21 @@ class _ConvBase(LayerBase):
             dX.append(L.to_numpy(dx) if as_np else dx)
         return dX[0] if len(self.X) == 1 else dX
 
-    def _bwd(self, dLdy, X, Z, retain_grads=True):
+    def backward_from_dz(self, dZ, retain_grads=True, index=-1):
+        """Backward of ONE retained forward from dZ = dLdy * act'(Z) itself: for callers that have already applied this
+        layer's activation derivative inside another pass (BatchNorm2D.backward_act folds it into its dX pass)."""
+        assert self.trainable, "Layer is frozen"
+        from .activations import Identity
+        return self._bwd(L.to_device(dZ, L.torch_dtype(self.mode)), self.X[index], self.derived_variables["Z"][index],
+                         retain_grads, act=Identity())
+
+    def _bwd(self, dLdy, X, Z, retain_grads=True, act=None):
         W = self.parameters["W"] = _as_param(self.parameters["W"])
         pre = "npml_conv2d_" if self._layer_name == "Conv2D" else "npml_deconv2d_"
         conv = self._layer_name == "Conv2D"
         # Conv2D: db is one more accumulator row of the wgrad pass; Deconv2D: db comes with the dZ prologue
-        dZ = _dz_prep(dLdy, Z, self.act_fn, X.dtype, self.gradients["b"] if (retain_grads and not conv) else None)
+        dZ = _dz_prep(dLdy, Z, self.act_fn if act is None else act, X.dtype,
+                      self.gradients["b"] if (retain_grads and not conv) else None)
         d = self._desc(tuple(X.shape), accumulate=1)
         # parameter gradients first (the reference's order, layers.py:3106-3114): a data-parallel bucket can then
         # all-reduce dW / db on its own stream while dX is still being computed (dist.GradBucket, overlap=True)
@@ -688,6 +697,85 @@ class BatchNorm2D(LayerBase):
             self.X.append(Xd)
             self._saved.append((mean, rstd) if use_batch else None)
         return L.to_numpy(y) if as_np else y
+
+    # ---- pieces of forward / backward for callers that fuse the normalisation into their own pass (modules.py) ----
+    def forward_stats(self, X):
+        """Training-mode statistics of X without normalising it: per-channel (mean, rstd) of the batch (all ranks
+        under `sync`), the running-statistics update (layers.py:1146-1150), and X retained for the backward pass.  The
+        caller normalises inside a fused pass (npml_bn2d_pair_add_act_fwd)."""
+        assert self.trainable, "Layer is frozen"
+        Xd = L.to_device(X, X.dtype if X.dtype != torch.float64 else torch.float32)
+        if not self.is_initialized:
+            self.in_ch = self.out_ch = Xd.shape[3]
+            self._init_params()
+        P = self.parameters
+        for k in P:
+            P[k] = _as_param(P[k])
+        ch = Xd.shape[3]
+        rows = Xd.numel() // ch
+        lib = L.load()
+        ws = self._ws(rows, ch)
+        sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
+        mean = torch.empty(ch, dtype=torch.float32, device=Xd.device)
+        rstd = torch.empty(ch, dtype=torch.float32, device=Xd.device)
+        total = rows
+        with L.profiled("npml_bn2d_stats"):
+            L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(), L.stream()),
+                    "npml_bn2d_stats")
+            if self.sync:
+                from . import dist as D
+                D.require_equal_shards(rows)
+                D.allreduce_sum_f64(sums)
+                total = rows * D.world_size()
+            L.check(lib.npml_bn2d_finalize(total, ch, L.ptr(sums), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
+                                           float(self.momentum), float(self.epsilon), L.ptr(mean), L.ptr(rstd), L.stream()),
+                    "npml_bn2d_finalize")
+        self.X.append(Xd)
+        self._saved.append((mean, rstd))
+        return mean, rstd
+
+    def normalise_with(self, X, saved):
+        """scaler * (X - mean) * rstd + intercept for given (mean, rstd): what `forward` would have returned for a
+        retained input whose normalisation was fused into another pass (used to materialise derived variables)."""
+        P, (mean, rstd) = self.parameters, saved
+        ch = X.shape[3]
+        y = torch.empty_like(X)
+        zero = torch.zeros_like(X)
+        L.check(L.load().npml_bn2d_pair_add_act_fwd(X.numel() // ch, ch, L.ptr(X), L.ptr(zero), L.code_of(X),
+                                                    L.ptr(P["scaler"]), L.ptr(P["intercept"]), L.ptr(mean), L.ptr(rstd),
+                                                    None, None, None, None, 0, 0.0, 0.0, None, L.ptr(y), L.stream()),
+                "npml_bn2d_pair_add_act_fwd")
+        return y
+
+    def backward_act(self, dLdy, act, zm=None, retain_grads=True, index=-1):
+        """Backward of ONE retained forward whose dX pass also applies act'(z) of the layer in front of this one
+        (x = act(z)): returns dZ = BN'(dLdy) * act'(z) (npml_bn2d_bwd_act).  zm: z, or None for ReLU / identity."""
+        assert self.trainable, "Layer is frozen"
+        X, saved = self.X[index], self._saved[index]
+        dLdy = L.to_device(dLdy, X.dtype)
+        P, G = self.parameters, self.gradients
+        ch = X.shape[3]
+        rows = X.numel() // ch
+        mean, rstd = saved if saved is not None else self._batch_stats(X)
+        dZ = torch.empty_like(X)
+        ws = self._ws(rows, ch)
+        lib = L.load()
+        local = glob = None
+        total = rows
+        with L.profiled("npml_bn2d_bwd"):
+            if self.sync and saved is not None:
+                from . import dist as D
+                local = torch.empty(2 * ch, dtype=torch.float64, device=X.device)
+                L.check(lib.npml_bn2d_bwd_stats(rows, ch, L.ptr(dLdy), L.ptr(X), L.code_of(X), L.ptr(mean), L.ptr(rstd),
+                                                L.ptr(local), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_bwd_stats")
+                glob = D.allreduce_sum_f64(local.clone()) if D.world_size() > 1 else local
+                total = rows * D.world_size()
+            L.check(lib.npml_bn2d_bwd_act(rows, total, ch, L.ptr(dLdy), L.ptr(X), L.ptr(dZ), L.code_of(X),
+                                          L.ptr(_as_param(P["scaler"])), L.ptr(mean), L.ptr(rstd), L.ptr(local), L.ptr(glob),
+                                          L.ptr(G["scaler"]) if retain_grads else None,
+                                          L.ptr(G["intercept"]) if retain_grads else None, 1, act.code, act.p0, act.p1,
+                                          L.ptr(zm), L.ptr(ws), ws.numel(), L.stream()), "npml_bn2d_bwd_act")
+        return dZ
 
     def backward(self, dLdy, retain_grads=True):
         assert self.trainable, "Layer is frozen"

@@ -25,6 +25,80 @@ def _device_add(a, b):
     return out
 
 
+class _Lazy(object):
+    """A derived variable that the fused passes never write to memory (e.g. batchnorm2_out inside
+    Y = act(BN2(..) + BNskip(..))): computed from what WAS retained the first time somebody reads it."""
+
+    def __init__(self, fn):
+        self.fn, self.value = fn, None
+
+    def get(self):
+        if self.value is None:
+            self.value = self.fn()
+        return self.value
+
+
+def _resolve(dv):
+    return {k: (v.get() if isinstance(v, _Lazy) else v) for k, v in dv.items()}
+
+
+def _pair_add_act(bn_a, xa, saved_a, bn_b, xb, saved_b, act, want_sum):
+    """Y = act(BN_a(xa) + BN_b(xb)) in one pass (bn_b None: xb is added as it is).  Returns (sum or None, Y)."""
+    ch = xa.shape[3]
+    Y = torch.empty_like(xa)
+    S = torch.empty_like(xa) if want_sum else None
+    Pa = bn_a.parameters
+    args_b = [None] * 4
+    if bn_b is not None:
+        Pb = bn_b.parameters
+        args_b = [L.ptr(Pb["scaler"]), L.ptr(Pb["intercept"]), L.ptr(saved_b[0]), L.ptr(saved_b[1])]
+    with L.profiled("npml_bn2d_pair_add_act_fwd"):
+        L.check(L.load().npml_bn2d_pair_add_act_fwd(xa.numel() // ch, ch, L.ptr(xa), L.ptr(xb), L.code_of(xa),
+                                                    L.ptr(Pa["scaler"]), L.ptr(Pa["intercept"]), L.ptr(saved_a[0]),
+                                                    L.ptr(saved_a[1]), *args_b, act.code, act.p0, act.p1, L.ptr(S), L.ptr(Y),
+                                                    L.stream()), "npml_bn2d_pair_add_act_fwd")
+    return S, Y
+
+
+def _pair_bwd(dY, S, act, bn_a, xa, saved_a, bn_b, xb, saved_b, retain_grads, want_dxb=True):
+    """(dxa, dxb) = (BN_a'(g), BN_b'(g)) with g = dY * act'(S) formed on the fly; the parameter gradients of both
+    BatchNorm2D layers accumulate (layers.py:1192-1215).  bn_b None: dxb = g (identity shortcut)."""
+    lib = L.load()
+    ch = xa.shape[3]
+    rows = xa.numel() // ch
+    ws = bn_a._ws(rows, ch)
+    sums = torch.empty(3 * ch, dtype=torch.float64, device=xa.device)
+    mb = [None, None] if bn_b is None else [L.ptr(saved_b[0]), L.ptr(saved_b[1])]
+    dxa = torch.empty_like(xa)
+    dxb = torch.empty_like(xa) if want_dxb else None
+    Ga, Pa = bn_a.gradients, bn_a.parameters
+    total = rows
+    with L.profiled("npml_bn2d_pair_bwd"):
+        L.check(lib.npml_bn2d_pair_bwd_stats(rows, ch, L.ptr(dY), L.ptr(S), act.code, act.p0, act.p1, L.ptr(xa),
+                                             L.ptr(xb) if bn_b is not None else None, L.code_of(xa), L.ptr(saved_a[0]),
+                                             L.ptr(saved_a[1]), mb[0], mb[1], L.ptr(sums), L.ptr(ws), ws.numel(), L.stream()),
+                "npml_bn2d_pair_bwd_stats")
+        glob = sums
+        if bn_a.sync:
+            from . import dist as D
+            if D.world_size() > 1:
+                glob = D.allreduce_sum_f64(sums.clone())
+                total = rows * D.world_size()
+        gb = [None] * 5
+        if bn_b is not None:
+            Gb, Pb = bn_b.gradients, bn_b.parameters
+            gb = [L.ptr(Pb["scaler"]), L.ptr(saved_b[0]), L.ptr(saved_b[1]),
+                  L.ptr(Gb["scaler"]) if retain_grads else None, L.ptr(Gb["intercept"]) if retain_grads else None]
+        L.check(lib.npml_bn2d_pair_bwd_apply(rows, total, ch, L.ptr(dY), L.ptr(S), act.code, act.p0, act.p1, L.ptr(xa),
+                                             L.ptr(xb) if bn_b is not None else None, L.code_of(xa), L.ptr(Pa["scaler"]),
+                                             L.ptr(saved_a[0]), L.ptr(saved_a[1]), gb[0], gb[1], gb[2], L.ptr(sums),
+                                             L.ptr(glob), L.ptr(dxa), L.ptr(dxb),
+                                             L.ptr(Ga["scaler"]) if retain_grads else None,
+                                             L.ptr(Ga["intercept"]) if retain_grads else None, gb[3], gb[4], 1, L.ptr(ws),
+                                             ws.numel(), L.stream()), "npml_bn2d_pair_bwd_apply")
+    return dxa, dxb
+
+
 class ModuleBase(ABC):
     """modules.py:21-116."""
 
@@ -67,6 +141,7 @@ class ModuleBase(ABC):
         assert self.trainable, "Layer is frozen"
         self.X = []
         self._dv = {}
+        self._tail = None
         comps = self.components
         buckets = {id(getattr(c, "_bucket", None)) for c in comps if c.gradients}
         shared = getattr(comps[0], "_bucket", None) if len(buckets) == 1 else None
@@ -95,6 +170,11 @@ class SkipConnectionConvModule(ModuleBase):
     # inference (retain_derived=False) forwards fold each BatchNorm2D into the epilogue of the convolution before it;
     # set to False to run the seven layers one by one as in training
     fuse_inference = True
+    # training forwards / backwards run the residual tail -- batchnorm2, batchnorm_skip, add3 and its activation
+    # (modules.py:931-937, 941-953) -- as ONE pass each way, and fold conv1's activation derivative into batchnorm1's
+    # backward; the tensors that are then never written (batchnorm2_out, batchnorm_skip_out, dLdBn2, dLdBnSkip,
+    # dLdConv1) are materialised on demand by `derived_variables`.  Set to False to run the seven layers one by one.
+    fuse_training = True
 
     def __init__(self, out_ch1, out_ch2, kernel_shape1, kernel_shape2, kernel_shape_skip, pad1=0, pad2=0, stride1=1,
                  stride2=1, act_fn=None, epsilon=1e-5, momentum=0.9, stride_skip=1, optimizer=None,
@@ -189,8 +269,12 @@ class SkipConnectionConvModule(ModuleBase):
     def derived_variables(self):
         dv = {"conv1_out": None, "conv2_out": None, "conv_skip_out": None, "batchnorm1_out": None,
               "batchnorm2_out": None, "batchnorm_skip_out": None, "components": self._by_component("derived_variables")}
-        dv.update(self._dv)
+        dv.update(_resolve(self._dv))
         return dv
+
+    def _fusable(self):
+        comps = [self.conv1, self.conv2, self.conv_skip, self.batchnorm1, self.batchnorm2, self.batchnorm_skip]
+        return self.fuse_training and self.trainable and all(c.trainable for c in comps) and len(self.conv1.X) == 0
 
     def forward(self, X, retain_derived=True):
         """modules.py:905-937."""
@@ -199,6 +283,26 @@ class SkipConnectionConvModule(ModuleBase):
         if not hasattr(self, "conv_skip"):
             self._init_conv_skip(tuple(Xd.shape))
             self.in_ch = Xd.shape[3]
+        self._tail = None
+        if retain_derived and self._fusable():
+            conv1_out = self.conv1.forward(Xd, True)
+            bn1_out = self.batchnorm1.forward(conv1_out, True)
+            conv2_out = self.conv2.forward(bn1_out, True)
+            conv_skip_out = self.conv_skip.forward(Xd, True)
+            bn2, bns, act = self.batchnorm2, self.batchnorm_skip, self.act_fn
+            s2 = bn2.forward_stats(conv2_out)
+            ss = bns.forward_stats(conv_skip_out)
+            # ReLU / identity need no stored sum: Y > 0 <=> sum > 0
+            want_sum = act.code not in (0, 2)
+            S, Y = _pair_add_act(bn2, conv2_out, s2, bns, conv_skip_out, ss, act, want_sum)
+            self._tail = (S if want_sum else Y, conv2_out, s2, conv_skip_out, ss)
+            self.add3.X.append([None, None])                 # the Add layer's own bookkeeping (layers.py:700-703)
+            self.add3.derived_variables["sum"].append(S if want_sum else None)
+            self._dv.update({"conv1_out": conv1_out, "conv2_out": conv2_out, "conv_skip_out": conv_skip_out,
+                             "batchnorm1_out": bn1_out,
+                             "batchnorm2_out": _Lazy(lambda: bn2.normalise_with(conv2_out, s2)),
+                             "batchnorm_skip_out": _Lazy(lambda: bns.normalise_with(conv_skip_out, ss))})
+            return L.to_numpy(Y) if as_np else Y
         if not retain_derived and self.fuse_inference:
             # inference: every BatchNorm2D is the affine of its running statistics (layers.py:1141-1146) and nothing is
             # retained, so each conv -> BN pair is ONE kernel (bias, activation and BN affine in the epilogue)
@@ -224,6 +328,24 @@ class SkipConnectionConvModule(ModuleBase):
         """modules.py:939-984."""
         as_np = isinstance(dLdY, np.ndarray)
         dY = L.to_device(dLdY, L.torch_dtype(self.mode))
+        if getattr(self, "_tail", None) is not None:
+            S, conv2_out, s2, conv_skip_out, ss = self._tail
+            act = self.act_fn
+            dConv2_out, dConvskip_out = _pair_bwd(dY, S, act, self.batchnorm2, conv2_out, s2, self.batchnorm_skip,
+                                                  conv_skip_out, ss, retain_grads)
+            dX = self.conv_skip.backward(dConvskip_out, retain_grads)
+            dBn1_out = self.conv2.backward(dConv2_out, retain_grads)
+            a1 = self.conv1.act_fn
+            z1 = None if a1.code in (0, 2) else self.conv1.derived_variables["Z"][-1]
+            dZ1 = self.batchnorm1.backward_act(dBn1_out, a1, z1, retain_grads)
+            dX = _device_add(dX, self.conv1.backward_from_dz(dZ1, retain_grads))
+            if retain_grads:
+                bn1 = self.batchnorm1
+                g = _Lazy(lambda: _dz_prep(dY, S, act, dY.dtype) if act.code != 0 else dY)
+                self._dv.update({"dLdAdd3_X": dX, "dLdBn2": g, "dLdBn1": dBn1_out, "dLdConv2": dConv2_out,
+                                 "dLdConv1": _Lazy(lambda: bn1._bwd(dBn1_out, bn1.X[-1], bn1._saved[-1], False)),
+                                 "dLdBnSkip": g, "dLdConvSkip": dConvskip_out})
+            return L.to_numpy(dX) if as_np else dX
         dBnskip_out, dBn2_out = self.add3.backward(dY)
         dConvskip_out = self.batchnorm_skip.backward(dBnskip_out)
         dX = self.conv_skip.backward(dConvskip_out)

@@ -150,8 +150,9 @@ def test_bn_add_golden(cuda_device):
             close(g[-1], z[i + "/dX"], 1e-6, i + " dX")
 
 
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused-tail", "layer-by-layer"])
 @pytest.mark.parametrize("mode", MODES)
-def test_skip_conv_module_golden(cuda_device, mode):
+def test_skip_conv_module_golden(cuda_device, mode, fuse):
     pkg = npml()
     z, cases = load_golden("skip_conv_module.npz")
     tol = TOL_BN[mode]
@@ -163,6 +164,7 @@ def test_skip_conv_module_golden(cuda_device, mode):
                                          kernel_shape_skip=tuple(c["kernel_shape_skip"]), pad1=to_pad(c["pad1"]),
                                          pad2=to_pad(c["pad2"]), stride1=c["stride1"], stride2=c["stride2"],
                                          stride_skip=c["stride_skip"], act_fn=act, mode=mode)
+        M.fuse_training = fuse          # one pass each way over the residual tail (default) / the seven layers one by one
         X = z[i + "/X"]
         M.forward(X, retain_derived=False)
         assert list(M.pad_skip) == list(z[i + "/pad_skip"])
@@ -417,6 +419,7 @@ def test_skip_modules_fused_inference(cuda_device, mode, module):
         short = X
     ref, _ = O.add_fwd([short, h2], act)
     tol = TOL_BN[mode]
+    M.forward(X, retain_derived=False)              # the convolutions pack the newly assigned weights once
     pkg.launch_count(reset=True)
     Y = M.forward(X, retain_derived=False)
     fused_launches = pkg.launch_count(reset=True)
@@ -786,7 +789,8 @@ def test_full_size_skip_conv_module_against_oracle(cuda_device, mode):
         bn.reset_running_stats()
     M.flush_gradients()
     Y = M.forward(Xd)
-    z1_dev, total_dev = M.conv1.derived_variables["Z"][0], M.add3.derived_variables["sum"][0]
+    # the fused tail keeps Y instead of the sum for ReLU (Y > 0 <=> sum > 0): either works as the mask's argument
+    z1_dev, total_dev = M.conv1.derived_variables["Z"][0], M._tail[0]
     dX = M.backward(dYd)
     tol = TOL_BN[mode]
     bad = {}
@@ -798,7 +802,7 @@ def test_full_size_skip_conv_module_against_oracle(cuda_device, mode):
 
     chk("Y", Y, fwd["Y"])
     chk("Z1", z1_dev, fwd["_z1"])
-    chk("sum", total_dev, fwd["_total"])
+    chk("relu(sum)", total_dev, np.maximum(fwd["_total"], 0))
     for t, bn in (("1", M.batchnorm1), ("2", M.batchnorm2), ("s", M.batchnorm_skip)):
         chk("rm" + t, bn.parameters["running_mean"], fwd["rm" + t])
         chk("rv" + t, bn.parameters["running_var"], fwd["rv" + t])
