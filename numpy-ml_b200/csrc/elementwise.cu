@@ -387,52 +387,48 @@ struct BnNormF {
   }
 };
 
+// raw column sums [sum dy, sum dy*x]; the finalize kernels turn them into sum dy*nhat = rstd*(sum dy*x - mean*sum dy)
+// in double, so the pass itself carries no per-channel constants (registers -> occupancy -> bytes in flight)
 struct BnBwdStatsF {
-  static constexpr int kConsts = 2;
+  static constexpr int kConsts = 0;
   static constexpr int kIn = 2;
-  static constexpr int kBatch = 1;      // measured: batching the two-input BatchNorm backward passes is slower (95 vs 88 us)
+  static constexpr int kBatch = 2;
   const void* dy; const void* x; int dt;
-  const float* mean; const float* rstd;
   template <int VEC>
-  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[2][VEC]) const {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int c = c0 + j < ch ? c0 + j : ch - 1;
-      kc[0][j] = mean[c]; kc[1][j] = rstd[c];
-    }
-  }
+  __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
   template <int VEC, int DT>
   __device__ __forceinline__ void load(int64_t i, float (&in)[2][VEC]) const {
     load_vec<VEC>(dy, sel<DT>(dt), i, in[0]);
     load_vec<VEC>(x, sel<DT>(dt), i, in[1]);
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void finish(int64_t, const float (&kc)[2][VEC], float (&in)[2][VEC], float (&out)[2][VEC]) const {
+  __device__ __forceinline__ void finish(int64_t, const float (&)[1][VEC], float (&in)[2][VEC], float (&out)[2][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       out[0][j] = in[0][j];
-      out[1][j] = in[0][j] * ((in[1][j] - kc[0][j]) * kc[1][j]);
+      out[1][j] = in[0][j] * in[1][j];
     }
   }
 };
 
-// dx = g*rstd*(dy - m1 - nhat*m2), nhat = (x - mean)*rstd; coef: [5][ch] = mean, rstd, g*rstd, m1, m2.
+// dx = g*rstd*(dy - m1 - nhat*m2), nhat = (x - mean)*rstd, regrouped as dx = A1*dy + A2*x + A3 with
+// coef: [3][ch] = A1 = g*rstd, A2 = -A1*m2*rstd, A3 = -A1*m1 - A2*mean (formed in double by the finalize kernel).
 // act != identity: the layer in front of this BatchNorm2D ends in an activation (x = act(z)); its backward prologue
 // dZ = dx * act'(z) (layers/layers.py:3103) is applied here, in the same pass, instead of in a pass of its own.  ReLU
 // needs no extra tensor (x > 0 <=> z > 0); every other activation reads z from `zm`.
 struct BnBwdDxF {
-  static constexpr int kConsts = 5;
+  static constexpr int kConsts = 3;
   static constexpr int kIn = 3;
-  static constexpr int kBatch = 1;      // measured: batching the two-input BatchNorm backward passes is slower (95 vs 88 us)
+  static constexpr int kBatch = 1;
   const void* dy; const void* x; void* dx; int dt;
   const float* coef;
   int act = NPML_ACT_IDENTITY;
   float p0 = 0.f, p1 = 0.f;
   const void* zm = nullptr;
   template <int VEC>
-  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[5][VEC]) const {
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[3][VEC]) const {
 #pragma unroll
-    for (int a = 0; a < 5; ++a)
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
@@ -443,13 +439,12 @@ struct BnBwdDxF {
     if (zm != nullptr) load_vec<VEC>(zm, sel<DT>(dt), i, in[2]);
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[5][VEC], float (&in)[3][VEC], float (&)[1][VEC]) const {
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[3][VEC], float (&in)[3][VEC], float (&)[1][VEC]) const {
     float (&v)[VEC] = in[1];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const float xv = v[j];
-      const float nh = (xv - kc[0][j]) * kc[1][j];
-      float d = kc[2][j] * (in[0][j] - kc[3][j] - nh * kc[4][j]);
+      float d = fmaf(kc[0][j], in[0][j], fmaf(kc[1][j], xv, kc[2][j]));
       if (act == NPML_ACT_RELU) {
         d = (zm != nullptr ? in[2][j] : xv) > 0.f ? d : 0.f;
       } else if (act != NPML_ACT_IDENTITY) {
@@ -467,7 +462,7 @@ struct BnBwdDxF {
 // Forward: Y = act(BN_a(xa) + BN_b(xb)) in ONE pass over (xa, xb) instead of two BatchNorm2D passes and an Add pass.
 // `b` may be a plain tensor (identity shortcut: scaler_b == nullptr -> xb is added as it is).
 struct BnPairAddActF {
-  static constexpr int kConsts = 6;
+  static constexpr int kConsts = 3;      // a_a, a_b, c: sum = a_a*xa + a_b*xb + c
   static constexpr int kIn = 2;
   static constexpr int kBatch = 2;
   const void* xa; const void* xb; void* sum; void* Y; int dt;
@@ -475,13 +470,17 @@ struct BnPairAddActF {
   const float* scaler_b; const float* intercept_b; const float* mean_b; const float* rstd_b;
   int act; float p0, p1;
   template <int VEC>
-  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[6][VEC]) const {
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[3][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       const int c = c0 + j < ch ? c0 + j : ch - 1;
-      kc[0][j] = mean_a[c]; kc[1][j] = scaler_a[c] * rstd_a[c]; kc[2][j] = intercept_a[c];
-      if (scaler_b != nullptr) { kc[3][j] = mean_b[c]; kc[4][j] = scaler_b[c] * rstd_b[c]; kc[5][j] = intercept_b[c]; }
-      else { kc[3][j] = 0.f; kc[4][j] = 1.f; kc[5][j] = 0.f; }
+      const double aa = (double)scaler_a[c] * (double)rstd_a[c];
+      double ab = 1.0, k = (double)intercept_a[c] - aa * (double)mean_a[c];
+      if (scaler_b != nullptr) {
+        ab = (double)scaler_b[c] * (double)rstd_b[c];
+        k += (double)intercept_b[c] - ab * (double)mean_b[c];
+      }
+      kc[0][j] = (float)aa; kc[1][j] = (float)ab; kc[2][j] = (float)k;
     }
   }
   template <int VEC, int DT>
@@ -490,13 +489,11 @@ struct BnPairAddActF {
     load_vec<VEC>(xb, sel<DT>(dt), i, in[1]);
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[6][VEC], float (&in)[2][VEC], float (&)[1][VEC]) const {
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[3][VEC], float (&in)[2][VEC], float (&)[1][VEC]) const {
     float (&v)[VEC] = in[0];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      const float ya = fmaf(kc[1][j], v[j] - kc[0][j], kc[2][j]);
-      const float yb = fmaf(kc[4][j], in[1][j] - kc[3][j], kc[5][j]);
-      float t = ya + yb;
+      float t = fmaf(kc[0][j], v[j], fmaf(kc[1][j], in[1][j], kc[2][j]));
       if (sel<DT>(dt) == NPML_BF16) t = __bfloat162float(__float2bfloat16_rn(t));   // activations see the stored sum
       v[j] = t;
     }
@@ -514,34 +511,27 @@ struct BnPairAddActF {
   }
 };
 
-// Backward, pass 1: g = dY * act'(s) is never written; its three column sums are all the two BatchNorm backwards
-// need: [sum g, sum g * nhat_a, sum g * nhat_b] (dIntercept of both, dScaler_a, dScaler_b; layers/layers.py:1207-1213).
-// For ReLU `s` may be the OUTPUT Y (Y > 0 <=> sum > 0); identity reads no s at all.
+// Backward, pass 1: g = dY * act'(s) is never written; its raw column sums [sum g, sum g*xa, sum g*xb] are all the two
+// BatchNorm backwards need (pair_stats_fix_kernel turns them into sum g*nhat; dIntercept of both, dScaler_a, dScaler_b;
+// layers/layers.py:1207-1213).  For ReLU `s` may be the OUTPUT Y (Y > 0 <=> sum > 0); identity reads no s at all.
 struct BnPairBwdStatsF {
-  static constexpr int kConsts = 4;
+  static constexpr int kConsts = 0;
   static constexpr int kIn = 4;
   static constexpr int kBatch = 1;
   const void* dY; const void* s; const void* xa; const void* xb; int dt;
-  const float* mean_a; const float* rstd_a; const float* mean_b; const float* rstd_b;
+  int has_b;
   int act; float p0, p1;
   template <int VEC>
-  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[4][VEC]) const {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int c = c0 + j < ch ? c0 + j : ch - 1;
-      kc[0][j] = mean_a[c]; kc[1][j] = rstd_a[c];
-      kc[2][j] = mean_b ? mean_b[c] : 0.f; kc[3][j] = rstd_b ? rstd_b[c] : 0.f;
-    }
-  }
+  __device__ __forceinline__ void init(int, int, float (&)[1][VEC]) const {}
   template <int VEC, int DT>
   __device__ __forceinline__ void load(int64_t i, float (&in)[4][VEC]) const {
     load_vec<VEC>(dY, sel<DT>(dt), i, in[0]);
     if (act != NPML_ACT_IDENTITY) load_vec<VEC>(s, sel<DT>(dt), i, in[1]);
     load_vec<VEC>(xa, sel<DT>(dt), i, in[2]);
-    if (mean_b != nullptr) load_vec<VEC>(xb, sel<DT>(dt), i, in[3]);
+    if (has_b) load_vec<VEC>(xb, sel<DT>(dt), i, in[3]);
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void finish(int64_t, const float (&kc)[4][VEC], float (&in)[4][VEC], float (&out)[3][VEC]) const {
+  __device__ __forceinline__ void finish(int64_t, const float (&)[1][VEC], float (&in)[4][VEC], float (&out)[3][VEC]) const {
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float g = in[0][j];
@@ -549,16 +539,27 @@ struct BnPairBwdStatsF {
       else if (act != NPML_ACT_IDENTITY) g *= act_grad_ool(act, in[1][j], p0, p1);
       if (sel<DT>(dt) == NPML_BF16) g = __bfloat162float(__float2bfloat16_rn(g));      // the value the unfused path stores
       out[0][j] = g;
-      out[1][j] = g * ((in[2][j] - kc[0][j]) * kc[1][j]);
-      out[2][j] = mean_b != nullptr ? g * ((in[3][j] - kc[2][j]) * kc[3][j]) : 0.f;
+      out[1][j] = g * in[2][j];
+      out[2][j] = has_b ? g * in[3][j] : 0.f;
     }
   }
 };
 
+// raw [sum g, sum g*xa, sum g*xb] -> [sum g, sum g*nhat_a, sum g*nhat_b] (double; linear, so it commutes with the
+// all-reduce of sync-BN as long as mean / rstd are the global ones, which they are)
+__global__ void pair_stats_fix_kernel(int ch, double* sums, const float* mean_a, const float* rstd_a, const float* mean_b,
+                                      const float* rstd_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  const double sg = sums[c];
+  sums[ch + c] = (double)rstd_a[c] * (sums[ch + c] - (double)mean_a[c] * sg);
+  sums[2 * ch + c] = mean_b != nullptr ? (double)rstd_b[c] * (sums[2 * ch + c] - (double)mean_b[c] * sg) : 0.0;
+}
+
 // Backward, pass 2: dxa = BN_a'(g), dxb = BN_b'(g) (or dxb = g for an identity shortcut), both from one read of
-// (dY, s, xa, xb).  coef: [8][ch] = mean_a, rstd_a, scaler_a*rstd_a, m2a, mean_b, rstd_b, scaler_b*rstd_b, m2b; m1 (shared).
+// (dY, s, xa, xb): dx = A1*g + A2*x + A3 per BatchNorm2D (see BnBwdDxF).  coef: [6][ch] = A1a, A2a, A3a, A1b, A2b, A3b.
 struct BnPairBwdDxF {
-  static constexpr int kConsts = 9;
+  static constexpr int kConsts = 6;
   static constexpr int kIn = 4;
   static constexpr int kBatch = 1;
   const void* dY; const void* s; const void* xa; const void* xb; void* dxa; void* dxb; int dt;
@@ -566,9 +567,9 @@ struct BnPairBwdDxF {
   int has_b;
   int act; float p0, p1;
   template <int VEC>
-  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[9][VEC]) const {
+  __device__ __forceinline__ void init(int c0, int ch, float (&kc)[6][VEC]) const {
 #pragma unroll
-    for (int a = 0; a < 9; ++a)
+    for (int a = 0; a < 6; ++a)
 #pragma unroll
       for (int j = 0; j < VEC; ++j) kc[a][j] = coef[a * ch + (c0 + j < ch ? c0 + j : ch - 1)];
   }
@@ -580,22 +581,17 @@ struct BnPairBwdDxF {
     if (has_b) load_vec<VEC>(xb, sel<DT>(dt), i, in[3]);
   }
   template <int VEC, int DT>
-  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[9][VEC], float (&in)[4][VEC], float (&)[1][VEC]) const {
-    float da[VEC], db[VEC];
+  __device__ __forceinline__ void finish(int64_t i, const float (&kc)[6][VEC], float (&in)[4][VEC], float (&)[1][VEC]) const {
+    float (&da)[VEC] = in[2];
+    float (&db)[VEC] = in[3];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
       float g = in[0][j];
       if (act == NPML_ACT_RELU) g = in[1][j] > 0.f ? g : 0.f;
       else if (act != NPML_ACT_IDENTITY) g *= act_grad_ool(act, in[1][j], p0, p1);
       if (sel<DT>(dt) == NPML_BF16) g = __bfloat162float(__float2bfloat16_rn(g));
-      const float na = (in[2][j] - kc[0][j]) * kc[1][j];
-      da[j] = kc[2][j] * (g - kc[8][j] - na * kc[3][j]);
-      if (has_b) {
-        const float nb = (in[3][j] - kc[4][j]) * kc[5][j];
-        db[j] = kc[6][j] * (g - kc[8][j] - nb * kc[7][j]);
-      } else {
-        db[j] = g;
-      }
+      da[j] = fmaf(kc[0][j], g, fmaf(kc[1][j], da[j], kc[2][j]));
+      db[j] = has_b ? fmaf(kc[3][j], g, fmaf(kc[4][j], db[j], kc[5][j])) : g;
     }
     store_vec<VEC>(dxa, sel<DT>(dt), i, da);
     if (dxb) store_vec<VEC>(dxb, sel<DT>(dt), i, db);
@@ -603,7 +599,7 @@ struct BnPairBwdDxF {
 };
 
 // per-channel epilogue of the pair backward: parameter gradients from this rank's sums, dX coefficients from the
-// sums over all ranks (sync-BN; the same buffer otherwise)
+// sums over all ranks (sync-BN; the same buffer otherwise).  sums = [sum g, sum g*nhat_a, sum g*nhat_b].
 __global__ void bn_pair_bwd_finalize_kernel(int ch, int accumulate, double inv_m, const double* __restrict__ local,
                                             const double* __restrict__ global, const float* scaler_a, const float* mean_a,
                                             const float* rstd_a, const float* scaler_b, const float* mean_b,
@@ -616,16 +612,23 @@ __global__ void bn_pair_bwd_finalize_kernel(int ch, int accumulate, double inv_m
   if (d_scaler_a) d_scaler_a[c] = accumulate ? d_scaler_a[c] + la : la;
   if (d_intercept_b) d_intercept_b[c] = accumulate ? d_intercept_b[c] + l0 : l0;
   if (d_scaler_b) d_scaler_b[c] = accumulate ? d_scaler_b[c] + lb : lb;
-  coef[c] = mean_a[c];
-  coef[ch + c] = rstd_a[c];
-  coef[2 * ch + c] = scaler_a[c] * rstd_a[c];
-  coef[3 * ch + c] = (float)(global[ch + c] * inv_m);
-  const bool has_b = scaler_b != nullptr;
-  coef[4 * ch + c] = has_b ? mean_b[c] : 0.f;
-  coef[5 * ch + c] = has_b ? rstd_b[c] : 0.f;
-  coef[6 * ch + c] = has_b ? scaler_b[c] * rstd_b[c] : 0.f;
-  coef[7 * ch + c] = has_b ? (float)(global[2 * ch + c] * inv_m) : 0.f;
-  coef[8 * ch + c] = (float)(global[c] * inv_m);
+  const double m1 = global[c] * inv_m;
+  {
+    const double a1 = (double)scaler_a[c] * (double)rstd_a[c];
+    const double a2 = -a1 * (global[ch + c] * inv_m) * (double)rstd_a[c];
+    coef[c] = (float)a1;
+    coef[ch + c] = (float)a2;
+    coef[2 * ch + c] = (float)(-a1 * m1 - a2 * (double)mean_a[c]);
+  }
+  if (scaler_b != nullptr) {
+    const double b1 = (double)scaler_b[c] * (double)rstd_b[c];
+    const double b2 = -b1 * (global[2 * ch + c] * inv_m) * (double)rstd_b[c];
+    coef[3 * ch + c] = (float)b1;
+    coef[4 * ch + c] = (float)b2;
+    coef[5 * ch + c] = (float)(-b1 * m1 - b2 * (double)mean_b[c]);
+  } else {
+    coef[3 * ch + c] = 0.f; coef[4 * ch + c] = 0.f; coef[5 * ch + c] = 0.f;
+  }
 }
 
 // part [nblk][width] -> sums[width] (double), fixed order
@@ -700,7 +703,8 @@ __global__ void bn_fold_kernel(int ch, float eps, const float* running_mean, con
 }
 
 // sums_local / sums_global != nullptr (sync-BN): the parameter gradients accumulate this rank's sums (the gradient
-// bucket is all-reduced later), the dX coefficients use the sums over all ranks
+// bucket is all-reduced later), the dX coefficients use the sums over all ranks.  `part` holds RAW partial sums
+// [sum dy, sum dy*x] (BnBwdStatsF); sums_local / sums_global hold [sum dy, sum dy*nhat] (npml_bn2d_bwd_stats).
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk, int ch, int accumulate,
                                        float* d_scaler, float* d_intercept, double inv_m, const float* mean,
                                        const float* rstd, const float* scaler, float* coef,
@@ -715,17 +719,25 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk
     l2 = c < ch ? sums_local[ch + c] : 0.0;
   } else {
     s1 = l1 = block_col_sum<double>(part, nblk, 2 * ch, c, c < ch, red);
-    s2 = l2 = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+    const double raw = block_col_sum<double>(part, nblk, 2 * ch, ch + c, c < ch, red);
+    s2 = l2 = c < ch ? (double)rstd[c] * (raw - (double)mean[c] * s1) : 0.0;
   }
   if (threadIdx.y != 0 || c >= ch) return;
   const float di = (float)l1, ds = (float)l2;
   if (d_intercept) d_intercept[c] = accumulate ? d_intercept[c] + di : di;
   if (d_scaler) d_scaler[c] = accumulate ? d_scaler[c] + ds : ds;
-  coef[c] = mean[c];
-  coef[ch + c] = rstd[c];
-  coef[2 * ch + c] = scaler[c] * rstd[c];
-  coef[3 * ch + c] = (float)(s1 * inv_m);
-  coef[4 * ch + c] = (float)(s2 * inv_m);
+  const double a1 = (double)scaler[c] * (double)rstd[c];
+  const double a2 = -a1 * (s2 * inv_m) * (double)rstd[c];
+  coef[c] = (float)a1;
+  coef[ch + c] = (float)a2;
+  coef[2 * ch + c] = (float)(-a1 * (s1 * inv_m) - a2 * (double)mean[c]);
+}
+
+// raw [sum dy, sum dy*x] -> [sum dy, sum dy*nhat] (the form that crosses ranks under sync-BN)
+__global__ void bwd_stats_fix_kernel(int ch, double* sums, const float* mean, const float* rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ch) return;
+  sums[ch + c] = (double)rstd[c] * (sums[ch + c] - (double)mean[c] * sums[c]);
 }
 
 // ---- flat elementwise ------------------------------------------------------------------------------
@@ -1135,7 +1147,7 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   double* part = (double*)ws;
   double* sums = (double*)((char*)ws + part_bytes);
   float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
-  BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
+  BnBwdStatsF fs{dy, x, dtype};
   if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
                                                                   1.0 / (double)rows, save_mean, save_rstd, scaler, coef,
@@ -1199,9 +1211,11 @@ extern "C" int npml_bn2d_bwd_stats(int64_t rows, int32_t ch, const void* dy, con
   ColPlan p = plan_cols(rows, ch, vec, true);
   NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 2 * ch * sizeof(double), "workspace too small");
   double* part = (double*)ws;
-  BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
+  BnBwdStatsF fs{dy, x, dtype};
   if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
+  NPML_LAUNCH_OK();
+  bwd_stats_fix_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, sums, save_mean, save_rstd);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -1247,7 +1261,7 @@ extern "C" int npml_bn2d_bwd_act(int64_t rows, int64_t rows_total, int32_t ch, c
   double* part = (double*)ws;
   float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   if (sums_global == nullptr) {
-    BnBwdStatsF fs{dy, x, dtype, save_mean, save_rstd};
+    BnBwdStatsF fs{dy, x, dtype};
     if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   }
   bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
@@ -1300,13 +1314,18 @@ extern "C" int npml_bn2d_pair_bwd_stats(int64_t rows, int32_t ch, const void* dY
   NPML_CHECK((mean_b == nullptr) == (rstd_b == nullptr) && (mean_b == nullptr || xb), "incomplete second BatchNorm2D");
   const bool vec_ok = aligned_for_vec4(dY, dtype) && aligned_for_vec4(s, dtype) && aligned_for_vec4(xa, dtype) &&
                       aligned_for_vec4(xb, dtype);
-  const int vec = pick_vec(ch, vec_ok, aligned16(dY) && aligned16(s) && aligned16(xa) && aligned16(xb));
+  // four input tensors: 4 channels per thread keep the pass at 64 registers (4 blocks per SM); with 8 it needs 97 and
+  // the lower occupancy costs more bytes in flight than the wider loads bring (measured: 300 us -> see profiles/)
+  int vec = pick_vec(ch, vec_ok, aligned16(dY) && aligned16(s) && aligned16(xa) && aligned16(xb));
+  if (vec > 4) vec = 4;
   ColPlan p = plan_cols(rows, ch, vec, true);
   NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)p.grid.x * 3 * ch * sizeof(double), "workspace too small");
   double* part = (double*)ws;
-  BnPairBwdStatsF f{dY, s, xa, xb, dtype, mean_a, rstd_a, mean_b, rstd_b, act, p0, p1};
+  BnPairBwdStatsF f{dY, s, xa, xb, dtype, mean_b != nullptr ? 1 : 0, act, p0, p1};
   if (int e = launch_col_pass<3, double>(p, f, part, st, dtype)) return e;
   col_sums_kernel<<<(3 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 3 * ch, sums);
+  NPML_LAUNCH_OK();
+  pair_stats_fix_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, sums, mean_a, rstd_a, mean_b, rstd_b);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -1334,8 +1353,9 @@ extern "C" int npml_bn2d_pair_bwd_apply(int64_t rows, int64_t rows_total, int32_
   NPML_LAUNCH_OK();
   const bool vec_ok = aligned_for_vec4(dY, dtype) && aligned_for_vec4(s, dtype) && aligned_for_vec4(xa, dtype) &&
                       aligned_for_vec4(xb, dtype) && aligned_for_vec4(dxa, dtype) && aligned_for_vec4(dxb, dtype);
-  const int vec = pick_vec(ch, vec_ok, aligned16(dY) && aligned16(s) && aligned16(xa) && aligned16(xb) && aligned16(dxa) &&
-                                           aligned16(dxb));
+  int vec = pick_vec(ch, vec_ok, aligned16(dY) && aligned16(s) && aligned16(xa) && aligned16(xb) && aligned16(dxa) &&
+                                     aligned16(dxb));
+  if (vec > 4) vec = 4;                                   // see npml_bn2d_pair_bwd_stats
   BnPairBwdDxF f{dY, s, xa, xb, dxa, dxb, dtype, coef, has_b ? 1 : 0, act, p0, p1};
   return launch_col_pass<0, float>(plan_cols(rows, ch, vec, false), f, (float*)nullptr, st, dtype);
 }

@@ -175,12 +175,19 @@ def test_skip_conv_module_golden(cuda_device, mode, fuse):
         M.flush_gradients()
         Y = M.forward(X)
         dX = M.backward(z[i + "/dLdY"])
+        # backward through a kinked activation in a reduced-precision mode: a pre-activation within rounding distance
+        # of the kink may land on the other side, and ONE flipped mask among these ~1 000 elements is already a 3 %
+        # normwise error (same bound as test_skip_conv_module_vs_oracle; the full-size test removes the effect by
+        # evaluating the oracle at the device's own pre-activations)
+        tol_b = tol if (mode == "fp32" or c["act"] not in KINKED) else {"tf32": 5e-2, "bf16": 1.5e-1}[mode]
         close(Y, z[i + "/Y"], tol, i + " Y")
-        close(dX, z[i + "/dX"], tol, i + " dX")
+        close(dX, z[i + "/dX"], tol_b, i + " dX")
         dv = M.derived_variables
-        for k in ["conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "conv_skip_out", "batchnorm_skip_out",
-                  "dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2", "dLdBnSkip", "dLdConvSkip"]:
+        for k in ["conv1_out", "conv2_out", "batchnorm1_out", "batchnorm2_out", "conv_skip_out", "batchnorm_skip_out"]:
             close(dv[k], z["{}/{}".format(i, k)], tol, i + " " + k)
+        for k in ["dLdBn1", "dLdBn2", "dLdConv1", "dLdConv2", "dLdBnSkip", "dLdConvSkip"]:
+            close(dv[k], z["{}/{}".format(i, k)], tol_b, i + " " + k)
+        tol, tol_fwd = tol_b, tol
         for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2), ("s", M.conv_skip, M.batchnorm_skip)):
             close(conv.gradients["W"], z["{}/dW{}".format(i, t)], tol, i + " dW" + t)
             # conv biases feed straight into a BatchNorm, so their true gradient is ~0 (pure cancellation):
@@ -191,8 +198,9 @@ def test_skip_conv_module_golden(cuda_device, mode, fuse):
             assert np.linalg.norm((db - db_ref).ravel()) <= tol * max(scale, 1.0), i + " db" + t
             close(bn.gradients["scaler"], z["{}/dg{}".format(i, t)], tol, i + " dg" + t)
             close(bn.gradients["intercept"], z["{}/dh{}".format(i, t)], tol, i + " dh" + t)
-            close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol, i + " rm" + t)
-            close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol, i + " rv" + t)
+            close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol_fwd, i + " rm" + t)
+            close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol_fwd, i + " rv" + t)
+        tol = tol_fwd
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1148,8 +1156,9 @@ def test_skip_identity_module_golden(cuda_device, mode):
             dh = pkg.to_numpy(bn.gradients["intercept"])
             scale = max(np.linalg.norm(z["{}/dg{}".format(i, t)].ravel()), np.linalg.norm(dh_ref.ravel()), 1.0)
             assert np.linalg.norm((dh - dh_ref).ravel()) <= tol * scale, i + " dh" + t
-            close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol, i + " rm" + t)
-            close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol, i + " rv" + t)
+            close(bn.parameters["running_mean"], z["{}/rm{}".format(i, t)], tol_fwd, i + " rm" + t)
+            close(bn.parameters["running_var"], z["{}/rv{}".format(i, t)], tol_fwd, i + " rv" + t)
+        tol = tol_fwd
         assert M.hyperparameters["component_ids"] == ["conv1", "batchnorm1", "conv2", "batchnorm2", "add3"]
 
 
