@@ -194,7 +194,7 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
     }
     case NPML_OP_BN: {
       const int64_t rows = (int64_t)d->N * d->OH * d->OW;
-      bytes += colpass_ws_bytes(rows, d->K, 2);
+      bytes += colpass_ws_bytes(rows, d->K, 3);       // up to three column sums per channel (npml_bn2d_pair_bwd_stats)
       break;
     }
   }

@@ -325,6 +325,316 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   return true;
 }
 
+
+// =====================================================================================================================
+//  Narrow outputs (out_ch <= 64): column-shifted dZ windows stacked along N
+// =====================================================================================================================
+// With N = out_ch = 64 a 128x64x16 tcgen05.mma fetches 6 KB of operands for 32 clk of math and is paced by the
+// shared-memory port at 48 clk (profiles/r1g_mma_rate.txt).  Both wgrad operands are spatial, so shifts compose:
+//
+//     sum_s X[s + a, ci] * dZ[s + b, co]  =  dW[tap at offset a - b][ci, co]
+//
+// The B operand of ONE MMA is therefore fc windows of the same dZ slab, shifted by j*D slots (j = 0 .. fc-1) and
+// stacked along N through the descriptor's leading-dimension offset (D*128 bytes: the windows overlap in memory),
+// while the A operand stacks two windows of the X slab that sit at filter COLUMN fc-1 of two filter rows.  A
+// 128 x (fc*64) x 16 MMA then yields the 2 x fc taps {(r0, fc-1-j), (r1, fc-1-j)}: for a 3x3 filter two MMAs per K step
+// (rows {0, 1}; row 2 + the ones window for db) of 10 KB operands / 96 clk math each instead of five of 6 KB / 32 clk.
+// Work units are ranges of KS*16 consecutive slots of the flat padded-slot sequence (not whole rows), so no K step
+// ever overruns its unit; the sequence starts (fc-1)*D slots early so that every shifted window sees every slot.
+struct NsParams {
+  CUtensorMap xmap, gmap;
+  uint32_t a16[kMaxMT];
+  uint32_t lbo16[kMaxMT];
+  int16_t row[kMaxMT][2];        // filter row of each A window (-1 = the ones window, i.e. db)
+  int16_t cb[kMaxMT][2];
+  uint8_t kind[kMaxMT];          // 0 = (X, X), 1 = (X, ones), 2 = (ones, ones)
+  int nmt_total, mt_per_group, n_mgroups;
+  int ncb, fc, NN, D, shift;
+  int N, Hp, Wp, pady, padx, CI, CO, Mrows;
+  int SRX, SRG, KS, num_units;
+  int xplane_bytes, xstage_bytes, gstage_bytes;
+  uint32_t idesc;
+  int wait_ns;
+};
+
+__device__ __forceinline__ int ns_floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+template <int NT>
+__device__ __forceinline__ void ns_issue(const NsParams& P, int mt0, bool leader, uint32_t tmem_base, uint64_t* full_bar,
+                                         uint64_t* empty_bar, uint64_t* acc_bar, uint32_t xs_u32, uint32_t gs_u32,
+                                         uint32_t ones_u32) {
+  const uint32_t idesc = P.idesc, NN = (uint32_t)P.NN;
+  const int KS = P.KS, num_units = P.num_units, Wp = P.Wp, shift = P.shift;
+  const uint32_t xs16 = xs_u32 >> 4, gs16 = gs_u32 >> 4, ones16 = ones_u32 >> 4;
+  const uint32_t xstage16 = (uint32_t)P.xstage_bytes >> 4, gstage16 = (uint32_t)P.gstage_bytes >> 4;
+  constexpr uint64_t kStep = (kKI * kRowBytes) >> 4;
+  constexpr uint64_t kHi64 = (uint64_t)kHi << 32;
+  uint64_t d0[NT];
+#pragma unroll
+  for (int i = 0; i < NT - 1; ++i) d0[i] = kHi64 | (uint64_t)((xs16 + P.a16[mt0 + i]) | (P.lbo16[mt0 + i] << 16));
+  int64_t dk_last, ds_last, do_last;          // last tile: change per K step / per stage / per 16 bytes of unit offset
+  {
+    const int gi = mt0 + NT - 1;
+    const uint32_t kind = P.kind[gi];
+    const uint32_t s = xs16 + P.a16[gi];
+    if (kind == 0) {
+      d0[NT - 1] = kHi64 | (uint64_t)(s | (P.lbo16[gi] << 16));
+      dk_last = (int64_t)kStep; ds_last = (int64_t)xstage16; do_last = 1;
+    } else if (kind == 1) {       // window 1 = ones: its distance from window 0 shrinks as window 0 advances
+      d0[NT - 1] = kHi64 | (uint64_t)(s | ((ones16 - s) << 16));
+      dk_last = (int64_t)kStep - ((int64_t)kStep << 16); ds_last = (int64_t)xstage16 - ((int64_t)xstage16 << 16);
+      do_last = 1 - ((int64_t)1 << 16);
+    } else {
+      d0[NT - 1] = kHi64 | (uint64_t)ones16;
+      dk_last = 0; ds_last = 0; do_last = 0;
+    }
+  }
+  const uint64_t g0 = kHi64 | (uint64_t)(gs16 | (((uint32_t)P.D * (kRowBytes >> 4)) << 16));
+  uint32_t uc = 0;
+  for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
+    const uint32_t st = uc & 1u;
+    const int slot0 = unit * KS * kKI - shift;
+    const uint32_t off16 = (uint32_t)(slot0 - ns_floordiv(slot0, Wp) * Wp) * (kRowBytes >> 4);
+    ptx::mbar_wait(&full_bar[st], (uc >> 1) & 1u);
+    ptx::tc_fence_after();
+    uint64_t ad[NT];
+#pragma unroll
+    for (int i = 0; i < NT - 1; ++i) ad[i] = d0[i] + (uint64_t)(st * xstage16 + off16);
+    ad[NT - 1] = d0[NT - 1] + (uint64_t)((st ? ds_last : (int64_t)0) + do_last * (int64_t)off16);
+    uint64_t bd = g0 + (uint64_t)(st * gstage16 + off16);
+#pragma unroll 2
+    for (int k = 0; k < KS; ++k) {
+      if (leader) {
+        const uint32_t acc = (uc | (uint32_t)k) ? 1u : 0u;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) ptx::mma_ss<false>(tmem_base + (uint32_t)i * NN, ad[i], bd, idesc, acc);
+      }
+#pragma unroll
+      for (int i = 0; i < NT - 1; ++i) ad[i] += kStep;
+      ad[NT - 1] += (uint64_t)dk_last;
+      bd += kStep;
+    }
+    if (leader) ptx::tc_commit(&empty_bar[st]);
+  }
+  if (leader) ptx::tc_commit(acc_bar);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_ns_kernel(const __grid_constant__ NsParams P,
+                                                                       float* __restrict__ part,
+                                                                       float* __restrict__ part_db) {
+  // [X stage 0][X stage 1][dZ stage 0][dZ stage 1][ones][barriers]
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* xs = smem_raw;
+  uint8_t* gs = xs + 2 * (size_t)P.xstage_bytes;
+  uint8_t* ones = gs + 2 * (size_t)P.gstage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ones + kKI * kRowBytes);
+  uint64_t* empty_bar = full_bar + 2;
+  uint64_t* acc_bar = empty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  if ((ptx::smem_u32(smem_raw) & 1023u) != 0) asm volatile("trap;");
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int mt0 = blockIdx.y * P.mt_per_group;
+  const int nmt = min(P.mt_per_group, P.nmt_total - mt0);
+
+  for (int i = threadIdx.x; i < kKI * kRowBytes / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+  ptx::fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&full_bar[i], 1); ptx::mbar_init(&empty_bar[i], 1); }
+    ptx::mbar_init(acc_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: the padded rows that hold slots [slot0, slot0 + KS*16 + halo) of X and [.., + shift) of dZ =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&P.xmap);
+      ptx::prefetch_tmap(&P.gmap);
+      const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
+      const uint32_t tx = (uint32_t)(P.ncb * P.SRX + P.SRG) * row_bytes;
+      const int nrow = P.SRX > P.SRG ? P.SRX : P.SRG;
+      uint32_t uc = 0;
+      for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x, ++uc) {
+        const uint32_t st = uc & 1u;
+        ptx::mbar_wait_sleep(&empty_bar[st], ((uc >> 1) & 1u) ^ 1u, (uint32_t)P.wait_ns);
+        ptx::mbar_expect_tx(&full_bar[st], tx);
+        const int slot0 = unit * P.KS * kKI - P.shift;
+        const int rho0 = ns_floordiv(slot0, P.Wp);
+        int n = ns_floordiv(rho0, P.Hp), yp = rho0 - n * P.Hp;      // n = -1 / n >= N: out of bounds, zero-filled
+        uint8_t* xd = xs + (size_t)st * P.xstage_bytes;
+        uint8_t* gd = gs + (size_t)st * P.gstage_bytes;
+        for (int i = 0; i < nrow; ++i) {
+          if (i < P.SRX)
+            for (int c = 0; c < P.ncb; ++c)
+              ptx::tma_load_4d(xd + (size_t)c * P.xplane_bytes + (size_t)i * row_bytes, &P.xmap, &full_bar[st], c * 64, -P.padx,
+                               yp - P.pady, n);
+          if (i < P.SRG) ptx::tma_load_4d(gd + (size_t)i * row_bytes, &P.gmap, &full_bar[st], 0, 0, yp, n);
+          if (++yp == P.Hp) { yp = 0; ++n; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = ptx::elect_one();
+    const uint32_t xs_u32 = ptx::smem_u32(smem_raw);
+    const uint32_t gs_u32 = xs_u32 + 2u * (uint32_t)P.xstage_bytes;
+    const uint32_t ones_u32 = gs_u32 + 2u * (uint32_t)P.gstage_bytes;
+    switch (nmt) {
+      case 1: ns_issue<1>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 2: ns_issue<2>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 3: ns_issue<3>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      default: ns_issue<4>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (once): TMEM -> this CTA's fp32 partial; column block j of a tile is filter column fc-1-j =====
+    const int qd = warp & 3;
+    const int l = qd * 32 + lane;
+    const int w = l >> 6, cl = l & 63;
+    ptx::mbar_wait_sleep(acc_bar, 0, (uint32_t)P.wait_ns * 4u);
+    ptx::tc_fence_after();
+    for (int i = 0; i < nmt; ++i) {
+      const int gi = mt0 + i;
+      const int r = P.row[gi][w];
+      const int ci = P.cb[gi][w] * 64 + cl;
+      const bool is_db = r == -1 && cl == 0 && (w == 0 || P.kind[gi] == 1);
+      for (int c = 0; c < P.NN; c += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(i * P.NN + c), v);
+        ptx::tmem_ld_wait();
+        const int j = c >> 6, co = c & 63;
+        float* out = nullptr;
+        if (r >= 0) {
+          if (ci < P.CI) out = part + ((int64_t)blockIdx.x * P.Mrows + (int64_t)(r * P.fc + (P.fc - 1 - j)) * P.CI + ci) * P.CO;
+        } else if (is_db && j == 0) {
+          out = part_db + (int64_t)blockIdx.x * P.CO;
+        }
+        if (out != nullptr) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (co + 4 * q < P.CO)
+              *reinterpret_cast<uint4*>(out + co + 4 * q) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct NsPlan {
+  NsParams P;
+  dim3 grid;
+  size_t smem = 0, part_bytes = 0, partdb_bytes = 0;
+  int splits = 0;
+};
+
+bool plan_ns_wgrad(const GatherWgrad& g, int mode, NsPlan& pl) {
+  if (mode != NPML_MODE_BF16 || std::getenv("NPML_DISABLE_SLAB") || std::getenv("NPML_DISABLE_WGRAD_NS")) return false;
+  if (g.s != 1 || g.N < 1 || g.CI % 8 || g.CO % 8) return false;
+  if (g.CO > 64 || g.fc * 64 > 256) return false;       // N = fc * 64 accumulator columns per tile
+  if (g.fc < 2) return false;                            // nothing to stack: the plain kernel
+  const int Hp = g.OH + (g.fr - 1) * g.D, Wp = g.OW + (g.fc - 1) * g.D;
+  if (Wp > 256) return false;
+  if ((int64_t)g.N * Hp * Wp >= (1LL << 30)) return false;
+  if ((int64_t)g.N * g.IH * g.IW * g.CI >= (1LL << 31) || (int64_t)g.N * g.OH * g.OW * g.CO >= (1LL << 31)) return false;
+  NsParams& P = pl.P;
+  memset(&P, 0, sizeof(P));
+  P.N = g.N; P.Hp = Hp; P.Wp = Wp; P.pady = g.pr; P.padx = g.pc; P.CI = g.CI; P.CO = g.CO;
+  P.Mrows = g.fr * g.fc * g.CI;
+  P.ncb = ceildiv(g.CI, 64);
+  P.fc = g.fc; P.NN = g.fc * 64; P.D = g.D; P.shift = (g.fc - 1) * g.D;
+  P.idesc = ptx::instr_desc(1, 1, 1, 128, P.NN);
+  P.wait_ns = wait_ns();
+  const int halo = (g.fr - 1) * g.D * Wp + P.shift;
+  int KS = 0;
+  for (int ks = 64; ks >= 4; --ks) {
+    const int srx = ceildiv(Wp - 1 + ks * kKI + halo, Wp), srg = ceildiv(Wp - 1 + ks * kKI + P.shift, Wp);
+    const size_t need = 2 * (size_t)(P.ncb * srx + srg) * Wp * kRowBytes + kKI * kRowBytes + 256;
+    if (need <= (size_t)kSmemLimit) {
+      KS = ks; P.SRX = srx; P.SRG = srg; pl.smem = need;
+      break;
+    }
+  }
+  if (KS == 0) return false;
+  P.KS = KS;
+  P.xplane_bytes = P.SRX * Wp * kRowBytes;
+  P.xstage_bytes = P.ncb * P.xplane_bytes;
+  P.gstage_bytes = P.SRG * Wp * kRowBytes;
+  const int64_t total_slots = (int64_t)g.N * Hp * Wp + P.shift;
+  P.num_units = (int)((total_slots + (int64_t)KS * kKI - 1) / ((int64_t)KS * kKI));
+  struct Win { int row, cb; uint32_t a16; };
+  std::vector<Win> wins;
+  for (int c = 0; c < P.ncb; ++c)
+    for (int r = 0; r < g.fr; ++r)
+      wins.push_back({r, c, (uint32_t)(((size_t)c * P.xplane_bytes + (size_t)(r * g.D * Wp + P.shift) * kRowBytes) >> 4)});
+  wins.push_back({-1, 0, 0});
+  if (wins.size() & 1) wins.push_back({-1, 0, 0});
+  const int nmt = (int)wins.size() / 2;
+  if (nmt > kMaxMT) return false;
+  for (int i = 0; i < nmt; ++i) {
+    const Win &a = wins[2 * i], &b = wins[2 * i + 1];
+    P.row[i][0] = (int16_t)a.row; P.row[i][1] = (int16_t)b.row;
+    P.cb[i][0] = (int16_t)a.cb; P.cb[i][1] = (int16_t)b.cb;
+    P.a16[i] = a.a16;
+    if (a.row >= 0 && b.row >= 0) { P.kind[i] = 0; P.lbo16[i] = b.a16 - a.a16; if (P.lbo16[i] >= (1u << 14)) return false; }
+    else if (a.row >= 0) P.kind[i] = 1;
+    else P.kind[i] = 2;
+  }
+  P.nmt_total = nmt;
+  int cap = 512 / P.NN;
+  if (cap > 4) cap = 4;
+  P.n_mgroups = ceildiv(nmt, cap);
+  P.mt_per_group = ceildiv(nmt, P.n_mgroups);
+  // the ones window sorts last, so the only tile with run-time descriptor deltas is the last tile of the last group,
+  // which is what ns_issue assumes
+  int ctas = num_sms() / P.n_mgroups;
+  if (ctas < 1) ctas = 1;
+  if (ctas > P.num_units) ctas = P.num_units;
+  pl.splits = ctas;
+  pl.grid = dim3((unsigned)ctas, (unsigned)P.n_mgroups, 1);
+  pl.part_bytes = align_up((size_t)ctas * P.Mrows * g.CO * sizeof(float), 256);
+  pl.partdb_bytes = align_up((size_t)ctas * g.CO * sizeof(float), 256);
+  return true;
+}
+
+int ns_wgrad(const GatherWgrad& g, NsPlan& pl, const void* in, const void* grad, float* dW, float* db, void* ws,
+             size_t ws_bytes, cudaStream_t st) {
+  NPML_CHECK(ws != nullptr && ws_bytes >= pl.part_bytes + pl.partdb_bytes, "workspace too small");
+  NPML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0,
+             "activation pointers must be 16-byte aligned");
+  NsParams& P = pl.P;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
+    const uint64_t strides[4] = {2, (uint64_t)g.CI * 2, (uint64_t)g.IW * g.CI * 2, (uint64_t)g.IH * g.IW * g.CI * 2};
+    const uint32_t box[4] = {64, (uint32_t)P.Wp, 1, 1};
+    if (int e = make_tmap(&P.xmap, true, const_cast<void*>(in), 4, dims, strides, box, false)) return e;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)g.CO, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
+    const uint64_t strides[4] = {2, (uint64_t)g.CO * 2, (uint64_t)g.OW * g.CO * 2, (uint64_t)g.OH * g.OW * g.CO * 2};
+    const uint32_t box[4] = {64, (uint32_t)P.Wp, 1, 1};
+    if (int e = make_tmap(&P.gmap, true, const_cast<void*>(grad), 4, dims, strides, box, false)) return e;
+  }
+  float* part = reinterpret_cast<float*>(ws);
+  float* part_db = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
+  auto kern = tc_slab_wgrad_ns_kernel;
+  NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, part, part_db);
+  NPML_LAUNCH_OK();
+  return launch_wgrad_reduce(part, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st,
+                             db != nullptr ? part_db : nullptr, db);
+}
+
 }  // namespace
 
 bool slab_wgrad_supported(const GatherWgrad& g, int mode) {
@@ -335,12 +645,19 @@ bool slab_wgrad_supported(const GatherWgrad& g, int mode) {
 size_t slab_wgrad_ws_bytes(const GatherWgrad& g, int mode) {
   SlabWgradPlan pl;
   if (!plan_slab_wgrad(g, mode, pl)) return 0;
-  return pl.part_bytes + pl.partdb_bytes + 256;
+  size_t need = pl.part_bytes + pl.partdb_bytes;
+  NsPlan ns;
+  if (plan_ns_wgrad(g, mode, ns) && ns.part_bytes + ns.partdb_bytes > need) need = ns.part_bytes + ns.partdb_bytes;
+  return need + 256;
 }
 
 // dW (+)= X (*) dZ and, when db != nullptr, db (+)= column sums of dZ, both from one pass over X and dZ.
 int slab_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad, float* dW, float* db, void* ws,
                size_t ws_bytes, cudaStream_t st) {
+  {
+    NsPlan ns;                 // out_ch <= 64: column-shifted dZ windows stacked along N
+    if (plan_ns_wgrad(g, mode, ns)) return ns_wgrad(g, ns, in, grad, dW, db, ws, ws_bytes, st);
+  }
   SlabWgradPlan pl;
   NPML_CHECK(plan_slab_wgrad(g, mode, pl), "shape not supported by the slab wgrad path");
   NPML_CHECK(ws != nullptr && ws_bytes >= pl.part_bytes + pl.partdb_bytes, "workspace too small");
