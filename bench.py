@@ -370,16 +370,24 @@ def timed_graph(ctx, step, steps, flush_l2):
     """Capture `step` once, replay it `steps` times; returns (ms_total max over ranks, launches/step, profile, host ms)."""
     import torch
     L, D = ctx.pkg._lib, ctx.pkg.dist
-    graph, prof, launches = None, None, 0
+    graph, pgraph, prof, launches = None, None, None, 0
     if not ctx.args.no_graph:
         try:
+            # two captures of the same step: `graph` is what the timed region replays (kernels only); `pgraph` carries
+            # an external event-record node on either side of every C-ABI call and is replayed for the per-call times
             torch.cuda.synchronize()
-            L.PROFILE, L.PROFILE_EXTERNAL = [], True
+            L.PROFILE, L.PROFILE_EXTERNAL = None, False
             L.launch_count(reset=True)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 step()
-            graph, prof, launches = g, L.PROFILE, L.launch_count()
+            graph, launches = g, L.launch_count()
+            torch.cuda.synchronize()
+            L.PROFILE, L.PROFILE_EXTERNAL = [], True
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                step()
+            pgraph, prof = g2, L.PROFILE
         except Exception as e:      # capture not possible: eager timed region
             if ctx.rank == 0:
                 print("bench: CUDA graph capture failed ({}); timing eagerly".format(str(e).splitlines()[0]), file=sys.stderr)
@@ -409,13 +417,15 @@ def timed_graph(ctx, step, steps, flush_l2):
     q1.record()
     torch.cuda.synchronize()
     burst = int(min(64, max(4, 3.0 / max(q0.elapsed_time(q1) / 5.0, 1e-3))))
+    if ctx.args.quick:
+        burst = 1
     per_call = {}
     if graph is not None:
-        for _ in range(max(30, ctx.args.kernel_reps)):
+        for _ in range(1 if ctx.args.quick else max(30, ctx.args.kernel_reps)):
             for i in range(burst):
                 if flush_l2 and i == burst - 1:
                     ctx.flush_buf.zero_()           # the sampled replay starts with a cold L2, like the timed steps
-                graph.replay()
+                pgraph.replay()
             torch.cuda.synchronize()
             acc = {}
             for name, a, z in prof:
@@ -424,7 +434,7 @@ def timed_graph(ctx, step, steps, flush_l2):
                 per_call.setdefault(name, []).append(v)
     else:
         L.PROFILE = []
-        for _ in range(10):
+        for _ in range(1 if ctx.args.quick else 10):
             step()
         torch.cuda.synchronize()
         acc = {}
@@ -440,7 +450,7 @@ def timed_graph(ctx, step, steps, flush_l2):
     p1.record()
     torch.cuda.synchronize()
     est_ms = max(D.all_reduce_max(p0.elapsed_time(p1)) / 5.0, 1e-3)
-    for _ in range(int(min(3000, max(10, ctx.preroll_ms / est_ms)))):
+    for _ in range(0 if ctx.args.quick else int(min(3000, max(10, ctx.preroll_ms / est_ms)))):
         one()
     torch.cuda.synchronize()
     if graph is None:
@@ -473,6 +483,9 @@ def timed_graph(ctx, step, steps, flush_l2):
     if graph is None:
         launches = L.launch_count() / float(steps)
     ms_total = D.all_reduce_max(ms_total)
+    if pgraph is not None:
+        prof = None
+        pgraph.reset()
     return ms_total, launches, per_call, host_ms, graph
 
 
@@ -559,8 +572,7 @@ def measure(ctx, cfg, headline):
         if g2 is not None:
             g2.reset()
         out["allreduce"] = {"bytes": int(bucket.flat.numel() * 4), "exposed_ms_per_step": max(0.0, (ms_total - ms_nored) / steps),
-                            "step_ms_without": ms_nored / steps, "collective": "one fused local-reduce + all-reduce of the flat dW||db bucket"
-                            if getattr(D, "FUSED_ALLREDUCE", False) else "ncclAllReduce(SUM, fp32) per layer slice on a side stream, overlapped with dgrad"}
+                            "step_ms_without": ms_nored / steps, "collective": D.collective_name() + ", one call per layer slice on a side stream, overlapped with dgrad"}
         if n % world == 0 and n // world >= 1:
             ns = n // world
             xs, dys = Xd[:ns].contiguous(), dYd[:ns].contiguous()
@@ -751,6 +763,8 @@ def main():
     ap.add_argument("--host-dtype", default="f32", choices=["f32", "bf16", "f16"], help="dtype of the pinned host inputs")
     ap.add_argument("--host-out", default="mode", choices=["mode", "f32"], help="dtype of the pinned host outputs")
     ap.add_argument("--kernel-reps", type=int, default=30, help="synchronised replays behind roofline.kernel_ms")
+    ap.add_argument("--quick", action="store_true", help="no pre-roll / bursts: the few launches a profiler run needs "
+                    "(a number printed by such a run is not a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         cfg = dict(CONFIGS[args.config]); cfg["_id"] = args.config

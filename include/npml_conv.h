@@ -83,6 +83,14 @@ enum { NPML_FLAG_WEIGHTS_PACKED = 1 };
  * layers/layers.py:3037-3038).  Z (pre-activation) and/or Y (= act(Z)) may be NULL. */
 int npml_conv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b,
                       void* Z, void* Y, void* ws, size_t ws_bytes, void* stream);
+/* fprop that also leaves the statistics of its OUTPUT for the training-mode BatchNorm2D behind it (the
+ * "optional per-channel sum / sum of squares for BN" of npml_conv2d_fprop): bn_sums[2*K] (double, device) = per-channel
+ * [sum y, sum y^2] over (N, OH, OW) of y = act(conv + b) (of Z when Y is NULL), i.e. what layers/layers.py:1146-1147
+ * reduces.  The slab kernel forms them in its epilogue from the fp32 accumulators (per-warp partial rows, added in a
+ * fixed order); every other kernel is followed by one column pass over the tensor it just wrote.  Feed them to
+ * npml_bn2d_apply / npml_bn2d_finalize (all-reduced first under sync-BN). */
+int npml_conv2d_fprop_stats(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
+                            double* bn_sums, void* ws, size_t ws_bytes, void* stream);
 /* fprop with a FROZEN BatchNorm2D folded into the same epilogue (north_star: "the BatchNorm2D affine [is a] fused
  * epilogue"; modules/modules.py:905-937 runs conv -> BatchNorm2D back to back, and with retain_derived=False or a frozen
  * layer BatchNorm2D.forward is the per-channel affine of its running statistics, layers/layers.py:1141-1156):
@@ -281,6 +289,24 @@ int npml_comm_init_rank(const void* id128, int32_t nranks, int32_t rank);
 int npml_allreduce_sum_f32(float* buf, int64_t n, void* stream);
 int npml_allreduce_sum_f64(double* buf, int64_t n, void* stream);   /* sync-BN statistics */
 int npml_comm_destroy(void);
+
+/* ---- all-reduce over NVLink / NVSwitch peer memory (csrc/peer.cu) -----------------------------------------------
+ * The collectives of the data-parallel step are small (dW || db of a layer: 1 KB - 2 MB; sync-BN statistics: 2 KB) and
+ * latency-bound, so they are ONE kernel each instead of a NCCL call: every rank pushes its slice into an inbox in every
+ * peer's memory, releases a per-block flag there, waits on its own flags and adds the copies in rank order (the same
+ * order on every rank: bit-identical results everywhere, run after run).  Graph-capturable (the call counter lives in
+ * device memory).  Setup: every rank calls npml_peer_alloc (cudaMalloc + cudaIpcGetMemHandle of its region -- the one
+ * allocation this library makes, at init), the host gathers the 64-byte handles, every rank calls npml_peer_open and
+ * passes a host barrier.  `channel` (0..3): calls on one channel must be issued in the same order by every rank; use
+ * different channels for streams that run concurrently.  n * sizeof(element) <= 4 MiB, buf 16-byte aligned. */
+size_t npml_peer_region_bytes(void);
+int npml_peer_alloc(void* handle64);
+int npml_peer_open(const void* handles, int32_t world, int32_t rank);
+int npml_peer_ready(void);
+int npml_peer_allreduce_sum_f32(float* buf, int64_t n, int32_t channel, void* stream);
+int npml_peer_allreduce_sum_f64(double* buf, int64_t n, int32_t channel, void* stream);
+int npml_peer_status(void);      /* 0 ok, 1 a block timed out waiting for a peer (synchronises the device) */
+int npml_peer_close(void);
 
 /* ---- misc --------------------------------------------------------------------------------- */
 const char* npml_last_error(void);

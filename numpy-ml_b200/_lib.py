@@ -34,6 +34,7 @@ _DESC = C.POINTER(ConvDesc)
 # name -> (restype, argtypes); kept in step with include/npml_conv.h (tests check every symbol)
 SIGNATURES = {
     "npml_conv2d_fprop": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "npml_conv2d_fprop_stats": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_fprop_bn": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_wgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
@@ -76,6 +77,14 @@ SIGNATURES = {
     "npml_allreduce_sum_f32": (C.c_int, [_P, _I64, _P]),
     "npml_allreduce_sum_f64": (C.c_int, [_P, _I64, _P]),
     "npml_comm_destroy": (C.c_int, []),
+    "npml_peer_region_bytes": (_SZ, []),
+    "npml_peer_alloc": (C.c_int, [_P]),
+    "npml_peer_open": (C.c_int, [_P, _I32, _I32]),
+    "npml_peer_ready": (C.c_int, []),
+    "npml_peer_allreduce_sum_f32": (C.c_int, [_P, _I64, _I32, _P]),
+    "npml_peer_allreduce_sum_f64": (C.c_int, [_P, _I64, _I32, _P]),
+    "npml_peer_status": (C.c_int, []),
+    "npml_peer_close": (C.c_int, []),
     "npml_last_error": (C.c_char_p, []),
     "npml_uses_tensor_cores": (C.c_int, [_DESC, C.c_int]),
     "npml_debug_ws_plan": (C.c_int, [_DESC, C.c_int, C.c_int, _P, _I32]),

@@ -75,7 +75,26 @@ struct SlabParams {
   int epi2;                     // 1: warps 8..11 take every other tile (their rows go straight to global memory)
   int wait_ns;                  // sleep between mbarrier polls of the producer / epilogue warps (npml::wait_ns())
   int affine;                   // 1: Y = scale[co] * act(z + b) + shift[co] (frozen BatchNorm2D folded into the epilogue)
+  int stats_width;              // > 0: per-channel sum / sum of squares of the output for a BatchNorm2D that follows
+                                // (row width of the partials = 2 * out_ch)
 };
+
+// Column sums of a 32 x 32 register tile held one ROW per lane: after five exchange rounds lane c holds the sum of
+// column c over the warp's 32 rows (31 shuffles instead of 32 x 5): in round s a lane keeps the half of its values
+// whose column has bit s equal to its own lane bit and hands the other half to lane ^ s.
+__device__ __forceinline__ float warp_col_sums32(float (&t)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? t[i + s] : t[i];
+      const float send = up ? t[i] : t[i + s];
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return t[0];
+}
 
 // Measured on B200: the 128B swizzle of both the TMA write and the UMMA read is a function of the ABSOLUTE
 // shared-memory address bits (chunk ^= (addr >> 7) & 7), so an operand start address that is only 128-byte
@@ -90,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
                                                                    const float* __restrict__ bias,
                                                                    const float* __restrict__ post_scale,
                                                                    const float* __restrict__ post_shift, T* __restrict__ Z,
-                                                                   T* __restrict__ Y) {
+                                                                   T* __restrict__ Y, float* __restrict__ stats_part) {
   constexpr bool kTf32 = sizeof(T) == 4;
   // [weights (1024-aligned base)] [2 slab planes (128-aligned)] [epilogue staging] [bias | scale | shift] [barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -369,6 +388,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     };
     const bool direct = P.epi_direct != 0 || grp == 1;
     uint32_t tseq = 0;                            // running tile number of this CTA
+    // BatchNorm2D statistics of the output (stats_width > 0): lane c of this warp accumulates, over every tile the warp
+    // drains, sum and sum of squares of channel (chunk * 32 + c); one row of partials per epilogue warp at the end
+    float st1[8], st2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { st1[i] = 0.f; st2[i] = 0.f; }
 
     for (int unit = (grp == 0 || P.epi2) ? (int)blockIdx.x : P.num_units; unit < P.num_units; unit += gridDim.x) {
       const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
@@ -410,8 +434,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
             if (direct) emit_direct(Z, v, my_pix, co);
             else emit(Z, v, my_pix, co);
           }
+          if (Y) act_apply32(P.act, P.p0, P.p1, v);
+          if (P.stats_width > 0) {                 // of the layer output act(z + b), before any folded affine
+            float t[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = row_ok ? v[i] : 0.f;
+            const float s1 = warp_col_sums32(t, lane);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = row_ok ? v[i] * v[i] : 0.f;
+            const float s2 = warp_col_sums32(t, lane);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q == (c >> 5)) { st1[q] += s1; st2[q] += s2; }
+          }
           if (Y) {
-            act_apply32(P.act, P.p0, P.p1, v);
             if (P.affine) {                         // frozen BatchNorm2D: per-channel scale / shift after the activation
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
@@ -426,6 +462,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
           }
         }
         if (++slot == (uint32_t)n_acc) { slot = 0; sph ^= 1u; }
+      }
+    }
+    if (P.stats_width > 0) {
+      float* row = stats_part + (size_t)(blockIdx.x * 8 + (warp - 4)) * P.stats_width;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int ch = co0 + q * 32 + lane;
+        if (q * 32 < BN && ch < CO) { row[ch] = st1[q]; row[CO + ch] = st2[q]; }
       }
     }
   }
@@ -619,7 +663,7 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
       if (int e = make_tmap(&P.amap[i], bf16, base, 4, dims, strides, box, false)) return e;
     }
   }
-  typedef void (*Kern)(const SlabParams, const float*, const float*, const float*, T*, T*);
+  typedef void (*Kern)(const SlabParams, const float*, const float*, const float*, T*, T*, float*);
   Kern kern = nullptr;
 #define NPML_SLAB_UT(NTV)                                                          \
   switch (P.UT) {                                                                  \
@@ -633,7 +677,9 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
   else { NPML_SLAB_UT(0) }
 #undef NPML_SLAB_UT
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, g.post_scale, g.post_shift, (T*)Z, (T*)Y);
+  P.stats_width = g.stats_part != nullptr ? 2 * g.CO : 0;
+  if (g.stats_rows != nullptr) *g.stats_rows = (int)pl.grid.x * 8;
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, g.post_scale, g.post_shift, (T*)Z, (T*)Y, g.stats_part);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -650,6 +696,14 @@ size_t slab_conv_ws_bytes(const GatherConv& g, int mode) {
   const int es = mode == NPML_MODE_BF16 ? 2 : 4;       // the repacked weights Wt[tap][co][ci], both slab kernels
   return align_up((size_t)g.fr * g.fc * g.CO * g.CI * es, 256) + 256;
 }
+
+// true: slab_gather_conv will take the kernel whose epilogue can emit BatchNorm2D statistics (GatherConv::stats_part)
+bool slab_conv_emits_stats(const GatherConv& g, int mode) {
+  SlabPlan pl;
+  return !slab3_conv_supported(g, mode) && plan_slab(g, mode, pl) && pl.P.BN <= 256;
+}
+
+int slab_stats_rows() { return num_sms() * 8; }          // upper bound of the partial rows a launch writes
 
 int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
                      void* ws, size_t ws_bytes, cudaStream_t st) {

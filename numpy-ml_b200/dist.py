@@ -14,7 +14,9 @@ import torch
 
 from . import _lib as L
 
-_state = {"ready": False, "world": 1, "rank": 0, "backend": None}
+_state = {"ready": False, "world": 1, "rank": 0, "backend": None, "peer": False, "peer_why": "single process"}
+PEER_SLOT_BYTES = 4 << 20          # csrc/peer.cu: kSlotBytes
+CH_MAIN, CH_SIDE = 0, 1            # peer all-reduce channels: the caller's stream / the gradient side stream
 
 
 def init(backend=None):
@@ -43,8 +45,51 @@ def init(backend=None):
         dist.broadcast(ident, src=0)
         raw = (C.c_ubyte * 128)(*ident.tolist())
         L.check(lib.npml_comm_init_rank(raw, world, rank), "npml_comm_init_rank")
+        _init_peer(lib, world, rank)
     _state["ready"] = True
     return _state
+
+
+def _init_peer(lib, world, rank):
+    """Map every rank's peer region (csrc/peer.cu) into this process.  All ranks agree on the outcome: if any of them
+    cannot (no peer access between two of the GPUs, IPC disabled, NPML_PEER=0) everybody stays on NCCL."""
+    import torch.distributed as dist
+    ok, why = 1, ""
+    handle = (C.c_ubyte * 64)()
+    if os.environ.get("NPML_PEER", "1") == "0" or world > 8:
+        ok, why = 0, "disabled (NPML_PEER=0)" if world <= 8 else "more than 8 ranks"
+    elif lib.npml_peer_alloc(handle) != 0:
+        ok, why = 0, lib.npml_last_error().decode()
+    mine = torch.tensor(list(handle) + [ok], dtype=torch.uint8)
+    every = [torch.zeros(65, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(every, mine)
+    if all(int(t[64]) for t in every):
+        raw = (C.c_ubyte * (64 * world))(*torch.cat([t[:64] for t in every]).tolist())
+        if lib.npml_peer_open(raw, world, rank) != 0:
+            ok, why = 0, lib.npml_last_error().decode()
+    else:
+        ok, why = 0, why or "a peer rank could not allocate its region"
+    agree = torch.tensor([ok], dtype=torch.int32)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)          # also the barrier npml_peer_open asks for
+    _state["peer"] = bool(int(agree[0]))
+    _state["peer_why"] = "peer-memory push all-reduce kernel (csrc/peer.cu)" if _state["peer"] else \
+        "ncclAllReduce ({})".format(why or "a peer rank could not map the regions")
+
+
+def collective_name():
+    return _state["peer_why"] if _state["world"] > 1 else "none (single process)"
+
+
+def _allreduce(buf, channel):
+    """In-place SUM over ranks of a contiguous fp32 / fp64 device tensor on the current stream."""
+    lib, n = L.load(), buf.numel()
+    f64 = buf.dtype == torch.float64
+    if _state["peer"] and n * buf.element_size() <= PEER_SLOT_BYTES and buf.data_ptr() % 16 == 0:
+        fn = lib.npml_peer_allreduce_sum_f64 if f64 else lib.npml_peer_allreduce_sum_f32
+        L.check(fn(L.ptr(buf), n, channel, L.stream()), "npml_peer_allreduce_sum")
+    else:
+        fn = lib.npml_allreduce_sum_f64 if f64 else lib.npml_allreduce_sum_f32
+        L.check(fn(L.ptr(buf), n, L.stream()), "npml_allreduce_sum")
 
 
 def world_size():
@@ -136,10 +181,10 @@ class GradBucket(object):
         theirs = {id(l) for l in layers if l.gradients}
         return mine == theirs
 
-    def _reduce(self, off, n):
+    def _reduce(self, off, n, channel=CH_MAIN):
         buf = self.flat[off:off + n]
         if _state["backend"] == "nccl":
-            L.check(L.load().npml_allreduce_sum_f32(L.ptr(buf), n, L.stream()), "npml_allreduce_sum_f32")
+            _allreduce(buf, channel)
         else:
             import torch.distributed as dist
             dist.all_reduce(buf, op=dist.ReduceOp.SUM)
@@ -154,7 +199,7 @@ class GradBucket(object):
         off, n = self.slices[id(layer)]
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
-            self._reduce(off, n)
+            self._reduce(off, n, CH_SIDE)
         self._done.add(id(layer))
 
     def allreduce(self):
@@ -173,7 +218,7 @@ class GradBucket(object):
         with torch.cuda.stream(self._side):
             for l in self.layers:
                 if id(l) not in self._done:
-                    self._reduce(*self.slices[id(l)])
+                    self._reduce(*self.slices[id(l)], CH_SIDE)
         torch.cuda.current_stream().wait_stream(self._side)
         self._done, self._dirty = set(), set()
         return self.flat
@@ -184,7 +229,7 @@ def allreduce_sum_f64(t):
     if _state["world"] == 1:
         return t
     if _state["backend"] == "nccl":
-        L.check(L.load().npml_allreduce_sum_f64(L.ptr(t), t.numel(), L.stream()), "npml_allreduce_sum_f64")
+        _allreduce(t, CH_MAIN)
     else:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -210,7 +255,11 @@ def all_reduce_max(value):
 def destroy():
     import torch.distributed as dist
     if _state["backend"] == "nccl" and _state["world"] > 1:
+        if _state["peer"]:
+            if L.load().npml_peer_status() != 0:
+                raise RuntimeError("a peer all-reduce timed out waiting for another rank (results are invalid)")
+            L.load().npml_peer_close()
         L.load().npml_comm_destroy()
     if dist.is_initialized():
         dist.destroy_process_group()
-    _state.update(ready=False, world=1, rank=0)
+    _state.update(ready=False, world=1, rank=0, peer=False)

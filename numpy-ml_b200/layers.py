@@ -245,9 +245,14 @@ class _ConvBase(LayerBase):
             X_shape = tuple(self.X[-1].shape) if self.X else self._last_shape
         return bool(L.load().npml_uses_tensor_cores(self._desc(tuple(X_shape)), self._ops[0]))
 
-    def forward(self, X, retain_derived=True, fused_bn=None):
+    def forward(self, X, retain_derived=True, fused_bn=None, stats_out=None):
         """Y = act_fn(conv(X, W) + b); bias and activation are the kernel's epilogue
         (layers.py:3006-3046 / 3438-3478).
+
+        `stats_out` (an extension, Conv2D only): a float64 device vector of 2 * out_ch entries that receives the
+        per-channel [sum Y, sum Y^2] over (n_ex, rows, cols) -- the reductions of a training-mode BatchNorm2D that
+        directly follows (layers.py:1146-1147) -- from the convolution's own epilogue (npml_conv2d_fprop_stats), so
+        that BatchNorm2D does not have to read Y again for them (`BatchNorm2D.forward(Y, sums=stats_out)`).
 
         `fused_bn` (an extension): a BatchNorm2D that directly follows this layer and is in inference mode for this
         call (frozen, or `retain_derived=False`: layers.py:1141-1146 then normalises with the running statistics).
@@ -275,8 +280,15 @@ class _ConvBase(LayerBase):
         else:
             Z = torch.empty(out_shape, dtype=Xd.dtype, device=Xd.device)
             Y = Z if self.act_fn.code == 0 else torch.empty_like(Z)
-            self._call_w(pre + "fprop", d, self._ops[0], W, L.ptr(Xd), L.ptr(W), L.ptr(b),
-                         L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
+            zy = (L.ptr(Z) if (retain_derived or Y is Z) else None, None if Y is Z else L.ptr(Y))
+            if stats_out is not None:
+                if self._layer_name != "Conv2D" or d.N == 0:
+                    raise ValueError("stats_out is implemented for non-empty Conv2D forwards")
+                assert stats_out.dtype == torch.float64 and stats_out.numel() == 2 * d.K
+                self._call_w(pre + "fprop_stats", d, self._ops[0], W, L.ptr(Xd), L.ptr(W), L.ptr(b), zy[0], zy[1],
+                             L.ptr(stats_out))
+            else:
+                self._call_w(pre + "fprop", d, self._ops[0], W, L.ptr(Xd), L.ptr(W), L.ptr(b), zy[0], zy[1])
         if retain_derived:
             self.X.append(Xd)
             self.derived_variables["Z"].append(Z)
@@ -653,7 +665,9 @@ class BatchNorm2D(LayerBase):
         d = U.make_desc(1, 1, 1, 1, ch, 1, 1, 1, 1, (0, 0, 0, 0), 1, int(rows))
         return L.workspace(L.load().npml_workspace_bytes(d, L.OP_BN))
 
-    def forward(self, X, retain_derived=True):
+    def forward(self, X, retain_derived=True, sums=None):
+        """layers.py:1095-1158.  `sums` (an extension): the per-channel [sum x, sum x^2] of X if the producer of X has
+        already reduced them (Conv2D.forward(..., stats_out=)); the statistics pass over X is then skipped."""
         as_np = isinstance(X, np.ndarray)
         Xd = L.to_device(X, torch.float32) if as_np else L.to_device(X, X.dtype if X.dtype != torch.float64
                                                                    else torch.float32)
@@ -670,16 +684,19 @@ class BatchNorm2D(LayerBase):
         rstd = torch.empty(ch, dtype=torch.float32, device=Xd.device)
         use_batch = 1 if (self.trainable and retain_derived) else 0
         ws = self._ws(rows, ch)
-        if use_batch and self.sync:
+        if use_batch and (self.sync or sums is not None):
             from . import dist as D
             lib = L.load()
-            D.require_equal_shards(rows)       # total = rows * world below; raises on ragged / empty shards
-            sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
+            total = rows
             with L.profiled("npml_bn2d_fwd"):
-                L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(),
-                                            L.stream()), "npml_bn2d_stats")
-                D.allreduce_sum_f64(sums)
-                total = rows * D.world_size()
+                if sums is None:
+                    sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
+                    L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(),
+                                                L.stream()), "npml_bn2d_stats")
+                if self.sync:
+                    D.require_equal_shards(rows)       # total = rows * world below; raises on ragged / empty shards
+                    D.allreduce_sum_f64(sums)
+                    total = rows * D.world_size()
                 L.check(lib.npml_bn2d_apply(rows, total, ch, L.ptr(Xd), L.ptr(y), L.code_of(Xd), L.ptr(P["scaler"]),
                                             L.ptr(P["intercept"]), L.ptr(P["running_mean"]), L.ptr(P["running_var"]),
                                             float(self.momentum), float(self.epsilon), L.ptr(sums), L.ptr(mean),
@@ -699,8 +716,8 @@ class BatchNorm2D(LayerBase):
         return L.to_numpy(y) if as_np else y
 
     # ---- pieces of forward / backward for callers that fuse the normalisation into their own pass (modules.py) ----
-    def forward_stats(self, X):
-        """Training-mode statistics of X without normalising it: per-channel (mean, rstd) of the batch (all ranks
+    def forward_stats(self, X, sums=None):
+        """Training-mode statistics of X without normalising it (`sums`: already reduced by the producer of X): per-channel (mean, rstd) of the batch (all ranks
         under `sync`), the running-statistics update (layers.py:1146-1150), and X retained for the backward pass.  The
         caller normalises inside a fused pass (npml_bn2d_pair_add_act_fwd)."""
         assert self.trainable, "Layer is frozen"
@@ -715,13 +732,14 @@ class BatchNorm2D(LayerBase):
         rows = Xd.numel() // ch
         lib = L.load()
         ws = self._ws(rows, ch)
-        sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
         mean = torch.empty(ch, dtype=torch.float32, device=Xd.device)
         rstd = torch.empty(ch, dtype=torch.float32, device=Xd.device)
         total = rows
         with L.profiled("npml_bn2d_stats"):
-            L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(), L.stream()),
-                    "npml_bn2d_stats")
+            if sums is None:
+                sums = torch.empty(2 * ch, dtype=torch.float64, device=Xd.device)
+                L.check(lib.npml_bn2d_stats(rows, ch, L.ptr(Xd), L.code_of(Xd), L.ptr(sums), L.ptr(ws), ws.numel(),
+                                            L.stream()), "npml_bn2d_stats")
             if self.sync:
                 from . import dist as D
                 D.require_equal_shards(rows)

@@ -285,13 +285,17 @@ class SkipConnectionConvModule(ModuleBase):
             self.in_ch = Xd.shape[3]
         self._tail = None
         if retain_derived and self._fusable():
-            conv1_out = self.conv1.forward(Xd, True)
-            bn1_out = self.batchnorm1.forward(conv1_out, True)
-            conv2_out = self.conv2.forward(bn1_out, True)
-            conv_skip_out = self.conv_skip.forward(Xd, True)
+            # every convolution leaves the [sum, sum of squares] of its output for the BatchNorm2D behind it
+            # (npml_conv2d_fprop_stats): no statistics pass over conv1_out / conv2_out / conv_skip_out
+            q1, q2, qs = (torch.empty(2 * c.out_ch, dtype=torch.float64, device=Xd.device)
+                          for c in (self.conv1, self.conv2, self.conv_skip))
+            conv1_out = self.conv1.forward(Xd, True, stats_out=q1)
+            bn1_out = self.batchnorm1.forward(conv1_out, True, sums=q1)
+            conv2_out = self.conv2.forward(bn1_out, True, stats_out=q2)
+            conv_skip_out = self.conv_skip.forward(Xd, True, stats_out=qs)
             bn2, bns, act = self.batchnorm2, self.batchnorm_skip, self.act_fn
-            s2 = bn2.forward_stats(conv2_out)
-            ss = bns.forward_stats(conv_skip_out)
+            s2 = bn2.forward_stats(conv2_out, sums=q2)
+            ss = bns.forward_stats(conv_skip_out, sums=qs)
             # ReLU / identity need no stored sum: Y > 0 <=> sum > 0
             want_sum = act.code not in (0, 2)
             S, Y = _pair_add_act(bn2, conv2_out, s2, bns, conv_skip_out, ss, act, want_sum)

@@ -62,5 +62,12 @@ def full(src, dst):
             f.write("\n")
 
 
+def count(src, pattern):
+    """number of launches in a launch-list CSV whose kernel name matches `pattern` (for ncu's -s)"""
+    import re
+    rows = [r for r in csv.reader(open(src)) if len(r) > 14 and r[0].isdigit() and r[12] == "gpu__time_duration.sum"]
+    print(sum(1 for r in rows if re.search(pattern, r[4])))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "count": count}[sys.argv[1]](sys.argv[2], sys.argv[3])

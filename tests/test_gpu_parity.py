@@ -4,6 +4,8 @@
 in the three arithmetic modes with the tolerances BASELINE.json states (normwise relative error
 <= 1e-5 fp32, <= 5e-3 TF32, <= 2e-2 BF16), plus size-independent properties at the full
 benchmark shapes.  Nothing here reads /root/reference."""
+import os
+
 import numpy as np
 import pytest
 
@@ -600,6 +602,47 @@ def test_layer_state_semantics(cuda_device):
     assert s["layer"] == "Conv2D" and s["hyperparameters"]["kernel_shape"] == (3, 3)
     with pytest.raises(ValueError):
         pkg.Conv2D(2, (5, 5)).forward(np.zeros((1, 3, 3, 1)))            # kernel > input (utils.py:463-467)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_conv_epilogue_emits_batchnorm_statistics(cuda_device, mode):
+    """npml_conv2d_fprop_stats: the per-channel [sum Y, sum Y^2] a training-mode BatchNorm2D reduces (layers.py:1146-1147)
+    come out of the convolution call itself -- from the slab kernel's epilogue (64 / 128 / 256-channel shapes, several
+    work units per CTA, ragged last tile) or from the column pass that follows the other kernels -- and BatchNorm2D fed
+    with them equals BatchNorm2D that reads the tensor itself."""
+    import torch
+    pkg = npml()
+    shapes = [((9, 20, 20, 64), 64, (3, 3), 1, 1, "relu"), ((5, 13, 11, 64), 128, (3, 3), 1, 1, "identity"),
+              ((3, 9, 9, 64), 256, (1, 1), 0, 1, "tanh"), ((4, 12, 12, 128), 128, (3, 3), 1, 1, "relu"),
+              ((2, 28, 28, 128), 64, (3, 3), 0, 2, "identity"), ((3, 7, 7, 5), 6, (3, 3), 1, 1, "sigmoid")]
+    for ctas in (None, 2):
+        for xs, oc, ks, pad, s, act in shapes:
+            if ctas is not None:
+                os.environ["NPML_MAX_CTAS"] = str(ctas)
+            try:
+                rng = np.random.default_rng(77)
+                L_ = pkg.Conv2D(oc, ks, pad=pad, stride=s, act_fn=make_act(pkg, act, 0, 0), mode=mode)
+                X = _f32(rng, xs)
+                sums = torch.zeros(2 * oc, dtype=torch.float64, device="cuda")
+                L_.forward(X[:1], retain_derived=False)
+                L_.parameters["b"] = _f32(rng, (1, 1, 1, oc), 0.2)
+                Xd = pkg._lib.to_device(X, pkg._lib.torch_dtype(mode))
+                Y = L_.forward(Xd, stats_out=sums)
+                Yd = Y.double().reshape(-1, oc)
+                # the kernel sums the fp32 values before they are rounded to the storage type: compare at the mode's tolerance
+                tol = {"fp32": 1e-6, "tf32": 1e-6, "bf16": 4e-3}[mode]
+                got = sums.cpu().numpy()
+                ref1, ref2 = Yd.sum(0).cpu().numpy(), (Yd * Yd).sum(0).cpu().numpy()
+                scale = float(Yd.abs().sum(0).max())
+                assert np.abs(got[:oc] - ref1).max() <= tol * scale, (mode, xs, oc, "sum")
+                assert np.abs(got[oc:] - ref2).max() <= 2 * tol * float(ref2.max()), (mode, xs, oc, "sumsq")
+                bn_a, bn_b = pkg.BatchNorm2D(), pkg.BatchNorm2D()
+                np.random.seed(3); ya = bn_a.forward(Y, sums=sums)
+                np.random.seed(3); yb = bn_b.forward(Y)
+                close(ya.float(), pkg.to_numpy(yb), {"fp32": 1e-5, "tf32": 1e-5, "bf16": 1e-2}[mode], "bn from conv stats")
+                close(bn_a.parameters["running_var"], pkg.to_numpy(bn_b.parameters["running_var"]), 1e-3, "running var")
+            finally:
+                os.environ.pop("NPML_MAX_CTAS", None)
 
 
 def test_backward_naive_cross_check(cuda_device):
