@@ -248,6 +248,7 @@ ColPlan plan_cols(int64_t rows, int ch, int vec, bool reduce = true) {
   p.cg.rows = rows;
   p.cg.ch = ch;
   p.cg.rows_per_block = (rows + nblk - 1) / nblk;
+  if (p.cg.rows_per_block < 1) p.cg.rows_per_block = 1;      // rows == 0 (an empty batch): one idle block
   p.cg.TX = TX;
   p.cg.TY = TY;
   nblk = (rows + p.cg.rows_per_block - 1) / p.cg.rows_per_block;
