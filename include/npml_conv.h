@@ -86,9 +86,9 @@ int npml_conv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, co
 /* fprop that also leaves the statistics of its OUTPUT for the training-mode BatchNorm2D behind it (the
  * "optional per-channel sum / sum of squares for BN" of npml_conv2d_fprop): bn_sums[2*K] (double, device) = per-channel
  * [sum y, sum y^2] over (N, OH, OW) of y = act(conv + b) (of Z when Y is NULL), i.e. what layers/layers.py:1146-1147
- * reduces.  The slab kernel forms them in its epilogue from the fp32 accumulators (per-warp partial rows, added in a
- * fixed order); every other kernel is followed by one column pass over the tensor it just wrote.  Feed them to
- * npml_bn2d_apply / npml_bn2d_finalize (all-reduced first under sync-BN). */
+ * reduces.  One call: the convolution kernel, then a fixed-order column pass over the tensor it has just written (still
+ * in L2 for the benchmark shapes) -- forming the sums inside the tcgen05 epilogue was measured and is slower, see
+ * DESIGN.md.  Feed them to npml_bn2d_apply / npml_bn2d_finalize (all-reduced first under sync-BN). */
 int npml_conv2d_fprop_stats(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
                             double* bn_sums, void* ws, size_t ws_bytes, void* stream);
 /* fprop with a FROZEN BatchNorm2D folded into the same epilogue (north_star: "the BatchNorm2D affine [is a] fused

@@ -974,12 +974,6 @@ __global__ void col2im_kernel(npml_conv_desc d, const float* __restrict__ Xc, fl
 
 }  // namespace
 
-// fixed-order column sums of fp32 partial rows [nblk][width] -> sums[width] (double); used for the BatchNorm2D
-// statistics that the convolution epilogue leaves behind (tc_slab_conv.cu)
-int colsum_final_f32(const float* part, int nblk, int width, double* sums, cudaStream_t st) {
-  return launch_col_final<float>(part, nblk, width, sums, st);
-}
-
 size_t colpass_ws_bytes(int64_t rows, int ch, int nv) {
   ColPlan p = plan_cols(rows, ch, 1);     // vec = 1 gives the largest grid.x any plan for this shape can have
   return align_up((size_t)p.grid.x * nv * ch * sizeof(double), 256) + align_up((size_t)nv * ch * sizeof(double), 256) +

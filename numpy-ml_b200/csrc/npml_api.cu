@@ -72,7 +72,6 @@ static GatherWgrad make_wgrad(const npml_conv_desc* d, int op) {
 }
 
 size_t colpass_ws_bytes(int64_t rows, int ch, int nv);
-int colsum_final_f32(const float* part, int nblk, int width, double* sums, cudaStream_t st);
 
 // workspace bytes of the convolution kernel run_gather would pick (the packed weights)
 static size_t gather_ws_bytes(const GatherConv& g, int mode) {
@@ -81,7 +80,6 @@ static size_t gather_ws_bytes(const GatherConv& g, int mode) {
   if (mode != NPML_MODE_FP32 && tc_conv_supported(g, mode)) return tc_conv_ws_bytes(g, mode);
   return 0;
 }
-static size_t stats_part_bytes(int K) { return align_up((size_t)slab_stats_rows() * 2 * K * sizeof(float), 256); }
 
 static int run_gather(const npml_conv_desc* d, int op, const void* in, const float* W, const float* b, void* Z,
                       void* Y, void* ws, size_t ws_bytes, cudaStream_t st, const float* post_scale = nullptr,
@@ -96,25 +94,17 @@ static int run_gather(const npml_conv_desc* d, int op, const void* in, const flo
   g.post_scale = post_scale; g.post_shift = post_shift;
   if (g.act == NPML_ACT_IDENTITY && Z == nullptr && post_scale == nullptr) { Z = Y; Y = nullptr; }
   if (bn_sums != nullptr) {
-    // statistics of the layer output for the BatchNorm2D behind it: from the convolution's own epilogue where the
-    // kernel can (slab kernel), else one column pass over the output that was just written (still this one call)
+    // statistics of the layer output for the BatchNorm2D behind it: one column pass over the tensor the convolution
+    // has just written (L2-hot), inside the same call.  Forming them in the tcgen05 kernels' epilogue was measured and
+    // LOSES (cfg4, three convolutions: 208 us with the pass, 263 us with a shuffle transpose-reduce in the epilogue,
+    // 308 us on the staged read-back path with one epilogue group; profiles/r2j_cfg4_conv_stats_ab.md): those kernels
+    // are bound by their epilogue already.
     const size_t wbytes = align_up(gather_ws_bytes(g, d->mode), 256);
-    const size_t pbytes = stats_part_bytes(d->K);
     const int64_t rows = (int64_t)d->N * d->OH * d->OW;
-    NPML_CHECK(ws != nullptr && ws_bytes >= wbytes + pbytes + colpass_ws_bytes(rows, d->K, 2), "workspace too small");
-    const bool fused = d->mode != NPML_MODE_FP32 && !(d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode)) &&
-                       slab_conv_supported(g, d->mode) && slab_conv_emits_stats(g, d->mode);
-    if (fused) {
-      int nrows = 0;
-      g.stats_part = reinterpret_cast<float*>((char*)ws + wbytes);
-      g.stats_rows = &nrows;
-      if (int e = slab_gather_conv(g, d->mode, in, W, b, Z, Y, ws, wbytes, st)) return e;
-      return colsum_final_f32(g.stats_part, nrows, 2 * d->K, bn_sums, st);
-    }
+    NPML_CHECK(ws != nullptr && ws_bytes >= wbytes + colpass_ws_bytes(rows, d->K, 2), "workspace too small");
     if (int e = run_gather(d, op, in, W, b, Z, Y, ws, wbytes, st, post_scale, post_shift)) return e;
     const void* out = Y ? Y : Z;
-    return npml_bn2d_stats(rows, d->K, out, act_dtype(d->mode), bn_sums, (char*)ws + wbytes + pbytes,
-                           ws_bytes - wbytes - pbytes, (void*)st);
+    return npml_bn2d_stats(rows, d->K, out, act_dtype(d->mode), bn_sums, (char*)ws + wbytes, ws_bytes - wbytes, (void*)st);
   }
   if (d->mode == NPML_MODE_BF16 && ws_conv_supported(g, d->mode))
     return ws_gather_conv(g, d->mode, in, W, b, Z, Y, ws, ws_bytes, st);
@@ -209,8 +199,8 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
     case NPML_OP_CONV_FPROP: case NPML_OP_CONV_DGRAD: case NPML_OP_DECONV_FPROP: case NPML_OP_DECONV_DGRAD: {
       GatherConv g = make_gather(d, op);
       bytes += align_up(gather_ws_bytes(g, d->mode), 256);
-      if (op == NPML_OP_CONV_FPROP)       // npml_conv2d_fprop_stats: partial rows of the epilogue / the fallback column pass
-        bytes += stats_part_bytes(d->K) + colpass_ws_bytes((int64_t)d->N * d->OH * d->OW, d->K, 2);
+      if (op == NPML_OP_CONV_FPROP)       // npml_conv2d_fprop_stats: the column pass behind the convolution
+        bytes += colpass_ws_bytes((int64_t)d->N * d->OH * d->OW, d->K, 2);
       break;
     }
     case NPML_OP_CONV_WGRAD: case NPML_OP_DECONV_WGRAD: {

@@ -174,11 +174,6 @@ struct GatherConv {
   const float* post_shift;
   // NPML_FLAG_WEIGHTS_PACKED: the workspace already holds Wt for these weights; launch_repack_weights is a no-op
   bool weights_packed;
-  // BatchNorm2D statistics of the output from the convolution's own epilogue (npml_conv2d_fprop_stats): fp32 partial
-  // rows [*stats_rows][2 * CO] = per-channel (sum, sum of squares) of act(z + b); only the kernels for which
-  // slab_conv_emits_stats() is true look at these
-  float* stats_part;
-  int* stats_rows;
 };
 
 __device__ __forceinline__ float post_affine(const GatherConv& g, int co, float y) {
@@ -210,8 +205,6 @@ int tc_gather_conv(const GatherConv& g, int mode, const void* in, const float* w
                    void* Y, void* ws, size_t ws_bytes, cudaStream_t st);
 // persistent slab kernel for stride-1 gather convolutions, tc_slab_conv.cu
 bool slab_conv_supported(const GatherConv& g, int mode);
-bool slab_conv_emits_stats(const GatherConv& g, int mode);
-int slab_stats_rows();
 size_t slab_conv_ws_bytes(const GatherConv& g, int mode);
 int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z,
                      void* Y, void* ws, size_t ws_bytes, cudaStream_t st);

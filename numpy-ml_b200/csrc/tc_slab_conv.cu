@@ -75,8 +75,6 @@ struct SlabParams {
   int epi2;                     // 1: warps 8..11 take every other tile (their rows go straight to global memory)
   int wait_ns;                  // sleep between mbarrier polls of the producer / epilogue warps (npml::wait_ns())
   int affine;                   // 1: Y = scale[co] * act(z + b) + shift[co] (frozen BatchNorm2D folded into the epilogue)
-  int stats_width;              // > 0: per-channel sum / sum of squares of the output for a BatchNorm2D that follows
-                                // (row width of the partials = 2 * out_ch); BN <= 128, one (staged) epilogue group
 };
 
 // Measured on B200: the 128B swizzle of both the TMA write and the UMMA read is a function of the ABSOLUTE
@@ -87,12 +85,12 @@ struct SlabParams {
 // layout SWIZZLE_128B.  descriptor = kDesc64 + (shared address >> 4).
 constexpr uint64_t kDesc64 = ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (1u << 16);
 
-template <typename T, int NT, int UT, bool kStats>
+template <typename T, int NT, int UT>
 __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_constant__ SlabParams P,
                                                                    const float* __restrict__ bias,
                                                                    const float* __restrict__ post_scale,
                                                                    const float* __restrict__ post_shift, T* __restrict__ Z,
-                                                                   T* __restrict__ Y, float* __restrict__ stats_part) {
+                                                                   T* __restrict__ Y) {
   constexpr bool kTf32 = sizeof(T) == 4;
   // [weights (1024-aligned base)] [2 slab planes (128-aligned)] [epilogue staging] [bias | scale | shift] [barriers]
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -310,41 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     const int rd_row0 = lane / kCPR, rd_cc = lane % kCPR;
     uint32_t slot = 0, sph = 0;
 
-    // BatchNorm2D statistics of the output (stats_width > 0), taken in the read-back pass of `emit`, where a lane holds
-    // kVec consecutive channels of kCPR rows -- the STORED (rounded) values, exactly what a statistics pass over the
-    // tensor would read.  Lane accumulators are indexed statically (chunk through a switch) so they stay in registers;
-    // the lanes that share a channel group are added once, at the end of the kernel.
-    constexpr int kSQ = kStats ? 4 : 1, kSV = kStats ? kVec : 1;      // (no registers in the plain instantiations)
-    float sa[kSQ][kSV], sq[kSQ][kSV];
-#pragma unroll
-    for (int q = 0; q < kSQ; ++q)
-#pragma unroll
-      for (int j = 0; j < kSV; ++j) { sa[q][j] = 0.f; sq[q][j] = 0.f; }
-    auto stat_add = [&](const uint4& u, int cq) {
-      if constexpr (!kStats) return;
-      float x[kVec];
-      if constexpr (sizeof(T) == 2) {
-        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w4[j]);
-          x[2 * j] = __low2float(h); x[2 * j + 1] = __high2float(h);
-        }
-      } else {
-        x[0] = __uint_as_float(u.x); x[1] = __uint_as_float(u.y); x[2] = __uint_as_float(u.z); x[3] = __uint_as_float(u.w);
-      }
-      switch (cq) {
-#define NPML_STAT_CASE(Q)                                                                             \
-        case Q:                                                                                       \
-          _Pragma("unroll") for (int j = 0; j < kSV; ++j) { sa[Q % kSQ][j] += x[j]; sq[Q % kSQ][j] = fmaf(x[j], x[j], sq[Q % kSQ][j]); } \
-          break;
-        NPML_STAT_CASE(0) NPML_STAT_CASE(1) NPML_STAT_CASE(2) NPML_STAT_CASE(3)
-#undef NPML_STAT_CASE
-        default: break;
-      }
-    };
-
-    auto emit = [&](T* __restrict__ out, const float (&v)[32], int my_pix, int co, bool stats) {
+    auto emit = [&](T* __restrict__ out, const float (&v)[32], int my_pix, int co) {
       // registers -> staging (row = lane), 16-byte pieces XOR-swizzled
 #pragma unroll
       for (int cc = 0; cc < kCPR; ++cc) {
@@ -374,10 +338,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
         const uint32_t addr = stg_u32 + (uint32_t)(r * kRB + ((rd_cc ^ swz) << 4));
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
         const int c_el = co + rd_cc * kVec;
-        if (pr >= 0 && c_el < CO) {
-          *reinterpret_cast<uint4*>(out + (int64_t)pr * CO + c_el) = u;
-          if (kStats && stats) stat_add(u, (co - co0) >> 5);
-        }
+        if (pr >= 0 && c_el < CO) *reinterpret_cast<uint4*>(out + (int64_t)pr * CO + c_el) = u;
       }
       __syncwarp();
     };
@@ -408,7 +369,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
     };
     const bool direct = P.epi_direct != 0 || grp == 1;
     uint32_t tseq = 0;                            // running tile number of this CTA
-    const bool want_stats = kStats && P.stats_width > 0;
 
     for (int unit = (grp == 0 || P.epi2) ? (int)blockIdx.x : P.num_units; unit < P.num_units; unit += gridDim.x) {
       const int cls = P.ncls > 1 ? unit / P.units_per_cls : 0;
@@ -448,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
           const int co = co0 + c;
           if (Z) {
             if (direct) emit_direct(Z, v, my_pix, co);
-            else emit(Z, v, my_pix, co, want_stats && Y == nullptr);
+            else emit(Z, v, my_pix, co);
           }
           if (Y) {
             act_apply32(P.act, P.p0, P.p1, v);
@@ -462,33 +422,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_conv_kernel(const __grid_
               }
             }
             if (direct) emit_direct(Y, v, my_pix, co);
-            else emit(Y, v, my_pix, co, want_stats);
+            else emit(Y, v, my_pix, co);
           }
         }
         if (++slot == (uint32_t)n_acc) { slot = 0; sph ^= 1u; }
-      }
-    }
-    if (kStats && want_stats && grp == 0) {
-      // the lanes with the same channel group (lane % kCPR) hold different rows: add them (xor kCPR, 2 kCPR, ...), then
-      // lanes 0 .. kCPR-1 write the warp's row of partials
-#pragma unroll
-      for (int q = 0; q < kSQ; ++q)
-#pragma unroll
-        for (int j = 0; j < kSV; ++j)
-#pragma unroll
-          for (int sh = kCPR; sh < 32; sh <<= 1) {
-            sa[q][j] += __shfl_xor_sync(0xffffffffu, sa[q][j], sh);
-            sq[q][j] += __shfl_xor_sync(0xffffffffu, sq[q][j], sh);
-          }
-      float* row = stats_part + (size_t)(blockIdx.x * 4 + (warp - 4)) * P.stats_width;
-      if (lane < kCPR) {
-#pragma unroll
-        for (int q = 0; q < kSQ; ++q)
-#pragma unroll
-          for (int j = 0; j < kSV; ++j) {
-            const int ch = co0 + q * 32 + lane * kVec + j;
-            if (q * 32 < BN && ch < CO) { row[ch] = sa[q][j]; row[CO + ch] = sq[q][j]; }
-          }
       }
     }
   }
@@ -682,28 +619,21 @@ int launch_slab(const GatherConv& g, SlabPlan& pl, const void* in, const float* 
       if (int e = make_tmap(&P.amap[i], bf16, base, 4, dims, strides, box, false)) return e;
     }
   }
-  typedef void (*Kern)(const SlabParams, const float*, const float*, const float*, T*, T*, float*);
+  typedef void (*Kern)(const SlabParams, const float*, const float*, const float*, T*, T*);
   Kern kern = nullptr;
-  P.stats_width = g.stats_part != nullptr ? 2 * g.CO : 0;
-#define NPML_SLAB_UT(NTV, ST)                                                      \
+#define NPML_SLAB_UT(NTV)                                                          \
   switch (P.UT) {                                                                  \
-    case 1: kern = tc_slab_conv_kernel<T, NTV, 1, ST>; break;                      \
-    case 2: kern = tc_slab_conv_kernel<T, NTV, 2, ST>; break;                      \
-    case 3: kern = tc_slab_conv_kernel<T, NTV, 3, ST>; break;                      \
-    default: kern = tc_slab_conv_kernel<T, NTV, 4, ST>; break;                     \
+    case 1: kern = tc_slab_conv_kernel<T, NTV, 1>; break;                          \
+    case 2: kern = tc_slab_conv_kernel<T, NTV, 2>; break;                          \
+    case 3: kern = tc_slab_conv_kernel<T, NTV, 3>; break;                          \
+    default: kern = tc_slab_conv_kernel<T, NTV, 4>; break;                         \
   }
-  if (P.stats_width > 0) {                 // statistics variant: stride-1 3x3 / 1x1 / generic taps
-    if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 9) { NPML_SLAB_UT(9, true) }
-    else if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 1) { NPML_SLAB_UT(1, true) }
-    else { NPML_SLAB_UT(0, true) }
-  } else if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 9) { NPML_SLAB_UT(9, false) }
-  else if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 1) { NPML_SLAB_UT(1, false) }
-  else { NPML_SLAB_UT(0, false) }
+  if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 9) { NPML_SLAB_UT(9) }
+  else if (P.ncls == 1 && P.nplanes == 1 && P.ntaps == 1) { NPML_SLAB_UT(1) }
+  else { NPML_SLAB_UT(0) }
 #undef NPML_SLAB_UT
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-  if (P.stats_width > 0) { P.epi2 = 0; P.epi_direct = 0; }       // statistics ride on the staged read-back pass
-  if (g.stats_rows != nullptr) *g.stats_rows = (int)pl.grid.x * 4;
-  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, g.post_scale, g.post_shift, (T*)Z, (T*)Y, g.stats_part);
+  kern<<<pl.grid, kThreads, pl.smem, st>>>(P, bias, g.post_scale, g.post_shift, (T*)Z, (T*)Y);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -720,16 +650,6 @@ size_t slab_conv_ws_bytes(const GatherConv& g, int mode) {
   const int es = mode == NPML_MODE_BF16 ? 2 : 4;       // the repacked weights Wt[tap][co][ci], both slab kernels
   return align_up((size_t)g.fr * g.fc * g.CO * g.CI * es, 256) + 256;
 }
-
-// true: slab_gather_conv will take the kernel whose epilogue can emit BatchNorm2D statistics (GatherConv::stats_part)
-bool slab_conv_emits_stats(const GatherConv& g, int mode) {
-  SlabPlan pl;
-  if (const char* e = std::getenv("NPML_CONV_STATS"))      // A/B switch: 0 = always the separate column pass
-    if (e[0] == '0') return false;
-  return !slab3_conv_supported(g, mode) && plan_slab(g, mode, pl) && pl.P.BN <= 128;
-}
-
-int slab_stats_rows() { return num_sms() * 4; }          // upper bound of the partial rows a launch writes
 
 int slab_gather_conv(const GatherConv& g, int mode, const void* in, const float* w, const float* bias, void* Z, void* Y,
                      void* ws, size_t ws_bytes, cudaStream_t st) {
