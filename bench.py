@@ -568,7 +568,9 @@ def measure(ctx, cfg, headline):
     if world > 1:
         if graph is not None:
             graph.reset()
+        bucket.suspended = True                     # the same step without any gradient exchange
         ms_nored, _, _, _, g2 = timed_graph(ctx, make_step(Xd, dYd, reduce=False), steps, flush_l2)
+        bucket.suspended = False
         if g2 is not None:
             g2.reset()
         out["allreduce"] = {"bytes": int(bucket.flat.numel() * 4), "exposed_ms_per_step": max(0.0, (ms_total - ms_nored) / steps),

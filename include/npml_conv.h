@@ -292,13 +292,13 @@ int npml_comm_destroy(void);
 
 /* ---- all-reduce over NVLink / NVSwitch peer memory (csrc/peer.cu) -----------------------------------------------
  * The collectives of the data-parallel step are small (dW || db of a layer: 1 KB - 2 MB; sync-BN statistics: 2 KB) and
- * latency-bound, so they are ONE kernel each instead of a NCCL call: every rank pushes its slice into an inbox in every
- * peer's memory, releases a per-block flag there, waits on its own flags and adds the copies in rank order (the same
- * order on every rank: bit-identical results everywhere, run after run).  Graph-capturable (the call counter lives in
- * device memory).  Setup: every rank calls npml_peer_alloc (cudaMalloc + cudaIpcGetMemHandle of its region -- the one
+ * latency-bound, so they are ONE kernel each instead of a NCCL call: every rank pushes each 32-bit word of its buffer,
+ * paired with the call number in one 8-byte store, into an inbox in every peer's memory, polls its own inbox and adds the
+ * copies in rank order (the same order on every rank: bit-identical results everywhere, run after run).
+ * Graph-capturable (the call counter lives in device memory).  Setup: every rank calls npml_peer_alloc (cudaMalloc + cudaIpcGetMemHandle of its region -- the one
  * allocation this library makes, at init), the host gathers the 64-byte handles, every rank calls npml_peer_open and
  * passes a host barrier.  `channel` (0..3): calls on one channel must be issued in the same order by every rank; use
- * different channels for streams that run concurrently.  n * sizeof(element) <= 4 MiB, buf 16-byte aligned. */
+ * different channels for streams that run concurrently.  n * sizeof(element) <= 2.5 MiB. */
 size_t npml_peer_region_bytes(void);
 int npml_peer_alloc(void* handle64);
 int npml_peer_open(const void* handles, int32_t world, int32_t rank);

@@ -2,17 +2,21 @@
 // MEMORY, written as one kernel per call instead of a NCCL collective (dW || db of a layer is 1 KB - 2 MB,
 // the sync-BN statistics 2 KB -- all latency-bound).
 //
-//   push   every rank writes its slice of the buffer straight into an inbox in every peer's memory (posted NVLink
-//          stores, no round trip), then releases one flag per block in every peer's flag array (st.release.sys);
-//   sum    every rank waits on its OWN (local) flags, then adds the `world` inbox copies in RANK ORDER -- the same
-//          order on every rank, so all ranks hold bit-identical results, run after run (the reference sums the batch in
-//          one fixed order too, layers/layers.py:3109-3110).
+//   push   every rank writes each 32-bit word of its buffer, paired with the call number, as ONE 8-byte store straight
+//          into an inbox in every peer's memory (posted NVLink stores; data and flag arrive together, so there is no
+//          fence and no separate flag round trip -- the "LL" idea);
+//   sum    every rank polls its OWN (local) inbox until the word of rank r carries this call's number and adds the
+//          copies in RANK ORDER -- the same order on every rank, so all ranks hold bit-identical results, run after
+//          run (the reference sums the batch in one fixed order too, layers/layers.py:3109-3110).
 //
-// Block b of rank r only ever waits for block b of the other ranks, which wait for nobody before they push: no
-// co-residency requirement, no grid barrier.  The call number ("epoch") lives in device memory and is advanced by the
-// last block of a launch, so a captured CUDA graph replays correctly.  Calls alternate between two inbox halves, which
-// is enough: a rank can finish call k+1 only after every peer has finished READING call k (stream order on the peer).
+// A thread only ever waits for words that the peers push without waiting for anybody: no co-residency requirement, no
+// grid barrier.  The call number ("epoch") lives in device memory and is advanced by the last block of a launch, so a
+// captured CUDA graph replays correctly.  Calls alternate between two inbox halves, which is enough: a rank can finish
+// call k+1 only after every peer has pushed call k+1, i.e. after that peer finished READING call k (stream order).
 // Independent streams (the gradient side stream, the sync-BN statistics on the main stream) use different channels.
+// The price of the flag is 2x the bytes on the wire, so the host only takes this path while (world-1) * 2 * bytes stays
+// small (numpy-ml_b200/dist.py); larger buffers go to ncclAllReduce.  First version of this file used 16-byte stores, a
+// __threadfence_system and one flag per block: 15 us for 144 KB on 2 GPUs against NCCL's 12 (profiles/r2k_mgpu.log).
 //
 // Memory: one cudaMalloc'ed region per rank, exported with cudaIpcGetMemHandle and opened by every peer at init time
 // (host side: numpy-ml_b200/dist.py).  This is the one allocation the library makes itself -- at init, never on the
@@ -25,19 +29,16 @@ namespace {
 
 constexpr int kMaxRanks = 8;
 constexpr int kChannels = 4;
-constexpr int kMaxBlocks = 1024;
 constexpr int kThreads = 256;
-constexpr size_t kSlotBytes = 4u << 20;          // largest message per call (cfg5: 2.1 MB)
-constexpr unsigned kSpinLimit = 1u << 23;        // a few seconds of polling: a peer that never arrives must not hang the box
+constexpr int kMaxBlocks = 592;                  // 4 per SM: plenty of words in flight, still cheap to launch
+constexpr size_t kSlotBytes = 5u << 20;          // inbox per (channel, half, source): 2 x the largest message (cfg5: 2.1 MB)
+constexpr unsigned kSpinLimit = 1u << 24;        // seconds of polling: a peer that never arrives must not hang the box
 
 // region layout (identical on every rank)
-//   ctrl  [kChannels] { epoch, arrived }                              local bookkeeping
-//   flags [kChannels][2][kMaxRanks][kMaxBlocks] uint32               written by peers
-//   inbox [kChannels][2][kMaxRanks][kSlotBytes]                      written by peers
+//   ctrl  [kChannels] { epoch, arrived, error }                       local bookkeeping
+//   inbox [kChannels][2][kMaxRanks][kSlotBytes]                       written by peers: (word, epoch) pairs
 struct Ctrl { unsigned epoch, arrived, error, pad; };
-constexpr size_t kCtrlBytes = 4096;
-constexpr size_t kFlagBytes = (size_t)kChannels * 2 * kMaxRanks * kMaxBlocks * sizeof(unsigned);
-constexpr size_t kInboxOff = kCtrlBytes + kFlagBytes;
+constexpr size_t kInboxOff = 4096;
 constexpr size_t kRegionBytes = kInboxOff + (size_t)kChannels * 2 * kMaxRanks * kSlotBytes;
 
 struct PeerTable {
@@ -53,83 +54,69 @@ struct Peer {
 };
 Peer g_peer;
 
-__device__ __forceinline__ unsigned* flag_ptr(char* base, int ch, int half, int src, int blk) {
-  return reinterpret_cast<unsigned*>(base + kCtrlBytes) + (((size_t)ch * 2 + half) * kMaxRanks + src) * kMaxBlocks + blk;
+__device__ __forceinline__ uint2* inbox_ptr(char* base, int ch, int half, int src) {
+  return reinterpret_cast<uint2*>(base + kInboxOff + (((size_t)ch * 2 + half) * kMaxRanks + src) * kSlotBytes);
 }
-__device__ __forceinline__ char* inbox_ptr(char* base, int ch, int half, int src) {
-  return base + kInboxOff + (((size_t)ch * 2 + half) * kMaxRanks + src) * kSlotBytes;
+__device__ __forceinline__ void st_pair(uint2* p, unsigned v, unsigned f) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(f) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ uint2 ld_pair(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
 }
 
-// T = float or double; 16-byte vectors of VEC = 16 / sizeof(T) elements.  Block b owns vectors [b*vpb, (b+1)*vpb).
-template <typename T>
-__global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab, T* __restrict__ buf, int64_t n, int vpb,
+// W = 32-bit words per element (1: float, 2: double).  Element e of the buffer is handled by one thread on every rank.
+template <typename T, int W>
+__global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab, T* __restrict__ buf, int64_t n,
                                                                   int channel) {
-  constexpr int VEC = 16 / (int)sizeof(T);
   char* mine = tab.base[tab.rank];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(mine) + channel;
   const unsigned epoch = ctrl->epoch + 1u;           // every block reads it before the last block advances it
   const int half = (int)(epoch & 1u);
-  const int b = blockIdx.x;
-  const int64_t nvec = (n + VEC - 1) / VEC;
-  const int64_t v0 = (int64_t)b * vpb;
-  const int64_t v1 = v0 + vpb < nvec ? v0 + vpb : nvec;
-
-  // ---- push my slice into every rank's inbox (my own included: the sum below reads all copies the same way) ----
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-    uint4 u;
-    if ((v + 1) * VEC <= n) {
-      u = *reinterpret_cast<const uint4*>(buf + v * VEC);
-    } else {                                          // ragged tail: pad with zeros
-      T tmp[VEC];
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  unsigned* words = reinterpret_cast<unsigned*>(buf);
+  // ---- push: my words (with the call number) into every peer's inbox ----
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride) {
+    unsigned w[W];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) tmp[j] = v * VEC + j < n ? buf[v * VEC + j] : (T)0;
-      u = *reinterpret_cast<const uint4*>(tmp);
-    }
-    for (int p = 0; p < tab.world; ++p) {
-      const int dst = (tab.rank + p) % tab.world;     // stagger the targets so the ranks do not all hit one peer first
-      reinterpret_cast<uint4*>(inbox_ptr(tab.base[dst], channel, half, tab.rank))[v] = u;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < tab.world) {
-    __threadfence_system();                           // the block's stores are ordered before the flag
-    st_release_sys(flag_ptr(tab.base[threadIdx.x], channel, half, tab.rank, b), epoch);
-  }
-  // ---- wait for every rank's block b (local flags), then add the copies in rank order ----
-  if (threadIdx.x < tab.world) {
-    const unsigned* f = flag_ptr(mine, channel, half, threadIdx.x, b);
-    unsigned spins = 0;
-    while (ld_acquire_sys(f) != epoch) {
-      if (++spins > kSpinLimit) { ctrl->error = 1u; break; }
-    }
-  }
-  __syncthreads();
-  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
-    T acc[VEC];
+    for (int k = 0; k < W; ++k) w[k] = words[e * W + k];
+    for (int p = 1; p < tab.world; ++p) {
+      const int dst = (tab.rank + p) % tab.world;     // staggered so that the ranks do not all start on the same peer
+      uint2* box = inbox_ptr(tab.base[dst], channel, half, tab.rank) + e * W;
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = (T)0;
+      for (int k = 0; k < W; ++k) st_pair(box + k, w[k], epoch);
+    }
+  }
+  // ---- sum: poll the local inbox, add in rank order (my own contribution at position `rank`) ----
+  bool timed_out = false;
+  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride) {
+    T acc = (T)0;
     for (int r = 0; r < tab.world; ++r) {
-      const uint4 u = __ldcg(reinterpret_cast<const uint4*>(inbox_ptr(mine, channel, half, r)) + v);
-      const T* e = reinterpret_cast<const T*>(&u);
+      T x;
+      if (r == tab.rank) {
+        x = buf[e];
+      } else {
+        const uint2* box = inbox_ptr(mine, channel, half, r) + e * W;
+        unsigned w[W];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) acc[j] += e[j];
+        for (int k = 0; k < W; ++k) {
+          uint2 v = ld_pair(box + k);
+          unsigned spins = 0;
+          while (v.y != epoch) {
+            if (++spins > kSpinLimit) { timed_out = true; break; }
+            v = ld_pair(box + k);
+          }
+          w[k] = v.x;
+        }
+        if (W == 1) x = (T)__uint_as_float(w[0]);
+        else x = (T)__hiloint2double((int)w[W - 1], (int)w[0]);
+      }
+      acc += x;
     }
-    if ((v + 1) * VEC <= n) {
-      *reinterpret_cast<uint4*>(buf + v * VEC) = *reinterpret_cast<const uint4*>(acc);
-    } else {
-#pragma unroll
-      for (int j = 0; j < VEC; ++j)
-        if (v * VEC + j < n) buf[v * VEC + j] = acc[j];
-    }
+    buf[e] = acc;
   }
+  if (timed_out) ctrl->error = 1u;
   // ---- the last block of the launch advances the epoch (stream order makes it visible to the next call) ----
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -142,19 +129,15 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab,
   }
 }
 
-template <typename T>
+template <typename T, int W>
 int peer_allreduce(T* buf, int64_t n, int channel, cudaStream_t st) {
   NPML_CHECK(g_peer.ready, "peer memory is not initialised (npml_peer_open)");
   NPML_CHECK(channel >= 0 && channel < kChannels, "bad channel");
   if (n <= 0) return 0;
-  NPML_CHECK((size_t)n * sizeof(T) <= kSlotBytes, "message larger than a peer inbox slot");
-  NPML_CHECK((reinterpret_cast<uintptr_t>(buf) & 15) == 0, "buffer must be 16-byte aligned");
-  constexpr int VEC = 16 / (int)sizeof(T);
-  const int64_t nvec = (n + VEC - 1) / VEC;
-  int vpb = kThreads;                                 // one vector per thread ...
-  while ((nvec + vpb - 1) / vpb > kMaxBlocks) vpb *= 2;   // ... unless that needs more blocks than there are flags
-  const int blocks = (int)((nvec + vpb - 1) / vpb);
-  peer_allreduce_kernel<T><<<blocks, kThreads, 0, st>>>(g_peer.t, buf, n, vpb, channel);
+  NPML_CHECK((size_t)n * W * 8 <= kSlotBytes, "message larger than a peer inbox slot");
+  int64_t blocks = (n + kThreads - 1) / kThreads;
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  peer_allreduce_kernel<T, W><<<(int)blocks, kThreads, 0, st>>>(g_peer.t, buf, n, channel);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -170,7 +153,7 @@ int npml_peer_alloc(void* handle64) {
   NPML_CHECK(handle64 != nullptr, "handle buffer is NULL");
   NPML_CHECK(g_peer.local == nullptr, "peer region already allocated");
   NPML_CUDA(cudaMalloc(&g_peer.local, kRegionBytes));
-  NPML_CUDA(cudaMemset(g_peer.local, 0, kInboxOff));          // ctrl + flags
+  NPML_CUDA(cudaMemset(g_peer.local, 0, kRegionBytes));       // epoch 0 everywhere: no word of call 1 is "there" yet
   cudaIpcMemHandle_t h;
   NPML_CUDA(cudaIpcGetMemHandle(&h, g_peer.local));
   static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -202,10 +185,10 @@ int npml_peer_open(const void* handles, int32_t world, int32_t rank) {
 int npml_peer_ready(void) { return g_peer.ready ? 1 : 0; }
 
 int npml_peer_allreduce_sum_f32(float* buf, int64_t n, int32_t channel, void* stream) {
-  return peer_allreduce<float>(buf, n, channel, (cudaStream_t)stream);
+  return peer_allreduce<float, 1>(buf, n, channel, (cudaStream_t)stream);
 }
 int npml_peer_allreduce_sum_f64(double* buf, int64_t n, int32_t channel, void* stream) {
-  return peer_allreduce<double>(buf, n, channel, (cudaStream_t)stream);
+  return peer_allreduce<double, 2>(buf, n, channel, (cudaStream_t)stream);
 }
 
 // 0 = fine; 1 = a block gave up waiting for a peer (the results of that call are garbage).  Synchronises.

@@ -15,7 +15,7 @@ import torch
 from . import _lib as L
 
 _state = {"ready": False, "world": 1, "rank": 0, "backend": None, "peer": False, "peer_why": "single process"}
-PEER_SLOT_BYTES = 4 << 20          # csrc/peer.cu: kSlotBytes
+PEER_WIRE_BYTES = 5 << 20          # csrc/peer.cu: a call takes the peer path while (world - 1) * 2 * bytes fits this
 CH_MAIN, CH_SIDE = 0, 1            # peer all-reduce channels: the caller's stream / the gradient side stream
 
 
@@ -84,7 +84,9 @@ def _allreduce(buf, channel):
     """In-place SUM over ranks of a contiguous fp32 / fp64 device tensor on the current stream."""
     lib, n = L.load(), buf.numel()
     f64 = buf.dtype == torch.float64
-    if _state["peer"] and n * buf.element_size() <= PEER_SLOT_BYTES and buf.data_ptr() % 16 == 0:
+    # the (word, call number) pairs double the bytes on the wire and every rank pushes to every peer: beyond a few MB
+    # per call NCCL's ring / in-switch reduction wins, below it the one-kernel push has the lower latency
+    if _state["peer"] and (_state["world"] - 1) * 2 * n * buf.element_size() <= PEER_WIRE_BYTES:
         fn = lib.npml_peer_allreduce_sum_f64 if f64 else lib.npml_peer_allreduce_sum_f32
         L.check(fn(L.ptr(buf), n, channel, L.stream()), "npml_peer_allreduce_sum")
     else:
@@ -163,6 +165,7 @@ class GradBucket(object):
             l._bucket = self
         self.overlap = bool(overlap) and _state["world"] > 1 and self.flat.is_cuda
         self._done, self._dirty = set(), set()
+        self.suspended = False     # True: steps run without any reduction (a caller measuring the step alone)
         self._side = torch.cuda.Stream() if self.overlap else None
         if self.overlap:
             for l in self.layers:
@@ -191,6 +194,8 @@ class GradBucket(object):
 
     def _on_ready(self, layer):
         """dW / db of `layer` are enqueued on the current stream: reduce that slice on the side stream."""
+        if self.suspended:
+            return
         if id(layer) in self._done or len(layer.X) > 1:
             # a second backward into the same slice (list-valued backward, index=): an early reduce would mix reduced
             # and local contributions -- leave this layer to the deferred reduce in allreduce()
