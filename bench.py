@@ -416,7 +416,8 @@ def timed_graph(ctx, step, steps, flush_l2):
         one()
     q1.record()
     torch.cuda.synchronize()
-    burst = int(min(64, max(4, 3.0 / max(q0.elapsed_time(q1) / 5.0, 1e-3))))
+    # (max over ranks: every rank must replay the same number of steps, they contain collectives)
+    burst = int(min(64, max(4, 3.0 / max(D.all_reduce_max(q0.elapsed_time(q1)) / 5.0, 1e-3))))
     if ctx.args.quick:
         burst = 1
     per_call = {}

@@ -32,7 +32,7 @@ constexpr int kChannels = 4;
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = 592;                  // 4 per SM: plenty of words in flight, still cheap to launch
 constexpr size_t kSlotBytes = 5u << 20;          // inbox per (channel, half, source): 2 x the largest message (cfg5: 2.1 MB)
-constexpr unsigned kSpinLimit = 1u << 24;        // seconds of polling: a peer that never arrives must not hang the box
+constexpr unsigned kSpinLimit = 1u << 23;        // seconds of polling: a peer that never arrives must not hang the box
 
 // region layout (identical on every rank)
 //   ctrl  [kChannels] { epoch, arrived, error }                       local bookkeeping
@@ -89,7 +89,9 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab,
     }
   }
   // ---- sum: poll the local inbox, add in rank order (my own contribution at position `rank`) ----
-  bool timed_out = false;
+  // once a wait has timed out (a peer that never made this call: a bug on the host side) nothing waits any more --
+  // this call and all later ones rush through with garbage, npml_peer_status() reports it, nothing hangs
+  bool timed_out = ctrl->error != 0u;
   for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride) {
     T acc = (T)0;
     for (int r = 0; r < tab.world; ++r) {
@@ -103,8 +105,8 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab,
         for (int k = 0; k < W; ++k) {
           uint2 v = ld_pair(box + k);
           unsigned spins = 0;
-          while (v.y != epoch) {
-            if (++spins > kSpinLimit) { timed_out = true; break; }
+          while (v.y != epoch && !timed_out) {
+            if (++spins > kSpinLimit) timed_out = true;
             v = ld_pair(box + k);
           }
           w[k] = v.x;
