@@ -367,6 +367,7 @@ class SkipConnectionIdentityModule(ModuleBase):
     """modules/modules.py:360-612: conv1('same', act) -> BN1 -> conv2('same', affine, out_ch = in_ch) -> BN2 ->
     Add([X, BN2]) -> act.  Same kernels as SkipConnectionConvModule, the input itself is the shortcut."""
     fuse_inference = True
+    fuse_training = True          # see SkipConnectionConvModule: Y = act(X + BN2(conv2_out)) and its backward in one pass each
 
     def __init__(self, out_ch, kernel_shape1, kernel_shape2, stride1=1, stride2=1, act_fn=None, epsilon=1e-5,
                  momentum=0.9, optimizer=None, init="glorot_uniform", mode="fp32", sync_bn=False):
@@ -427,8 +428,12 @@ class SkipConnectionIdentityModule(ModuleBase):
     def derived_variables(self):
         dv = {"conv1_out": None, "conv2_out": None, "batchnorm1_out": None, "batchnorm2_out": None,
               "components": self._by_component("derived_variables")}
-        dv.update(self._dv)
+        dv.update(_resolve(self._dv))
         return dv
+
+    def _fusable(self):
+        comps = [self.conv1, self.conv2, self.batchnorm1, self.batchnorm2]
+        return self.fuse_training and self.trainable and all(c.trainable for c in comps) and len(self.conv1.X) == 0
 
     def forward(self, X, retain_derived=True):
         """modules.py:574-594."""
@@ -441,6 +446,22 @@ class SkipConnectionIdentityModule(ModuleBase):
             bn1_out = self.conv1.forward(Xd, False, fused_bn=self.batchnorm1)
             bn2_out = self.conv2.forward(bn1_out, False, fused_bn=self.batchnorm2)
             Y = self.add3.forward([Xd, bn2_out], False)
+            return L.to_numpy(Y) if as_np else Y
+        self._tail = None
+        if retain_derived and self._fusable():
+            q1, q2 = (torch.empty(2 * c.out_ch, dtype=torch.float64, device=Xd.device) for c in (self.conv1, self.conv2))
+            conv1_out = self.conv1.forward(Xd, True, stats_out=q1)
+            bn1_out = self.batchnorm1.forward(conv1_out, True, sums=q1)
+            conv2_out = self.conv2.forward(bn1_out, True, stats_out=q2)
+            bn2, act = self.batchnorm2, self.act_fn
+            s2 = bn2.forward_stats(conv2_out, sums=q2)
+            want_sum = act.code not in (0, 2)
+            S, Y = _pair_add_act(bn2, conv2_out, s2, None, Xd, None, act, want_sum)
+            self._tail = (S if want_sum else Y, conv2_out, s2)
+            self.add3.X.append([None, None])
+            self.add3.derived_variables["sum"].append(S if want_sum else None)
+            self._dv.update({"conv1_out": conv1_out, "conv2_out": conv2_out, "batchnorm1_out": bn1_out,
+                             "batchnorm2_out": _Lazy(lambda: bn2.normalise_with(conv2_out, s2))})
             return L.to_numpy(Y) if as_np else Y
         conv1_out = self.conv1.forward(Xd, retain_derived)
         bn1_out = self.batchnorm1.forward(conv1_out, retain_derived)
@@ -456,6 +477,19 @@ class SkipConnectionIdentityModule(ModuleBase):
         """modules.py:596-612 (dLdAdd3_X is the returned dX: the reference accumulates into it in place)."""
         as_np = isinstance(dLdY, np.ndarray)
         dY = L.to_device(dLdY, L.torch_dtype(self.mode))
+        if getattr(self, "_tail", None) is not None:
+            S, conv2_out, s2 = self._tail
+            act = self.act_fn
+            dConv2_out, dX0 = _pair_bwd(dY, S, act, self.batchnorm2, conv2_out, s2, None, None, None, retain_grads)
+            dBn1_out = self.conv2.backward(dConv2_out, retain_grads)
+            a1 = self.conv1.act_fn
+            z1 = None if a1.code in (0, 2) else self.conv1.derived_variables["Z"][-1]
+            dZ1 = self.batchnorm1.backward_act(dBn1_out, a1, z1, retain_grads)
+            dX = _device_add(dX0, self.conv1.backward_from_dz(dZ1, retain_grads))
+            bn1 = self.batchnorm1
+            self._dv.update({"dLdAdd3_X": dX, "dLdBn2": dX0, "dLdBn1": dBn1_out, "dLdConv2": dConv2_out,
+                             "dLdConv1": _Lazy(lambda: bn1._bwd(dBn1_out, bn1.X[-1], bn1._saved[-1], False))})
+            return L.to_numpy(dX) if as_np else dX
         dX0, dBn2_out = self.add3.backward(dY, retain_grads)
         dConv2_out = self.batchnorm2.backward(dBn2_out, retain_grads)
         dBn1_out = self.conv2.backward(dConv2_out, retain_grads)

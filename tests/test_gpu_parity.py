@@ -1175,8 +1175,9 @@ def test_pool2d_vs_oracle_vae_shape(cuda_device, dtype, mode):
         close(P.backward(dYd).float(), dXr, 1e-6 if dtype == "fp32" else 4e-3, "dX")
 
 
+@pytest.mark.parametrize("fuse", [True, False], ids=["fused-tail", "layer-by-layer"])
 @pytest.mark.parametrize("mode", MODES)
-def test_skip_identity_module_golden(cuda_device, mode):
+def test_skip_identity_module_golden(cuda_device, mode, fuse):
     pkg = npml()
     z, cases = load_golden("skip_identity_module.npz")
     tol = TOL_BN[mode]
@@ -1187,6 +1188,7 @@ def test_skip_identity_module_golden(cuda_device, mode):
         act = None if c["act"] == "identity" else make_act(pkg, c["act"], c["p0"], c["p1"])
         M = pkg.SkipConnectionIdentityModule(out_ch=c["out_ch"], kernel_shape1=tuple(c["kernel_shape1"]),
                                              kernel_shape2=tuple(c["kernel_shape2"]), act_fn=act, mode=mode)
+        M.fuse_training = fuse
         X = z[i + "/X"]
         M.forward(X, retain_derived=False)
         for t, conv, bn in (("1", M.conv1, M.batchnorm1), ("2", M.conv2, M.batchnorm2)):
