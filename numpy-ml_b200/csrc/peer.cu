@@ -14,8 +14,9 @@
 // captured CUDA graph replays correctly.  Calls alternate between two inbox halves, which is enough: a rank can finish
 // call k+1 only after every peer has pushed call k+1, i.e. after that peer finished READING call k (stream order).
 // Independent streams (the gradient side stream, the sync-BN statistics on the main stream) use different channels.
-// The price of the flag is 2x the bytes on the wire, so the host only takes this path while (world-1) * 2 * bytes stays
-// small (numpy-ml_b200/dist.py); larger buffers go to ncclAllReduce.  First version of this file used 16-byte stores, a
+// The price of the flag is 2x the bytes on the wire; buffers whose one-shot wire bytes (world-1) * 2 * bytes pass 3 MB
+// take the two-shot form below (owner-reduces, then broadcasts), and anything above 2.5 MB goes to ncclAllReduce
+// (numpy-ml_b200/dist.py).  First version of this file used 16-byte stores, a
 // __threadfence_system and one flag per block: 15 us for 144 KB on 2 GPUs against NCCL's 12 (profiles/r2k_mgpu.log).
 //
 // Memory: one cudaMalloc'ed region per rank, exported with cudaIpcGetMemHandle and opened by every peer at init time
@@ -30,16 +31,18 @@ namespace {
 constexpr int kMaxRanks = 8;
 constexpr int kChannels = 4;
 constexpr int kThreads = 256;
-constexpr int kMaxBlocks = 592;                  // 4 per SM: plenty of words in flight, still cheap to launch
-constexpr size_t kSlotBytes = 5u << 20;          // inbox per (channel, half, source): 2 x the largest message (cfg5: 2.1 MB)
-constexpr unsigned kSpinLimit = 1u << 23;        // seconds of polling: a peer that never arrives must not hang the box
+constexpr size_t kMaxMsgBytes = (size_t)5 << 19;     // 2.5 MB per call (cfg5: 2.1 MB)
+constexpr size_t kOneShotWire = (size_t)3 << 20;      // (world - 1) * 2 * bytes up to here: one-shot, beyond: two-shot
+constexpr unsigned kSpinLimit = 1u << 23;             // seconds of polling: a peer that never arrives must not hang the box
 
 // region layout (identical on every rank)
 //   ctrl  [kChannels] { epoch, arrived, error }                       local bookkeeping
-//   inbox [kChannels][2][kMaxRanks][kSlotBytes]                       written by peers: (word, epoch) pairs
+//   area  [kChannels][2] of kAreaBytes, written by peers as (word, epoch) pairs:
+//         one-shot: [source rank][n] pairs;   two-shot: reduce-scatter inbox [source rank][slice] + all-gather inbox [n]
 struct Ctrl { unsigned epoch, arrived, error, pad; };
-constexpr size_t kInboxOff = 4096;
-constexpr size_t kRegionBytes = kInboxOff + (size_t)kChannels * 2 * kMaxRanks * kSlotBytes;
+constexpr size_t kAreaOff = 4096;
+constexpr size_t kAreaBytes = 4 * kMaxMsgBytes + 4096;               // two-shot: 2 x (8-byte pair per 4-byte word) x 2 inboxes
+constexpr size_t kRegionBytes = kAreaOff + (size_t)kChannels * 2 * kAreaBytes;
 
 struct PeerTable {
   char* base[kMaxRanks];       // base[r]: rank r's region as mapped into THIS process
@@ -54,8 +57,8 @@ struct Peer {
 };
 Peer g_peer;
 
-__device__ __forceinline__ uint2* inbox_ptr(char* base, int ch, int half, int src) {
-  return reinterpret_cast<uint2*>(base + kInboxOff + (((size_t)ch * 2 + half) * kMaxRanks + src) * kSlotBytes);
+__device__ __forceinline__ uint2* area_ptr(char* base, int ch, int half) {
+  return reinterpret_cast<uint2*>(base + kAreaOff + ((size_t)ch * 2 + half) * kAreaBytes);
 }
 __device__ __forceinline__ void st_pair(uint2* p, unsigned v, unsigned f) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(f) : "memory");
@@ -65,60 +68,117 @@ __device__ __forceinline__ uint2 ld_pair(const uint2* p) {
   asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
   return r;
 }
-
-// W = 32-bit words per element (1: float, 2: double).  Element e of the buffer is handled by one thread on every rank.
+// wait until the pair carries this call's number; `dead` (a wait has timed out before): do not wait at all
+__device__ __forceinline__ unsigned poll_word(const uint2* p, unsigned epoch, bool& dead) {
+  uint2 v = ld_pair(p);
+  unsigned spins = 0;
+  while (v.y != epoch && !dead) {
+    if (++spins > kSpinLimit) dead = true;
+    v = ld_pair(p);
+  }
+  return v.x;
+}
 template <typename T, int W>
+__device__ __forceinline__ T from_words(const unsigned (&w)[W]) {
+  if (W == 1) return (T)__uint_as_float(w[0]);
+  return (T)__hiloint2double((int)w[W - 1], (int)w[0]);
+}
+
+// W = 32-bit words per element (1: float, 2: double).  Element e of the buffer is handled by the same thread on every
+// rank.  TWO_SHOT = false: every rank pushes everything to everybody and adds all copies itself.  TWO_SHOT = true
+// (larger buffers): element e is OWNED by rank e / slice; the other ranks push their copy to the owner, the owner adds
+// the copies in rank order and pushes the sum back to everybody -- 2 (world-1)/world of the one-shot wire bytes.
+template <typename T, int W, bool TWO_SHOT>
 __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab, T* __restrict__ buf, int64_t n,
-                                                                  int channel) {
+                                                                  int64_t slice, int channel) {
   char* mine = tab.base[tab.rank];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(mine) + channel;
   const unsigned epoch = ctrl->epoch + 1u;           // every block reads it before the last block advances it
   const int half = (int)(epoch & 1u);
   const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t e0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int world = tab.world, me = tab.rank;
   unsigned* words = reinterpret_cast<unsigned*>(buf);
-  // ---- push: my words (with the call number) into every peer's inbox ----
-  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride) {
-    unsigned w[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) w[k] = words[e * W + k];
-    for (int p = 1; p < tab.world; ++p) {
-      const int dst = (tab.rank + p) % tab.world;     // staggered so that the ranks do not all start on the same peer
-      uint2* box = inbox_ptr(tab.base[dst], channel, half, tab.rank) + e * W;
-#pragma unroll
-      for (int k = 0; k < W; ++k) st_pair(box + k, w[k], epoch);
-    }
-  }
-  // ---- sum: poll the local inbox, add in rank order (my own contribution at position `rank`) ----
   // once a wait has timed out (a peer that never made this call: a bug on the host side) nothing waits any more --
   // this call and all later ones rush through with garbage, npml_peer_status() reports it, nothing hangs
-  bool timed_out = ctrl->error != 0u;
-  for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < n; e += stride) {
-    T acc = (T)0;
-    for (int r = 0; r < tab.world; ++r) {
-      T x;
-      if (r == tab.rank) {
-        x = buf[e];
-      } else {
-        const uint2* box = inbox_ptr(mine, channel, half, r) + e * W;
-        unsigned w[W];
+  bool dead = ctrl->error != 0u;
+  uint2* my_area = area_ptr(mine, channel, half);
+  if (!TWO_SHOT) {
+    // ---- push: my words (with the call number) into every peer's inbox [me][e] ----
+    for (int64_t e = e0; e < n; e += stride) {
+      unsigned w[W];
 #pragma unroll
-        for (int k = 0; k < W; ++k) {
-          uint2 v = ld_pair(box + k);
-          unsigned spins = 0;
-          while (v.y != epoch && !timed_out) {
-            if (++spins > kSpinLimit) timed_out = true;
-            v = ld_pair(box + k);
-          }
-          w[k] = v.x;
-        }
-        if (W == 1) x = (T)__uint_as_float(w[0]);
-        else x = (T)__hiloint2double((int)w[W - 1], (int)w[0]);
+      for (int k = 0; k < W; ++k) w[k] = words[e * W + k];
+      for (int p = 1; p < world; ++p) {
+        const int dst = (me + p) % world;             // staggered so that the ranks do not all start on the same peer
+        uint2* box = area_ptr(tab.base[dst], channel, half) + ((int64_t)me * n + e) * W;
+#pragma unroll
+        for (int k = 0; k < W; ++k) st_pair(box + k, w[k], epoch);
       }
-      acc += x;
     }
-    buf[e] = acc;
+    // ---- sum: poll the local inbox, add in rank order (my own contribution at position `me`) ----
+    for (int64_t e = e0; e < n; e += stride) {
+      T acc = (T)0;
+      for (int r = 0; r < world; ++r) {
+        T x;
+        if (r == me) {
+          x = buf[e];
+        } else {
+          unsigned w[W];
+#pragma unroll
+          for (int k = 0; k < W; ++k) w[k] = poll_word(my_area + ((int64_t)r * n + e) * W + k, epoch, dead);
+          x = from_words<T, W>(w);
+        }
+        acc += x;
+      }
+      buf[e] = acc;
+    }
+  } else {
+    uint2* my_gather = my_area + (int64_t)world * slice * W;      // behind the reduce-scatter inbox [world][slice]
+    // ---- reduce-scatter push: my copy of element e goes to its owner's inbox [me][e - owner * slice] ----
+    for (int64_t e = e0; e < n; e += stride) {
+      const int owner = (int)(e / slice);
+      if (owner == me) continue;
+      uint2* box = area_ptr(tab.base[owner], channel, half) + ((int64_t)me * slice + (e - (int64_t)owner * slice)) * W;
+#pragma unroll
+      for (int k = 0; k < W; ++k) st_pair(box + k, words[e * W + k], epoch);
+    }
+    // ---- owner: add the copies in rank order, keep the sum and push it to every peer's gather inbox [e] ----
+    for (int64_t e = e0; e < n; e += stride) {
+      if ((int)(e / slice) != me) continue;
+      const int64_t el = e - (int64_t)me * slice;
+      T acc = (T)0;
+      for (int r = 0; r < world; ++r) {
+        T x;
+        if (r == me) {
+          x = buf[e];
+        } else {
+          unsigned w[W];
+#pragma unroll
+          for (int k = 0; k < W; ++k) w[k] = poll_word(my_area + ((int64_t)r * slice + el) * W + k, epoch, dead);
+          x = from_words<T, W>(w);
+        }
+        acc += x;
+      }
+      buf[e] = acc;
+      const unsigned* aw = reinterpret_cast<const unsigned*>(&acc);
+      for (int p = 1; p < world; ++p) {
+        const int dst = (me + p) % world;
+        uint2* box = area_ptr(tab.base[dst], channel, half) + ((int64_t)world * slice + e) * W;
+#pragma unroll
+        for (int k = 0; k < W; ++k) st_pair(box + k, aw[k], epoch);
+      }
+    }
+    // ---- everybody else: take the owner's sum ----
+    for (int64_t e = e0; e < n; e += stride) {
+      if ((int)(e / slice) == me) continue;
+      unsigned w[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) w[k] = poll_word(my_gather + e * W + k, epoch, dead);
+      buf[e] = from_words<T, W>(w);
+    }
   }
-  if (timed_out) ctrl->error = 1u;
+  if (dead) ctrl->error = 1u;
   // ---- the last block of the launch advances the epoch (stream order makes it visible to the next call) ----
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -136,10 +196,24 @@ int peer_allreduce(T* buf, int64_t n, int channel, cudaStream_t st) {
   NPML_CHECK(g_peer.ready, "peer memory is not initialised (npml_peer_open)");
   NPML_CHECK(channel >= 0 && channel < kChannels, "bad channel");
   if (n <= 0) return 0;
-  NPML_CHECK((size_t)n * W * 8 <= kSlotBytes, "message larger than a peer inbox slot");
-  int64_t blocks = (n + kThreads - 1) / kThreads;
-  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-  peer_allreduce_kernel<T, W><<<(int)blocks, kThreads, 0, st>>>(g_peer.t, buf, n, channel);
+  const size_t bytes = (size_t)n * sizeof(T);
+  NPML_CHECK(bytes <= kMaxMsgBytes, "message larger than the peer inbox");
+  const int world = g_peer.t.world;
+  const bool two_shot = (size_t)(world - 1) * 2 * bytes > kOneShotWire && world > 2;
+  // a few elements per thread and a small grid: these blocks poll next to the persistent convolution kernels
+  // (148 blocks of 256 spinning threads cost the overlapped dgrad 10 % at 8 GPUs; profiles/r2n)
+  int64_t blocks = (n + 4 * kThreads - 1) / (4 * kThreads);
+  const int64_t cap = two_shot ? 128 : 48;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (two_shot) {
+    const int64_t slice = (n + world - 1) / world;
+    NPML_CHECK((size_t)(world * slice + n) * W * 8 <= kAreaBytes, "message larger than the peer inbox");
+    peer_allreduce_kernel<T, W, true><<<(int)blocks, kThreads, 0, st>>>(g_peer.t, buf, n, slice, channel);
+  } else {
+    NPML_CHECK((size_t)world * n * W * 8 <= kAreaBytes, "message larger than the peer inbox");
+    peer_allreduce_kernel<T, W, false><<<(int)blocks, kThreads, 0, st>>>(g_peer.t, buf, n, n, channel);
+  }
   NPML_LAUNCH_OK();
   return 0;
 }

@@ -15,7 +15,7 @@ import torch
 from . import _lib as L
 
 _state = {"ready": False, "world": 1, "rank": 0, "backend": None, "peer": False, "peer_why": "single process"}
-PEER_WIRE_BYTES = 5 << 20          # csrc/peer.cu: a call takes the peer path while (world - 1) * 2 * bytes fits this
+PEER_MAX_BYTES = 5 << 19           # csrc/peer.cu kMaxMsgBytes: larger buffers go to ncclAllReduce
 CH_MAIN, CH_SIDE = 0, 1            # peer all-reduce channels: the caller's stream / the gradient side stream
 
 
@@ -84,9 +84,9 @@ def _allreduce(buf, channel):
     """In-place SUM over ranks of a contiguous fp32 / fp64 device tensor on the current stream."""
     lib, n = L.load(), buf.numel()
     f64 = buf.dtype == torch.float64
-    # the (word, call number) pairs double the bytes on the wire and every rank pushes to every peer: beyond a few MB
-    # per call NCCL's ring / in-switch reduction wins, below it the one-kernel push has the lower latency
-    if _state["peer"] and (_state["world"] - 1) * 2 * n * buf.element_size() <= PEER_WIRE_BYTES:
+    # dW || db of a layer and the sync-BN statistics (<= 2.5 MB): the one-kernel peer-memory exchange; anything larger
+    # is bandwidth-bound and goes to NCCL's ring / in-switch reduction
+    if _state["peer"] and n * buf.element_size() <= PEER_MAX_BYTES:
         fn = lib.npml_peer_allreduce_sum_f64 if f64 else lib.npml_peer_allreduce_sum_f32
         L.check(fn(L.ptr(buf), n, channel, L.stream()), "npml_peer_allreduce_sum")
     else:

@@ -38,11 +38,13 @@ def main():
             gr = torch.Generator(device=dev); gr.manual_seed(100 * it + r)
             xr = torch.randn(n + 4, generator=gr, device=dev, dtype=dt)[4:] if dt == torch.float32 and n % 4 == 0 else \
                 torch.randn(n, generator=gr, device=dev, dtype=dt)
-            want = (want.to(dt) + xr).double() if True else want
+            want = (want.to(dt) + xr).double()
         got = x.clone()
         D._allreduce(got, it % 2)
         torch.cuda.synchronize()
-        if not torch.equal(got.double(), want):
+        via_nccl = n * got.element_size() > D.PEER_MAX_BYTES          # NCCL adds in its own order: compare with a tolerance
+        good = torch.allclose(got.double(), want, rtol=0, atol=1e-5) if via_nccl else torch.equal(got.double(), want)
+        if not good:
             ok = False
             print("rank {}: MISMATCH n={} dtype={} max err {}".format(rank, n, dt, (got.double() - want).abs().max().item()), flush=True)
     # 2. CUDA graph replay: the call counter lives in device memory
@@ -62,7 +64,7 @@ def main():
         print("rank {}: graph replay mismatch {}".format(rank, buf[:4].tolist()), flush=True)
     # 3. latency of the gradient-sized messages against NCCL (device time, max over ranks is taken by the reader)
     for n in (320, 36928, 295168, 524416):
-        x = torch.randn(n, device=dev)
+        x = torch.randn(n, device=dev) * 1e-3
         res = {}
         for name, fn in (("peer", lambda: lib.npml_peer_allreduce_sum_f32(L.ptr(x), n, 0, L.stream())),
                          ("nccl", lambda: lib.npml_allreduce_sum_f32(L.ptr(x), n, L.stream()))):
