@@ -73,6 +73,7 @@ __device__ __forceinline__ unsigned poll_word(const uint2* p, unsigned epoch, bo
   uint2 v = ld_pair(p);
   unsigned spins = 0;
   while (v.y != epoch && !dead) {
+    __nanosleep(40);                       // these threads share SMs with the persistent convolution kernels
     if (++spins > kSpinLimit) dead = true;
     v = ld_pair(p);
   }
@@ -82,6 +83,32 @@ template <typename T, int W>
 __device__ __forceinline__ T from_words(const unsigned (&w)[W]) {
   if (W == 1) return (T)__uint_as_float(w[0]);
   return (T)__hiloint2double((int)w[W - 1], (int)w[0]);
+}
+
+// mine + the copies of the other ranks at inbox[r * stride_r + idx], added in RANK order.  All world-1 loads are issued
+// before the first one is looked at (one L2 round trip instead of world-1); only words that had not arrived are re-polled.
+template <typename T, int W>
+__device__ __forceinline__ T sum_in_rank_order(const uint2* inbox, int64_t stride_r, int64_t idx, T mine, int me, int world,
+                                               unsigned epoch, bool& dead) {
+  uint2 v[kMaxRanks][W];
+#pragma unroll
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (r < world && r != me) {
+#pragma unroll
+      for (int k = 0; k < W; ++k) v[r][k] = ld_pair(inbox + ((int64_t)r * stride_r + idx) * W + k);
+    }
+  T acc = (T)0;
+#pragma unroll
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (r >= world) continue;
+    if (r == me) { acc += mine; continue; }
+    unsigned w[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      w[k] = v[r][k].y == epoch ? v[r][k].x : poll_word(inbox + ((int64_t)r * stride_r + idx) * W + k, epoch, dead);
+    acc += from_words<T, W>(w);
+  }
+  return acc;
 }
 
 // W = 32-bit words per element (1: float, 2: double).  Element e of the buffer is handled by the same thread on every
@@ -117,22 +144,7 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab,
       }
     }
     // ---- sum: poll the local inbox, add in rank order (my own contribution at position `me`) ----
-    for (int64_t e = e0; e < n; e += stride) {
-      T acc = (T)0;
-      for (int r = 0; r < world; ++r) {
-        T x;
-        if (r == me) {
-          x = buf[e];
-        } else {
-          unsigned w[W];
-#pragma unroll
-          for (int k = 0; k < W; ++k) w[k] = poll_word(my_area + ((int64_t)r * n + e) * W + k, epoch, dead);
-          x = from_words<T, W>(w);
-        }
-        acc += x;
-      }
-      buf[e] = acc;
-    }
+    for (int64_t e = e0; e < n; e += stride) buf[e] = sum_in_rank_order<T, W>(my_area, n, e, buf[e], me, world, epoch, dead);
   } else {
     uint2* my_gather = my_area + (int64_t)world * slice * W;      // behind the reduce-scatter inbox [world][slice]
     // ---- reduce-scatter push: my copy of element e goes to its owner's inbox [me][e - owner * slice] ----
@@ -147,19 +159,7 @@ __global__ void __launch_bounds__(kThreads) peer_allreduce_kernel(PeerTable tab,
     for (int64_t e = e0; e < n; e += stride) {
       if ((int)(e / slice) != me) continue;
       const int64_t el = e - (int64_t)me * slice;
-      T acc = (T)0;
-      for (int r = 0; r < world; ++r) {
-        T x;
-        if (r == me) {
-          x = buf[e];
-        } else {
-          unsigned w[W];
-#pragma unroll
-          for (int k = 0; k < W; ++k) w[k] = poll_word(my_area + ((int64_t)r * slice + el) * W + k, epoch, dead);
-          x = from_words<T, W>(w);
-        }
-        acc += x;
-      }
+      const T acc = sum_in_rank_order<T, W>(my_area, slice, el, buf[e], me, world, epoch, dead);
       buf[e] = acc;
       const unsigned* aw = reinterpret_cast<const unsigned*>(&acc);
       for (int p = 1; p < world; ++p) {
@@ -202,8 +202,8 @@ int peer_allreduce(T* buf, int64_t n, int channel, cudaStream_t st) {
   const bool two_shot = (size_t)(world - 1) * 2 * bytes > kOneShotWire && world > 2;
   // a few elements per thread and a small grid: these blocks poll next to the persistent convolution kernels
   // (148 blocks of 256 spinning threads cost the overlapped dgrad 10 % at 8 GPUs; profiles/r2n)
-  int64_t blocks = (n + 4 * kThreads - 1) / (4 * kThreads);
-  const int64_t cap = two_shot ? 128 : 48;
+  int64_t blocks = (n + 2 * kThreads - 1) / (2 * kThreads);
+  const int64_t cap = two_shot ? 148 : 74;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (two_shot) {
