@@ -230,35 +230,51 @@ __global__ void __launch_bounds__(128) thin_co_conv_kernel(GatherConv g, const T
   float acc[CO_T];
 #pragma unroll
   for (int co = 0; co < CO_T; ++co) acc[co] = 0.f;
-  for (int r = 0; r < g.fr; ++r) {
-    int iy;
-    if (g.form == 0) iy = y * g.s + r * g.D - g.pr;
-    else { const int ny = y + g.pr - r * g.D; if (ny < 0 || ny % g.s) continue; iy = ny / g.s; }
-    if (iy < 0 || iy >= g.IH) continue;
-    for (int t = 0; t < g.fc; ++t) {
-      int ix;
-      if (g.form == 0) ix = x * g.s + t * g.D - g.pc;
-      else { const int nx = x + g.pc - t * g.D; if (nx < 0 || nx % g.s) continue; ix = nx / g.s; }
-      if (ix < 0 || ix >= g.IW) continue;
-      const TIn* src = in + (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI;
-      const float* wt = ws_ + (size_t)(r * g.fc + t) * g.CI * CO_T;
-      for (int c0 = c_lo; c0 < c_hi; c0 += V) {
-        float v[V];
-        const uint4 u = *reinterpret_cast<const uint4*>(src + c0);
-        if constexpr (sizeof(TIn) == 4) {
-          v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
-        } else {
-          const uint32_t q[4] = {u.x, u.y, u.z, u.w};
+  // The taps are walked in batches of kTB: all loads of a batch are issued before the first FMA, so a pixel costs
+  // ceil(taps / kTB) global-memory round trips instead of one per tap (measured on cfg1: this kernel is pure latency,
+  // 12.5 us for 1.6 MB with the one-tap-at-a-time loop).
+  constexpr int kTB = 9;
+  for (int c0 = c_lo; c0 < c_hi; c0 += V) {
+    for (int tp0 = 0; tp0 < taps; tp0 += kTB) {
+      uint4 u[kTB];
+      bool ok[kTB];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&q[j]);
-            v[2 * j] = __low2float(h); v[2 * j + 1] = __high2float(h);
+      for (int j = 0; j < kTB; ++j) {
+        const int tp = tp0 + j;
+        const int r = tp / g.fc, t = tp - r * g.fc;
+        int iy, ix;
+        bool v = tp < taps;
+        if (g.form == 0) {
+          iy = y * g.s + r * g.D - g.pr; ix = x * g.s + t * g.D - g.pc;
+        } else {
+          const int ny = y + g.pr - r * g.D, nx = x + g.pc - t * g.D;
+          v = v && ny >= 0 && nx >= 0 && ny % g.s == 0 && nx % g.s == 0;
+          iy = ny / g.s; ix = nx / g.s;
+        }
+        v = v && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+        ok[j] = v;
+        u[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (v) u[j] = *reinterpret_cast<const uint4*>(in + (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + c0);
+      }
+#pragma unroll
+      for (int j = 0; j < kTB; ++j) {
+        if (!ok[j]) continue;
+        const float* wt = ws_ + (size_t)(tp0 + j) * g.CI * CO_T;
+        float v[V];
+        if constexpr (sizeof(TIn) == 4) {
+          v[0] = __uint_as_float(u[j].x); v[1] = __uint_as_float(u[j].y); v[2] = __uint_as_float(u[j].z); v[3] = __uint_as_float(u[j].w);
+        } else {
+          const uint32_t q[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&q[k]);
+            v[2 * k] = __low2float(h); v[2 * k + 1] = __high2float(h);
           }
         }
 #pragma unroll
-        for (int j = 0; j < V; ++j)
+        for (int k = 0; k < V; ++k)
 #pragma unroll
-          for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(v[j], wt[(c0 + j) * CO_T + co], acc[co]);
+          for (int co = 0; co < CO_T; ++co) acc[co] = fmaf(v[k], wt[(c0 + k) * CO_T + co], acc[co]);
       }
     }
   }
@@ -300,24 +316,34 @@ __global__ void __launch_bounds__(256) thin_ci_conv_kernel(GatherConv g, const T
   const int pi = (int)(idx / cog);
   const int x = pi % g.OW, y = (pi / g.OW) % g.OH, n = pi / (g.OW * g.OH);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int r = 0; r < g.fr; ++r) {
-    int iy;
-    if (g.form == 0) iy = y * g.s + r * g.D - g.pr;
-    else { const int ny = y + g.pr - r * g.D; if (ny < 0 || ny % g.s) continue; iy = ny / g.s; }
-    if (iy < 0 || iy >= g.IH) continue;
-    for (int t = 0; t < g.fc; ++t) {
-      int ix;
-      if (g.form == 0) ix = x * g.s + t * g.D - g.pc;
-      else { const int nx = x + g.pc - t * g.D; if (nx < 0 || nx % g.s) continue; ix = nx / g.s; }
-      if (ix < 0 || ix >= g.IW) continue;
-      const int64_t base = (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI;
-      const float* wt = ws_ + (size_t)(r * g.fc + t) * g.CI * g.CO + c4;
-      for (int ci = 0; ci < g.CI; ++ci) {
-        const float a = ld_f(in, base + ci);
-        const float4 wv = *reinterpret_cast<const float4*>(wt + (size_t)ci * g.CO);
-        acc[0] = fmaf(a, wv.x, acc[0]); acc[1] = fmaf(a, wv.y, acc[1]);
-        acc[2] = fmaf(a, wv.z, acc[2]); acc[3] = fmaf(a, wv.w, acc[3]);
+  // K = taps * CI gathered inputs, kKB at a time: every load of a batch is in flight before the first FMA (one
+  // round trip per batch instead of one per input; this kernel is latency, not bandwidth, on cfg1)
+  constexpr int kKB = 9;
+  for (int k0 = 0; k0 < K; k0 += kKB) {
+    float a[kKB];
+#pragma unroll
+    for (int j = 0; j < kKB; ++j) {
+      const int k = k0 + j;
+      const int tp = k / g.CI, ci = k - tp * g.CI;
+      const int r = tp / g.fc, t = tp - r * g.fc;
+      int iy, ix;
+      bool v = k < K;
+      if (g.form == 0) {
+        iy = y * g.s + r * g.D - g.pr; ix = x * g.s + t * g.D - g.pc;
+      } else {
+        const int ny = y + g.pr - r * g.D, nx = x + g.pc - t * g.D;
+        v = v && ny >= 0 && nx >= 0 && ny % g.s == 0 && nx % g.s == 0;
+        iy = ny / g.s; ix = nx / g.s;
       }
+      v = v && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
+      a[j] = v ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kKB; ++j) {
+      if (k0 + j >= K) break;
+      const float4 wv = *reinterpret_cast<const float4*>(ws_ + (size_t)(k0 + j) * g.CO + c4);
+      acc[0] = fmaf(a[j], wv.x, acc[0]); acc[1] = fmaf(a[j], wv.y, acc[1]);
+      acc[2] = fmaf(a[j], wv.z, acc[2]); acc[3] = fmaf(a[j], wv.w, acc[3]);
     }
   }
   const int64_t o = (int64_t)pi * g.CO + c4;
@@ -351,20 +377,45 @@ __global__ void __launch_bounds__(1024) thin_m_wgrad_kernel(GatherWgrad g, const
   for (int64_t p0 = p_begin; p0 < p_end; p0 += kThinPix) {
     const int np = (int)((p_end - p0 < kThinPix) ? p_end - p0 : kThinPix);
     __syncthreads();
-    for (int i = threadIdx.x; i < np * M1; i += nthr) {
-      const int pp = i / M1, mm = i - pp * M1;
-      float a = 1.f;
-      if (mm < M) {
-        const int q = (int)(p0 + pp);
-        const int x = q % g.OW, y = (q / g.OW) % g.OH, n = q / (g.OW * g.OH);
-        const int tap = mm / g.CI, ci = mm - tap * g.CI;
-        const int r = tap / g.fc, t = tap - r * g.fc;
-        const int iy = y * g.s + r * g.D - g.pr, ix = x * g.s + t * g.D - g.pc;
-        a = (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+    // staging loads four at a time: issued back to back, stored afterwards (one round trip per four elements; with a
+    // load -> store per iteration the 64-pixel round was a chain of ~9 global-memory latencies)
+    for (int i0 = threadIdx.x; i0 < np * M1; i0 += 4 * nthr) {
+      float a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        a[u] = 1.f;
+        if (i < np * M1) {
+          const int pp = i / M1, mm = i - pp * M1;
+          if (mm < M) {
+            const int q = (int)(p0 + pp);
+            const int x = q % g.OW, y = (q / g.OW) % g.OH, n = q / (g.OW * g.OH);
+            const int tap = mm / g.CI, ci = mm - tap * g.CI;
+            const int r = tap / g.fc, t = tap - r * g.fc;
+            const int iy = y * g.s + r * g.D - g.pr, ix = x * g.s + t * g.D - g.pc;
+            a[u] = (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW) ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+          }
+        }
       }
-      As[i] = a;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        if (i < np * M1) As[i] = a[u];
+      }
     }
-    for (int i = threadIdx.x; i < np * g.CO; i += nthr) Gs[i] = ld_f(grad, p0 * g.CO + i);
+    for (int i0 = threadIdx.x; i0 < np * g.CO; i0 += 4 * nthr) {
+      float gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        gv[u] = i < np * g.CO ? ld_f(grad, p0 * g.CO + i) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nthr;
+        if (i < np * g.CO) Gs[i] = gv[u];
+      }
+    }
     __syncthreads();
 #pragma unroll 4
     for (int pp = 0; pp < np; ++pp) acc = fmaf(As[pp * M1 + m], Gs[pp * g.CO + co], acc);

@@ -29,6 +29,7 @@ int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, in
 namespace {
 
 constexpr int kMaxMT = 40;           // M tiles (pairs of windows) over all groups
+constexpr int kMaxMGroups = 16;
 constexpr int kRowBytes = 128;
 constexpr int kKI = 16;              // slots (K) per tcgen05.mma for 16-bit operands
 constexpr int kThreads = 256;
@@ -42,7 +43,12 @@ struct SlabWgradParams {
   int16_t tap[kMaxMT][2];        // filter tap of each window (-1 = the ones window, i.e. db)
   int16_t cb[kMaxMT][2];         // channel block of each window
   uint8_t kind[kMaxMT];          // 0 = (X, X), 1 = (X, ones), 2 = (ones, ones)
-  int nmt_total, mt_per_group, n_mgroups;
+  int nmt_total, n_mgroups;
+  // M tiles are cut into groups of at most 512 / BN accumulators; group g owns tiles [g_mt0, g_mt0 + g_nmt) and CTAs
+  // [g_cta0, g_cta0 + g_nctas) of grid.x.  The CTA counts are PROPORTIONAL to the tile counts (a group with half the
+  // tiles per K step gets half the CTAs), so all groups finish together; max_splits = the largest g_nctas.
+  int16_t g_mt0[kMaxMGroups], g_nmt[kMaxMGroups], g_cta0[kMaxMGroups], g_nctas[kMaxMGroups];
+  int max_splits;
   int ncb, nb, BN;
   int N, Hp, Wp, pady, padx, CI, CO, Mrows;
   int R, SRX, KS, num_units;
@@ -56,8 +62,8 @@ struct SlabWgradParams {
 // plain (X, X) pairs whose descriptor advances by a compile-time constant per K step; only the last tile of the
 // last group can involve the ones window (kinds 1, 2) and carries run-time deltas.
 template <int NT>
-__device__ __forceinline__ void issue_units(const SlabWgradParams& P, int mt0, bool leader, uint32_t tmem_base,
-                                            uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar,
+__device__ __forceinline__ void issue_units(const SlabWgradParams& P, int mt0, int bidx, int nctas, bool leader,
+                                            uint32_t tmem_base, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar,
                                             uint32_t xs_u32, uint32_t gs_u32, uint32_t ones_u32) {
   const uint32_t idesc = P.idesc, BN = (uint32_t)P.BN;
   const int KS = P.KS, num_units = P.num_units;
@@ -86,7 +92,7 @@ __device__ __forceinline__ void issue_units(const SlabWgradParams& P, int mt0, b
   }
   const uint64_t g0 = kHi64 | (uint64_t)(gs16 | (((uint32_t)P.gplane_bytes >> 4) << 16));
   uint32_t uc = 0;
-  for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++uc) {
+  for (int unit = bidx; unit < num_units; unit += nctas, ++uc) {
     const uint32_t st = uc & 1u;
     ptx::mbar_wait(&full_bar[st], (uc >> 1) & 1u);
     ptx::tc_fence_after();
@@ -129,10 +135,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
   // warp index broadcast from lane 0: tells ptxas it is warp-uniform, so the role branches are uniform branches and
   // everything the MMA issuer computes stays on the uniform datapath (no R2UR per descriptor)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int mgroup = blockIdx.y, cotile = blockIdx.z;   // (no division: keeps the tile indices warp-uniform)
+  const int cotile = blockIdx.z;
   const int co0 = cotile * P.BN;
-  const int mt0 = mgroup * P.mt_per_group;
-  const int nmt = min(P.mt_per_group, P.nmt_total - mt0);
+  int mgroup = 0;                                         // (a scan, no division: keeps the indices warp-uniform)
+  for (int gq = 1; gq < P.n_mgroups; ++gq)
+    if ((int)blockIdx.x >= P.g_cta0[gq]) mgroup = gq;
+  const int mt0 = P.g_mt0[mgroup], nmt = P.g_nmt[mgroup];
+  const int bidx = (int)blockIdx.x - P.g_cta0[mgroup], nctas = P.g_nctas[mgroup];
   const int rows_g = P.R * P.Wp;                 // dZ slots the TMA writes per plane
 
   // constant regions: the ones window and the zero slack behind every dZ plane (K steps may overrun the unit)
@@ -164,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
       const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
       const uint32_t tx = (uint32_t)(P.ncb * P.SRX + P.nb * P.R) * row_bytes;
       uint32_t uc = 0;
-      for (int unit = blockIdx.x; unit < P.num_units; unit += gridDim.x, ++uc) {
+      for (int unit = bidx; unit < P.num_units; unit += nctas, ++uc) {
         const uint32_t st = uc & 1u;
         ptx::mbar_wait_sleep(&empty_bar[st], ((uc >> 1) & 1u) ^ 1u, (uint32_t)P.wait_ns);
         ptx::mbar_expect_tx(&full_bar[st], tx);
@@ -193,14 +202,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
     const uint32_t gs_u32 = xs_u32 + 2u * (uint32_t)P.xstage_bytes;
     const uint32_t ones_u32 = gs_u32 + 2u * (uint32_t)P.gstage_bytes;
     switch (nmt) {
-      case 1: issue_units<1>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      case 2: issue_units<2>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      case 3: issue_units<3>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      case 4: issue_units<4>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      case 5: issue_units<5>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      case 6: issue_units<6>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      case 7: issue_units<7>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
-      default: issue_units<8>(P, mt0, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 1: issue_units<1>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 2: issue_units<2>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 3: issue_units<3>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 4: issue_units<4>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 5: issue_units<5>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 6: issue_units<6>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      case 7: issue_units<7>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
+      default: issue_units<8>(P, mt0, bidx, nctas, leader, tmem_base, full_bar, empty_bar, acc_bar, xs_u32, gs_u32, ones_u32); break;
     }
   } else if (warp >= 4) {
     // ===== epilogue (once): TMEM -> this CTA's fp32 partial =====
@@ -214,10 +223,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
       const int tap = P.tap[gi][w];
       const int ci = P.cb[gi][w] * 64 + cl;
       float* out = nullptr;
+      int64_t split_stride = 0;                    // distance between two split slots of this row
       if (tap >= 0) {
-        if (ci < P.CI) out = part + ((int64_t)blockIdx.x * P.Mrows + (int64_t)tap * P.CI + ci) * P.CO;
+        if (ci < P.CI) out = part + ((int64_t)bidx * P.Mrows + (int64_t)tap * P.CI + ci) * P.CO;
+        split_stride = (int64_t)P.Mrows * P.CO;
       } else if (tap == -1 && cl == 0 && (w == 0 || P.kind[gi] == 1)) {
-        out = part_db + (int64_t)blockIdx.x * P.CO;
+        out = part_db + (int64_t)bidx * P.CO;
+        split_stride = P.CO;
       }
       for (int c = 0; c < P.BN; c += 32) {
         uint32_t r[32];
@@ -229,6 +241,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
           for (int j = 0; j < 8; ++j)
             if (co + 4 * j < P.CO)
               *reinterpret_cast<uint4*>(out + co + 4 * j) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          // the fixed-order reduction adds max_splits slots of every row: this group has fewer CTAs than the largest
+          // one, so its unused slots are written as zeros (by the CTAs it does have, round robin)
+          for (int sidx = bidx + nctas; sidx < P.max_splits; sidx += nctas) {
+            float* zo = out + (int64_t)(sidx - bidx) * split_stride;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (co + 4 * j < P.CO) *reinterpret_cast<uint4*>(zo + co + 4 * j) = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
       }
     }
@@ -311,17 +331,29 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
     else P.kind[i] = 2;
   }
   P.nmt_total = nmt;
-  const int cap = 512 / bn;                       // accumulator tiles that fit in TMEM
+  int cap = 512 / bn;                             // accumulator tiles that fit in TMEM
+  if (cap > 8) cap = 8;                           // issue_units<NT> is instantiated up to 8
   P.n_mgroups = ceildiv(nmt, cap);
-  P.mt_per_group = ceildiv(nmt, P.n_mgroups);
-  const int ngroups = P.n_mgroups * ncot;
-  int ctas = num_sms() / ngroups;
-  if (ctas < 1) ctas = 1;
-  if (ctas > P.num_units) ctas = P.num_units;
-  pl.splits = ctas;
-  pl.grid = dim3((unsigned)ctas, (unsigned)P.n_mgroups, (unsigned)ncot);
-  pl.part_bytes = align_up((size_t)ctas * P.Mrows * g.CO * sizeof(float), 256);
-  pl.partdb_bytes = align_up((size_t)ctas * g.CO * sizeof(float), 256);
+  if (P.n_mgroups > kMaxMGroups) return false;
+  // tiles as evenly as possible over the groups, CTAs in proportion to the tiles (measured on cfg4 conv2: 10 tiles
+  // as 4 + 4 + 2 with 49 CTAs each left a third of the SMs idle for half of the kernel)
+  int budget = num_sms() / ncot;
+  if (budget < P.n_mgroups) budget = P.n_mgroups;
+  int mt0 = 0, cta0 = 0, max_splits = 0;
+  for (int q = 0; q < P.n_mgroups; ++q) {
+    const int tiles = nmt / P.n_mgroups + (q < nmt % P.n_mgroups ? 1 : 0);
+    int ctas = (int)((int64_t)budget * (mt0 + tiles) / nmt) - (int)((int64_t)budget * mt0 / nmt);
+    if (ctas < 1) ctas = 1;
+    if (ctas > P.num_units) ctas = P.num_units;
+    P.g_mt0[q] = (int16_t)mt0; P.g_nmt[q] = (int16_t)tiles; P.g_cta0[q] = (int16_t)cta0; P.g_nctas[q] = (int16_t)ctas;
+    mt0 += tiles; cta0 += ctas;
+    max_splits = ctas > max_splits ? ctas : max_splits;
+  }
+  P.max_splits = max_splits;
+  pl.splits = max_splits;
+  pl.grid = dim3((unsigned)cta0, 1, (unsigned)ncot);
+  pl.part_bytes = align_up((size_t)max_splits * P.Mrows * g.CO * sizeof(float), 256);
+  pl.partdb_bytes = align_up((size_t)max_splits * g.CO * sizeof(float), 256);
   return true;
 }
 

@@ -47,7 +47,10 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    if src.endswith(".csv"):                   # the raw page exported on the GPU box (scripts/profile_round.sh)
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:

@@ -12,12 +12,18 @@ for c in $cfgs; do
     cfg1) pat="direct|thin|reduce"; cnt=6;;
     cfg2) pat="tc_slab|wgrad_reduce"; cnt=4;;
     cfg3) pat="tc_slab|tc_gather|tc_wgrad|wgrad_reduce"; cnt=5;;
-    cfg4) pat="tc_slab|wgrad_reduce|col_pass"; cnt=24;;
+    cfg4) pat="tc_slab|wgrad_reduce|col_pass"; cnt=20;;
     cfg5) pat="tc_slab|tc_wgrad|wgrad_reduce|col_pass"; cnt=6;;
   esac
   # skip the launches of warm-up (3 steps) so that the captured ones belong to a steady-state step
   nwarm=$(python scripts/ncu_summary.py count gpurun_out/${tag}_launches_${c}.csv "$pat" 2>/dev/null || echo 0)
   skip=$(( nwarm * 5 / 8 ))
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$pat" -s $skip -c $cnt -o gpurun_out/${tag}_${c} -f $cmd > gpurun_out/${tag}_ncu_full_${c}.log 2>&1
-  ls -la gpurun_out/${tag}_${c}.ncu-rep 2>/dev/null
+  # the reports are large (--import-source): bring back the raw metric table of every config, the report itself only
+  # for the headline config (gpurun merges at most 64 MiB)
+  if [ -f gpurun_out/${tag}_${c}.ncu-rep ]; then
+    ncu -i gpurun_out/${tag}_${c}.ncu-rep --page raw --csv > gpurun_out/${tag}_${c}_raw.csv 2>/dev/null
+    if [ "$c" != "cfg2" ]; then rm -f gpurun_out/${tag}_${c}.ncu-rep; fi
+  fi
+  ls -la gpurun_out/${tag}_${c}* 2>/dev/null
 done
