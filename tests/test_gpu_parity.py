@@ -645,6 +645,76 @@ def test_conv_epilogue_emits_batchnorm_statistics(cuda_device, mode):
                 os.environ.pop("NPML_MAX_CTAS", None)
 
 
+GUARD_CASES = [0, 1, 2, 3, 4, 6, 8, 9, 11, 12, 15, 16, 18, 19, 22]      # indices into CONV_CASES: every kernel family
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_no_writes_outside_the_output_buffers(cuda_device, mode):
+    """compute-sanitizer is closed on this pool (profiles/r2s_sanitizer_closed.md), so out-of-bounds WRITES are hunted
+    directly: every convolution entry point is called through the C ABI with each output tensor and the workspace placed
+    between two 64 KB guard bands; the bands must come back untouched, and the results must still match the oracle."""
+    import ctypes as C
+    import torch
+    pkg = npml()
+    L_, U_ = pkg._lib, pkg.utils
+    lib = L_.load()
+    G = 65536
+    dt = L_.torch_dtype(mode)
+
+    class Guarded(object):
+        def __init__(self, nbytes, fill=0xA5):
+            self.n = int(nbytes)
+            self.raw = torch.full((self.n + 2 * G + 512,), fill, dtype=torch.uint8, device="cuda")
+            off = (-self.raw.data_ptr() - G) % 256                      # 256-byte aligned payload
+            self.lo = G + off
+            self.payload = self.raw[self.lo:self.lo + self.n]
+
+        def view(self, shape, dtype):
+            return self.payload.view(dtype).view(shape)
+
+        def intact(self):
+            a, b = self.raw[:self.lo], self.raw[self.lo + self.n:]
+            return bool((a == 0xA5).all().item()) and bool((b == 0xA5).all().item())
+
+    def ptr(t):
+        return C.c_void_p(t.data_ptr())
+
+    for case in GUARD_CASES:
+        xs, oc, ks, pad, s, d, act = CONV_CASES[case]
+        rng = np.random.default_rng(500 + case)
+        X = _f32(rng, xs)
+        W = _f32(rng, ks + (xs[3], oc), 1.0 / np.sqrt(ks[0] * ks[1] * xs[3]))
+        b = _f32(rng, (1, 1, 1, oc), 0.1)
+        p4 = U_.resolve_pad_2D(xs, pad, ks, s, d)
+        oh, ow = U_.conv_out_hw(xs[1], xs[2], ks[0], ks[1], p4, s, d)
+        desc = U_.make_desc(xs[0], xs[1], xs[2], xs[3], oc, ks[0], ks[1], s, d + 1, p4, oh, ow, mode)
+        Xd, Wd, bd = L_.to_device(X, dt), L_.to_device(W, torch.float32), L_.to_device(b, torch.float32)
+        es = 2 if mode == "bf16" else 4
+        n_out, n_in = xs[0] * oh * ow * oc, int(np.prod(xs))
+        gZ, gdX = Guarded(n_out * es), Guarded(n_in * es)
+        gdW, gdb = Guarded(W.size * 4, 0xA5), Guarded(oc * 4, 0xA5)
+        ws = [Guarded(max(256, lib.npml_workspace_bytes(desc, op))) for op in (0, 1, 2)]
+        Z = gZ.view((xs[0], oh, ow, oc), dt)
+        st = L_.stream()
+        L_.check(lib.npml_conv2d_fprop(desc, ptr(Xd), ptr(Wd), ptr(bd), ptr(Z), None, ptr(ws[0].payload), ws[0].n, st), "fprop")
+        Zr = O.conv2D(X, W, s, pad, d) + b
+        close(Z, Zr, TOL[mode], "guarded Z")
+        dZ = L_.to_device(_f32(rng, Zr.shape), dt)
+        dX = gdX.view(xs, dt)
+        L_.check(lib.npml_conv2d_dgrad(desc, ptr(dZ), ptr(Wd), ptr(dX), ptr(ws[1].payload), ws[1].n, st), "dgrad")
+        dW, db = gdW.view(W.shape, torch.float32), gdb.view((1, 1, 1, oc), torch.float32)
+        desc.accumulate = 0
+        L_.check(lib.npml_conv2d_wgrad_db(desc, ptr(Xd), ptr(dZ), ptr(dW), ptr(db), ptr(ws[2].payload), ws[2].n, st), "wgrad")
+        torch.cuda.synchronize()
+        dXr, dWr, dbr = O.conv2d_layer_bwd(pkg.to_numpy(dZ), pkg.to_numpy(Xd), Zr, W, s, pad, d)
+        close(dX, dXr, TOL[mode], "guarded dX")
+        close(dW, dWr, TOL[mode], "guarded dW")
+        close(db, dbr, TOL[mode], "guarded db")
+        for name, gbuf in (("Z", gZ), ("dX", gdX), ("dW", gdW), ("db", gdb), ("ws fprop", ws[0]), ("ws dgrad", ws[1]),
+                           ("ws wgrad", ws[2])):
+            assert gbuf.intact(), "case {} ({}): a kernel wrote outside {}".format(case, mode, name)
+
+
 def test_backward_naive_cross_check(cuda_device):
     """Conv2D._backward_naive (layers.py:3118-3178): the loop-form backward agrees with the oracle at fp32 tolerance
     from a layer that runs in bf16 mode, and accumulates into the same gradients."""
