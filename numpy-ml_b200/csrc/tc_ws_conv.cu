@@ -102,6 +102,17 @@ __device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)
       : "memory");
 }
 
+// Four 8x8 b16 matrices, each stored TRANSPOSED: the fragment a thread holds for matrix m (register m: row t / 4,
+// columns 2 (t % 4), 2 (t % 4) + 1 -- exactly the packed tcgen05.ld.16x256b accumulator fragment, channels along rows,
+// pixels along columns) lands as 8 rows of [pixel][8 channels] (16 bytes each) at the addresses given by threads
+// 8 m .. 8 m + 7.  One instruction replaces 32 two-byte st.shared per thread-quad: the [co][pixel] -> NHWC transpose
+// of the weight-stationary epilogue costs nothing.
+__device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1),
+               "r"(r2), "r"(r3)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_constant__ WsParams P,
                                                                  const __nv_bfloat16* __restrict__ wt,
                                                                  const float* __restrict__ bias,
@@ -331,15 +342,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
                     }
                   }
                 }
-                // registers -> staging tile [pixel][channel] (bf16), 16-byte pieces XOR-swizzled with (pixel >> 1) & 3
+                // registers -> staging tile [pixel][channel] (bf16): pack the (pixel, pixel + 1) pairs of a channel and
+                // store the eight 8 x 8 blocks transposed (stmatrix), 16-byte pieces XOR-swizzled with pixel & 7
+                uint32_t pk[8];                               // pk[2 j + kh]: columns 8 j .. 8 j + 7, rows rq + 8 kh
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int q = 2 * h + ((i >> 1) & 1);
-                  const int pp = cb + 8 * (i >> 2) + 2 * cq + (i & 1);
-                  const int co = cos[q];
-                  const uint32_t addr = stg_u32 + (uint32_t)(pp * RB + ((((co >> 3) ^ ((pp >> 1) & 3))) << 4) + (co & 7) * 2);
-                  const __nv_bfloat16 hv = __float2bfloat16_rn(v[i]);
-                  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const uint16_t*>(&hv)) : "memory");
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                  for (int kh = 0; kh < 2; ++kh) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4 * j + 2 * kh], v[4 * j + 2 * kh + 1]);
+                    pk[2 * j + kh] = *reinterpret_cast<const uint32_t*>(&h2);
+                  }
+                // thread `lane` addresses row (lane & 7) of matrix (lane >> 3): matrices 0..3 = (j0, kh 0), (j0, kh 1),
+                // (j0 + 1, kh 0), (j0 + 1, kh 1)
+                const int mr = lane & 7, mm = lane >> 3;
+                const int cbase = (pair ? 16 * qd : 32 * qd + 16 * h) + 8 * (mm & 1);
+#pragma unroll
+                for (int j0 = 0; j0 < 4; j0 += 2) {
+                  const int pp = cb + 8 * (j0 + (mm >> 1)) + mr;
+                  const uint32_t addr = stg_u32 + (uint32_t)(pp * RB + (((cbase >> 3) ^ (pp & 7)) << 4));
+                  stmatrix_x4_trans(addr, pk[2 * j0], pk[2 * j0 + 1], pk[2 * j0 + 2], pk[2 * j0 + 3]);
                 }
               }
             };
@@ -361,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
                   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pix) : "r"(ptab_u32 + 4u * pp) : "memory");
                   if (pix >= 0) {
                     uint4 u;
-                    const uint32_t addr = stg_u32 + pp * (uint32_t)RB + ((k ^ ((pp >> 1) & 3u)) << 4);
+                    const uint32_t addr = stg_u32 + pp * (uint32_t)RB + ((k ^ (pp & 7u)) << 4);
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
                     *reinterpret_cast<uint4*>(out + ((int64_t)pix * CO + 8 * k)) = u;
                   }
