@@ -64,6 +64,7 @@ struct WsParams {
   uint32_t idesc;
   int act, affine;
   float p0, p1;
+  int dbg;                   // NPML_WS_DBG (scripts/ws_probe.py: timing experiments only, results are wrong): 1 = epilogue without shared / global traffic, 2 = no TMA refills
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
         for (int kb = 0; kb < P.nkb; ++kb, ++p) {
           const int st = p & 1;
           ptx::mbar_wait(&slab_empty[st], ((p >> 1) & 1u) ^ 1u);
+          if ((P.dbg & 2) && p >= 2) { ptx::mbar_arrive(&slab_full[st]); continue; }
           ptx::mbar_expect_tx(&slab_full[st], (uint32_t)P.SR * row_bytes);
           uint8_t* dst = smem + (size_t)st * P.plane_bytes;
           int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
@@ -295,6 +297,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_ws_conv_kernel(const __grid_co
             asm volatile("st.shared.b32 [%0], %1;" ::"r"(ptab_u32 + 4u * (uint32_t)tid_g), "r"(pix) : "memory");
           }
           for (int pass = 0; pass < npass; ++pass) {
+            if (P.dbg & 1) {                                  // timing experiment: release the slot, touch nothing else
+              if (pass == npass - 1) { ptx::tc_fence_before(); __syncwarp(); if (lane == 0) ptx::mbar_arrive(&acc_empty[slot]); }
+              continue;
+            }
             const bool is_y = (Z == nullptr) || pass == 1;
             const bool last_pass = pass == npass - 1;
             __nv_bfloat16* __restrict__ out = is_y ? Y : Z;
@@ -513,6 +519,7 @@ bool plan_ws(const GatherConv& g, int mode, WsPlan& pl) {
   if (!found) return false;
   P.num_units = ceildiv(P.total_tiles, P.UT);
   P.act = g.act; P.p0 = g.p0; P.p1 = g.p1;
+  if (const char* e = std::getenv("NPML_WS_DBG")) P.dbg = atoi(e);
   P.affine = g.post_scale != nullptr ? 1 : 0;
   int ctas = num_sms();
   if (ctas > P.num_units) ctas = P.num_units;

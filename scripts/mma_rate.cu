@@ -71,7 +71,7 @@ __device__ __forceinline__ void tmem_dealloc_cg(uint32_t addr) {
 }
 
 // CG: cta_group; TS: A from tensor memory; N: MMA N (whole pair for CG = 2); NACC: accumulators cycled through
-template <int CG, int TS, int N, int NACC>
+template <int CG, int TS, int N, int NACC, int M = 128>
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* a_s = smem;                        // 128 rows x 128 B, K-major, 128B swizzle
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, long long* 
   long long dt = 0;
   if (warp == 1) {
     const bool lane0 = ptx::elect_one();
-    const uint32_t idesc = ptx::instr_desc(1, 0, 0, 128 * CG, N);
+    const uint32_t idesc = ptx::instr_desc(1, 0, 0, M * CG, N);
     const uint64_t ad = kDesc64 + (ptx::smem_u32(a_s) >> 4), bd = kDesc64 + (ptx::smem_u32(b_s) >> 4);
     const uint32_t a_t = tmem + (uint32_t)(NACC * N);      // A (4 K-steps x 8 columns) sits after the accumulators
     if (leader_cta && lane0) {
@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, long long* 
   }
 }
 
-template <int CG, int TS, int N, int NACC>
+template <int CG, int TS, int N, int NACC, int M = 128>
 void run(const char* name, int grid, int iters, long long* d_out) {
-  auto kern = mma_rate_kernel<CG, TS, N, NACC>;
+  auto kern = mma_rate_kernel<CG, TS, N, NACC, M>;
   const size_t smem = 16384 + 32768;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
@@ -180,6 +180,28 @@ int main(int argc, char** argv) {
   VARIANT(2, 0, 256, 1, "SS cg2 N=256")
   VARIANT(2, 1, 128, 1, "TS cg2 N=128")
   VARIANT(2, 1, 256, 1, "TS cg2 N=256")
+  // N extents of the weight-stationary convolution (tile of NT slots + 8 columns for the paired tap)
+  VARIANT(1, 1, 72, 1, "TS cg1 N=72")
+  VARIANT(1, 1, 80, 1, "TS cg1 N=80")
+  VARIANT(1, 1, 96, 1, "TS cg1 N=96")
+  VARIANT(1, 1, 104, 1, "TS cg1 N=104")
+  VARIANT(1, 1, 112, 1, "TS cg1 N=112")
+  VARIANT(1, 1, 120, 1, "TS cg1 N=120")
+  VARIANT(1, 1, 136, 1, "TS cg1 N=136")
+  VARIANT(1, 1, 144, 1, "TS cg1 N=144")
+  VARIANT(1, 1, 160, 1, "TS cg1 N=160")
+  VARIANT(1, 1, 192, 1, "TS cg1 N=192")
+  VARIANT(1, 1, 200, 1, "TS cg1 N=200")
+  VARIANT(1, 1, 136, 2, "TS cg1 N=136 2 acc")
+  VARIANT(1, 0, 136, 1, "SS cg1 N=136")
+  VARIANT(1, 0, 192, 1, "SS cg1 N=192")
+  // M = 64: does a half-height MMA cost half the cycles?  (floor printed for M = 128)
+  if (which < 0 || which == v) run<1, 1, 136, 1, 64>("TS cg1 M=64 N=136", grid, iters, d_out);
+  ++v;
+  if (which < 0 || which == v) run<1, 0, 128, 1, 64>("SS cg1 M=64 N=128", grid, iters, d_out);
+  ++v;
+  if (which < 0 || which == v) run<1, 1, 256, 1, 64>("TS cg1 M=64 N=256", grid, iters, d_out);
+  ++v;
   if (which >= v) return 3;
   return 0;
 }

@@ -4,8 +4,8 @@
 out=${1:-gpurun_out/mma_rate.txt}
 : > "$out"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader >> "$out"
-for grid in 2 148; do
-  for v in 0 1 2 3 4 5 6 7 8 9 10 11 12; do
+for grid in ${GRIDS:-2 148}; do
+  for v in ${VARIANTS:-0 1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 23 24 25 26}; do
     timeout 20 build/mma_rate $v $grid >> "$out" 2>&1 || echo "variant $v grid $grid: exit $?" >> "$out"
   done
 done
