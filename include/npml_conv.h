@@ -48,7 +48,7 @@ enum { NPML_F32 = 0, NPML_BF16 = 1, NPML_F64 = 2 };
 enum {
   NPML_OP_CONV_FPROP = 0, NPML_OP_CONV_DGRAD = 1, NPML_OP_CONV_WGRAD = 2,
   NPML_OP_DECONV_FPROP = 3, NPML_OP_DECONV_DGRAD = 4, NPML_OP_DECONV_WGRAD = 5,
-  NPML_OP_DZ_PREP = 6, NPML_OP_BN = 7
+  NPML_OP_DZ_PREP = 6, NPML_OP_BN = 7, NPML_OP_CONV_BWD = 8
 };
 
 /*
@@ -113,6 +113,15 @@ int npml_conv2d_wgrad(const npml_conv_desc* d, const void* X, const void* dZ, fl
  * npml_workspace_bytes(d, NPML_OP_CONV_WGRAD). */
 int npml_conv2d_wgrad_db(const npml_conv_desc* d, const void* X, const void* dZ, float* dW, float* db,
                          void* ws, size_t ws_bytes, void* stream);
+
+/* The whole of Conv2D._bwd in one call (layers/layers.py:3093-3116): dW (+)= ..., db (+)= ... (desc.accumulate) and
+ * dX = ... from dZ = dLdy * act'(Z).  For thin stride-1 "same" shapes (in_ch <= 4, out_ch <= 64: cfg1) it is ONE kernel
+ * launch that reads dZ once (csrc/thin_bwd.cu; npml_conv2d_bwd_is_fused says whether a shape takes it); every other shape
+ * runs npml_conv2d_wgrad_db followed by npml_conv2d_dgrad.  db may be NULL.  Workspace:
+ * npml_workspace_bytes(d, NPML_OP_CONV_BWD). */
+int npml_conv2d_bwd(const npml_conv_desc* d, const void* X, const void* dZ, const float* W, float* dW, float* db,
+                    void* dX, void* ws, size_t ws_bytes, void* stream);
+int npml_conv2d_bwd_is_fused(const npml_conv_desc* d);
 
 /* ---- Deconv2D (layers/layers.py:3353-3568, utils/utils.py:720-794) ------------------------
  * fprop: Z[n, iy*s + r - pr1, ix*s + t - pc1, k] += X[n,iy,ix,c] * W[r,t,c,k]  (no zero-stuffing)

@@ -17,7 +17,7 @@ MODES = {"fp32": 0, "tf32": 1, "bf16": 2}
 F32, BF16, F64 = 0, 1, 2
 OP_CONV_FPROP, OP_CONV_DGRAD, OP_CONV_WGRAD = 0, 1, 2
 OP_DECONV_FPROP, OP_DECONV_DGRAD, OP_DECONV_WGRAD = 3, 4, 5
-OP_DZ_PREP, OP_BN = 6, 7
+OP_DZ_PREP, OP_BN, OP_CONV_BWD = 6, 7, 8
 FLAG_WEIGHTS_PACKED = 1
 
 
@@ -39,6 +39,8 @@ SIGNATURES = {
     "npml_conv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_wgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),
     "npml_conv2d_wgrad_db": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _SZ, _P]),
+    "npml_conv2d_bwd": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "npml_conv2d_bwd_is_fused": (C.c_int, [_DESC]),
     "npml_deconv2d_fprop": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_fprop_bn": (C.c_int, [_DESC, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "npml_deconv2d_dgrad": (C.c_int, [_DESC, _P, _P, _P, _P, _SZ, _P]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnpmlconv.so")
-SOURCES = ["npml_api.cu", "direct_fp32.cu", "elementwise.cu", "pool.cu", "comm.cu", "peer.cu", "tc_conv.cu", "tc_slab_conv.cu", "tc_slab3_conv.cu", "tc_ws_conv.cu", "tc_wgrad.cu", "tc_slab_wgrad.cu"]
+SOURCES = ["npml_api.cu", "direct_fp32.cu", "thin_bwd.cu", "elementwise.cu", "pool.cu", "comm.cu", "peer.cu", "tc_conv.cu", "tc_slab_conv.cu", "tc_slab3_conv.cu", "tc_ws_conv.cu", "tc_wgrad.cu", "tc_slab_wgrad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 

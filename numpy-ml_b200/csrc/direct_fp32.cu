@@ -300,12 +300,25 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) thin_ci_conv_kernel(GatherConv g, const TIn* __restrict__ in,
                                                            const float* __restrict__ w, const float* __restrict__ bias,
                                                            TOut* __restrict__ Z, TOut* __restrict__ Y) {
-  extern __shared__ __align__(16) float ws_[];          // [tap*CI + ci][co]
+  extern __shared__ __align__(16) float ws_[];          // [tap*CI + ci][co], then the per-k offset table
   const int K = g.fr * g.fc * g.CI;
-  for (int i = threadIdx.x; i < K * g.CO; i += blockDim.x) {
-    const int co = i % g.CO, k = i / g.CO;
+  // k -> (r*D, t*D, ci) once per block: the gather loop below was two integer divisions per input (ncu: 60 % of
+  // this kernel's instructions were index arithmetic)
+  int* ktab = reinterpret_cast<int*>(ws_ + K * g.CO);
+  const bool w_dense = g.w_co == 1 && g.w_ci == g.CO && g.w_tap == (int64_t)g.CI * g.CO;
+  if (w_dense) {
+    for (int i = threadIdx.x; i < K * g.CO; i += blockDim.x) ws_[i] = w[i];
+  } else {
+    for (int i = threadIdx.x; i < K * g.CO; i += blockDim.x) {
+      const int co = i % g.CO, k = i / g.CO;
+      const int tp = k / g.CI, ci = k - tp * g.CI;
+      ws_[i] = w[(int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co];
+    }
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const int tp = k / g.CI, ci = k - tp * g.CI;
-    ws_[i] = w[(int64_t)tp * g.w_tap + ci * g.w_ci + co * g.w_co];
+    const int r = tp / g.fc, t = tp - r * g.fc;
+    ktab[k] = (r * g.D) | ((t * g.D) << 10) | (ci << 20);
   }
   __syncthreads();
   const int cog = g.CO >> 2;                              // groups of 4 output channels
@@ -319,24 +332,25 @@ __global__ void __launch_bounds__(256) thin_ci_conv_kernel(GatherConv g, const T
   // K = taps * CI gathered inputs, kKB at a time: every load of a batch is in flight before the first FMA (one
   // round trip per batch instead of one per input; this kernel is latency, not bandwidth, on cfg1)
   constexpr int kKB = 9;
+  const TIn* img = in + (int64_t)n * g.IH * g.IW * g.CI;
   for (int k0 = 0; k0 < K; k0 += kKB) {
     float a[kKB];
 #pragma unroll
     for (int j = 0; j < kKB; ++j) {
       const int k = k0 + j;
-      const int tp = k / g.CI, ci = k - tp * g.CI;
-      const int r = tp / g.fc, t = tp - r * g.fc;
-      int iy, ix;
       bool v = k < K;
+      const int e = ktab[v ? k : 0];
+      const int rD = e & 1023, tD = (e >> 10) & 1023, ci = e >> 20;
+      int iy, ix;
       if (g.form == 0) {
-        iy = y * g.s + r * g.D - g.pr; ix = x * g.s + t * g.D - g.pc;
+        iy = y * g.s + rD - g.pr; ix = x * g.s + tD - g.pc;
       } else {
-        const int ny = y + g.pr - r * g.D, nx = x + g.pc - t * g.D;
+        const int ny = y + g.pr - rD, nx = x + g.pc - tD;
         v = v && ny >= 0 && nx >= 0 && ny % g.s == 0 && nx % g.s == 0;
         iy = ny / g.s; ix = nx / g.s;
       }
       v = v && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
-      a[j] = v ? ld_f(in, (((int64_t)n * g.IH + iy) * g.IW + ix) * g.CI + ci) : 0.f;
+      a[j] = v ? ld_f(img, (iy * g.IW + ix) * g.CI + ci) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < kKB; ++j) {
@@ -465,6 +479,56 @@ __global__ void __launch_bounds__(512) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// The same reduction with 16-byte loads: thread (x, y) of a (32, 16) block adds the splits z = y, y + 16, ... of FOUR
+// consecutive outputs, four loads in flight at a time; the 16 group sums are added in a fixed order.  The partials
+// were just written and sit in L2: 148 splits x 147 KB (cfg2) took 11.3 us with 4-byte loads and 19 dependent
+// round trips per thread (2 TB/s).  Needs CO % 4 == 0 (then M * CO and the db tail are multiples of 4 too).
+__global__ void __launch_bounds__(512) wgrad_reduce_v4_kernel(const float* __restrict__ part, int splits, int M, int CO,
+                                                              int CI, int64_t o_tap, int64_t o_ci, int64_t o_co,
+                                                              int accumulate, float* __restrict__ dW,
+                                                              const float* __restrict__ part_db, float* __restrict__ db) {
+  __shared__ float4 red[16][32];
+  const int64_t total = (int64_t)M * CO;
+  const int64_t total_all = total + (part_db != nullptr ? CO : 0);
+  for (int64_t i0 = (int64_t)blockIdx.x * 128; i0 < total_all; i0 += (int64_t)gridDim.x * 128) {
+    const int64_t i = i0 + 4 * threadIdx.x;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < total_all) {
+      const float* src = i < total ? part + i : part_db + (i - total);
+      const int64_t stride = i < total ? total : (int64_t)CO;
+      for (int z = threadIdx.y; z < splits; z += 64) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = (z + 16 * u < splits) ? *reinterpret_cast<const float4*>(src + (int64_t)(z + 16 * u) * stride)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+      }
+    }
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y < 4) {                               // thread (x, e) finishes element e of the four
+      const int64_t ie = i + threadIdx.y;
+      if (ie < total_all) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 16; ++y) t += reinterpret_cast<const float*>(&red[y][threadIdx.x])[threadIdx.y];
+        if (ie < total) {
+          const int m = (int)(ie / CO), co = (int)(ie - (int64_t)m * CO);
+          const int tap = m / CI, ci = m - tap * CI;
+          const int64_t o = tap * o_tap + ci * o_ci + co * o_co;
+          dW[o] = accumulate ? dW[o] + t : t;
+        } else {
+          const int co = (int)(ie - total);
+          db[co] = accumulate ? db[co] + t : t;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // few splits: one thread per output element is enough
 __global__ void wgrad_reduce_simple_kernel(const float* __restrict__ part, int splits, int M, int CO, int CI,
                                            int64_t o_tap, int64_t o_ci, int64_t o_co, int accumulate,
@@ -570,6 +634,15 @@ int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, in
     NPML_LAUNCH_OK();
     return 0;
   }
+  if (CO % 4 == 0 && (reinterpret_cast<uintptr_t>(part) & 15) == 0 &&
+      (part_db == nullptr || (reinterpret_cast<uintptr_t>(part_db) & 15) == 0)) {
+    int blocks = (int)((total + 127) / 128);
+    if (blocks > 8192) blocks = 8192;
+    wgrad_reduce_v4_kernel<<<blocks, dim3(32, 16), 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW,
+                                                            part_db, db);
+    NPML_LAUNCH_OK();
+    return 0;
+  }
   int blocks = (int)((total + 63) / 64);
   if (blocks > 8192) blocks = 8192;
   wgrad_reduce_kernel<<<blocks, dim3(64, 8), 0, st>>>(part, splits, M, CO, CI, o_tap, o_ci, o_co, accumulate, dW, part_db, db);
@@ -601,14 +674,16 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
     NPML_LAUNCH_OK();
     return 0;
   }
-  if (g.fr * g.fc * g.CI <= 64 && g.CO % 4 == 0 && wn <= 40 * 1024 && P * (g.CO / 4) < (1LL << 31)) {
+  if (g.fr * g.fc * g.CI <= 64 && g.CO % 4 == 0 && wn <= 40 * 1024 && P * (g.CO / 4) < (1LL << 31) &&
+      (g.fr - 1) * g.D < 1024 && (g.fc - 1) * g.D < 1024 && (int64_t)g.IH * g.IW * g.CI < (1LL << 31)) {
     const int64_t total = P * (g.CO / 4);
     const unsigned blocks = (unsigned)((total + 255) / 256);
+    const size_t wk = wn + (size_t)g.fr * g.fc * g.CI * sizeof(int);        // weights + the per-k offset table
     if (dtype == NPML_F32)
-      thin_ci_conv_kernel<float, float><<<blocks, 256, wn, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
+      thin_ci_conv_kernel<float, float><<<blocks, 256, wk, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
     else
       thin_ci_conv_kernel<__nv_bfloat16, __nv_bfloat16>
-          <<<blocks, 256, wn, st>>>(g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y);
+          <<<blocks, 256, wk, st>>>(g, (const __nv_bfloat16*)in, w, bias, (__nv_bfloat16*)Z, (__nv_bfloat16*)Y);
     NPML_LAUNCH_OK();
     return 0;
   }

@@ -178,6 +178,20 @@ int npml_conv2d_wgrad_db(const npml_conv_desc* d, const void* X, const void* dZ,
                          size_t ws_bytes, void* stream) {
   return run_wgrad(d, NPML_OP_CONV_WGRAD, X, dZ, dW, ws, ws_bytes, (cudaStream_t)stream, db);
 }
+int npml_conv2d_bwd_is_fused(const npml_conv_desc* d) {
+  return d != nullptr && d->N > 0 && d->dil > 0 && thin_bwd_supported(d) ? 1 : 0;
+}
+int npml_conv2d_bwd(const npml_conv_desc* d, const void* X, const void* dZ, const float* W, float* dW, float* db, void* dX,
+                    void* ws, size_t ws_bytes, void* stream) {
+  if (check_desc(d, false)) return 1;
+  NPML_CHECK(dW != nullptr && dX != nullptr, "dW / dX is NULL");
+  if (d->N > 0 && thin_bwd_supported(d)) {
+    NPML_CHECK(X && dZ && W, "NULL input");
+    return thin_bwd(d, X, dZ, W, dW, db, dX, ws, ws_bytes, (cudaStream_t)stream);
+  }
+  if (int e = run_wgrad(d, NPML_OP_CONV_WGRAD, X, dZ, dW, ws, ws_bytes, (cudaStream_t)stream, db)) return e;
+  return run_gather(d, NPML_OP_CONV_DGRAD, dZ, W, nullptr, dX, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
 int npml_deconv2d_fprop(const npml_conv_desc* d, const void* X, const float* W, const float* b, void* Z, void* Y,
                         void* ws, size_t ws_bytes, void* stream) {
   return run_gather(d, NPML_OP_DECONV_FPROP, X, W, b, Z, Y, ws, ws_bytes, (cudaStream_t)stream);
@@ -211,6 +225,12 @@ size_t npml_workspace_bytes(const npml_conv_desc* d, int op) {
       else w = direct_wgrad_ws_bytes(g);
       const size_t c = colpass_ws_bytes((int64_t)d->N * d->OH * d->OW, d->K, 1);   // db fallback of npml_conv2d_wgrad_db
       bytes += w > c ? w : c;
+      break;
+    }
+    case NPML_OP_CONV_BWD: {
+      const size_t a = npml_workspace_bytes(d, NPML_OP_CONV_WGRAD), b = npml_workspace_bytes(d, NPML_OP_CONV_DGRAD);
+      const size_t c = d->N > 0 && d->dil > 0 && thin_bwd_supported(d) ? thin_bwd_ws_bytes(d) : 0;
+      bytes += (a > b ? a : b) > c ? (a > b ? a : b) : c;
       break;
     }
     case NPML_OP_DZ_PREP: {

@@ -198,6 +198,12 @@ size_t direct_wgrad_ws_bytes(const GatherWgrad& g);
 int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* dW, int dtype, void* ws,
                  size_t ws_bytes, cudaStream_t st, float* db = nullptr, bool* db_done = nullptr);
 
+// one-launch backward (dX, dW, db) of thin stride-1 "same" convolutions, thin_bwd.cu
+bool thin_bwd_supported(const npml_conv_desc* d);
+size_t thin_bwd_ws_bytes(const npml_conv_desc* d);
+int thin_bwd(const npml_conv_desc* d, const void* X, const void* dZ, const float* W, float* dW, float* db, void* dX,
+             void* ws, size_t ws_bytes, cudaStream_t st);
+
 // tensor-core (tcgen05) kernels, tc_conv.cu / tc_wgrad.cu
 bool tc_conv_supported(const GatherConv& g, int mode);
 size_t tc_conv_ws_bytes(const GatherConv& g, int mode);

@@ -333,6 +333,15 @@ class _ConvBase(LayerBase):
         d = self._desc(tuple(X.shape), accumulate=1)
         # parameter gradients first (the reference's order, layers.py:3106-3114): a data-parallel bucket can then
         # all-reduce dW / db on its own stream while dX is still being computed (dist.GradBucket, overlap=True)
+        if retain_grads and conv and L.load().npml_conv2d_bwd_is_fused(d):
+            # thin shapes (cfg1): dW, db and dX from one pass over dZ, one launch (csrc/thin_bwd.cu)
+            dX = torch.empty_like(X)
+            self._call("npml_conv2d_bwd", d, L.OP_CONV_BWD, L.ptr(X), L.ptr(dZ), L.ptr(W), L.ptr(self.gradients["W"]),
+                       L.ptr(self.gradients["b"]), L.ptr(dX))
+            hook = getattr(self, "_grads_ready_hook", None)
+            if hook is not None:
+                hook(self)
+            return dX
         if retain_grads and conv:
             self._call("npml_conv2d_wgrad_db", d, self._ops[2], L.ptr(X), L.ptr(dZ), L.ptr(self.gradients["W"]),
                        L.ptr(self.gradients["b"]))

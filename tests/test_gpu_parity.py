@@ -249,6 +249,12 @@ CONV_CASES = [
     ((2, 30, 30, 64), 64, (4, 4), 1, 2, 0, "tanh"),                 # 4x4 s2 (the Deconv2D adjoint shape)
     ((4, 12, 12, 1), 32, (3, 3), "same", 1, 0, "identity"),         # cfg1 miniature
     ((3, 7, 9, 24), 2, (3, 3), 1, 1, 0, "sigmoid"),                 # out_ch = 2 forward
+    # one-launch backward of thin stride-1 'same' shapes (csrc/thin_bwd.cu): 256 blocks = 16 reduction groups; 25 taps
+    # with dilation 2; an even kernel ('same' pads asymmetrically), 16 lanes per pixel; one lane per pixel
+    ((64, 12, 12, 2), 16, (3, 3), "same", 1, 0, "relu"),
+    ((3, 9, 11, 3), 8, (5, 5), "same", 1, 1, "tanh"),
+    ((2, 10, 7, 4), 64, (3, 2), "same", 1, 0, "identity"),
+    ((5, 8, 8, 1), 4, (3, 3), "same", 1, 0, "sigmoid"),
     # wide outputs on the slab kernel: one N = 144 / 256 tile spanning two TMEM accumulators, 320 = 128 + 128 + 64
     ((2, 8, 8, 64), 144, (3, 3), 1, 1, 0, "relu"),
     ((3, 9, 9, 64), 256, (3, 3), 1, 1, 0, "identity"),
@@ -283,6 +289,51 @@ def test_conv2d_vs_oracle(cuda_device, mode, case):
     close(dX, dXr, tol, "dX")
     close(L.gradients["W"], dWr, tol, "dW")
     close(L.gradients["b"], dbr, tol, "db")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_fused_thin_backward_equals_the_three_kernel_path(cuda_device, mode, monkeypatch):
+    """npml_conv2d_bwd (one launch: dX, dW, db with the in-kernel fixed-order reduction) against the same backward run
+    as wgrad + reduce + dgrad (NPML_DISABLE_THIN_BWD=1), gradient accumulation over two backward calls, and bitwise
+    run-to-run determinism of the in-kernel reduction (the grid barrier must be reusable launch after launch)."""
+    import torch
+    pkg = npml()
+    rng = np.random.default_rng(7)
+    xs, oc = (40, 28, 28, 1), 32                                       # cfg1 shape
+    L = pkg.Conv2D(out_ch=oc, kernel_shape=(3, 3), pad="same", mode=mode)
+    X, dY = _f32(rng, xs), _f32(rng, xs[:3] + (oc,))
+    L.forward(X, retain_derived=False)
+    L.parameters["W"], L.parameters["b"] = _f32(rng, (3, 3, 1, oc), 1 / 3.0), _f32(rng, (1, 1, 1, oc), 0.1)
+
+    def run(times=1):
+        L.flush_gradients()
+        for _ in range(times):
+            L.forward(X)
+        dX = L.backward([dY] * times) if times > 1 else L.backward(dY)
+        torch.cuda.synchronize()
+        dX = dX[-1] if isinstance(dX, list) else dX
+        return pkg.to_numpy(dX), pkg.to_numpy(L.gradients["W"]).copy(), pkg.to_numpy(L.gradients["b"]).copy()
+
+    d = L._desc((40, 28, 28, 1))
+    assert pkg._lib.load().npml_conv2d_bwd_is_fused(d) == 1
+    a = run()
+    b = run()
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)                                     # bitwise, run after run
+    a2 = run(times=2)                                                   # two retained forwards: gradients add up
+    close(a2[1], 2 * a[1], 1e-6, "dW accumulated")
+    close(a2[2], 2 * a[2], 1e-6, "db accumulated")
+    monkeypatch.setenv("NPML_MAX_CTAS", "3")                            # 12 resident blocks walk 560 tiles
+    m = run()
+    monkeypatch.delenv("NPML_MAX_CTAS")
+    for u, v, w in zip(a, m, ("dX", "dW", "db")):
+        close(u, v, 1e-6 if mode != "bf16" else 2e-3, w + " (few blocks, many tiles each)")
+    monkeypatch.setenv("NPML_DISABLE_THIN_BWD", "1")
+    assert pkg._lib.load().npml_conv2d_bwd_is_fused(d) == 0
+    c = run()
+    tol = 1e-6 if mode != "bf16" else 2e-3                             # same operands, different summation order
+    for u, v, w in zip(a, c, ("dX", "dW", "db")):
+        close(u, v, tol, w)
 
 
 DECONV_CASES = [
