@@ -67,6 +67,7 @@ static GatherWgrad make_wgrad(const npml_conv_desc* d, int op) {
   } else {                         // dW[r,t,c,k] = sum dZ[n, iy*s + r - pr1, ...][k] X[n,iy,ix,c]
     g.IH = d->OH; g.IW = d->OW; g.CI = d->K; g.OH = d->H; g.OW = d->W; g.CO = d->C;
     g.o_ci = 1; g.o_co = d->K;
+    g.no_db = 1;
   }
   return g;
 }

@@ -189,6 +189,7 @@ struct GatherWgrad {
   int fr, fc, s, D, pr, pc;
   int64_t o_tap, o_ci, o_co;
   int accumulate;
+  int no_db;            // the caller never asks this problem for db (Deconv2D: its db is a column sum of the OTHER operand)
 };
 
 // direct (CUDA-core, fp32 accumulate) kernels, direct_fp32.cu

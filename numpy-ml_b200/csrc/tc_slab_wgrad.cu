@@ -12,11 +12,19 @@
 // descriptor's leading-dimension offset is simply the byte distance between the two windows.  db rides along
 // as one more window made of ones.  Accumulators for all taps stay in TMEM for the CTA's whole slot range;
 // each CTA writes one fp32 partial and a second kernel adds the partials in a fixed order (deterministic).
+//
+// Stride s > 1 (strided Conv2D dW; Deconv2D dW, where the shifted operand is dZ -- cfg5): tap (r, t) reads row
+// y*s + r*D - pr = s*(y + dy) + py of X, i.e. row y + dy of the input PARITY PLANE py.  The taps of one plane form a
+// stride-1 problem on a strided view of X (a tensor map with s-fold strides), so every plane becomes its own group of
+// M tiles with its own X slab, all on one common slot grid, in ONE launch.  The per-tile kernel (tc_wgrad.cu) needs
+// 94 B/clk of L2 -> shared-memory traffic per SM at cfg5 against the 42 B/clk the chip delivers to 148 SMs at once
+// (0.47 of the tensor peak); here a slot costs 512 B for 4 x 64 clk of MMAs.
 #include <cstdlib>
 #include <vector>
 
 #include "npml_common.cuh"
 #include "tc_ptx.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace npml {
 
@@ -30,14 +38,17 @@ namespace {
 
 constexpr int kMaxMT = 40;           // M tiles (pairs of windows) over all groups
 constexpr int kMaxMGroups = 16;
+constexpr int kMaxPlanes = 9;        // input parity planes of a stride-2 / stride-3 convolution
 constexpr int kRowBytes = 128;
 constexpr int kKI = 16;              // slots (K) per tcgen05.mma for 16-bit operands
 constexpr int kThreads = 256;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
 
+__device__ GridBar g_bar_slab, g_bar_ns;     // one per kernel (two launches of the same kernel never overlap: one stream)
+
 struct SlabWgradParams {
-  CUtensorMap xmap, gmap;
+  CUtensorMap xmap[kMaxPlanes], gmap;   // stride s > 1: one strided view of X per input parity plane (stride 1: one)
   uint32_t a16[kMaxMT];          // start of window 0 inside an X stage, >> 4 (kind 2: unused)
   uint32_t lbo16[kMaxMT];        // kind 0: byte distance window 0 -> window 1, >> 4
   int16_t tap[kMaxMT][2];        // filter tap of each window (-1 = the ones window, i.e. db)
@@ -48,6 +59,8 @@ struct SlabWgradParams {
   // [g_cta0, g_cta0 + g_nctas) of grid.x.  The CTA counts are PROPORTIONAL to the tile counts (a group with half the
   // tiles per K step gets half the CTAs), so all groups finish together; max_splits = the largest g_nctas.
   int16_t g_mt0[kMaxMGroups], g_nmt[kMaxMGroups], g_cta0[kMaxMGroups], g_nctas[kMaxMGroups];
+  // the X plane a group reads and where the plane's slot (0, 0) sits in it (its taps' smallest offsets, negated)
+  int16_t g_plane[kMaxMGroups], g_pady[kMaxMGroups], g_padx[kMaxMGroups];
   int max_splits;
   int ncb, nb, BN;
   int N, Hp, Wp, pady, padx, CI, CO, Mrows;
@@ -55,6 +68,7 @@ struct SlabWgradParams {
   int xplane_bytes, xstage_bytes, gplane_bytes, gstage_bytes;
   uint32_t idesc;
   int wait_ns;                 // sleep between mbarrier polls of the producer / epilogue warps (npml::wait_ns())
+  FusedReduce red;             // the split reduction behind a grid barrier, inside this kernel (wgrad_reduce.cuh)
 };
 
 // The MMA issue loop for a group of NT accumulator tiles.  The whole warp walks the loops in convergent control
@@ -168,7 +182,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
   if (warp == 0) {
     // ===== producer: X rows [u*R, u*R + SRX) of every channel block, dZ rows [u*R, u*R + R) of the CO tile =====
     if (ptx::elect_one()) {
-      ptx::prefetch_tmap(&P.xmap);
+      const CUtensorMap* xmap = &P.xmap[P.g_plane[mgroup]];
+      const int pady = P.g_pady[mgroup], padx = P.g_padx[mgroup];
+      ptx::prefetch_tmap(xmap);
       ptx::prefetch_tmap(&P.gmap);
       const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
       const uint32_t tx = (uint32_t)(P.ncb * P.SRX + P.nb * P.R) * row_bytes;
@@ -183,8 +199,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
         uint8_t* gd = gs + (size_t)st * P.gstage_bytes;
         for (int i = 0; i < P.SRX; ++i) {
           for (int c = 0; c < P.ncb; ++c)
-            ptx::tma_load_4d(xd + (size_t)c * P.xplane_bytes + (size_t)i * row_bytes, &P.xmap, &full_bar[st], c * 64, -P.padx,
-                             yp - P.pady, n);
+            ptx::tma_load_4d(xd + (size_t)c * P.xplane_bytes + (size_t)i * row_bytes, xmap, &full_bar[st], c * 64, -padx,
+                             yp - pady, n);
           if (i < P.R)
             for (int b = 0; b < P.nb; ++b)
               ptx::tma_load_4d(gd + (size_t)b * P.gplane_bytes + (size_t)i * row_bytes, &P.gmap, &full_bar[st], co0 + b * 64, 0,
@@ -259,29 +275,87 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
+  if (P.red.enabled) {
+    // the operand stages are free now: their first bytes serve as the reduction's scratch
+    const int nctas = (int)(gridDim.x * gridDim.z), cta = (int)(blockIdx.x + gridDim.x * blockIdx.z);
+    grid_barrier(&g_bar_slab, (unsigned)nctas);
+    wgrad_reduce_slices(P.red, part, part_db, P.Mrows, P.CO, P.CI, cta, nctas, reinterpret_cast<float4*>(smem_raw));
+  }
 }
 
 inline int ceildiv(int a, int b) { return (a + b - 1) / b; }
+
+// The in-kernel reduction needs every CTA of the grid resident at once (it meets at a grid barrier): one CTA per SM,
+// so at most as many CTAs as the device has SMs.  NPML_DISABLE_FUSED_REDUCE=1: the separate reduce kernel (A/B).
+inline FusedReduce fused_reduce(const GatherWgrad& g, dim3 grid, int splits, float* dW, float* db) {
+  FusedReduce r{};
+  r.dW = dW; r.db = db; r.o_tap = g.o_tap; r.o_ci = g.o_ci; r.o_co = g.o_co; r.accumulate = g.accumulate; r.splits = splits;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t ctas = (int64_t)grid.x * grid.y * grid.z;
+  // (o_co != 1: Deconv2D's transposed dW, whose stores want the shared-memory transpose of wgrad_reduce_t_kernel)
+  r.enabled = (g.CO % 4 == 0 && g.o_co == 1 && ctas <= sms && std::getenv("NPML_DISABLE_FUSED_REDUCE") == nullptr) ? 1 : 0;
+  return r;
+}
 
 struct SlabWgradPlan {
   SlabWgradParams P;
   dim3 grid;
   size_t smem = 0, part_bytes = 0, partdb_bytes = 0;
   int splits = 0;
+  int nplanes = 1, plane_py[kMaxPlanes] = {0}, plane_px[kMaxPlanes] = {0};
 };
+
+inline int posmod(int a, int b) { const int m = a % b; return m < 0 ? m + b : m; }
+inline int floordiv(int a, int b) { return (a - posmod(a, b)) / b; }
 
 bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   if (mode != NPML_MODE_BF16) return false;       // MN-major tf32 needs the 32B-atom layout: tc_wgrad.cu
   if (std::getenv("NPML_DISABLE_SLAB")) return false;
-  if (g.s != 1 || g.N < 1) return false;
+  if (g.s < 1 || g.s > 3 || g.N < 1) return false;
+  // Opt-in (NPML_SLAB_WGRAD_PLANES=1): validated (parity tests run it) but it LOSES to the per-tile kernel at cfg5,
+  // 58 + 22 us (kernel + 18-way reduce) against 44 + 9 us.  ncu (profiles/r3l_*): the MMAs need 33 k of the 73 k cycles,
+  // the issuer waits for operands -- a strided plane is a gather of 128-byte granules (pixel stride s * CI * 2 bytes) and
+  // the TMA delivers those at ~15 B/clk per SM, half of what 4 accumulator tiles consume (the same limit finding 16
+  // met at cfg4 conv2, whose 128-channel rows are 128-byte granules 256 bytes apart).
+  if (g.s > 1 && !std::getenv("NPML_SLAB_WGRAD_PLANES")) return false;
   if (g.CI % 8 || g.CO % 8) return false;
-  const int Hp = g.OH + (g.fr - 1) * g.D, Wp = g.OW + (g.fc - 1) * g.D;
+  // ---- taps by input parity plane: row y*s + r*D - pr = s*(y + dy) + py --------------------------------------
+  struct Tap { int id, dy, dx; };
+  struct Plane { int py, px, lo_y, lo_x; std::vector<Tap> taps; };
+  std::vector<Plane> planes;
+  int span_y = 0, span_x = 0;
+  for (int py = 0; py < g.s; ++py)
+    for (int px = 0; px < g.s; ++px) {
+      if (py >= g.IH || px >= g.IW) continue;
+      Plane pn{py, px, 1 << 30, 1 << 30, {}};
+      int hi_y = -(1 << 30), hi_x = -(1 << 30);
+      for (int r = 0; r < g.fr; ++r)
+        for (int t = 0; t < g.fc; ++t) {
+          const int oy = r * g.D - g.pr, ox = t * g.D - g.pc;
+          if (posmod(oy, g.s) != py || posmod(ox, g.s) != px) continue;
+          const int dy = floordiv(oy, g.s), dx = floordiv(ox, g.s);
+          pn.taps.push_back({r * g.fc + t, dy, dx});
+          pn.lo_y = dy < pn.lo_y ? dy : pn.lo_y; hi_y = dy > hi_y ? dy : hi_y;
+          pn.lo_x = dx < pn.lo_x ? dx : pn.lo_x; hi_x = dx > hi_x ? dx : hi_x;
+        }
+      if (pn.taps.empty()) continue;
+      span_y = hi_y - pn.lo_y > span_y ? hi_y - pn.lo_y : span_y;
+      span_x = hi_x - pn.lo_x > span_x ? hi_x - pn.lo_x : span_x;
+      planes.push_back(pn);
+    }
+  if (planes.empty() || (int)planes.size() > kMaxPlanes) return false;
+  const int Hp = g.OH + span_y, Wp = g.OW + span_x;
   if (Wp > 256) return false;
+  // the flat slot grid computes Hp*Wp slots per OH*OW outputs: small strided planes under a wide filter footprint waste
+  // too much (cfg3: 14x14 slots per 11x11 outputs); the per-tile kernel keeps those
+  if (g.s > 1 && (double)Hp * Wp > 1.3 * g.OH * g.OW) return false;
   if ((int64_t)g.N * Hp * Wp >= (1LL << 30)) return false;
   if ((int64_t)g.N * g.IH * g.IW * g.CI >= (1LL << 31) || (int64_t)g.N * g.OH * g.OW * g.CO >= (1LL << 31)) return false;
   SlabWgradParams& P = pl.P;
   memset(&P, 0, sizeof(P));
-  P.N = g.N; P.Hp = Hp; P.Wp = Wp; P.pady = g.pr; P.padx = g.pc; P.CI = g.CI; P.CO = g.CO;
+  P.N = g.N; P.Hp = Hp; P.Wp = Wp; P.pady = -planes[0].lo_y; P.padx = -planes[0].lo_x; P.CI = g.CI; P.CO = g.CO;
   P.Mrows = g.fr * g.fc * g.CI;
   P.ncb = ceildiv(g.CI, 64);
   int bn = ceildiv(g.CO, 64) * 64;
@@ -291,7 +365,7 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   const int ncot = ceildiv(g.CO, bn);
   P.idesc = ptx::instr_desc(1, 1, 1, 128, bn);
   P.wait_ns = wait_ns();
-  const int halo = (g.fr - 1) * g.D * Wp + (g.fc - 1) * g.D;
+  const int halo = span_y * Wp + span_x;
   // largest unit (R padded rows) whose two stages fit
   int R = 0;
   for (int r = 32; r >= 1; --r) {
@@ -310,43 +384,66 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   if (R == 0) return false;
   P.R = R;
   P.num_units = ceildiv(g.N * Hp, R);
-  // windows: every (channel block, tap) in ascending smem address order, then the ones window (db)
-  struct Win { int tap, cb; uint32_t a16; };
-  std::vector<Win> wins;
-  for (int c = 0; c < P.ncb; ++c)
-    for (int r = 0; r < g.fr; ++r)
-      for (int t = 0; t < g.fc; ++t)
-        wins.push_back({r * g.fc + t, c, (uint32_t)(((size_t)c * P.xplane_bytes + (size_t)(r * g.D * Wp + t * g.D) * kRowBytes) >> 4)});
-  wins.push_back({-1, 0, 0});
-  if (wins.size() & 1) wins.push_back({-1, 0, 0});
-  const int nmt = (int)wins.size() / 2;
-  if (nmt > kMaxMT) return false;
-  for (int i = 0; i < nmt; ++i) {
-    const Win &a = wins[2 * i], &b = wins[2 * i + 1];
-    P.tap[i][0] = (int16_t)a.tap; P.tap[i][1] = (int16_t)b.tap;
-    P.cb[i][0] = (int16_t)a.cb; P.cb[i][1] = (int16_t)b.cb;
-    P.a16[i] = a.a16;
-    if (a.tap >= 0 && b.tap >= 0) { P.kind[i] = 0; P.lbo16[i] = b.a16 - a.a16; if (P.lbo16[i] >= (1u << 14)) return false; }
-    else if (a.tap >= 0) P.kind[i] = 1;
-    else P.kind[i] = 2;
+  // ---- per plane: every (channel block, tap) window in ascending smem address order, paired into M tiles; the ones
+  // window (db) closes the LAST plane's list, so the only tile with run-time descriptor deltas is the last tile of the
+  // last group (what issue_units assumes).  A plane's tiles are cut into groups of at most 512 / BN accumulators.
+  const int cap = 512 / bn > 8 ? 8 : 512 / bn;   // issue_units<NT> is instantiated up to 8
+  int nmt = 0, ngroups = 0;
+  int group_tiles[kMaxMGroups];
+  for (size_t q = 0; q < planes.size(); ++q) {
+    const Plane& pn = planes[q];
+    struct Win { int tap, cb; uint32_t a16; };
+    std::vector<Win> wins;
+    for (int c = 0; c < P.ncb; ++c) {
+      std::vector<Win> blk;
+      for (const Tap& tp : pn.taps)
+        blk.push_back({tp.id, c, (uint32_t)(((size_t)c * P.xplane_bytes + (size_t)((tp.dy - pn.lo_y) * Wp + (tp.dx - pn.lo_x)) * kRowBytes) >> 4)});
+      for (size_t i = 1; i < blk.size(); ++i)            // ascending address (insertion sort: a handful of taps)
+        for (size_t j = i; j > 0 && blk[j].a16 < blk[j - 1].a16; --j) std::swap(blk[j], blk[j - 1]);
+      wins.insert(wins.end(), blk.begin(), blk.end());
+    }
+    if (q + 1 == planes.size() && !g.no_db) wins.push_back({-1, 0, 0});
+    if (wins.size() & 1) wins.push_back({-1, 0, 0});    // (a zero-weight filler: tap -1 rows are never stored twice)
+    const int tiles_q = (int)wins.size() / 2;
+    if (nmt + tiles_q > kMaxMT) return false;
+    for (int i = 0; i < tiles_q; ++i) {
+      const Win &a = wins[2 * i], &b = wins[2 * i + 1];
+      const int gi = nmt + i;
+      P.tap[gi][0] = (int16_t)a.tap; P.tap[gi][1] = (int16_t)b.tap;
+      P.cb[gi][0] = (int16_t)a.cb; P.cb[gi][1] = (int16_t)b.cb;
+      P.a16[gi] = a.a16;
+      if (a.tap >= 0 && b.tap >= 0) { P.kind[gi] = 0; P.lbo16[gi] = b.a16 - a.a16; if (P.lbo16[gi] >= (1u << 14)) return false; }
+      else if (a.tap >= 0) P.kind[gi] = 1;
+      else P.kind[gi] = 2;
+      // a filler / ones window anywhere but in the last tile of the last plane would break issue_units' assumption
+      if (P.kind[gi] != 0 && !(q + 1 == planes.size() && i + 1 == tiles_q)) return false;
+    }
+    const int ng_q = ceildiv(tiles_q, cap);
+    if (ngroups + ng_q > kMaxMGroups) return false;
+    int t0 = 0;
+    for (int k = 0; k < ng_q; ++k) {
+      const int tiles = tiles_q / ng_q + (k < tiles_q % ng_q ? 1 : 0);
+      P.g_mt0[ngroups] = (int16_t)(nmt + t0); P.g_nmt[ngroups] = (int16_t)tiles;
+      P.g_plane[ngroups] = (int16_t)q; P.g_pady[ngroups] = (int16_t)(-pn.lo_y); P.g_padx[ngroups] = (int16_t)(-pn.lo_x);
+      group_tiles[ngroups] = tiles;
+      t0 += tiles; ++ngroups;
+    }
+    nmt += tiles_q;
   }
   P.nmt_total = nmt;
-  int cap = 512 / bn;                             // accumulator tiles that fit in TMEM
-  if (cap > 8) cap = 8;                           // issue_units<NT> is instantiated up to 8
-  P.n_mgroups = ceildiv(nmt, cap);
-  if (P.n_mgroups > kMaxMGroups) return false;
-  // tiles as evenly as possible over the groups, CTAs in proportion to the tiles (measured on cfg4 conv2: 10 tiles
-  // as 4 + 4 + 2 with 49 CTAs each left a third of the SMs idle for half of the kernel)
+  P.n_mgroups = ngroups;
+  // CTAs in proportion to the tiles of a group (measured on cfg4 conv2: 10 tiles as 4 + 4 + 2 with 49 CTAs each left a
+  // third of the SMs idle for half of the kernel)
   int budget = num_sms() / ncot;
-  if (budget < P.n_mgroups) budget = P.n_mgroups;
-  int mt0 = 0, cta0 = 0, max_splits = 0;
-  for (int q = 0; q < P.n_mgroups; ++q) {
-    const int tiles = nmt / P.n_mgroups + (q < nmt % P.n_mgroups ? 1 : 0);
-    int ctas = (int)((int64_t)budget * (mt0 + tiles) / nmt) - (int)((int64_t)budget * mt0 / nmt);
+  if (budget < ngroups) budget = ngroups;
+  int done = 0, cta0 = 0, max_splits = 0;
+  for (int q = 0; q < ngroups; ++q) {
+    const int tiles = group_tiles[q];
+    int ctas = (int)((int64_t)budget * (done + tiles) / nmt) - (int)((int64_t)budget * done / nmt);
     if (ctas < 1) ctas = 1;
     if (ctas > P.num_units) ctas = P.num_units;
-    P.g_mt0[q] = (int16_t)mt0; P.g_nmt[q] = (int16_t)tiles; P.g_cta0[q] = (int16_t)cta0; P.g_nctas[q] = (int16_t)ctas;
-    mt0 += tiles; cta0 += ctas;
+    P.g_cta0[q] = (int16_t)cta0; P.g_nctas[q] = (int16_t)ctas;
+    done += tiles; cta0 += ctas;
     max_splits = ctas > max_splits ? ctas : max_splits;
   }
   P.max_splits = max_splits;
@@ -354,6 +451,8 @@ bool plan_slab_wgrad(const GatherWgrad& g, int mode, SlabWgradPlan& pl) {
   pl.grid = dim3((unsigned)cta0, 1, (unsigned)ncot);
   pl.part_bytes = align_up((size_t)max_splits * P.Mrows * g.CO * sizeof(float), 256);
   pl.partdb_bytes = align_up((size_t)max_splits * g.CO * sizeof(float), 256);
+  pl.nplanes = (int)planes.size();
+  for (size_t q = 0; q < planes.size(); ++q) { pl.plane_py[q] = planes[q].py; pl.plane_px[q] = planes[q].px; }
   return true;
 }
 
@@ -387,6 +486,7 @@ struct NsParams {
   int xplane_bytes, xstage_bytes, gstage_bytes;
   uint32_t idesc;
   int wait_ns;
+  FusedReduce red;
 };
 
 __device__ __forceinline__ int ns_floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
@@ -561,6 +661,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_ns_kernel(const __g
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
+  if (P.red.enabled) {
+    const int nctas = (int)(gridDim.x * gridDim.y), cta = (int)(blockIdx.x + gridDim.x * blockIdx.y);
+    grid_barrier(&g_bar_ns, (unsigned)nctas);
+    wgrad_reduce_slices(P.red, part, part_db, P.Mrows, P.CO, P.CI, cta, nctas, reinterpret_cast<float4*>(smem_raw));
+  }
 }
 
 struct NsPlan {
@@ -661,8 +766,10 @@ int ns_wgrad(const GatherWgrad& g, NsPlan& pl, const void* in, const void* grad,
   float* part_db = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
   auto kern = tc_slab_wgrad_ns_kernel;
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  P.red = fused_reduce(g, pl.grid, pl.splits, dW, db);
   kern<<<pl.grid, kThreads, pl.smem, st>>>(P, part, part_db);
   NPML_LAUNCH_OK();
+  if (P.red.enabled) return 0;
   return launch_wgrad_reduce(part, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st,
                              db != nullptr ? part_db : nullptr, db);
 }
@@ -695,12 +802,17 @@ int slab_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad,
   NPML_CHECK(ws != nullptr && ws_bytes >= pl.part_bytes + pl.partdb_bytes, "workspace too small");
   NPML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0,
              "activation pointers must be 16-byte aligned");
+  NPML_CHECK(db == nullptr || !g.no_db, "db was requested from a problem planned without the ones window");
   SlabWgradParams& P = pl.P;
-  {
-    const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.N};
-    const uint64_t strides[4] = {2, (uint64_t)g.CI * 2, (uint64_t)g.IW * g.CI * 2, (uint64_t)g.IH * g.IW * g.CI * 2};
+  for (int q = 0; q < pl.nplanes; ++q) {
+    // plane (py, px) of X as a strided view: rows py, py + s, ... and columns px, px + s, ...
+    const int py = pl.plane_py[q], px = pl.plane_px[q];
+    const uint64_t dims[4] = {(uint64_t)g.CI, (uint64_t)((g.IW - px + g.s - 1) / g.s), (uint64_t)((g.IH - py + g.s - 1) / g.s),
+                              (uint64_t)g.N};
+    const uint64_t strides[4] = {2, (uint64_t)g.s * g.CI * 2, (uint64_t)g.s * g.IW * g.CI * 2, (uint64_t)g.IH * g.IW * g.CI * 2};
     const uint32_t box[4] = {64, (uint32_t)P.Wp, 1, 1};
-    if (int e = make_tmap(&P.xmap, true, const_cast<void*>(in), 4, dims, strides, box, false)) return e;
+    void* base = const_cast<char*>(reinterpret_cast<const char*>(in)) + ((int64_t)py * g.IW + px) * g.CI * 2;
+    if (int e = make_tmap(&P.xmap[q], true, base, 4, dims, strides, box, false)) return e;
   }
   {
     const uint64_t dims[4] = {(uint64_t)g.CO, (uint64_t)g.OW, (uint64_t)g.OH, (uint64_t)g.N};
@@ -712,8 +824,10 @@ int slab_wgrad(const GatherWgrad& g, int mode, const void* in, const void* grad,
   float* part_db = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + pl.part_bytes);
   auto kern = tc_slab_wgrad_kernel;
   NPML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+  P.red = fused_reduce(g, pl.grid, pl.splits, dW, db);
   kern<<<pl.grid, kThreads, pl.smem, st>>>(P, part, part_db);
   NPML_LAUNCH_OK();
+  if (P.red.enabled) return 0;
   return launch_wgrad_reduce(part, pl.splits, P.Mrows, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate, dW, st,
                              db != nullptr ? part_db : nullptr, db);
 }

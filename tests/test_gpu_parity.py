@@ -353,8 +353,11 @@ DECONV_CASES = [
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case", range(len(DECONV_CASES)))
-def test_deconv2d_vs_oracle(cuda_device, mode, case):
+def test_deconv2d_vs_oracle(cuda_device, mode, case, monkeypatch):
     pkg = npml()
+    if case % 2 == 0:
+        # opt-in variant of the strided wgrad: one slab group per input parity plane (csrc/tc_slab_wgrad.cu)
+        monkeypatch.setenv("NPML_SLAB_WGRAD_PLANES", "1")
     xs, oc, ks, pad, s, act = DECONV_CASES[case]
     rng = np.random.default_rng(200 + case)
     L = pkg.Deconv2D(out_ch=oc, kernel_shape=ks, pad=pad, stride=s, act_fn=make_act(pkg, act, 0, 0), mode=mode)
