@@ -553,6 +553,10 @@ def measure(ctx, cfg, headline):
                     "peak_source": pk["source"] + " bf16 sustained" if mode == "bf16" else "tf32: " + pk["tf32_source"]}
         else:
             byt = min_bytes_per_pass(cfg, n, esize)
+            if dominant == "npml_conv2d_bwd":
+                # the one-launch backward (csrc/thin_bwd.cu) reads dZ, X and W once and writes dX and dW: one more X and
+                # one more W than a single pass
+                byt += float(n * cfg["H"] * cfg["W"] * cfg["C"] * esize + cfg["k"][0] * cfg["k"][1] * cfg["C"] * cfg["K"] * 4)
             achieved = byt / (call_ms[dominant] * 1e-3) / 1e9
             roof = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"]}

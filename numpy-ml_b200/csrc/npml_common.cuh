@@ -112,8 +112,34 @@ __device__ __forceinline__ float act_fn(int act, float z, float p0, float p1) {
 // activation goes through ONE out-of-line copy of the switch (8 values per call) so that the tensor-core kernels
 // stay small enough for the instruction cache (4 values per call; 32 inlined copies of the full switch made the conv1 + ReLU
 // epilogue of cfg4 instruction-fetch bound).
+// The tensor-core epilogues (bf16 / tf32 modes, tolerances 2e-2 / 5e-3) evaluate the transcendental activations with the
+// hardware approximations: tanh.approx.f32 (max abs error 2^-11), __expf / __logf (2 ulp), one MUFU instead of the
+// 30-40 instruction libm paths.  Measured on cfg4's conv1 shape (scripts/epi_probe.py): tanh epilogue 90 -> 76 us
+// (identity: 43 us; what remains is the out-of-line call per four values).  The fp32 exactness mode never comes here
+// (its CUDA-core kernels call act_fn).
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float act_fn_fast(int act, float z, float p0, float p1) {
+  switch (act) {
+    case NPML_ACT_TANH: return tanh_fast(z);
+    case NPML_ACT_SIGMOID: return fmaf(0.5f, tanh_fast(0.5f * z), 0.5f);       // 1 / (1 + e^-z) = (1 + tanh(z/2)) / 2
+    case NPML_ACT_ELU: return z > 0.f ? z : p0 * (__expf(z) - 1.f);
+    case NPML_ACT_SELU: return NPML_SELU_SCALE * (z > 0.f ? z : NPML_SELU_ALPHA * (__expf(z) - 1.f));
+    case NPML_ACT_SOFTPLUS: return z > 15.f ? z : __logf(__expf(z) + 1.f);     // log(1 + e^z) = z + O(e^-z): 3e-7 at 15
+    case NPML_ACT_GELU: {
+      const float u = 0.7978845608028654f * (z + 0.044715f * z * z * z);
+      return 0.5f * z * (1.f + tanh_fast(u));
+    }
+    case NPML_ACT_EXPONENTIAL: return __expf(z);
+    default: return act_fn(act, z, p0, p1);
+  }
+}
 static __device__ __noinline__ float4 act_fn4(int act, float p0, float p1, float4 x) {
-  return make_float4(act_fn(act, x.x, p0, p1), act_fn(act, x.y, p0, p1), act_fn(act, x.z, p0, p1), act_fn(act, x.w, p0, p1));
+  return make_float4(act_fn_fast(act, x.x, p0, p1), act_fn_fast(act, x.y, p0, p1), act_fn_fast(act, x.z, p0, p1),
+                     act_fn_fast(act, x.w, p0, p1));
 }
 __device__ __forceinline__ void act_apply32(int act, float p0, float p1, float (&v)[32]) {
   if (act == NPML_ACT_IDENTITY) return;
