@@ -336,6 +336,42 @@ def test_fused_thin_backward_equals_the_three_kernel_path(cuda_device, mode, mon
         close(u, v, tol, w)
 
 
+def test_conv2d_bwd_entry_point_on_a_shape_that_is_not_fused(cuda_device):
+    """npml_conv2d_bwd documents a fallback (wgrad_db, then dgrad) for shapes the one-launch kernel does not take; the
+    host layer never calls it there, so the C ABI is driven directly and compared with the two separate calls."""
+    import torch
+    pkg = npml()
+    L = pkg._lib
+    lib = L.load()
+    rng = np.random.default_rng(11)
+    layer = pkg.Conv2D(out_ch=32, kernel_shape=(3, 3), pad=1, stride=2, mode="bf16")          # stride 2: never fused
+    X = L.to_device(_f32(rng, (3, 12, 12, 16)), torch.bfloat16)
+    layer.forward(X, retain_derived=False)
+    W = layer.parameters["W"]
+    d = layer._desc(tuple(X.shape), accumulate=0)
+    assert lib.npml_conv2d_bwd_is_fused(d) == 0
+    dZ = L.to_device(_f32(rng, (3, d.OH, d.OW, 32)), torch.bfloat16)
+    outs = []
+    for fused_entry in (True, False):
+        dW, db, dX = torch.zeros_like(W), torch.zeros(32, device=W.device), torch.empty_like(X)
+        if fused_entry:
+            ws = L.workspace(lib.npml_workspace_bytes(d, L.OP_CONV_BWD))
+            L.check(lib.npml_conv2d_bwd(d, L.ptr(X), L.ptr(dZ), L.ptr(W), L.ptr(dW), L.ptr(db), L.ptr(dX), L.ptr(ws),
+                                        ws.numel(), L.stream()), "npml_conv2d_bwd")
+        else:
+            ws = L.workspace(lib.npml_workspace_bytes(d, L.OP_CONV_WGRAD))
+            L.check(lib.npml_conv2d_wgrad_db(d, L.ptr(X), L.ptr(dZ), L.ptr(dW), L.ptr(db), L.ptr(ws), ws.numel(),
+                                             L.stream()), "npml_conv2d_wgrad_db")
+            ws = L.workspace(lib.npml_workspace_bytes(d, L.OP_CONV_DGRAD))
+            L.check(lib.npml_conv2d_dgrad(d, L.ptr(dZ), L.ptr(W), L.ptr(dX), L.ptr(ws), ws.numel(), L.stream()),
+                    "npml_conv2d_dgrad")
+        torch.cuda.synchronize()
+        outs.append([pkg.to_numpy(t) for t in (dW, db, dX)])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)                                     # the same kernels in the same order
+    assert np.abs(outs[0][0]).max() > 0 and np.abs(outs[0][2]).max() > 0
+
+
 DECONV_CASES = [
     ((2, 8, 8, 256), 128, (4, 4), 1, 2, "identity"),                 # cfg5 miniature
     ((3, 6, 5, 64), 64, (3, 3), 1, 1, "relu"),
