@@ -148,6 +148,23 @@ __device__ __forceinline__ void act_apply32(int act, float p0, float p1, float (
     for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : 0.f;
     return;
   }
+  // one- to three-instruction activations inline, the switch hoisted out of the element loop (scripts/epi_probe.py: the
+  // out-of-line call per four values cost a tanh epilogue 33 us on cfg4's conv1 shape)
+  if (act == NPML_ACT_TANH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = tanh_fast(v[i]);
+    return;
+  }
+  if (act == NPML_ACT_SIGMOID) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(0.5f, tanh_fast(0.5f * v[i]), 0.5f);
+    return;
+  }
+  if (act == NPML_ACT_LEAKY_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = v[i] < 0.f ? v[i] * p0 : v[i];
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {     // values travel in registers (by value), so v[] never needs a stack slot
     const float4 r = act_fn4(act, p0, p1, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
