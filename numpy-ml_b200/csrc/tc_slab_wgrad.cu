@@ -179,33 +179,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_slab_wgrad_kernel(const __grid
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===== producer: X rows [u*R, u*R + SRX) of every channel block, dZ rows [u*R, u*R + R) of the CO tile =====
+  if (warp == 0 || warp == 3) {
+    // ===== two producers: warp 0 loads the X rows [u*R, u*R + SRX) of every channel block, warp 3 the dZ rows
+    // [u*R, u*R + R) of the CO tile.  One elected thread issues a TMA box per padded row and plane; at Wp = 34 (cfg4)
+    // that is ~50 boxes of 4 KB per unit, and the issue loop of ONE thread was what the MMAs waited for: cfg4 conv2's
+    // wgrad 105.6 -> 94.7 us, conv1's 60.5 -> 53.5 us with two issuing warps (`gpurun_out/r3x_*`).  One three-dimensional
+    // box per plane and unit (units cut at image boundaries, 4 boxes instead of 50) was measured too: 97.8 / 54.2 us --
+    // the ragged last unit of every image costs what the shorter issue loop saves.  Warp 0 announces the bytes of both.
     if (ptx::elect_one()) {
+      const bool xside = warp == 0;
       const CUtensorMap* xmap = &P.xmap[P.g_plane[mgroup]];
       const int pady = P.g_pady[mgroup], padx = P.g_padx[mgroup];
-      ptx::prefetch_tmap(xmap);
-      ptx::prefetch_tmap(&P.gmap);
+      ptx::prefetch_tmap(xside ? xmap : &P.gmap);
       const uint32_t row_bytes = (uint32_t)P.Wp * kRowBytes;
       const uint32_t tx = (uint32_t)(P.ncb * P.SRX + P.nb * P.R) * row_bytes;
       uint32_t uc = 0;
       for (int unit = bidx; unit < P.num_units; unit += nctas, ++uc) {
         const uint32_t st = uc & 1u;
         ptx::mbar_wait_sleep(&empty_bar[st], ((uc >> 1) & 1u) ^ 1u, (uint32_t)P.wait_ns);
-        ptx::mbar_expect_tx(&full_bar[st], tx);
+        if (xside) ptx::mbar_expect_tx(&full_bar[st], tx);
         const int rho0 = unit * P.R;
         int n = rho0 / P.Hp, yp = rho0 - n * P.Hp;
         uint8_t* xd = xs + (size_t)st * P.xstage_bytes;
         uint8_t* gd = gs + (size_t)st * P.gstage_bytes;
-        for (int i = 0; i < P.SRX; ++i) {
-          for (int c = 0; c < P.ncb; ++c)
-            ptx::tma_load_4d(xd + (size_t)c * P.xplane_bytes + (size_t)i * row_bytes, xmap, &full_bar[st], c * 64, -padx,
-                             yp - pady, n);
-          if (i < P.R)
+        if (xside) {
+          for (int i = 0; i < P.SRX; ++i) {
+            for (int c = 0; c < P.ncb; ++c)
+              ptx::tma_load_4d(xd + (size_t)c * P.xplane_bytes + (size_t)i * row_bytes, xmap, &full_bar[st], c * 64, -padx,
+                               yp - pady, n);
+            if (++yp == P.Hp) { yp = 0; ++n; }
+          }
+        } else {
+          for (int i = 0; i < P.R; ++i) {
             for (int b = 0; b < P.nb; ++b)
               ptx::tma_load_4d(gd + (size_t)b * P.gplane_bytes + (size_t)i * row_bytes, &P.gmap, &full_bar[st], co0 + b * 64, 0,
                                yp, n);
-          if (++yp == P.Hp) { yp = 0; ++n; }
+            if (++yp == P.Hp) { yp = 0; ++n; }
+          }
         }
       }
     }
