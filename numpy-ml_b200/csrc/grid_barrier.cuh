@@ -27,7 +27,13 @@ __device__ __forceinline__ void grid_barrier(GridBar* b, unsigned int nblocks) {
       __threadfence();
       atomicAdd(&b->gen, 1u);
     } else {
-      while (*reinterpret_cast<volatile unsigned int*>(&b->gen) == g) __nanosleep(32);
+      // Bounded wait: the blocks of these kernels are resident by construction and a barrier takes microseconds; if
+      // that assumption is ever wrong (a smaller device, a grid sized by hand) the launch must FAIL, not hang the GPU:
+      // ~2 s of polling, then a trap (the host sees cudaErrorLaunchFailure on its next synchronising call).
+      for (unsigned long long polls = 0; *reinterpret_cast<volatile unsigned int*>(&b->gen) == g; ++polls) {
+        __nanosleep(polls < 4096 ? 32 : 256);       // short sleeps while a normal barrier would complete (wake-up latency)
+        if (polls > (8ull << 20)) asm volatile("trap;");
+      }
     }
     __threadfence();                                              // the other blocks' writes, after the release
   }
