@@ -122,6 +122,202 @@ __global__ void __launch_bounds__(NT) gather_conv_kernel(GatherConv g, const TIn
   }
 }
 
+// ---- fprop / dgrad, register-tiled (fp32 storage, in_ch % 4 == 0, out_ch % 4 == 0) --------------------------------
+// The kernel above is a 64 x 64 tile with 4 x 4 outputs per thread, scalar gathers and two barriers per K block:
+// 16 TFLOP/s at cfg2 (12.5 ms per fp32-mode step; the exactness mode is the constructor default).  Here a 128 x (16 TN)
+// tile, 8 x TN outputs per thread (four 16-byte shared loads per 16 TN FMAs), 16-byte gathers along in_ch with the tap
+// walked incrementally (no division in the loop), operands of the next K block in registers while the current one is
+// multiplied, and two shared-memory buffers (one barrier per K block).
+template <int TN>                                       // output channels per thread: 4 (64-wide tile) or 8 (128-wide)
+__global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, const float* __restrict__ in,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             float* __restrict__ Z, float* __restrict__ Y) {
+  constexpr int TBM = 128, TBN = 16 * TN, TBK = 16;
+  __shared__ __align__(16) float As[2][TBK][TBM];
+  __shared__ __align__(16) float Bs[2][TBK][TBN];
+  const int tid = threadIdx.x;
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int64_t m0 = (int64_t)blockIdx.x * TBM;
+  const int n0 = blockIdx.y * TBN;
+  const int Ktot = g.fr * g.fc * g.CI;
+  const int nkb = (Ktot + TBK - 1) / TBK;
+
+  // A gather: thread -> pixel am = tid % 128, k groups ag and ag + 2 (four consecutive in_ch each)
+  const int am = tid & 127, ag = tid >> 7;
+  const int64_t ap = m0 + am;
+  const bool apv = ap < P;
+  int ax, ay, an;
+  {
+    int64_t q = apv ? ap : 0;
+    ax = (int)(q % g.OW); q /= g.OW;
+    ay = (int)(q % g.OH); an = (int)(q / g.OH);
+  }
+  const float* aimg = in + (int64_t)an * g.IH * g.IW * g.CI;
+  // (tap, ci) of this thread's two k groups, advanced by 16 per K block without dividing
+  int kci[2], ktap[2], kr[2], kt[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int kk = 4 * (ag + 2 * u);
+    ktap[u] = kk / g.CI; kci[u] = kk - ktap[u] * g.CI;
+    kr[u] = ktap[u] / g.fc; kt[u] = ktap[u] - kr[u] * g.fc;
+  }
+  // B load: thread -> k row bk = tid / 16 (16 rows), columns 4 * (tid % 16) + 64 * v
+  const int bk = tid >> 4, bc = (tid & 15) * 4;
+  int bci = bk % g.CI, btap = bk / g.CI;
+  // dgrad reads W[tap][c][k] with the REDUCTION channel k contiguous (w_ci == 1): 16-byte loads along k for one output
+  // column, stored transposed like the A operand.  Thread -> column tn = tid % TBN, k groups tg + (256 / TBN) u
+  const bool b_trans = g.w_ci == 1 && g.w_co != 1;
+  constexpr int kGroupsPerPass = 256 / TBN;               // 4 (64-wide tile) or 2 (128-wide)
+  const int tn = tid % TBN, tg = tid / TBN;
+  int tci[TN / 4], ttap[TN / 4];
+#pragma unroll
+  for (int u = 0; u < TN / 4; ++u) {
+    const int kk = 4 * (tg + kGroupsPerPass * u);
+    ttap[u] = kk / g.CI; tci[u] = kk - ttap[u] * g.CI;
+  }
+
+  auto load_a = [&](int u) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (apv && ktap[u] < g.fr * g.fc) {
+      int iy, ix;
+      bool ok = true;
+      if (g.form == 0) {
+        iy = ay * g.s + kr[u] * g.D - g.pr;
+        ix = ax * g.s + kt[u] * g.D - g.pc;
+      } else {
+        const int ny = ay + g.pr - kr[u] * g.D, nx = ax + g.pc - kt[u] * g.D;
+        ok = ny >= 0 && nx >= 0 && (ny % g.s) == 0 && (nx % g.s) == 0;
+        iy = ny / g.s; ix = nx / g.s;
+      }
+      if (ok && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
+        v = *reinterpret_cast<const float4*>(aimg + ((int64_t)iy * g.IW + ix) * g.CI + kci[u]);
+    }
+    return v;
+  };
+  auto advance_a = [&]() {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      kci[u] += TBK;
+      while (kci[u] >= g.CI) {
+        kci[u] -= g.CI; ++ktap[u];
+        if (++kt[u] == g.fc) { kt[u] = 0; ++kr[u]; }
+      }
+    }
+  };
+  auto load_b = [&](float (&bv)[TN]) {
+    if (b_trans) {
+#pragma unroll
+      for (int u = 0; u < TN / 4; ++u) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ttap[u] < g.fr * g.fc && n0 + tn < g.CO)
+          q = *reinterpret_cast<const float4*>(w + (int64_t)ttap[u] * g.w_tap + (int64_t)(n0 + tn) * g.w_co + tci[u]);
+        bv[4 * u] = q.x; bv[4 * u + 1] = q.y; bv[4 * u + 2] = q.z; bv[4 * u + 3] = q.w;
+      }
+      return;
+    }
+    const bool kv = btap < g.fr * g.fc;
+    const float* src = w + (int64_t)btap * g.w_tap + (int64_t)bci * g.w_ci;
+#pragma unroll
+    for (int v = 0; v < TN / 4; ++v) {
+      const int co = n0 + bc + 64 * v;
+      if (g.w_co == 1 && kv && co + 3 < g.CO) {
+        const float4 q = *reinterpret_cast<const float4*>(src + co);
+        bv[4 * v] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bv[4 * v + e] = (kv && co + e < g.CO) ? src[(int64_t)(co + e) * g.w_co] : 0.f;
+      }
+    }
+  };
+  auto advance_b = [&]() {
+    bci += TBK;
+    while (bci >= g.CI) { bci -= g.CI; ++btap; }
+#pragma unroll
+    for (int u = 0; u < TN / 4; ++u) {
+      tci[u] += TBK;
+      while (tci[u] >= g.CI) { tci[u] -= g.CI; ++ttap[u]; }
+    }
+  };
+  auto store_tile = [&](int buf, const float4 (&av)[2], const float (&bv)[TN]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = 4 * (ag + 2 * u);
+      As[buf][k][am] = av[u].x; As[buf][k + 1][am] = av[u].y; As[buf][k + 2][am] = av[u].z; As[buf][k + 3][am] = av[u].w;
+    }
+    if (b_trans) {
+#pragma unroll
+      for (int u = 0; u < TN / 4; ++u) {
+        const int k = 4 * (tg + kGroupsPerPass * u);
+        Bs[buf][k][tn] = bv[4 * u]; Bs[buf][k + 1][tn] = bv[4 * u + 1]; Bs[buf][k + 2][tn] = bv[4 * u + 2]; Bs[buf][k + 3][tn] = bv[4 * u + 3];
+      }
+      return;
+    }
+#pragma unroll
+    for (int v = 0; v < TN / 4; ++v)
+      *reinterpret_cast<float4*>(&Bs[buf][bk][bc + 64 * v]) = make_float4(bv[4 * v], bv[4 * v + 1], bv[4 * v + 2], bv[4 * v + 3]);
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;                 // outputs: rows 4 ty + {0..3} (+ 64), columns 4 tx + {0..3} (+ 64)
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 av[2];
+  float bv[TN];
+  av[0] = load_a(0); av[1] = load_a(1);
+  load_b(bv);
+  store_tile(0, av, bv);
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1;
+    const bool more = kb + 1 < nkb;
+    if (more) {
+      advance_a(); advance_b();
+      av[0] = load_a(0); av[1] = load_a(1);
+      load_b(bv);
+    }
+#pragma unroll
+    for (int k = 0; k < TBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[TN];
+#pragma unroll
+      for (int v = 0; v < TN / 4; ++v) {
+        const float4 q = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4 + 64 * v]);
+        b[4 * v] = q.x; b[4 * v + 1] = q.y; b[4 * v + 2] = q.z; b[4 * v + 3] = q.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) store_tile(buf ^ 1, av, bv);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t p = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (p >= P) continue;
+#pragma unroll
+    for (int v = 0; v < TN / 4; ++v) {
+      const int co = n0 + tx * 4 + 64 * v;
+      if (co >= g.CO) continue;                          // CO % 4 == 0: a group of four is all in or all out
+      float z[4], y[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        z[e] = acc[i][4 * v + e] + (bias ? bias[co + e] : 0.f);
+        y[e] = Y ? post_affine(g, co + e, act_fn(g.act, z[e], g.p0, g.p1)) : 0.f;
+      }
+      if (Z) *reinterpret_cast<float4*>(Z + p * g.CO + co) = make_float4(z[0], z[1], z[2], z[3]);
+      if (Y) *reinterpret_cast<float4*>(Y + p * g.CO + co) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+  }
+}
+
 // ---- wgrad: split over pixel chunks, partials to workspace -----------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(NT) wgrad_partial_kernel(GatherWgrad g, const T* __restrict__ in,
@@ -452,6 +648,135 @@ __global__ void __launch_bounds__(1024) thin_m_wgrad_kernel(GatherWgrad g, const
   else part_db[(int64_t)blockIdx.x * g.CO + co] = acc;
 }
 
+// ---- wgrad, register-tiled (fp32 storage, in_ch % 4 == 0, out_ch % 4 == 0): the same 128 x (16 TN) tile as
+// gather_conv_rt_kernel with the pixels as the reduction dimension.  Both operands are read 16 bytes at a time along
+// their channel dimension and land in shared memory without a transpose; a thread's pixel coordinates advance
+// incrementally (no division in the loop).
+template <int TN>
+__global__ void __launch_bounds__(256, 2) wgrad_partial_rt_kernel(GatherWgrad g, const float* __restrict__ in,
+                                                                  const float* __restrict__ grad, float* __restrict__ part,
+                                                                  int64_t chunk) {
+  constexpr int TBM = 128, TBN = 16 * TN, TBK = 16;
+  __shared__ __align__(16) float As[2][TBK][TBM];
+  __shared__ __align__(16) float Bs[2][TBK][TBN];
+  const int tid = threadIdx.x;
+  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int M = g.fr * g.fc * g.CI;
+  const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+  const int64_t p_begin = (int64_t)blockIdx.z * chunk;
+  const int64_t p_end = (p_begin + chunk < P) ? p_begin + chunk : P;
+  const int nkb = (int)((p_end - p_begin + TBK - 1) / TBK);
+
+  // A: thread -> four consecutive rows m (one tap, four in_ch) of pixels ka and ka + 8 of the K block
+  const int am = m0 + (tid & 31) * 4, ka = tid >> 5;
+  const bool mv = am < M;
+  const int tap = mv ? am / g.CI : 0, ci = mv ? am - tap * g.CI : 0;
+  const int r = tap / g.fc, t = tap - r * g.fc;
+  int px[2], py[2], pn[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    int64_t q = p_begin + ka + 8 * u;
+    if (q >= P) q = P - 1;                                // (never loaded: p < p_end is checked)
+    px[u] = (int)(q % g.OW); q /= g.OW;
+    py[u] = (int)(q % g.OH); pn[u] = (int)(q / g.OH);
+  }
+  // B: thread -> pixel bk = tid / 16 of the K block, columns 4 (tid % 16) + 64 v
+  const int bk = tid >> 4, bc = (tid & 15) * 4;
+
+  auto load_a = [&](int kb, int u) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t p = p_begin + (int64_t)kb * TBK + ka + 8 * u;
+    if (mv && p < p_end) {
+      const int iy = py[u] * g.s + r * g.D - g.pr, ix = px[u] * g.s + t * g.D - g.pc;
+      if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
+        v = *reinterpret_cast<const float4*>(in + (((int64_t)pn[u] * g.IH + iy) * g.IW + ix) * g.CI + ci);
+    }
+    return v;
+  };
+  auto advance_a = [&]() {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      px[u] += TBK;
+      while (px[u] >= g.OW) {
+        px[u] -= g.OW;
+        if (++py[u] == g.OH) { py[u] = 0; ++pn[u]; }
+      }
+    }
+  };
+  auto load_b = [&](int kb, float (&bv)[TN]) {
+    const int64_t p = p_begin + (int64_t)kb * TBK + bk;
+#pragma unroll
+    for (int v = 0; v < TN / 4; ++v) {
+      const int co = n0 + bc + 64 * v;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < p_end && co < g.CO) q = *reinterpret_cast<const float4*>(grad + p * g.CO + co);
+      bv[4 * v] = q.x; bv[4 * v + 1] = q.y; bv[4 * v + 2] = q.z; bv[4 * v + 3] = q.w;
+    }
+  };
+  auto store_tile = [&](int buf, const float4 (&av)[2], const float (&bv)[TN]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) *reinterpret_cast<float4*>(&As[buf][ka + 8 * u][(tid & 31) * 4]) = av[u];
+#pragma unroll
+    for (int v = 0; v < TN / 4; ++v)
+      *reinterpret_cast<float4*>(&Bs[buf][bk][bc + 64 * v]) = make_float4(bv[4 * v], bv[4 * v + 1], bv[4 * v + 2], bv[4 * v + 3]);
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float4 av[2];
+  float bv[TN];
+  if (nkb > 0) {
+    av[0] = load_a(0, 0); av[1] = load_a(0, 1);
+    load_b(0, bv);
+    store_tile(0, av, bv);
+  }
+  __syncthreads();
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int buf = kb & 1;
+    const bool more = kb + 1 < nkb;
+    if (more) {
+      advance_a();
+      av[0] = load_a(kb + 1, 0); av[1] = load_a(kb + 1, 1);
+      load_b(kb + 1, bv);
+    }
+#pragma unroll
+    for (int k = 0; k < TBK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[TN];
+#pragma unroll
+      for (int v = 0; v < TN / 4; ++v) {
+        const float4 q = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4 + 64 * v]);
+        b[4 * v] = q.x; b[4 * v + 1] = q.y; b[4 * v + 2] = q.z; b[4 * v + 3] = q.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) store_tile(buf ^ 1, av, bv);
+    __syncthreads();
+  }
+  float* out = part + (int64_t)blockIdx.z * M * g.CO;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int v = 0; v < TN / 4; ++v) {
+      const int co = n0 + tx * 4 + 64 * v;
+      if (co < g.CO)
+        *reinterpret_cast<float4*>(out + (int64_t)m * g.CO + co) =
+            make_float4(acc[i][4 * v], acc[i][4 * v + 1], acc[i][4 * v + 2], acc[i][4 * v + 3]);
+    }
+  }
+}
+
 }  // namespace
 
 // Fixed-order reduction of split partials [splits][M][CO] -> dW (strided), shared with the tensor-core wgrad
@@ -702,6 +1027,20 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
     NPML_LAUNCH_OK();
     return 0;
   }
+  if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 16 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 4096 && !getenv("NPML_DISABLE_FP32_RT")) {
+    // register-tiled kernel: 128-wide N tile for wide outputs, 64-wide otherwise
+    if (g.CO > 64) {
+      dim3 grid((unsigned)((P + 127) / 128), (unsigned)((g.CO + 127) / 128));
+      gather_conv_rt_kernel<8><<<grid, 256, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
+    } else {
+      dim3 grid((unsigned)((P + 127) / 128), (unsigned)((g.CO + 63) / 64));
+      gather_conv_rt_kernel<4><<<grid, 256, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
+    }
+    NPML_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((g.CO + BN - 1) / BN));
   if (dtype == NPML_F32)
     gather_conv_kernel<float, float><<<grid, NT, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
@@ -769,6 +1108,20 @@ int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* 
   }
   int64_t chunk = (P + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
+  if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 4 && M >= 64 && P >= 4096 &&
+      (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && !getenv("NPML_DISABLE_FP32_RT")) {
+    if (g.CO > 64) {
+      dim3 grid((M + 127) / 128, (g.CO + 127) / 128, splits);
+      wgrad_partial_rt_kernel<8><<<grid, 256, 0, st>>>(g, (const float*)in, (const float*)grad, (float*)ws, chunk);
+    } else {
+      dim3 grid((M + 127) / 128, (g.CO + 63) / 64, splits);
+      wgrad_partial_rt_kernel<4><<<grid, 256, 0, st>>>(g, (const float*)in, (const float*)grad, (float*)ws, chunk);
+    }
+    NPML_LAUNCH_OK();
+    return launch_wgrad_reduce((const float*)ws, splits, M, g.CO, g.CI, g.o_tap, g.o_ci, g.o_co, g.accumulate,
+                               dW, st);
+  }
   dim3 grid((M + BM - 1) / BM, (g.CO + BN - 1) / BN, splits);
   if (dtype == NPML_F32)
     wgrad_partial_kernel<float><<<grid, NT, 0, st>>>(g, (const float*)in, (const float*)grad, (float*)ws, chunk);
