@@ -43,11 +43,20 @@ def test_workspace_query_and_tc_predicate_without_gpu():
     U, L = pkg.utils, pkg._lib
     d = U.make_desc(256, 56, 56, 64, 64, 3, 3, 1, 1, (1, 1, 1, 1), 56, 56, "bf16")
     lib = L.load()
-    for op in range(8):
+    for op in range(9):
         assert lib.npml_workspace_bytes(d, op) >= 256
     assert lib.npml_uses_tensor_cores(d, L.OP_CONV_FPROP) in (0, 1)
     d1 = U.make_desc(32, 28, 28, 1, 32, 3, 3, 1, 1, (1, 1, 1, 1), 28, 28, "bf16")
     assert lib.npml_uses_tensor_cores(d1, L.OP_CONV_FPROP) == 0      # in_ch = 1 -> CUDA-core path
+    # the one-launch backward (csrc/thin_bwd.cu) takes thin stride-1 'same' shapes only; its planner runs without a GPU
+    assert lib.npml_conv2d_bwd_is_fused(d1) == 1                      # cfg1
+    assert lib.npml_workspace_bytes(d1, L.OP_CONV_BWD) >= 256 + (3 * 3 * 1 + 1) * 32 * 4
+    assert lib.npml_conv2d_bwd_is_fused(d) == 0                       # cfg2: 64 input channels
+    for bad in (U.make_desc(32, 28, 28, 1, 32, 3, 3, 2, 1, (1, 1, 1, 1), 14, 14, "bf16"),      # stride 2
+                U.make_desc(32, 28, 28, 1, 32, 3, 3, 1, 1, (0, 0, 0, 0), 26, 26, "bf16"),      # 'valid': output != input size
+                U.make_desc(32, 28, 28, 1, 24, 3, 3, 1, 1, (1, 1, 1, 1), 28, 28, "bf16"),      # 6 lanes per pixel: not a power of two
+                U.make_desc(32, 28, 28, 8, 32, 3, 3, 1, 1, (1, 1, 1, 1), 28, 28, "bf16")):     # in_ch > 4
+        assert lib.npml_conv2d_bwd_is_fused(bad) == 0
 
 
 def test_geometry_against_reference_golden():
