@@ -128,18 +128,29 @@ __global__ void __launch_bounds__(NT) gather_conv_kernel(GatherConv g, const TIn
 // tile, 8 x TN outputs per thread (four 16-byte shared loads per 16 TN FMAs), 16-byte gathers along in_ch with the tap
 // walked incrementally (no division in the loop), operands of the next K block in registers while the current one is
 // multiplied, and two shared-memory buffers (one barrier per K block).
+// One launch covers one output parity class: the outputs (y0 + so yy, x0 + so xx) and the taps that reach them, as
+// offsets into the input: iy = yy * sin + dy[j].  The forward form (Conv2D.forward, Deconv2D dX) is ONE class with every
+// tap (so = 1, sin = stride); the transposed form (Conv2D dX, Deconv2D.forward) with stride s has s^2 classes with a
+// fraction of the taps each and sin = 1 -- walking all taps under a divisibility predicate instead wasted 3/4 of the
+// FMAs of a stride-2 problem (fp32 mode: cfg5 forward 4.0 ms, cfg3 dX 2.0 ms against 1.0 / 0.3 ms for their adjoints).
+constexpr int kRtMaxTaps = 64;
+struct RtClass {
+  int ntaps, y0, x0, so, sin, oh, ow;
+  int16_t dy[kRtMaxTaps], dx[kRtMaxTaps], wt[kRtMaxTaps];    // input offset and filter tap (index into W) of tap j
+};
+
 template <int TN>                                       // output channels per thread: 4 (64-wide tile) or 8 (128-wide)
-__global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, const float* __restrict__ in,
+__global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, const RtClass c, const float* __restrict__ in,
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              float* __restrict__ Z, float* __restrict__ Y) {
   constexpr int TBM = 128, TBN = 16 * TN, TBK = 16;
   __shared__ __align__(16) float As[2][TBK][TBM];
   __shared__ __align__(16) float Bs[2][TBK][TBN];
   const int tid = threadIdx.x;
-  const int64_t P = (int64_t)g.N * g.OH * g.OW;
+  const int64_t P = (int64_t)g.N * c.oh * c.ow;           // output pixels of this class
   const int64_t m0 = (int64_t)blockIdx.x * TBM;
   const int n0 = blockIdx.y * TBN;
-  const int Ktot = g.fr * g.fc * g.CI;
+  const int Ktot = c.ntaps * g.CI;
   const int nkb = (Ktot + TBK - 1) / TBK;
 
   // A gather: thread -> pixel am = tid % 128, k groups ag and ag + 2 (four consecutive in_ch each)
@@ -149,17 +160,16 @@ __global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, co
   int ax, ay, an;
   {
     int64_t q = apv ? ap : 0;
-    ax = (int)(q % g.OW); q /= g.OW;
-    ay = (int)(q % g.OH); an = (int)(q / g.OH);
+    ax = (int)(q % c.ow); q /= c.ow;
+    ay = (int)(q % c.oh); an = (int)(q / c.oh);
   }
   const float* aimg = in + (int64_t)an * g.IH * g.IW * g.CI;
   // (tap, ci) of this thread's two k groups, advanced by 16 per K block without dividing
-  int kci[2], ktap[2], kr[2], kt[2];
+  int kci[2], ktap[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int kk = 4 * (ag + 2 * u);
     ktap[u] = kk / g.CI; kci[u] = kk - ktap[u] * g.CI;
-    kr[u] = ktap[u] / g.fc; kt[u] = ktap[u] - kr[u] * g.fc;
   }
   // B load: thread -> k row bk = tid / 16 (16 rows), columns 4 * (tid % 16) + 64 * v
   const int bk = tid >> 4, bc = (tid & 15) * 4;
@@ -178,18 +188,9 @@ __global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, co
 
   auto load_a = [&](int u) -> float4 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (apv && ktap[u] < g.fr * g.fc) {
-      int iy, ix;
-      bool ok = true;
-      if (g.form == 0) {
-        iy = ay * g.s + kr[u] * g.D - g.pr;
-        ix = ax * g.s + kt[u] * g.D - g.pc;
-      } else {
-        const int ny = ay + g.pr - kr[u] * g.D, nx = ax + g.pc - kt[u] * g.D;
-        ok = ny >= 0 && nx >= 0 && (ny % g.s) == 0 && (nx % g.s) == 0;
-        iy = ny / g.s; ix = nx / g.s;
-      }
-      if (ok && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
+    if (apv && ktap[u] < c.ntaps) {
+      const int iy = ay * c.sin + c.dy[ktap[u]], ix = ax * c.sin + c.dx[ktap[u]];
+      if (iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW)
         v = *reinterpret_cast<const float4*>(aimg + ((int64_t)iy * g.IW + ix) * g.CI + kci[u]);
     }
     return v;
@@ -198,10 +199,7 @@ __global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, co
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       kci[u] += TBK;
-      while (kci[u] >= g.CI) {
-        kci[u] -= g.CI; ++ktap[u];
-        if (++kt[u] == g.fc) { kt[u] = 0; ++kr[u]; }
-      }
+      while (kci[u] >= g.CI) { kci[u] -= g.CI; ++ktap[u]; }
     }
   };
   auto load_b = [&](float (&bv)[TN]) {
@@ -209,14 +207,14 @@ __global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, co
 #pragma unroll
       for (int u = 0; u < TN / 4; ++u) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ttap[u] < g.fr * g.fc && n0 + tn < g.CO)
-          q = *reinterpret_cast<const float4*>(w + (int64_t)ttap[u] * g.w_tap + (int64_t)(n0 + tn) * g.w_co + tci[u]);
+        if (ttap[u] < c.ntaps && n0 + tn < g.CO)
+          q = *reinterpret_cast<const float4*>(w + (int64_t)c.wt[ttap[u]] * g.w_tap + (int64_t)(n0 + tn) * g.w_co + tci[u]);
         bv[4 * u] = q.x; bv[4 * u + 1] = q.y; bv[4 * u + 2] = q.z; bv[4 * u + 3] = q.w;
       }
       return;
     }
-    const bool kv = btap < g.fr * g.fc;
-    const float* src = w + (int64_t)btap * g.w_tap + (int64_t)bci * g.w_ci;
+    const bool kv = btap < c.ntaps;
+    const float* src = w + (int64_t)(kv ? c.wt[btap] : 0) * g.w_tap + (int64_t)bci * g.w_ci;
 #pragma unroll
     for (int v = 0; v < TN / 4; ++v) {
       const int co = n0 + bc + 64 * v;
@@ -300,8 +298,15 @@ __global__ void __launch_bounds__(256, 2) gather_conv_rt_kernel(GatherConv g, co
 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int64_t p = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    if (p >= P) continue;
+    const int64_t pc = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (pc >= P) continue;
+    int64_t p = pc;                                      // class pixel -> pixel of the whole output
+    if (c.so != 1 || c.oh != g.OH || c.ow != g.OW) {
+      const int xx = (int)(pc % c.ow);
+      const int64_t q = pc / c.ow;
+      const int yy = (int)(q % c.oh), nn = (int)(q / c.oh);
+      p = ((int64_t)nn * g.OH + c.y0 + c.so * yy) * g.OW + c.x0 + c.so * xx;
+    }
 #pragma unroll
     for (int v = 0; v < TN / 4; ++v) {
       const int co = n0 + tx * 4 + 64 * v;
@@ -1029,16 +1034,48 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
   }
   if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 16 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 4096 && !getenv("NPML_DISABLE_FP32_RT")) {
-    // register-tiled kernel: 128-wide N tile for wide outputs, 64-wide otherwise
-    if (g.CO > 64) {
-      dim3 grid((unsigned)((P + 127) / 128), (unsigned)((g.CO + 127) / 128));
-      gather_conv_rt_kernel<8><<<grid, 256, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
-    } else {
-      dim3 grid((unsigned)((P + 127) / 128), (unsigned)((g.CO + 63) / 64));
-      gather_conv_rt_kernel<4><<<grid, 256, 0, st>>>(g, (const float*)in, w, bias, (float*)Z, (float*)Y);
-    }
-    NPML_LAUNCH_OK();
+      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 4096 && g.fr * g.fc <= kRtMaxTaps &&
+      !getenv("NPML_DISABLE_FP32_RT")) {
+    // register-tiled kernel, one launch per output parity class: 128-wide N tile for wide outputs, 64-wide otherwise
+    auto pm = [](int a, int b) { const int m = a % b; return m < 0 ? m + b : m; };
+    const int nq = g.form == 1 ? g.s : 1;
+    for (int qy = 0; qy < nq; ++qy)
+      for (int qx = 0; qx < nq; ++qx) {
+        RtClass c;
+        memset(&c, 0, sizeof(c));
+        if (g.form == 0) {
+          c.y0 = 0; c.x0 = 0; c.so = 1; c.sin = g.s; c.oh = g.OH; c.ow = g.OW;
+          for (int r = 0; r < g.fr; ++r)
+            for (int t = 0; t < g.fc; ++t) {
+              c.dy[c.ntaps] = (int16_t)(r * g.D - g.pr); c.dx[c.ntaps] = (int16_t)(t * g.D - g.pc);
+              c.wt[c.ntaps++] = (int16_t)(r * g.fc + t);
+            }
+        } else {
+          // outputs y = y0 + s yy see the taps with (y + pr - r D) % s == 0, i.e. (r D) % s == qy where y0 = (qy - pr) mod s
+          c.y0 = pm(qy - g.pr, g.s); c.x0 = pm(qx - g.pc, g.s); c.so = g.s; c.sin = 1;
+          if (c.y0 >= g.OH || c.x0 >= g.OW) continue;
+          c.oh = (g.OH - c.y0 + g.s - 1) / g.s; c.ow = (g.OW - c.x0 + g.s - 1) / g.s;
+          for (int r = 0; r < g.fr; ++r) {
+            if (pm(r * g.D, g.s) != qy) continue;
+            for (int t = 0; t < g.fc; ++t) {
+              if (pm(t * g.D, g.s) != qx) continue;
+              c.dy[c.ntaps] = (int16_t)((c.y0 + g.pr - r * g.D) / g.s);      // exact by construction
+              c.dx[c.ntaps] = (int16_t)((c.x0 + g.pc - t * g.D) / g.s);
+              c.wt[c.ntaps++] = (int16_t)(r * g.fc + t);
+            }
+          }
+        }
+        const int64_t Pc = (int64_t)g.N * c.oh * c.ow;
+        if (Pc == 0) continue;
+        if (g.CO > 64) {
+          dim3 grid((unsigned)((Pc + 127) / 128), (unsigned)((g.CO + 127) / 128));
+          gather_conv_rt_kernel<8><<<grid, 256, 0, st>>>(g, c, (const float*)in, w, bias, (float*)Z, (float*)Y);
+        } else {
+          dim3 grid((unsigned)((Pc + 127) / 128), (unsigned)((g.CO + 63) / 64));
+          gather_conv_rt_kernel<4><<<grid, 256, 0, st>>>(g, c, (const float*)in, w, bias, (float*)Z, (float*)Y);
+        }
+        NPML_LAUNCH_OK();
+      }
     return 0;
   }
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((g.CO + BN - 1) / BN));

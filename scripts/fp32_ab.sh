@@ -4,7 +4,7 @@ tag=$1
 timeout 900 python -m pytest tests -m gpu -x -q -k "fp32" > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log; tail -3 gpurun_out/${tag}_pytest.log
 for v in on off; do
   if [ $v = off ]; then export NPML_DISABLE_FP32_RT=1; else unset NPML_DISABLE_FP32_RT; fi
-  for c in cfg2; do
+  for c in cfg2 cfg3 cfg5; do
     timeout 300 python bench.py --config $c --mode fp32 --single --no-cpu --no-e2e --steps 5 --warmup 3 > gpurun_out/${tag}_${c}_fp32_$v.json 2> gpurun_out/${tag}_${c}_$v.err || tail -3 gpurun_out/${tag}_${c}_$v.err
     python - "gpurun_out/${tag}_${c}_fp32_$v.json" <<'P'
 import json,sys
