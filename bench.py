@@ -639,8 +639,9 @@ def measure(ctx, cfg, headline):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             out["e2e_dropin"] = {"value": n / dt, "unit": "images/s", "ms_per_step": 1e3 * dt,
-                                 "h2d_bytes_per_step": int((Xn.size + dYn.size) * 4), "d2h_bytes_per_step": int((Yn.size + dXn.size) * 4),
-                                 "api": "layer.forward(np.float64) / layer.backward(np.float64) -> np.float64 (wall clock)"}
+                                 "h2d_bytes_per_step": int((Xn.size + dYn.size) * 8), "d2h_bytes_per_step": int((Yn.size + dXn.size) * 8),
+                                 "api": "layer.forward(np.float64) / layer.backward(np.float64) -> np.float64 (wall clock; the float64 bytes cross PCIe, "
+                                        "the dtype conversions run on the device)"}
             del Xn, dYn, Yn, dXn
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------------

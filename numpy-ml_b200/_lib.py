@@ -172,6 +172,9 @@ def torch_dtype(mode):
     return torch.bfloat16 if mode == "bf16" else torch.float32
 
 
+_F64_ON_DEVICE = 1 << 16     # elements from which float64 <-> device dtype conversions run on the device
+
+
 def code_of(t):
     return {torch.float32: F32, torch.bfloat16: BF16, torch.float64: F64}[t.dtype]
 
@@ -188,7 +191,12 @@ def cast(t, dtype):
 def to_device(x, dtype):
     """NumPy array (any float dtype) or torch tensor -> contiguous device tensor of `dtype`."""
     if isinstance(x, np.ndarray):
-        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device(), non_blocking=False)
+        if x.dtype == np.float64 and x.size >= _F64_ON_DEVICE:
+            # the reference's own dtype: ship the float64 bytes and round on the device (npml_cast, round-to-nearest like
+            # ndarray.astype) -- the host-side astype of a 51 M element batch costs more than the extra PCIe bytes
+            t = torch.from_numpy(np.ascontiguousarray(x)).to(device(), non_blocking=False)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(device(), non_blocking=False)
     elif isinstance(x, torch.Tensor):
         t = x if x.is_cuda else x.to(device())
         if not t.is_contiguous():
@@ -206,7 +214,10 @@ def to_numpy(t):
         return t
     if isinstance(t, (list, tuple)):
         return [to_numpy(v) for v in t]
-    return cast(t.detach(), torch.float32).cpu().numpy().astype(np.float64)
+    t = t.detach()
+    if t.numel() >= _F64_ON_DEVICE:
+        return cast(t, torch.float64).cpu().numpy()          # widen on the device, not with a host-side astype
+    return cast(t, torch.float32).cpu().numpy().astype(np.float64)
 
 
 _ws = {}
