@@ -1034,7 +1034,7 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
   }
   if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 16 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 4096 && g.fr * g.fc <= kRtMaxTaps &&
+      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 256 && g.fr * g.fc <= kRtMaxTaps &&
       !getenv("NPML_DISABLE_FP32_RT")) {
     // register-tiled kernel, one launch per output parity class: 128-wide N tile for wide outputs, 64-wide otherwise
     auto pm = [](int a, int b) { const int m = a % b; return m < 0 ? m + b : m; };
@@ -1145,7 +1145,7 @@ int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* 
   }
   int64_t chunk = (P + splits - 1) / splits;
   chunk = (chunk + BK - 1) / BK * BK;
-  if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 4 && M >= 64 && P >= 4096 &&
+  if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 4 && M >= 64 && P >= 256 &&
       (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(ws) & 15) == 0 && !getenv("NPML_DISABLE_FP32_RT")) {
     if (g.CO > 64) {
