@@ -189,22 +189,28 @@ __global__ void __launch_bounds__(256) col_pass_kernel(F f, ColGeom cg, Acc* __r
   }
 }
 
-// Fixed-order sum of column `c` over the `nblk` partial rows, for a (32, 32) thread block: thread (cx, sy) adds
-// rows sy, sy + 32, ...; the 32 row-lanes are then added in order by every thread of the column (deterministic).
+// Fixed-order sum of column `c` over the `nblk` partial rows, for an (8, 128) thread block: thread (cx, sy) adds rows
+// sy, sy + 128, ... (5 for the usual 592 partial rows; the (32, 32) shape of round 1 walked 19 per thread on a quarter of
+// the blocks: these kernels are nothing but that chain of L2 round trips), then 128 -> 8 lanes -> 1 in a fixed order.
+constexpr int kFinCols = 8, kFinRows = 128;
 template <typename Acc>
 __device__ __forceinline__ double block_col_sum(const Acc* __restrict__ part, int nblk, int width, int c, bool ok,
-                                                double (*red)[33]) {
+                                                double (*red)[kFinCols + 1]) {
   const int cx = threadIdx.x, sy = threadIdx.y;
-  // (a hand-unrolled version with eight loads in flight per thread measured SLOWER, in the step and under ncu: 27.5 vs
-  // 14.2 us for bn_bwd_finalize_kernel with a cold L2 -- the compiler already pipelines this loop)
   double s = 0.0;
   if (ok)
-    for (int b = sy; b < nblk; b += 32) s += (double)part[(int64_t)b * width + c];
+    for (int b = sy; b < nblk; b += kFinRows) s += (double)part[(int64_t)b * width + c];
   __syncthreads();
   red[sy][cx] = s;
   __syncthreads();
+  if (sy < 8) {
+    double t = 0.0;
+    for (int y = 0; y < 16; ++y) t += red[sy * 16 + y][cx];
+    red[sy * 16][cx] = t;                      // (row sy * 16 is read by this thread only)
+  }
+  __syncthreads();
   double t = 0.0;
-  for (int y = 0; y < 32; ++y) t += red[y][cx];
+  for (int y = 0; y < 8; ++y) t += red[y * 16][cx];
   return t;
 }
 
@@ -636,8 +642,8 @@ __global__ void bn_pair_bwd_finalize_kernel(int ch, int accumulate, double inv_m
 
 // part [nblk][width] -> sums[width] (double), fixed order
 __global__ void col_sums_kernel(const double* __restrict__ part, int nblk, int width, double* __restrict__ sums) {
-  __shared__ double red[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double red[kFinRows][kFinCols + 1];
+  const int c = blockIdx.x * kFinCols + threadIdx.x;
   const double s = block_col_sum<double>(part, nblk, width, c, c < width, red);
   if (threadIdx.y == 0 && c < width) sums[c] = s;
 }
@@ -673,8 +679,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ part, int nblk, in
                                    float eps, float* running_mean, float* running_var, float* save_mean,
                                    float* save_rstd, const float* scaler, const float* intercept, float* coef,
                                    const double* __restrict__ sums_in) {
-  __shared__ double red[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double red[kFinRows][kFinCols + 1];
+  const int c = blockIdx.x * kFinCols + threadIdx.x;
   double s1, s2;
   if (sums_in != nullptr) {
     s1 = c < ch ? sums_in[c] : 0.0;
@@ -730,8 +736,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ part, int nblk
                                        float* d_scaler, float* d_intercept, double inv_m, const float* mean,
                                        const float* rstd, const float* scaler, float* coef,
                                        const double* __restrict__ sums_local, const double* __restrict__ sums_global) {
-  __shared__ double red[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  __shared__ double red[kFinRows][kFinCols + 1];
+  const int c = blockIdx.x * kFinCols + threadIdx.x;
   double s1, s2, l1, l2;
   if (sums_global != nullptr) {
     s1 = c < ch ? sums_global[c] : 0.0;
@@ -1141,7 +1147,7 @@ extern "C" int npml_bn2d_fwd(int64_t rows, int32_t ch, const void* x, void* y, i
   if (use_batch_stats) {
     BnStatsF fs{x, dtype};
     if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
-    bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, 1.0 / (double)rows, momentum, eps,
+    bn_finalize_kernel<<<(ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(part, (int)p.grid.x, ch, 1.0 / (double)rows, momentum, eps,
                                                                 running_mean, running_var, save_mean, save_rstd, scaler,
                                                                 intercept, coef, nullptr);
     NPML_LAUNCH_OK();
@@ -1170,7 +1176,7 @@ extern "C" int npml_bn2d_bwd(int64_t rows, int32_t ch, const void* dy, const voi
   float* coef = (float*)((char*)ws + part_bytes + sums_bytes);
   BnBwdStatsF fs{dy, x, dtype};
   if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
-  bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
+  bn_bwd_finalize_kernel<<<(ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
                                                                   1.0 / (double)rows, save_mean, save_rstd, scaler, coef,
                                                                   nullptr, nullptr);
   NPML_LAUNCH_OK();
@@ -1199,7 +1205,7 @@ extern "C" int npml_bn2d_stats(int64_t rows, int32_t ch, const void* x, int32_t 
   double* part = (double*)ws;
   BnStatsF fs{x, dtype};
   if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
-  col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
+  col_sums_kernel<<<(2 * ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
   NPML_LAUNCH_OK();
   return 0;
 }
@@ -1213,7 +1219,7 @@ extern "C" int npml_bn2d_apply(int64_t rows, int64_t rows_total, int32_t ch, con
   NPML_CHECK(sums && save_mean && save_rstd && rows_total >= rows, "bad arguments");
   NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)3 * ch * sizeof(float), "workspace too small");
   float* coef = (float*)ws;
-  bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(nullptr, 0, ch, 1.0 / (double)rows_total, momentum, eps,
+  bn_finalize_kernel<<<(ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(nullptr, 0, ch, 1.0 / (double)rows_total, momentum, eps,
                                                               running_mean, running_var, save_mean, save_rstd, scaler,
                                                               intercept, coef, sums);
   NPML_LAUNCH_OK();
@@ -1234,7 +1240,7 @@ extern "C" int npml_bn2d_bwd_stats(int64_t rows, int32_t ch, const void* dy, con
   double* part = (double*)ws;
   BnBwdStatsF fs{dy, x, dtype};
   if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
-  col_sums_kernel<<<(2 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
+  col_sums_kernel<<<(2 * ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(part, (int)p.grid.x, 2 * ch, sums);
   NPML_LAUNCH_OK();
   bwd_stats_fix_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, sums, save_mean, save_rstd);
   NPML_LAUNCH_OK();
@@ -1250,7 +1256,7 @@ extern "C" int npml_bn2d_bwd_apply(int64_t rows, int64_t rows_total, int32_t ch,
   NPML_CHECK(sums_local && sums_global && rows_total >= rows, "bad arguments");
   NPML_CHECK(ws != nullptr && ws_bytes >= (size_t)5 * ch * sizeof(float), "workspace too small");
   float* coef = (float*)ws;
-  bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(nullptr, 0, ch, accumulate, d_scaler, d_intercept,
+  bn_bwd_finalize_kernel<<<(ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(nullptr, 0, ch, accumulate, d_scaler, d_intercept,
                                                                   1.0 / (double)rows_total, save_mean, save_rstd, scaler,
                                                                   coef, sums_local, sums_global);
   NPML_LAUNCH_OK();
@@ -1285,7 +1291,7 @@ extern "C" int npml_bn2d_bwd_act(int64_t rows, int64_t rows_total, int32_t ch, c
     BnBwdStatsF fs{dy, x, dtype};
     if (int e = launch_col_pass<2, double>(p, fs, part, st, dtype)) return e;
   }
-  bn_bwd_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
+  bn_bwd_finalize_kernel<<<(ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(part, (int)p.grid.x, ch, accumulate, d_scaler, d_intercept,
                                                                   1.0 / (double)rows_total, save_mean, save_rstd, scaler, coef,
                                                                   sums_local, sums_global);
   NPML_LAUNCH_OK();
@@ -1300,7 +1306,7 @@ extern "C" int npml_bn2d_finalize(int64_t rows_total, int32_t ch, const double* 
                                   void* stream) {
   if (ch <= 0) return 0;
   NPML_CHECK(sums && running_mean && running_var && save_mean && save_rstd && rows_total > 0, "bad arguments");
-  bn_finalize_kernel<<<(ch + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(nullptr, 0, ch, 1.0 / (double)rows_total,
+  bn_finalize_kernel<<<(ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, (cudaStream_t)stream>>>(nullptr, 0, ch, 1.0 / (double)rows_total,
                                                                                momentum, eps, running_mean, running_var,
                                                                                save_mean, save_rstd, nullptr, nullptr,
                                                                                nullptr, sums);
@@ -1344,7 +1350,7 @@ extern "C" int npml_bn2d_pair_bwd_stats(int64_t rows, int32_t ch, const void* dY
   double* part = (double*)ws;
   BnPairBwdStatsF f{dY, s, xa, xb, dtype, mean_b != nullptr ? 1 : 0, act, p0, p1};
   if (int e = launch_col_pass<3, double>(p, f, part, st, dtype)) return e;
-  col_sums_kernel<<<(3 * ch + 31) / 32, dim3(32, 32), 0, st>>>(part, (int)p.grid.x, 3 * ch, sums);
+  col_sums_kernel<<<(3 * ch + kFinCols - 1) / kFinCols, dim3(kFinCols, kFinRows), 0, st>>>(part, (int)p.grid.x, 3 * ch, sums);
   NPML_LAUNCH_OK();
   pair_stats_fix_kernel<<<(ch + 127) / 128, 128, 0, st>>>(ch, sums, mean_a, rstd_a, mean_b, rstd_b);
   NPML_LAUNCH_OK();
