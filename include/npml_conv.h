@@ -327,6 +327,10 @@ int npml_uses_tensor_cores(const npml_conv_desc* d, int op);
  * one (tap offset in slots, tap_a, tap_b) triple per MMA group.  Returns the number of ints written, < 0 on bad arguments.
  * tests/test_ws_plan_cpu.py checks it against the NumPy mirror that is itself checked against the oracle. */
 int npml_debug_ws_plan(const npml_conv_desc* d, int op, int variant, int32_t* out, int32_t cap);
+/* Host-only test hook: the output parity classes (and their taps) the fp32 register-tiled convolution kernel is launched
+ * with for `op` (csrc/direct_fp32.cu: build_rt_classes).  out = [classes, then per class ntaps, y0, x0, so, sin, oh, ow
+ * and ntaps triples (dy, dx, filter tap)]; returns the integers written or -1. */
+int npml_debug_rt_classes(const npml_conv_desc* d, int op, int32_t* out, int32_t cap);
 /* number of kernels launched by this library on the calling thread since the last reset */
 int64_t npml_launch_count(int32_t reset);
 int npml_version(void);

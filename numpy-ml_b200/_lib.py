@@ -90,6 +90,7 @@ SIGNATURES = {
     "npml_last_error": (C.c_char_p, []),
     "npml_uses_tensor_cores": (C.c_int, [_DESC, C.c_int]),
     "npml_debug_ws_plan": (C.c_int, [_DESC, C.c_int, C.c_int, _P, _I32]),
+    "npml_debug_rt_classes": (C.c_int, [_DESC, C.c_int, _P, _I32]),
     "npml_launch_count": (_I64, [_I32]),
     "npml_version": (C.c_int, []),
 }

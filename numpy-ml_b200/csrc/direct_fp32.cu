@@ -994,6 +994,64 @@ int launch_wgrad_reduce(const float* part, int splits, int M, int CO, int CI, in
   return 0;
 }
 
+// The output parity classes of a gather convolution for gather_conv_rt_kernel (see RtClass): one class with every tap
+// for the forward form, up to s^2 classes with the taps that reach them for the transposed form.
+constexpr int kRtMaxClasses = 9;
+static int build_rt_classes(const GatherConv& g, RtClass* out) {
+  auto pm = [](int a, int b) { const int m = a % b; return m < 0 ? m + b : m; };
+  const int nq = g.form == 1 ? g.s : 1;
+  int n = 0;
+  for (int qy = 0; qy < nq; ++qy)
+    for (int qx = 0; qx < nq; ++qx) {
+      if (n >= kRtMaxClasses) return n;
+      RtClass& c = out[n];
+      memset(&c, 0, sizeof(c));
+      if (g.form == 0) {
+        c.y0 = 0; c.x0 = 0; c.so = 1; c.sin = g.s; c.oh = g.OH; c.ow = g.OW;
+        for (int r = 0; r < g.fr; ++r)
+          for (int t = 0; t < g.fc; ++t) {
+            c.dy[c.ntaps] = (int16_t)(r * g.D - g.pr); c.dx[c.ntaps] = (int16_t)(t * g.D - g.pc);
+            c.wt[c.ntaps++] = (int16_t)(r * g.fc + t);
+          }
+      } else {
+        // outputs y = y0 + s yy see the taps with (y + pr - r D) % s == 0, i.e. (r D) % s == qy where y0 = (qy - pr) mod s
+        c.y0 = pm(qy - g.pr, g.s); c.x0 = pm(qx - g.pc, g.s); c.so = g.s; c.sin = 1;
+        if (c.y0 >= g.OH || c.x0 >= g.OW) continue;
+        c.oh = (g.OH - c.y0 + g.s - 1) / g.s; c.ow = (g.OW - c.x0 + g.s - 1) / g.s;
+        for (int r = 0; r < g.fr; ++r) {
+          if (pm(r * g.D, g.s) != qy) continue;
+          for (int t = 0; t < g.fc; ++t) {
+            if (pm(t * g.D, g.s) != qx) continue;
+            c.dy[c.ntaps] = (int16_t)((c.y0 + g.pr - r * g.D) / g.s);      // exact by construction
+            c.dx[c.ntaps] = (int16_t)((c.x0 + g.pc - t * g.D) / g.s);
+            c.wt[c.ntaps++] = (int16_t)(r * g.fc + t);
+          }
+        }
+      }
+      ++n;
+    }
+  return n;
+}
+
+// Host-only test hook (npml_debug_rt_classes): out = [classes, then per class ntaps, y0, x0, so, sin, oh, ow and ntaps
+// triples (dy, dx, filter tap)]; returns the number of integers written or -1 (tests/test_rt_classes_cpu.py).
+int rt_classes_debug(const GatherConv& g, int32_t* out, int32_t cap) {
+  if (g.fr * g.fc > kRtMaxTaps || g.s < 1 || g.s > 3) return -1;
+  RtClass cls[kRtMaxClasses];
+  const int ncls = build_rt_classes(g, cls);
+  int n = 0;
+  if (cap < 1) return -1;
+  out[n++] = ncls;
+  for (int q = 0; q < ncls; ++q) {
+    const RtClass& c = cls[q];
+    if (n + 7 + 3 * c.ntaps > cap) return -1;
+    const int32_t head[7] = {c.ntaps, c.y0, c.x0, c.so, c.sin, c.oh, c.ow};
+    for (int i = 0; i < 7; ++i) out[n++] = head[i];
+    for (int j = 0; j < c.ntaps; ++j) { out[n++] = c.dy[j]; out[n++] = c.dx[j]; out[n++] = c.wt[j]; }
+  }
+  return n;
+}
+
 int direct_gather_conv(const GatherConv& g, const void* in, const float* w, const float* bias, void* Z,
                        void* Y, int dtype, cudaStream_t st) {
   const int64_t P = (int64_t)g.N * g.OH * g.OW;
@@ -1034,48 +1092,24 @@ int direct_gather_conv(const GatherConv& g, const void* in, const float* w, cons
   }
   if (dtype == NPML_F32 && g.CI % 4 == 0 && g.CO % 4 == 0 && g.CI >= 16 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 256 && g.fr * g.fc <= kRtMaxTaps &&
+      (reinterpret_cast<uintptr_t>(Y) & 15) == 0 && P >= 256 && g.fr * g.fc <= kRtMaxTaps && g.s <= 3 &&
       !getenv("NPML_DISABLE_FP32_RT")) {
     // register-tiled kernel, one launch per output parity class: 128-wide N tile for wide outputs, 64-wide otherwise
-    auto pm = [](int a, int b) { const int m = a % b; return m < 0 ? m + b : m; };
-    const int nq = g.form == 1 ? g.s : 1;
-    for (int qy = 0; qy < nq; ++qy)
-      for (int qx = 0; qx < nq; ++qx) {
-        RtClass c;
-        memset(&c, 0, sizeof(c));
-        if (g.form == 0) {
-          c.y0 = 0; c.x0 = 0; c.so = 1; c.sin = g.s; c.oh = g.OH; c.ow = g.OW;
-          for (int r = 0; r < g.fr; ++r)
-            for (int t = 0; t < g.fc; ++t) {
-              c.dy[c.ntaps] = (int16_t)(r * g.D - g.pr); c.dx[c.ntaps] = (int16_t)(t * g.D - g.pc);
-              c.wt[c.ntaps++] = (int16_t)(r * g.fc + t);
-            }
-        } else {
-          // outputs y = y0 + s yy see the taps with (y + pr - r D) % s == 0, i.e. (r D) % s == qy where y0 = (qy - pr) mod s
-          c.y0 = pm(qy - g.pr, g.s); c.x0 = pm(qx - g.pc, g.s); c.so = g.s; c.sin = 1;
-          if (c.y0 >= g.OH || c.x0 >= g.OW) continue;
-          c.oh = (g.OH - c.y0 + g.s - 1) / g.s; c.ow = (g.OW - c.x0 + g.s - 1) / g.s;
-          for (int r = 0; r < g.fr; ++r) {
-            if (pm(r * g.D, g.s) != qy) continue;
-            for (int t = 0; t < g.fc; ++t) {
-              if (pm(t * g.D, g.s) != qx) continue;
-              c.dy[c.ntaps] = (int16_t)((c.y0 + g.pr - r * g.D) / g.s);      // exact by construction
-              c.dx[c.ntaps] = (int16_t)((c.x0 + g.pc - t * g.D) / g.s);
-              c.wt[c.ntaps++] = (int16_t)(r * g.fc + t);
-            }
-          }
-        }
-        const int64_t Pc = (int64_t)g.N * c.oh * c.ow;
-        if (Pc == 0) continue;
-        if (g.CO > 64) {
-          dim3 grid((unsigned)((Pc + 127) / 128), (unsigned)((g.CO + 127) / 128));
-          gather_conv_rt_kernel<8><<<grid, 256, 0, st>>>(g, c, (const float*)in, w, bias, (float*)Z, (float*)Y);
-        } else {
-          dim3 grid((unsigned)((Pc + 127) / 128), (unsigned)((g.CO + 63) / 64));
-          gather_conv_rt_kernel<4><<<grid, 256, 0, st>>>(g, c, (const float*)in, w, bias, (float*)Z, (float*)Y);
-        }
-        NPML_LAUNCH_OK();
+    RtClass cls[kRtMaxClasses];
+    const int ncls = build_rt_classes(g, cls);
+    for (int q = 0; q < ncls; ++q) {
+      const RtClass& c = cls[q];
+      const int64_t Pc = (int64_t)g.N * c.oh * c.ow;
+      if (Pc == 0) continue;
+      if (g.CO > 64) {
+        dim3 grid((unsigned)((Pc + 127) / 128), (unsigned)((g.CO + 127) / 128));
+        gather_conv_rt_kernel<8><<<grid, 256, 0, st>>>(g, c, (const float*)in, w, bias, (float*)Z, (float*)Y);
+      } else {
+        dim3 grid((unsigned)((Pc + 127) / 128), (unsigned)((g.CO + 63) / 64));
+        gather_conv_rt_kernel<4><<<grid, 256, 0, st>>>(g, c, (const float*)in, w, bias, (float*)Z, (float*)Y);
       }
+      NPML_LAUNCH_OK();
+    }
     return 0;
   }
   dim3 grid((unsigned)((P + BM - 1) / BM), (unsigned)((g.CO + BN - 1) / BN));

@@ -265,6 +265,11 @@ int npml_debug_ws_plan(const npml_conv_desc* d, int op, int variant, int32_t* ou
   return ws_plan_debug(g, d->mode, out, cap);
 }
 
+int npml_debug_rt_classes(const npml_conv_desc* d, int op, int32_t* out, int32_t cap) {
+  if (!d || !out || op < NPML_OP_CONV_FPROP || op > NPML_OP_DECONV_DGRAD) return -1;
+  return rt_classes_debug(make_gather(d, op), out, cap);
+}
+
 const char* npml_last_error(void) { return g_err.c_str(); }
 
 int64_t npml_launch_count(int32_t reset) {

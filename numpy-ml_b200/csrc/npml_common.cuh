@@ -238,6 +238,7 @@ struct GatherWgrad {
 // direct (CUDA-core, fp32 accumulate) kernels, direct_fp32.cu
 int direct_gather_conv(const GatherConv& g, const void* in, const float* w, const float* bias, void* Z,
                        void* Y, int dtype, cudaStream_t st);
+int rt_classes_debug(const GatherConv& g, int32_t* out, int32_t cap);   // host-only test hook
 size_t direct_wgrad_ws_bytes(const GatherWgrad& g);
 int direct_wgrad(const GatherWgrad& g, const void* in, const void* grad, float* dW, int dtype, void* ws,
                  size_t ws_bytes, cudaStream_t st, float* db = nullptr, bool* db_done = nullptr);
